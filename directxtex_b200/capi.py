@@ -1,0 +1,143 @@
+"""ctypes binding of include/dxtex_b200.h.  No codec logic here; no fallback path."""
+import ctypes as C
+import os
+import numpy as np
+
+from . import formats as F
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libdxtex_b200.so")
+
+SYMBOLS = [
+    "dxb200_version", "dxb200_init", "dxb200_shutdown", "dxb200_device_count", "dxb200_launch_count", "dxb200_last_error",
+    "dxb200_host_alloc", "dxb200_host_free", "dxb200_compute_pitch", "dxb200_calculate_mip_levels",
+    "dxb200_compress", "dxb200_compress_device", "dxb200_decompress", "dxb200_decompress_device",
+    "dxb200_convert", "dxb200_convert_device", "dxb200_generate_mipmaps", "dxb200_generate_mipmaps_device",
+]
+
+
+class Image(C.Structure):
+    """dxb200_image == DirectX::Image (DirectXTex.h:437-445)."""
+    _fields_ = [("width", C.c_size_t), ("height", C.c_size_t), ("format", C.c_uint32),
+                ("rowPitch", C.c_size_t), ("slicePitch", C.c_size_t), ("pixels", C.c_void_p)]
+
+
+class DxTexError(RuntimeError):
+    def __init__(self, hr, what):
+        self.hr = F.hr_u32(hr)
+        super().__init__("%s failed: HRESULT 0x%08X (%s)" % (what, self.hr, last_error()))
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libdxtex_b200.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                          "There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    IP = C.POINTER(Image)
+    lib.dxb200_version.restype = C.c_char_p
+    lib.dxb200_last_error.restype = C.c_char_p
+    lib.dxb200_launch_count.restype = C.c_uint64
+    lib.dxb200_host_alloc.restype = C.c_void_p
+    lib.dxb200_host_alloc.argtypes = [C.c_size_t]
+    lib.dxb200_host_free.argtypes = [C.c_void_p]
+    lib.dxb200_init.argtypes = [C.c_int]
+    lib.dxb200_compute_pitch.argtypes = [C.c_uint32, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    lib.dxb200_calculate_mip_levels.argtypes = [C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.dxb200_compress.argtypes = [IP, C.c_size_t, C.c_uint32, C.c_uint32, C.c_float, C.c_float, IP]
+    lib.dxb200_compress_device.argtypes = [IP, C.c_size_t, C.c_uint32, C.c_uint32, C.c_float, C.c_float, IP, C.c_void_p]
+    lib.dxb200_decompress.argtypes = [IP, C.c_size_t, C.c_uint32, IP]
+    lib.dxb200_decompress_device.argtypes = [IP, C.c_size_t, C.c_uint32, IP, C.c_void_p]
+    lib.dxb200_convert.argtypes = [IP, C.c_size_t, C.c_uint32, C.c_uint32, C.c_float, IP]
+    lib.dxb200_convert_device.argtypes = [IP, C.c_size_t, C.c_uint32, C.c_uint32, C.c_float, IP, C.c_void_p]
+    lib.dxb200_generate_mipmaps.argtypes = [IP, C.c_size_t, C.c_size_t, C.c_uint32]
+    lib.dxb200_generate_mipmaps_device.argtypes = [IP, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p]
+    for name in ("dxb200_init", "dxb200_device_count", "dxb200_compute_pitch", "dxb200_calculate_mip_levels", "dxb200_compress",
+                 "dxb200_compress_device", "dxb200_decompress", "dxb200_decompress_device", "dxb200_convert",
+                 "dxb200_convert_device", "dxb200_generate_mipmaps", "dxb200_generate_mipmaps_device"):
+        getattr(lib, name).restype = C.c_int32
+    return lib
+
+
+lib = _load()
+
+
+def last_error():
+    return (lib.dxb200_last_error() or b"").decode()
+
+
+def launch_count():
+    return int(lib.dxb200_launch_count())
+
+
+def make_image(ptr, w, h, fmt, row_pitch=0):
+    row, sl = F.compute_pitch(fmt, w, h)
+    if row_pitch and row_pitch != row:
+        sl = row_pitch * (max(1, (h + 3) // 4) if fmt in F.BLOCK_BYTES else h)
+        row = row_pitch
+    return Image(w, h, fmt, row, sl, ptr)
+
+
+def images(seq):
+    arr = (Image * len(seq))(*seq)
+    return arr
+
+
+def _np_ptr(a):
+    return a.ctypes.data
+
+
+# ------------------------------------------------------------------------------------------------
+# host-pointer calls (numpy in / numpy out) — what a DirectX::Compress caller sees
+def compress(src, w, h, src_fmt, dst_fmt, flags=0, threshold=0.5, alpha_weight=1.0):
+    """src: C-contiguous numpy array holding the image rows; returns uint8 array of blocks."""
+    src = np.ascontiguousarray(src)
+    _, sl = F.compute_pitch(dst_fmt, w, h) if dst_fmt in F.BLOCK_BYTES else (0, 0)
+    out = np.zeros(max(sl, 1), np.uint8)
+    s = images([make_image(_np_ptr(src), w, h, src_fmt)])
+    d = images([Image(w, h, dst_fmt, *(F.compute_pitch(dst_fmt, w, h) if dst_fmt in F.BLOCK_BYTES else (0, 0)), _np_ptr(out))])
+    hr = lib.dxb200_compress(s, 1, dst_fmt, flags, threshold, alpha_weight, d)
+    if hr != 0:
+        raise DxTexError(hr, "dxb200_compress")
+    return out[:sl]
+
+
+def compress_array(srcs, w, h, src_fmt, dst_fmt, flags=0, threshold=0.5):
+    srcs = [np.ascontiguousarray(s) for s in srcs]
+    row, sl = F.compute_pitch(dst_fmt, w, h)
+    outs = [np.zeros(sl, np.uint8) for _ in srcs]
+    s = images([make_image(_np_ptr(a), w, h, src_fmt) for a in srcs])
+    d = images([Image(w, h, dst_fmt, row, sl, _np_ptr(o)) for o in outs])
+    hr = lib.dxb200_compress(s, len(srcs), dst_fmt, flags, threshold, 1.0, d)
+    if hr != 0:
+        raise DxTexError(hr, "dxb200_compress")
+    return outs
+
+
+def convert(src, w, h, src_fmt, dst_fmt, filter=0, threshold=0.5):
+    src = np.ascontiguousarray(src)
+    if dst_fmt not in F.BYTES_PER_PIXEL:
+        out = np.zeros(16, np.uint8)
+        d = images([Image(w, h, dst_fmt, 0, 0, _np_ptr(out))])
+    else:
+        row, sl = F.compute_pitch(dst_fmt, w, h)
+        out = np.zeros(sl, np.uint8)
+        d = images([Image(w, h, dst_fmt, row, sl, _np_ptr(out))])
+    s = images([make_image(_np_ptr(src), w, h, src_fmt) if src_fmt in F.BYTES_PER_PIXEL or src_fmt in F.BLOCK_BYTES
+                else Image(w, h, src_fmt, 0, 0, _np_ptr(src))])
+    hr = lib.dxb200_convert(s, 1, dst_fmt, filter, threshold, d)
+    if hr != 0:
+        raise DxTexError(hr, "dxb200_convert")
+    return out
+
+
+def generate_mipmaps(src, w, h, fmt, filter=0, levels=0):
+    """Returns (chain bytes laid out as a ScratchImage would, layout list)."""
+    src = np.ascontiguousarray(src).view(np.uint8).reshape(-1)
+    layout, total = F.mip_chain_layout(fmt, w, h, levels)
+    chain = np.zeros(total, np.uint8)
+    chain[:layout[0][4]] = src[:layout[0][4]]
+    imgs = images([Image(lw, lh, fmt, row, sl, _np_ptr(chain) + off) for (off, lw, lh, row, sl) in layout])
+    hr = lib.dxb200_generate_mipmaps(imgs, 1, len(layout), filter)
+    if hr != 0:
+        raise DxTexError(hr, "dxb200_generate_mipmaps")
+    return chain, layout

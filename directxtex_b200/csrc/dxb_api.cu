@@ -1,0 +1,588 @@
+// dxb_api.cu — the extern "C" boundary of libdxtex_b200.so (see include/dxtex_b200.h) and the host
+// logic behind it: argument validation with the reference's HRESULTs, pitch rules, batching,
+// staging of host images through device memory, kernel launches on sm_100a.
+//
+// Compiled with: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false (bit-exact fp32 contract
+// of the BC1-5 / convert / mip kernels) -lineinfo.  There is no host implementation of any codec in
+// this file: if CUDA is unavailable every compute entry point returns E_FAIL.
+#include <cuda_runtime.h>
+#include <atomic>
+#include <mutex>
+#include <vector>
+#include <string>
+#include <cstring>
+#include <cstdio>
+#include <cmath>
+#include <algorithm>
+
+#include "../../include/dxtex_b200.h"
+#include "dxb_kernels.cuh"
+#include "dxb_host_tri.h"
+
+namespace {
+
+std::mutex g_mu;
+std::atomic<uint64_t> g_launches{0};
+thread_local std::string t_lastError;
+
+struct State
+{
+    bool inited = false;
+    int device = 0;
+    int numSMs = 148;
+    cudaStream_t streams[2] = { nullptr, nullptr };
+    void* dIn[2] = { nullptr, nullptr };  size_t dInCap[2] = { 0, 0 };
+    void* dOut[2] = { nullptr, nullptr }; size_t dOutCap[2] = { 0, 0 };
+    int gridBC15 = 0, gridBC7 = 0, gridRow = 0;
+} g;
+
+int32_t cuda_hr(cudaError_t e, const char* what)
+{
+    if (e == cudaSuccess) return DXB_S_OK;
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    t_lastError = buf;
+    (void)cudaGetLastError();
+    return (e == cudaErrorMemoryAllocation) ? DXB_E_OUTOFMEMORY : DXB_E_FAIL;
+}
+#define DXB_CUDA(call) do { const int32_t hr__ = cuda_hr((call), #call); if (hr__ != DXB_S_OK) return hr__; } while (0)
+
+int32_t ensure_init_locked()
+{
+    if (g.inited) return DXB_S_OK;
+    int n = 0;
+    DXB_CUDA(cudaGetDeviceCount(&n));
+    if (n <= 0) { t_lastError = "no CUDA device"; return DXB_E_FAIL; }
+    DXB_CUDA(cudaSetDevice(g.device));
+    cudaDeviceProp prop;
+    DXB_CUDA(cudaGetDeviceProperties(&prop, g.device));
+    g.numSMs = prop.multiProcessorCount;
+    for (int i = 0; i < 2; ++i) DXB_CUDA(cudaStreamCreateWithFlags(&g.streams[i], cudaStreamNonBlocking));
+    int b = 0;
+    DXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc15, 128, 0));
+    g.gridBC15 = g.numSMs * std::max(b, 1);
+    DXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc7, DXB_BC7_WARPS * 32, 0));
+    g.gridBC7 = g.numSMs * std::max(b, 1);
+    g.gridRow = g.numSMs * 8;
+    g.inited = true;
+    return DXB_S_OK;
+}
+
+int32_t ensure_buffer(void** p, size_t* cap, size_t need)
+{
+    if (*cap >= need) return DXB_S_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    const size_t want = (need + (size_t(1) << 20)) & ~((size_t(1) << 20) - 1);
+    DXB_CUDA(cudaMalloc(p, want));
+    *cap = want;
+    return DXB_S_OK;
+}
+
+// ---- format predicates (DirectXTex.inl:57-130 / DirectXTexUtil.cpp), implemented subset ----------
+bool is_compressed(uint32_t f) { return dxb_bc_block_bytes(f) != 0; }
+bool is_supported_pixel_format(uint32_t f) { return dxb_bytes_per_pixel(f) != 0; }
+
+int32_t compute_pitch(uint32_t fmt, size_t w, size_t h, size_t* row, size_t* slice)
+{
+    if (const uint32_t bs = dxb_bc_block_bytes(fmt))
+    {
+        const size_t nbw = std::max<size_t>(1, (w + 3) / 4), nbh = std::max<size_t>(1, (h + 3) / 4);
+        *row = nbw * bs; *slice = *row * nbh;
+        return DXB_S_OK;
+    }
+    if (const uint32_t bpp = dxb_bytes_per_pixel(fmt))
+    {
+        *row = w * bpp; *slice = *row * h;
+        return DXB_S_OK;
+    }
+    return DXB_E_NOT_SUPPORTED;
+}
+
+size_t count_mips(size_t w, size_t h)
+{
+    size_t n = 1;
+    while (h > 1 || w > 1) { if (h > 1) h >>= 1; if (w > 1) w >>= 1; ++n; }
+    return n;
+}
+
+// ---- generic launch helper ------------------------------------------------------------------
+template <typename J>
+struct DeviceJobs
+{
+    J* d = nullptr; cudaStream_t s = nullptr;
+    int32_t upload(const std::vector<J>& jobs, cudaStream_t stream)
+    {
+        s = stream;
+        if (jobs.size() <= 1) return DXB_S_OK;
+        DXB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d), jobs.size() * sizeof(J), stream));
+        DXB_CUDA(cudaMemcpyAsync(d, jobs.data(), jobs.size() * sizeof(J), cudaMemcpyHostToDevice, stream));
+        return DXB_S_OK;
+    }
+    void release() { if (d) { cudaFreeAsync(d, s); d = nullptr; } }
+};
+
+int32_t check_launch(const char* name)
+{
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cuda_hr(cudaGetLastError(), name);
+}
+
+// ---- Compress ---------------------------------------------------------------------------------
+struct CompressPlan { dxb_compress_params P; bool bc7; };
+
+// validation + flag resolution shared by host and device variants (DirectXTexCompress.cpp:664-676, 732-749, 72-107)
+int32_t plan_compress(const dxb200_image* src, size_t n, uint32_t dstFormat, uint32_t flags, float threshold,
+                      const dxb200_image* dst, CompressPlan* plan)
+{
+    if (!src || !dst || !n) return DXB_E_INVALIDARG;
+    const uint32_t srcFormat = src[0].format;
+    if (is_compressed(srcFormat) || !is_compressed(dstFormat)) return DXB_E_INVALIDARG;
+    if (!is_supported_pixel_format(srcFormat)) return DXB_E_NOT_SUPPORTED;        // no CPU fallback for other formats
+    if (dstFormat == DXB_FMT_BC6H_UF16 || dstFormat == DXB_FMT_BC6H_SF16) return DXB_E_NOT_SUPPORTED;   // round 2
+    for (size_t i = 0; i < n; ++i)
+    {
+        if (!src[i].pixels || !dst[i].pixels) return DXB_E_POINTER;
+        if (src[i].format != srcFormat || dst[i].format != dstFormat) return DXB_E_INVALIDARG;
+        if (src[i].width != dst[i].width || src[i].height != dst[i].height) return DXB_E_FAIL;
+        if (!src[i].width || !src[i].height || src[i].width > 0xFFFFFFFFull || src[i].height > 0xFFFFFFFFull) return DXB_E_INVALIDARG;
+    }
+    dxb_compress_params& P = plan->P;
+    P.srcFormat = srcFormat; P.dstFormat = dstFormat;
+    P.inF = dxb_convert_flags(srcFormat); P.outF = dxb_convert_flags(dstFormat);
+    uint32_t cflags = 0;                                                       // DetermineEncoderSettings :46-68
+    if (dstFormat == DXB_FMT_BC4_UNORM || dstFormat == DXB_FMT_BC4_SNORM) cflags = DXB_FILTER_RGB_COPY_RED;
+    if (dstFormat == DXB_FMT_BC5_UNORM || dstFormat == DXB_FMT_BC5_SNORM) cflags = DXB_FILTER_RGB_COPY_RED | DXB_FILTER_RGB_COPY_GREEN;
+    cflags |= (flags & DXB_FILTER_SRGB_MASK);                                  // GetSRGBFlags :37-44
+    P.cflags = dxb_resolve_srgb_convert(cflags, srcFormat, dstFormat);
+    P.bcflags = flags & (DXB_BC_FLAGS_DITHER_RGB | DXB_BC_FLAGS_DITHER_A | DXB_BC_FLAGS_UNIFORM |
+                         DXB_BC_FLAGS_USE_3SUBSETS | DXB_BC_FLAGS_FORCE_BC7_MODE6);                 // GetBCFlags :26-35
+    P.threshold = threshold;
+    plan->bc7 = (dstFormat == DXB_FMT_BC7_UNORM || dstFormat == DXB_FMT_BC7_UNORM_SRGB);
+    return DXB_S_OK;
+}
+
+// enqueue the kernel for images whose pixels already live on the device
+int32_t launch_compress(const CompressPlan& plan, const dxb200_image* src, const dxb200_image* dst, size_t n, cudaStream_t stream)
+{
+    std::vector<dxb_job> jobs(n);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; ++i)
+    {
+        dxb_job& j = jobs[i];
+        j.src = src[i].pixels; j.dst = dst[i].pixels;
+        j.srcPitch = src[i].rowPitch; j.dstPitch = dst[i].rowPitch;
+        j.width = (uint32_t)src[i].width; j.height = (uint32_t)src[i].height;
+        j.nbx = (j.width + 3) / 4; j.nby = (j.height + 3) / 4;
+        j.firstUnit = (uint32_t)total; j.pad = 0;
+        total += (uint64_t)j.nbx * j.nby;
+        if (total > 0x7FFFFFFFull) return DXB_E_INVALIDARG;                    // same 2^31-block limit as CompressBC_Parallel (:258)
+    }
+    dxb_compress_params P = plan.P;
+    P.totalUnits = (uint32_t)total; P.njobs = (uint32_t)n;
+    DeviceJobs<dxb_job> dj;
+    int32_t hr = dj.upload(jobs, stream);
+    if (hr != DXB_S_OK) return hr;
+    if (plan.bc7)
+    {
+        const uint32_t need = (uint32_t)((total + DXB_BC7_WARPS - 1) / DXB_BC7_WARPS);
+        const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridBC7 * 4u));
+        k_compress_bc7<<<grid, DXB_BC7_WARPS * 32, 0, stream>>>(dj.d, jobs[0], P);
+        hr = check_launch("k_compress_bc7");
+    }
+    else
+    {
+        const uint32_t need = (uint32_t)((total + 127) / 128);
+        const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridBC15 * 4u));
+        k_compress_bc15<<<grid, 128, 0, stream>>>(dj.d, jobs[0], P);
+        hr = check_launch("k_compress_bc15");
+    }
+    dj.release();
+    return hr;
+}
+
+// ---- host staging: run `fn(devSrc[], devDst[], count, stream)` over chunks of the batch -------------
+// Inputs are copied to the device, outputs copied back; two slots alternate so that the copies of one
+// chunk overlap the kernels of the other when the host memory is pinned.
+template <typename LaunchFn>
+int32_t run_staged(const dxb200_image* src, const dxb200_image* dst, size_t n, bool copyInput, bool copyAllOutput, LaunchFn fn)
+{
+    const size_t CHUNK = size_t(1) << 30;
+    size_t i = 0; int slot = 0;
+    int32_t hr = DXB_S_OK;
+    while (i < n && hr == DXB_S_OK)
+    {
+        size_t inBytes = 0, outBytes = 0, k = i;
+        while (k < n)
+        {
+            const size_t a = (src[k].slicePitch + 255) & ~size_t(255), b = (dst[k].slicePitch + 255) & ~size_t(255);
+            if (k > i && (inBytes + a + outBytes + b) > CHUNK) break;
+            inBytes += a; outBytes += b; ++k;
+        }
+        cudaStream_t st = g.streams[slot];
+        hr = cuda_hr(cudaStreamSynchronize(st), "slot sync"); if (hr) break;
+        hr = ensure_buffer(&g.dIn[slot], &g.dInCap[slot], inBytes); if (hr) break;
+        hr = ensure_buffer(&g.dOut[slot], &g.dOutCap[slot], outBytes); if (hr) break;
+        std::vector<dxb200_image> ds(src + i, src + k), dd(dst + i, dst + k);
+        size_t offIn = 0, offOut = 0;
+        for (size_t m = i; m < k && hr == DXB_S_OK; ++m)
+        {
+            ds[m - i].pixels = static_cast<uint8_t*>(g.dIn[slot]) + offIn;
+            dd[m - i].pixels = static_cast<uint8_t*>(g.dOut[slot]) + offOut;
+            if (copyInput)
+                hr = cuda_hr(cudaMemcpyAsync(ds[m - i].pixels, src[m].pixels, src[m].slicePitch, cudaMemcpyHostToDevice, st), "H2D");
+            offIn += (src[m].slicePitch + 255) & ~size_t(255);
+            offOut += (dst[m].slicePitch + 255) & ~size_t(255);
+        }
+        if (hr) break;
+        hr = fn(ds.data(), dd.data(), k - i, st); if (hr) break;
+        for (size_t m = i; m < k && hr == DXB_S_OK; ++m)
+            hr = cuda_hr(cudaMemcpyAsync(dst[m].pixels, dd[m - i].pixels, dst[m].slicePitch, cudaMemcpyDeviceToHost, st), "D2H");
+        (void)copyAllOutput;
+        i = k; slot ^= 1;
+    }
+    for (int s = 0; s < 2; ++s)
+    {
+        const int32_t h2 = cuda_hr(cudaStreamSynchronize(g.streams[s]), "final sync");
+        if (hr == DXB_S_OK) hr = h2;
+    }
+    return hr;
+}
+
+// ---- Convert ----------------------------------------------------------------------------------
+int32_t plan_convert(const dxb200_image* src, size_t n, uint32_t dstFormat, uint32_t filter, const dxb200_image* dst, dxb_convert_params* P)
+{
+    if (!src || !dst || !n) return DXB_E_INVALIDARG;
+    const uint32_t srcFormat = src[0].format;
+    // Convert/ConvertEx argument checks (DirectXTexConvert.cpp:5113-5125): same format, BC formats -> E_INVALIDARG
+    if (srcFormat == dstFormat) return DXB_E_INVALIDARG;
+    if (is_compressed(srcFormat) || is_compressed(dstFormat)) return DXB_E_INVALIDARG;
+    if (!is_supported_pixel_format(srcFormat) || !is_supported_pixel_format(dstFormat)) return DXB_E_NOT_SUPPORTED;
+    if (filter & DXB_FILTER_DITHER_MASK) return DXB_E_NOT_SUPPORTED;             // dithered stores: SURVEY 8(f) "next"
+    for (size_t i = 0; i < n; ++i)
+    {
+        if (!src[i].pixels || !dst[i].pixels) return DXB_E_POINTER;
+        if (src[i].format != srcFormat || dst[i].format != dstFormat) return DXB_E_INVALIDARG;
+        if (src[i].width != dst[i].width || src[i].height != dst[i].height) return DXB_E_FAIL;
+        if ((uint64_t)src[i].width * src[i].height > 0x7FFFFFFFull) return DXB_E_INVALIDARG;
+    }
+    P->srcFormat = srcFormat; P->dstFormat = dstFormat;
+    P->inF = dxb_convert_flags(srcFormat); P->outF = dxb_convert_flags(dstFormat);
+    P->flags = dxb_resolve_srgb_convert(filter, srcFormat, dstFormat);
+    return DXB_S_OK;
+}
+
+int32_t launch_convert(dxb_convert_params P, const dxb200_image* src, const dxb200_image* dst, size_t n, cudaStream_t stream)
+{
+    std::vector<dxb_job> jobs(n);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; ++i)
+    {
+        dxb_job& j = jobs[i];
+        j.src = src[i].pixels; j.dst = dst[i].pixels; j.srcPitch = src[i].rowPitch; j.dstPitch = dst[i].rowPitch;
+        j.width = (uint32_t)src[i].width; j.height = (uint32_t)src[i].height; j.nbx = j.nby = 0; j.pad = 0;
+        j.firstUnit = (uint32_t)total;
+        total += (uint64_t)j.width * j.height;
+        if (total > 0x7FFFFFFFull) return DXB_E_INVALIDARG;
+    }
+    P.totalUnits = (uint32_t)total; P.njobs = (uint32_t)n;
+    DeviceJobs<dxb_job> dj;
+    int32_t hr = dj.upload(jobs, stream);
+    if (hr != DXB_S_OK) return hr;
+    const uint32_t need = (uint32_t)((total + 255) / 256);
+    const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridRow * 8u));
+    k_convert<<<grid, 256, 0, stream>>>(dj.d, jobs[0], P);
+    hr = check_launch("k_convert");
+    dj.release();
+    return hr;
+}
+
+// ---- GenerateMipMaps ----------------------------------------------------------------------------
+bool ispow2(size_t x) { return ((x != 0) && !(x & (x - 1))); }
+
+int32_t plan_mips(const dxb200_image* chain, size_t items, size_t levels, uint32_t filter, uint32_t* mode)
+{
+    if (!chain || !items || levels < 2) return DXB_E_INVALIDARG;
+    const uint32_t fmt = chain[0].format;
+    if (is_compressed(fmt)) return DXB_E_NOT_SUPPORTED;                         // GenerateMipMaps :2852-2856
+    if (!is_supported_pixel_format(fmt)) return DXB_E_NOT_SUPPORTED;
+    const size_t w = chain[0].width, h = chain[0].height;
+    if (levels > count_mips(w, h)) return DXB_E_INVALIDARG;
+    for (size_t it = 0; it < items; ++it)
+    {
+        size_t lw = w, lh = h;
+        for (size_t l = 0; l < levels; ++l)
+        {
+            const dxb200_image& im = chain[it * levels + l];
+            if (!im.pixels) return DXB_E_POINTER;
+            if (im.format != fmt || im.width != lw || im.height != lh) return DXB_E_INVALIDARG;
+            if (lh > 1) lh >>= 1;
+            if (lw > 1) lw >>= 1;
+        }
+    }
+    uint32_t m = filter & DXB_FILTER_MODE_MASK;
+    if (!m) m = (ispow2(w) && ispow2(h)) ? DXB_FILTER_BOX : DXB_FILTER_LINEAR;   // :3169-3174
+    switch (m)
+    {
+    case DXB_FILTER_BOX: if (!ispow2(w) || !ispow2(h)) return DXB_E_FAIL; break;     // :1005-1006
+    case DXB_FILTER_POINT: case DXB_FILTER_LINEAR: case DXB_FILTER_CUBIC: case DXB_FILTER_TRIANGLE: break;
+    default: return DXB_E_NOT_SUPPORTED;
+    }
+    if ((uint64_t)w * h * items > 0x7FFFFFFFull) return DXB_E_INVALIDARG;
+    *mode = m;
+    return DXB_S_OK;
+}
+
+// chain[] holds DEVICE pointers; level 0 of each item is populated
+int32_t launch_mips(const dxb200_image* chain, size_t items, size_t levels, uint32_t filter, uint32_t mode, cudaStream_t stream)
+{
+    const uint32_t fmt = chain[0].format;
+    dxb_mip_params P; memset(&P, 0, sizeof(P));
+    P.format = fmt; P.mode = mode; P.filter = filter;
+    P.lflags = dxb_resolve_srgb_linear(filter & DXB_FILTER_SRGB_MASK, fmt);
+    int32_t hr = DXB_S_OK;
+    std::vector<const dxb200_image*> stale(items, nullptr);
+    for (size_t l = 1; l < levels && hr == DXB_S_OK; ++l)
+    {
+        if (mode == DXB_FILTER_TRIANGLE)
+        {
+            // one launch per item: the gather lists are per (level) and shared by all items, uploaded once
+            const dxb200_image& s0 = chain[l - 1]; const dxb200_image& d0 = chain[l];
+            TriLists tx, ty;
+            build_triangle_axis(s0.width, d0.width, (filter & DXB_FILTER_WRAP_U) != 0, tx);
+            build_triangle_axis(s0.height, d0.height, (filter & DXB_FILTER_WRAP_V) != 0, ty);
+            const size_t nOff = tx.off.size() + ty.off.size(), nEnt = tx.src.size() + ty.src.size();
+            uint32_t* dU = nullptr; float* dW = nullptr;
+            DXB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dU), (nOff + nEnt) * sizeof(uint32_t), stream));
+            DXB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dW), nEnt * sizeof(float), stream));
+            std::vector<uint32_t> hu; hu.reserve(nOff + nEnt);
+            hu.insert(hu.end(), tx.off.begin(), tx.off.end()); hu.insert(hu.end(), ty.off.begin(), ty.off.end());
+            hu.insert(hu.end(), tx.src.begin(), tx.src.end()); hu.insert(hu.end(), ty.src.begin(), ty.src.end());
+            std::vector<float> hw; hw.reserve(nEnt);
+            hw.insert(hw.end(), tx.w.begin(), tx.w.end()); hw.insert(hw.end(), ty.w.begin(), ty.w.end());
+            DXB_CUDA(cudaMemcpyAsync(dU, hu.data(), hu.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+            DXB_CUDA(cudaMemcpyAsync(dW, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+            DXB_CUDA(cudaStreamSynchronize(stream));      // host vectors go out of scope below
+            P.triX.off = dU; P.triY.off = dU + tx.off.size();
+            P.triX.src = dU + nOff; P.triY.src = dU + nOff + tx.src.size();
+            P.triX.w = dW; P.triY.w = dW + tx.w.size();
+        }
+        std::vector<dxb_mip_job> jobs(items);
+        uint64_t total = 0;
+        for (size_t it = 0; it < items; ++it)
+        {
+            const dxb200_image& s = chain[it * levels + l - 1]; const dxb200_image& d = chain[it * levels + l];
+            dxb_mip_job& j = jobs[it];
+            j.src = s.pixels; j.dst = d.pixels; j.srcPitch = s.rowPitch; j.dstPitch = d.rowPitch;
+            j.sw = (uint32_t)s.width; j.sh = (uint32_t)s.height; j.dw = (uint32_t)d.width; j.dh = (uint32_t)d.height;
+            j.firstUnit = (uint32_t)total; total += (uint64_t)j.dw * j.dh;
+            if (s.height == 2) stale[it] = &s;          // box filter quirk, see dxb_mip_box
+            j.stale = nullptr; j.stalePitch = 0;
+            if (mode == DXB_FILTER_BOX && s.height <= 1 && s.width > 1 && stale[it])
+            {
+                j.stale = stale[it]->pixels + stale[it]->rowPitch;      // row 1 of that level
+                j.stalePitch = stale[it]->rowPitch;
+            }
+        }
+        P.totalUnits = (uint32_t)total; P.njobs = (uint32_t)items;
+        DeviceJobs<dxb_mip_job> dj;
+        hr = dj.upload(jobs, stream);
+        if (hr != DXB_S_OK) break;
+        const uint32_t need = (uint32_t)((total + 255) / 256);
+        const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridRow * 8u));
+        k_mip_level<<<grid, 256, 0, stream>>>(dj.d, jobs[0], P);
+        hr = check_launch("k_mip_level");
+        dj.release();
+        if (mode == DXB_FILTER_TRIANGLE)
+        {
+            cudaFreeAsync(const_cast<uint32_t*>(P.triX.off), stream);
+            cudaFreeAsync(const_cast<float*>(P.triX.w), stream);
+        }
+    }
+    return hr;
+}
+
+} // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* dxb200_version(void) { return "dxtex_b200 0.1 (sm_100a)"; }
+const char* dxb200_last_error(void) { return t_lastError.c_str(); }
+uint64_t dxb200_launch_count(void) { return g_launches.load(); }
+
+int32_t dxb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    return n;
+}
+
+int32_t dxb200_init(int device)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g.inited && g.device == device) return DXB_S_OK;
+    if (g.inited) return DXB_E_INVALIDARG;       // one device per process (one process per GPU)
+    g.device = device;
+    return ensure_init_locked();
+}
+
+void dxb200_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g.inited) return;
+    for (int i = 0; i < 2; ++i)
+    {
+        if (g.streams[i]) { cudaStreamSynchronize(g.streams[i]); cudaStreamDestroy(g.streams[i]); g.streams[i] = nullptr; }
+        if (g.dIn[i]) { cudaFree(g.dIn[i]); g.dIn[i] = nullptr; g.dInCap[i] = 0; }
+        if (g.dOut[i]) { cudaFree(g.dOut[i]); g.dOut[i] = nullptr; g.dOutCap[i] = 0; }
+    }
+    g.inited = false;
+}
+
+void* dxb200_host_alloc(size_t bytes)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (ensure_init_locked() != DXB_S_OK) return nullptr;
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+void dxb200_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int32_t dxb200_compute_pitch(uint32_t format, size_t width, size_t height, size_t* rowPitch, size_t* slicePitch)
+{
+    if (!rowPitch || !slicePitch) return DXB_E_POINTER;
+    return compute_pitch(format, width, height, rowPitch, slicePitch);
+}
+
+int32_t dxb200_calculate_mip_levels(size_t width, size_t height, size_t* levels)
+{
+    if (!levels) return DXB_E_POINTER;
+    if (*levels > 1) { if (*levels > count_mips(width, height)) return DXB_E_INVALIDARG; }
+    else if (*levels == 0) *levels = count_mips(width, height);
+    else *levels = 1;
+    return DXB_S_OK;
+}
+
+// ---- Compress -----------------------------------------------------------------------------------
+int32_t dxb200_compress_device(const dxb200_image* src, size_t nimages, uint32_t dstFormat, uint32_t flags, float threshold,
+                               float alphaWeight, const dxb200_image* dst, void* stream)
+{
+    (void)alphaWeight;      // only the reference's DirectCompute path has an alpha weight (DirectXTex.h:919); the CPU encoder we match has none
+    CompressPlan plan;
+    int32_t hr = plan_compress(src, nimages, dstFormat, flags, threshold, dst, &plan);
+    if (hr != DXB_S_OK) return hr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        hr = ensure_init_locked();
+    }
+    if (hr != DXB_S_OK) return hr;
+    return launch_compress(plan, src, dst, nimages, static_cast<cudaStream_t>(stream));
+}
+
+int32_t dxb200_compress(const dxb200_image* src, size_t nimages, uint32_t dstFormat, uint32_t flags, float threshold,
+                        float alphaWeight, const dxb200_image* dst)
+{
+    (void)alphaWeight;
+    CompressPlan plan;
+    int32_t hr = plan_compress(src, nimages, dstFormat, flags, threshold, dst, &plan);
+    if (hr != DXB_S_OK) return hr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    hr = ensure_init_locked();
+    if (hr != DXB_S_OK) return hr;
+    return run_staged(src, dst, nimages, true, true,
+        [&](const dxb200_image* ds, const dxb200_image* dd, size_t cnt, cudaStream_t st) { return launch_compress(plan, ds, dd, cnt, st); });
+}
+
+// ---- Decompress (lands after the encode path) ------------------------------------
+int32_t dxb200_decompress_device(const dxb200_image*, size_t, uint32_t, const dxb200_image*, void*) { return DXB_E_NOTIMPL; }
+int32_t dxb200_decompress(const dxb200_image*, size_t, uint32_t, const dxb200_image*) { return DXB_E_NOTIMPL; }
+
+// ---- Convert ------------------------------------------------------------------------------------
+int32_t dxb200_convert_device(const dxb200_image* src, size_t nimages, uint32_t dstFormat, uint32_t filter, float threshold,
+                              const dxb200_image* dst, void* stream)
+{
+    (void)threshold;        // only used by 1-bit alpha destinations (B5G5R5A1), not in the implemented set
+    dxb_convert_params P;
+    int32_t hr = plan_convert(src, nimages, dstFormat, filter, dst, &P);
+    if (hr != DXB_S_OK) return hr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        hr = ensure_init_locked();
+    }
+    if (hr != DXB_S_OK) return hr;
+    return launch_convert(P, src, dst, nimages, static_cast<cudaStream_t>(stream));
+}
+
+int32_t dxb200_convert(const dxb200_image* src, size_t nimages, uint32_t dstFormat, uint32_t filter, float threshold, const dxb200_image* dst)
+{
+    (void)threshold;
+    dxb_convert_params P;
+    int32_t hr = plan_convert(src, nimages, dstFormat, filter, dst, &P);
+    if (hr != DXB_S_OK) return hr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    hr = ensure_init_locked();
+    if (hr != DXB_S_OK) return hr;
+    return run_staged(src, dst, nimages, true, true,
+        [&](const dxb200_image* ds, const dxb200_image* dd, size_t cnt, cudaStream_t st) { return launch_convert(P, ds, dd, cnt, st); });
+}
+
+// ---- GenerateMipMaps ----------------------------------------------------------------------------
+int32_t dxb200_generate_mipmaps_device(const dxb200_image* chain, size_t items, size_t levels, uint32_t filter, void* stream)
+{
+    uint32_t mode = 0;
+    int32_t hr = plan_mips(chain, items, levels, filter, &mode);
+    if (hr != DXB_S_OK) return hr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        hr = ensure_init_locked();
+    }
+    if (hr != DXB_S_OK) return hr;
+    return launch_mips(chain, items, levels, filter, mode, static_cast<cudaStream_t>(stream));
+}
+
+int32_t dxb200_generate_mipmaps(const dxb200_image* chain, size_t items, size_t levels, uint32_t filter)
+{
+    uint32_t mode = 0;
+    int32_t hr = plan_mips(chain, items, levels, filter, &mode);
+    if (hr != DXB_S_OK) return hr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    hr = ensure_init_locked();
+    if (hr != DXB_S_OK) return hr;
+    // stage whole items: all levels of an item live in one device allocation slice
+    const size_t CHUNK = size_t(1) << 30;
+    size_t it = 0;
+    cudaStream_t st = g.streams[0];
+    while (it < items && hr == DXB_S_OK)
+    {
+        size_t bytes = 0, k = it;
+        while (k < items)
+        {
+            size_t b = 0;
+            for (size_t l = 0; l < levels; ++l) b += (chain[k * levels + l].slicePitch + 255) & ~size_t(255);
+            if (k > it && bytes + b > CHUNK) break;
+            bytes += b; ++k;
+        }
+        hr = ensure_buffer(&g.dIn[0], &g.dInCap[0], bytes); if (hr) break;
+        std::vector<dxb200_image> dev(chain + it * levels, chain + k * levels);
+        size_t off = 0;
+        for (size_t m = 0; m < dev.size() && hr == DXB_S_OK; ++m)
+        {
+            dev[m].pixels = static_cast<uint8_t*>(g.dIn[0]) + off;
+            off += (dev[m].slicePitch + 255) & ~size_t(255);
+            if ((m % levels) == 0)
+                hr = cuda_hr(cudaMemcpyAsync(dev[m].pixels, chain[it * levels + m].pixels, dev[m].slicePitch, cudaMemcpyHostToDevice, st), "H2D");
+        }
+        if (hr) break;
+        hr = launch_mips(dev.data(), k - it, levels, filter, mode, st); if (hr) break;
+        for (size_t m = 0; m < dev.size() && hr == DXB_S_OK; ++m)
+            if ((m % levels) != 0)
+                hr = cuda_hr(cudaMemcpyAsync(chain[it * levels + m].pixels, dev[m].pixels, dev[m].slicePitch, cudaMemcpyDeviceToHost, st), "D2H");
+        if (hr) break;
+        hr = cuda_hr(cudaStreamSynchronize(st), "mips sync");
+        it = k;
+    }
+    return hr;
+}
+
+} // extern "C"

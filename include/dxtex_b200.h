@@ -1,0 +1,98 @@
+/* dxtex_b200.h — C ABI of libdxtex_b200.so, the B200 (sm_100a) backend for the DirectXTex hot path:
+ * DirectX::Compress / Decompress-side block codecs, DirectX::Convert, DirectX::GenerateMipMaps.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * repository microsoft/DirectXTex @ 0bb96f0).  The design precedent inside the reference for an
+ * accelerator boundary at per-image granularity is GPUCompressBC::{Initialize,Prepare,Compress}
+ * (DirectXTex/BCDirectCompute.cpp:109, 203, 373), used by DirectX::Compress(ID3D11Device*, ...)
+ * (DirectXTex/DirectXTexCompressGPU.cpp:249-319).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; all functions return an HRESULT bit pattern
+ *     (S_OK = 0; E_INVALIDARG, E_POINTER, E_OUTOFMEMORY, E_FAIL, HRESULT_E_NOT_SUPPORTED as in
+ *     DirectXTexP.h:210-234 / SURVEY.md 8(b)).  CUDA failures map to E_FAIL / E_OUTOFMEMORY.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with E_FAIL,
+ *     and format pairs the kernels do not implement fail with HRESULT_E_NOT_SUPPORTED.
+ *   - `dxb200_image` mirrors DirectX::Image (DirectXTex/DirectXTex.h:437-445) field for field.
+ *   - the host-pointer entry points never allocate caller-visible memory: the caller sizes the
+ *     destination exactly as ScratchImage::Initialize2D would (DirectXTexImage.cpp:405-455; pitches
+ *     from dxb200_compute_pitch == ComputePitch, DirectXTexUtil.cpp:961-1183) and the call fills it.
+ *   - `_device` variants take device pointers in the same struct and a CUstream/cudaStream_t
+ *     (as void*, may be NULL for the default stream); they only enqueue work.
+ *   - thread safety: entry points may be called concurrently from several host threads.
+ */
+#ifndef DXTEX_B200_H
+#define DXTEX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define DXB200_API __attribute__((visibility("default")))
+#else
+#define DXB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dxb200_image
+{
+    size_t   width;
+    size_t   height;
+    uint32_t format;      /* DXGI_FORMAT value */
+    size_t   rowPitch;
+    size_t   slicePitch;
+    uint8_t* pixels;
+} dxb200_image;
+
+/* library / device management (GPUCompressBC::Initialize, BCDirectCompute.cpp:109) */
+DXB200_API const char* dxb200_version(void);
+DXB200_API int32_t  dxb200_init(int device);                 /* bind the calling process to a CUDA device; idempotent */
+DXB200_API void     dxb200_shutdown(void);                   /* release cached device / pinned buffers */
+DXB200_API int32_t  dxb200_device_count(void);
+DXB200_API uint64_t dxb200_launch_count(void);               /* number of kernels this library has launched so far */
+DXB200_API const char* dxb200_last_error(void);              /* text of the last CUDA error seen by the calling thread's call */
+
+/* pinned host allocations for callers that want full-rate H2D/D2H (optional; any host pointer works) */
+DXB200_API void*    dxb200_host_alloc(size_t bytes);
+DXB200_API void     dxb200_host_free(void* p);
+
+/* ComputePitch (DirectXTexUtil.cpp:961-1183), CP_FLAGS_NONE, for the implemented formats */
+DXB200_API int32_t  dxb200_compute_pitch(uint32_t format, size_t width, size_t height, size_t* rowPitch, size_t* slicePitch);
+/* CalculateMipLevels (DirectXTexMipmaps.cpp:359-380): *levels==0 -> full chain */
+DXB200_API int32_t  dxb200_calculate_mip_levels(size_t width, size_t height, size_t* levels);
+
+/* DirectX::Compress / CompressEx, single image and array overloads
+ * (DirectXTexCompress.cpp:632-845; block walk CompressBC :72-205).
+ *   flags     = TEX_COMPRESS_FLAGS (DirectXTex.h:887-917); TEX_COMPRESS_PARALLEL is accepted and ignored
+ *   threshold = BC1 alpha threshold (TEX_THRESHOLD_DEFAULT 0.5)
+ * src[i] and dst[i] must have equal width/height; dst[i].format == dstFormat, pitches per dxb200_compute_pitch. */
+DXB200_API int32_t  dxb200_compress(const dxb200_image* src, size_t nimages, uint32_t dstFormat,
+                         uint32_t flags, float threshold, float alphaWeight, const dxb200_image* dst);
+DXB200_API int32_t  dxb200_compress_device(const dxb200_image* src, size_t nimages, uint32_t dstFormat,
+                                uint32_t flags, float threshold, float alphaWeight, const dxb200_image* dst, void* stream);
+
+/* DirectX::Decompress (DirectXTexCompress.cpp:852-979; DecompressBC :425-535) */
+DXB200_API int32_t  dxb200_decompress(const dxb200_image* src, size_t nimages, uint32_t dstFormat, const dxb200_image* dst);
+DXB200_API int32_t  dxb200_decompress_device(const dxb200_image* src, size_t nimages, uint32_t dstFormat, const dxb200_image* dst, void* stream);
+
+/* DirectX::Convert / ConvertEx (DirectXTexConvert.cpp:5091-5404; ConvertCustom no-dither path :4888-4908).
+ *   filter = TEX_FILTER_FLAGS; dithering flags -> HRESULT_E_NOT_SUPPORTED */
+DXB200_API int32_t  dxb200_convert(const dxb200_image* src, size_t nimages, uint32_t dstFormat,
+                        uint32_t filter, float threshold, const dxb200_image* dst);
+DXB200_API int32_t  dxb200_convert_device(const dxb200_image* src, size_t nimages, uint32_t dstFormat,
+                               uint32_t filter, float threshold, const dxb200_image* dst, void* stream);
+
+/* DirectX::GenerateMipMaps (DirectXTexMipmaps.cpp:2828-3247; Generate2DMips{Point,Box,Linear,Cubic,Triangle}Filter :907-1602).
+ *   chain = items*levels images laid out item-major, mip-minor (TexMetadata::ComputeIndex, DirectXTexUtil.cpp:1695-1741);
+ *   level 0 of every item is filled by the caller, levels 1.. are written.
+ *   filter = TEX_FILTER_FLAGS; mode 0 selects BOX for power-of-two sizes else LINEAR (:3169-3174). */
+DXB200_API int32_t  dxb200_generate_mipmaps(const dxb200_image* chain, size_t items, size_t levels, uint32_t filter);
+DXB200_API int32_t  dxb200_generate_mipmaps_device(const dxb200_image* chain, size_t items, size_t levels, uint32_t filter, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DXTEX_B200_H */

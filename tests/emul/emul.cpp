@@ -79,3 +79,56 @@ int32_t emul_convert(const uint8_t* src, size_t w, size_t h, uint32_t srcFmt, si
 }
 
 } // extern "C"
+
+// ---- mip chain emulation: same per-pixel functions as k_mip_level ---------------------------------
+#include "dxb_mips.cuh"
+#include "dxb_host_tri.h"
+
+extern "C" int32_t emul_generate_mipmaps(uint8_t* chainBase, const size_t* offsets, const size_t* widths, const size_t* heights,
+                                         const size_t* pitches, size_t levels, uint32_t fmt, uint32_t filter)
+{
+    if (!dxb_bytes_per_pixel(fmt)) return DXB_E_NOT_SUPPORTED;
+    uint32_t mode = filter & DXB_FILTER_MODE_MASK;
+    auto ispow2 = [](size_t x) { return x && !(x & (x - 1)); };
+    if (!mode) mode = (ispow2(widths[0]) && ispow2(heights[0])) ? DXB_FILTER_BOX : DXB_FILTER_LINEAR;
+    if (mode == DXB_FILTER_BOX && (!ispow2(widths[0]) || !ispow2(heights[0]))) return DXB_E_FAIL;
+    const uint32_t lflags = dxb_resolve_srgb_linear(filter & DXB_FILTER_SRGB_MASK, fmt);
+    const uint8_t* stale = nullptr; size_t stalePitch = 0;
+    for (size_t l = 1; l < levels; ++l)
+    {
+        dxb_mip_job j;
+        j.src = chainBase + offsets[l - 1]; j.dst = chainBase + offsets[l];
+        j.srcPitch = pitches[l - 1]; j.dstPitch = pitches[l];
+        j.sw = (uint32_t)widths[l - 1]; j.sh = (uint32_t)heights[l - 1]; j.dw = (uint32_t)widths[l]; j.dh = (uint32_t)heights[l];
+        j.firstUnit = 0;
+        if (j.sh == 2) { stale = j.src + j.srcPitch; stalePitch = j.srcPitch; }
+        j.stale = nullptr; j.stalePitch = 0;
+        if (mode == DXB_FILTER_BOX && j.sh <= 1 && j.sw > 1 && stale) { j.stale = stale; j.stalePitch = stalePitch; }
+        TriLists tx, ty; dxb_tri_axis ax{}, ay{};
+        if (mode == DXB_FILTER_TRIANGLE)
+        {
+            build_triangle_axis(j.sw, j.dw, (filter & DXB_FILTER_WRAP_U) != 0, tx);
+            build_triangle_axis(j.sh, j.dh, (filter & DXB_FILTER_WRAP_V) != 0, ty);
+            ax.off = tx.off.data(); ax.src = tx.src.data(); ax.w = tx.w.data();
+            ay.off = ty.off.data(); ay.src = ty.src.data(); ay.w = ty.w.data();
+        }
+        for (uint32_t y = 0; y < j.dh; ++y)
+            for (uint32_t x = 0; x < j.dw; ++x)
+            {
+                dxb_px v;
+                switch (mode)
+                {
+                case DXB_FILTER_POINT:
+                    v = dxb_mip_point(fmt, j, x, y);
+                    dxb_store_pixel(fmt, j.dst + (size_t)y * j.dstPitch, x, v);
+                    continue;
+                case DXB_FILTER_BOX: v = dxb_mip_box(fmt, j, x, y, lflags); break;
+                case DXB_FILTER_LINEAR: v = dxb_mip_linear(fmt, j, x, y, filter, lflags); break;
+                case DXB_FILTER_CUBIC: v = dxb_mip_cubic(fmt, j, x, y, filter, lflags); break;
+                default: v = dxb_mip_triangle(fmt, j, x, y, lflags, ax, ay); break;
+                }
+                dxb_store_linear(fmt, j.dst, j.dstPitch, x, y, v, lflags);
+            }
+    }
+    return DXB_S_OK;
+}

@@ -1,0 +1,171 @@
+"""TEST INFRASTRUCTURE: ctypes access to the oracle (oracle/_ref/libdxtex_ref.so = the unmodified reference
+sources) and to the host lock-step emulator of our own kernels (tests/emul).  Never imported by the product."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libdxtex_ref.so")
+EMUL_SO = os.path.join(ROOT, "tests", "emul", "_build", "libdxb_emul.so")
+
+from directxtex_b200 import formats as F
+
+
+def build_ref():
+    if os.path.isdir("/root/reference/DirectXTex"):
+        subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    if not os.path.exists(REF_SO):
+        raise RuntimeError("oracle/_ref/libdxtex_ref.so missing and /root/reference not mounted: cannot build the oracle")
+    return REF_SO
+
+
+def build_emul(force=False):
+    srcs = [os.path.join(ROOT, "tests", "emul", "emul.cpp")]
+    cs = os.path.join(ROOT, "directxtex_b200", "csrc")
+    srcs += [os.path.join(cs, f) for f in os.listdir(cs)]
+    stale = (not os.path.exists(EMUL_SO)) or any(os.path.getmtime(s) > os.path.getmtime(EMUL_SO) for s in srcs)
+    if force or stale:
+        subprocess.run([os.path.join(ROOT, "tests", "emul", "build.sh")], check=True, stdout=subprocess.DEVNULL)
+    return EMUL_SO
+
+
+class Ref:
+    def __init__(self, path):
+        L = self.L = C.CDLL(path)
+        sz, u32, vp, f32 = C.c_size_t, C.c_uint32, C.c_void_p, C.c_float
+        L.ref_compress.argtypes = [vp, sz, sz, u32, sz, u32, u32, f32, vp, sz]
+        L.ref_compress_timed.argtypes = [vp, sz, sz, u32, sz, u32, u32, f32]
+        L.ref_compress_timed.restype = C.c_double
+        L.ref_decompress.argtypes = [vp, sz, sz, u32, u32, vp, sz]
+        L.ref_convert.argtypes = [vp, sz, sz, u32, sz, u32, u32, f32, vp, sz]
+        L.ref_convert_timed.argtypes = [vp, sz, sz, u32, u32, u32, f32]
+        L.ref_convert_timed.restype = C.c_double
+        L.ref_generate_mipmaps.argtypes = [vp, sz, sz, u32, sz, u32, sz, vp, sz, C.POINTER(sz), C.POINTER(sz)]
+        L.ref_generate_mipmaps_timed.argtypes = [vp, sz, sz, u32, u32, sz]
+        L.ref_generate_mipmaps_timed.restype = C.c_double
+        L.ref_compute_mse.argtypes = [vp, u32, vp, u32, sz, sz, C.POINTER(f32), C.POINTER(f32), u32]
+        L.ref_encode_block.argtypes = [u32, vp, u32, f32, vp]
+        L.ref_decode_blocks.argtypes = [u32, vp, sz, vp]
+        L.ref_compute_pitch.argtypes = [u32, sz, sz, C.POINTER(sz), C.POINTER(sz)]
+        L.ref_omp_set_threads.argtypes = [C.c_int]
+
+    def threads(self):
+        return self.L.ref_omp_max_threads()
+
+    def compute_pitch(self, fmt, w, h):
+        r, s = C.c_size_t(), C.c_size_t()
+        hr = self.L.ref_compute_pitch(fmt, w, h, r, s)
+        return hr, r.value, s.value
+
+    def compress(self, src, w, h, src_fmt, dst_fmt, flags=0, threshold=0.5, parallel=True):
+        src = np.ascontiguousarray(src)
+        _, sl = F.compute_pitch(dst_fmt, w, h)
+        out = np.zeros(sl, np.uint8)
+        hr = self.L.ref_compress(src.ctypes.data, w, h, src_fmt, 0, dst_fmt, flags | (F.TEX_COMPRESS_PARALLEL if parallel else 0),
+                                 threshold, out.ctypes.data, out.nbytes)
+        return F.hr_u32(hr), out
+
+    def compress_seconds(self, src, w, h, src_fmt, dst_fmt, flags=0, threshold=0.5, parallel=True):
+        src = np.ascontiguousarray(src)
+        return self.L.ref_compress_timed(src.ctypes.data, w, h, src_fmt, 0, dst_fmt,
+                                         flags | (F.TEX_COMPRESS_PARALLEL if parallel else 0), threshold)
+
+    def convert(self, src, w, h, src_fmt, dst_fmt, filter=0, threshold=0.5):
+        src = np.ascontiguousarray(src)
+        n = w * h * F.BYTES_PER_PIXEL.get(dst_fmt, 16)
+        out = np.zeros(n, np.uint8)
+        hr = self.L.ref_convert(src.ctypes.data, w, h, src_fmt, 0, dst_fmt, filter, threshold, out.ctypes.data, n)
+        return F.hr_u32(hr), out
+
+    def generate_mipmaps(self, src, w, h, fmt, filter=0, levels=0):
+        src = np.ascontiguousarray(src)
+        _, total = F.mip_chain_layout(fmt, w, h, levels)
+        out = np.zeros(total, np.uint8)
+        nl, nb = C.c_size_t(), C.c_size_t()
+        hr = self.L.ref_generate_mipmaps(src.ctypes.data, w, h, fmt, 0, filter, levels, out.ctypes.data, total, nl, nb)
+        return F.hr_u32(hr), out
+
+    def decode_blocks(self, fmt, blocks, w, h):
+        """BC blocks (row-major block order) -> float32 image (h4*4, w4*4, 4) via D3DXDecodeBC*."""
+        nbx, nby = (w + 3) // 4, (h + 3) // 4
+        blocks = np.ascontiguousarray(blocks)
+        dec = np.zeros((nbx * nby, 16, 4), np.float32)
+        hr = self.L.ref_decode_blocks(fmt, blocks.ctypes.data, nbx * nby, dec.ctypes.data)
+        assert hr == 0
+        return dec.reshape(nby, nbx, 4, 4, 4).transpose(0, 2, 1, 3, 4).reshape(nby * 4, nbx * 4, 4)[:h, :w]
+
+    def encode_block(self, fmt, rgba16x4, bcflags=0, threshold=0.5):
+        px = np.ascontiguousarray(rgba16x4, np.float32)
+        out = np.zeros(16, np.uint8)
+        hr = self.L.ref_encode_block(fmt, px.ctypes.data, bcflags, threshold, out.ctypes.data)
+        assert hr == 0
+        return out[:F.BLOCK_BYTES[fmt]]
+
+
+class Emul:
+    def __init__(self, path):
+        L = self.L = C.CDLL(path)
+        sz, u32, vp, f32 = C.c_size_t, C.c_uint32, C.c_void_p, C.c_float
+        L.emul_compress.argtypes = [vp, sz, sz, u32, sz, u32, u32, f32, vp]
+        L.emul_convert.argtypes = [vp, sz, sz, u32, sz, u32, sz, u32, vp]
+        L.emul_generate_mipmaps.argtypes = [vp] + [C.POINTER(sz)] * 4 + [sz, u32, u32]
+
+    def compress(self, src, w, h, src_fmt, dst_fmt, flags=0, threshold=0.5):
+        src = np.ascontiguousarray(src)
+        _, sl = F.compute_pitch(dst_fmt, w, h)
+        out = np.zeros(sl, np.uint8)
+        hr = self.L.emul_compress(src.ctypes.data, w, h, src_fmt, 0, dst_fmt, flags, threshold, out.ctypes.data)
+        return F.hr_u32(hr), out
+
+    def convert(self, src, w, h, src_fmt, dst_fmt, filter=0):
+        src = np.ascontiguousarray(src)
+        out = np.zeros(w * h * F.BYTES_PER_PIXEL[dst_fmt], np.uint8)
+        hr = self.L.emul_convert(src.ctypes.data, w, h, src_fmt, 0, dst_fmt, 0, filter, out.ctypes.data)
+        return F.hr_u32(hr), out
+
+    def generate_mipmaps(self, src, w, h, fmt, filter=0, levels=0):
+        layout, total = F.mip_chain_layout(fmt, w, h, levels)
+        chain = np.zeros(total, np.uint8)
+        s = np.ascontiguousarray(src).view(np.uint8).reshape(-1)
+        chain[:layout[0][4]] = s[:layout[0][4]]
+        A = C.c_size_t * len(layout)
+        off, ws, hs, ps = A(*[l[0] for l in layout]), A(*[l[1] for l in layout]), A(*[l[2] for l in layout]), A(*[l[3] for l in layout])
+        hr = self.L.emul_generate_mipmaps(chain.ctypes.data, off, ws, hs, ps, len(layout), fmt, filter)
+        return F.hr_u32(hr), chain
+
+
+def load_ref():
+    return Ref(build_ref())
+
+
+def load_emul():
+    return Emul(build_emul())
+
+
+# ---- shared helpers ---------------------------------------------------------------------------------
+def bc7_ldr(img_f32):
+    """the reference's LDR staging (BC6HBC7.cpp:2794-2797) as float 0..255"""
+    t = img_f32.astype(np.float32) * np.float32(255.0) + np.float32(0.01)
+    return np.floor(np.clip(t, 0, 255)).astype(np.float32)
+
+
+def mse255(decoded01, src_f32):
+    d = decoded01.astype(np.float64) * 255.0
+    s = bc7_ldr(src_f32).astype(np.float64)
+    return float(((d - s) ** 2).mean())
+
+
+def psnr(mse):
+    return 10.0 * np.log10(255.0 ** 2 / max(mse, 1e-12))
+
+
+def random_image(fmt, w, h, rng):
+    bpp = F.BYTES_PER_PIXEL[fmt]
+    n = w * h * bpp
+    if fmt in (2, 6, 16, 41):
+        return (rng.random(n // 4).astype(np.float32) * 1.4 - 0.2).view(np.uint8)
+    if fmt in (10, 34, 54):
+        return (rng.random(n // 2) * 1.4 - 0.2).astype(np.float16).view(np.uint8)
+    return rng.integers(0, 256, n, dtype=np.uint8)

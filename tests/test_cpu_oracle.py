@@ -1,0 +1,139 @@
+"""CPU suite, part 1: the oracle (unmodified reference sources built by oracle/Makefile) against the committed
+golden vectors, and the host lock-step emulator of our kernels' arithmetic against the oracle.
+Nothing here runs product code paths; no GPU needed."""
+import numpy as np
+import pytest
+
+from directxtex_b200 import formats as F, synth
+from tests import golden_util, oracle_lib
+
+
+def test_oracle_matches_golden_compress(oracle):
+    n = 0
+    for name, src, meta, exp in golden_util.cases("compress_"):
+        w, h, sf, df, flags = (int(v) for v in meta)
+        hr, out = oracle.compress(src, w, h, sf, df, flags)
+        assert hr == 0
+        assert np.array_equal(out, exp), name
+        n += 1
+    assert n > 100
+
+
+def test_oracle_config1_bc1(oracle):
+    """BASELINE.json configs[0]: single 256x256 RGBA8 -> BC1 via the reference CPU Compress() on a Linux build."""
+    img = synth.c1_rgba8(256, 256)
+    hr, out = oracle.compress(img, 256, 256, F.DXGI_FORMAT_R8G8B8A8_UNORM, F.DXGI_FORMAT_BC1_UNORM, 0, parallel=False)
+    assert hr == 0 and out.nbytes == 32768
+    assert np.array_equal(out, golden_util.load()["config1_bc1_out"])
+    hr2, out2 = oracle.compress(img, 256, 256, 28, 71, 0, parallel=True)      # OpenMP path gives the same bytes
+    assert hr2 == 0 and np.array_equal(out, out2)
+
+
+def test_oracle_matches_golden_convert_and_mips(oracle):
+    for name, src, meta, exp in golden_util.cases("convert_"):
+        w, h, sf, df, fl = (int(v) for v in meta)
+        hr, out = oracle.convert(src, w, h, sf, df, fl)
+        assert hr == 0 and np.array_equal(out, exp), name
+    for name, src, meta, exp in golden_util.cases("mips_"):
+        w, h, fmt, fl = (int(v) for v in meta)
+        hr, out = oracle.generate_mipmaps(src, w, h, fmt, fl)
+        assert hr == 0 and np.array_equal(out, exp), name
+
+
+def test_emulator_bc15_bit_exact_vs_golden(emul):
+    for name, src, meta, exp in golden_util.cases("compress_"):
+        w, h, sf, df, flags = (int(v) for v in meta)
+        hr, out = emul.compress(src, w, h, sf, df, flags)
+        assert hr == 0
+        assert np.array_equal(out, exp), name
+
+
+@pytest.mark.parametrize("df", [71, 74, 77, 80, 81, 83, 84])
+def test_emulator_bc15_bit_exact_vs_oracle_random(oracle, emul, df):
+    rng = np.random.default_rng(100 + df)
+    for (w, h, sf) in [(96, 64, 28), (31, 17, 28), (40, 40, 2), (24, 24, 10), (64, 16, 61), (16, 16, 31), (20, 12, 41)]:
+        src = oracle_lib.random_image(sf, w, h, rng)
+        for flags in (0, F.TEX_COMPRESS_UNIFORM, F.TEX_COMPRESS_DITHER):
+            hr, a = oracle.compress(src, w, h, sf, df, flags)
+            he, b = emul.compress(src, w, h, sf, df, flags)
+            assert hr == 0 and he == 0
+            assert np.array_equal(a, b), (w, h, sf, df, hex(flags))
+
+
+def test_emulator_convert_bit_exact(oracle, emul):
+    for name, src, meta, exp in golden_util.cases("convert_"):
+        w, h, sf, df, fl = (int(v) for v in meta)
+        he, out = emul.convert(src, w, h, sf, df, fl)
+        assert he == 0 and np.array_equal(out, exp), name
+
+
+def test_emulator_mips_bit_exact(oracle, emul):
+    for name, src, meta, exp in golden_util.cases("mips_"):
+        w, h, fmt, fl = (int(v) for v in meta)
+        if h == 1 and (fl & 0xF00000) == F.TEX_FILTER_BOX:
+            continue   # reference reads uninitialised memory for height-1 top levels (box filter quirk)
+        he, out = emul.generate_mipmaps(src, w, h, fmt, fl)
+        assert he == 0 and np.array_equal(out, exp), name
+
+
+def test_emulator_srgb_within_one_code(oracle, emul):
+    """sRGB formats go through powf: glibc vs CUDA libm differ in the last ulp, so the contract is +-1 code."""
+    rng = np.random.default_rng(7)
+    src = oracle_lib.random_image(29, 32, 16, rng)
+    hr, a = oracle.generate_mipmaps(src, 32, 16, 29, F.TEX_FILTER_LINEAR)
+    he, b = emul.generate_mipmaps(src, 32, 16, 29, F.TEX_FILTER_LINEAR)
+    assert hr == 0 and he == 0
+    assert np.abs(a.astype(int) - b.astype(int)).max() <= 1
+
+
+def test_emulator_bc7_quality_vs_reference(oracle, emul):
+    """BC7 tolerance: RGBA MSE of our encoder <= 1.02 x the reference CPU encoder's MSE on the same
+    input (i.e. PSNR no more than 0.09 dB below), every block decodable by the reference decoder."""
+    z = golden_util.load()
+    for j in range(3):
+        w, h, seed = (int(v) for v in z["bc7_%d_meta" % j])
+        kind = bytes(z["bc7_%d_kind" % j]).decode()
+        img = synth.c2_rgba32f(w, h, seed) if kind == "c2" else synth.photo_rgba32f(w, h, seed, alpha=(kind == "alpha"))
+        ref_mse = float(z["bc7_%d_refmse" % j][0])
+        # golden self-check: decoding the stored reference blocks reproduces the stored MSE
+        assert abs(oracle_lib.mse255(oracle.decode_blocks(98, z["bc7_%d_blocks" % j], w, h), img) - ref_mse) < 1e-6
+        he, blocks = emul.compress(img, w, h, 2, 98, 0)
+        assert he == 0
+        mse = oracle_lib.mse255(oracle.decode_blocks(98, blocks, w, h), img)
+        assert mse <= ref_mse * 1.02, (kind, mse, ref_mse)
+
+
+def test_emulator_bc7_special_blocks(oracle, emul):
+    """solid, two-colour, fully transparent, extreme values, partial blocks: decodable and near-lossless where possible"""
+    img = np.zeros((16, 16, 4), np.float32)
+    img[0:4, 0:4] = [0.2, 0.4, 0.6, 1.0]
+    img[0:4, 4:8] = 0.0
+    img[0:4, 8:12] = 1.0
+    img[4:8, 0:4, :] = np.where((np.arange(4)[:, None] + np.arange(4)[None]) % 2 == 0, 1.0, 0.0)[..., None]
+    img[4:8, 4:8] = [1.0, 0.0, 0.0, 0.0]
+    img[8:12, :, :3] = np.linspace(0, 1, 16)[None, :, None]
+    img[8:12, :, 3] = 1.0
+    img[12:16, :, 3] = np.linspace(0, 1, 16)[None, :]
+    he, blocks = emul.compress(img, 16, 16, 2, 98, 0)
+    assert he == 0
+    dec = oracle.decode_blocks(98, blocks, 16, 16)
+    ldr = oracle_lib.bc7_ldr(img)
+    err = np.abs(dec * 255.0 - ldr)
+    assert err[0:4, 0:12].max() <= 1.01          # solid blocks reproduce within one code
+    assert err[4:8, 0:4].max() <= 1.01           # two-colour checkerboard (b/w) is exact up to endpoint precision
+    assert err.max() <= 24.0
+    # partial blocks
+    for (w, h) in [(5, 7), (1, 1), (2, 3)]:
+        sub = np.ascontiguousarray(img[:h, :w])
+        he, blocks = emul.compress(sub, w, h, 2, 98, 0)
+        assert he == 0 and blocks.nbytes == ((w + 3) // 4) * ((h + 3) // 4) * 16
+        dec = oracle.decode_blocks(98, blocks, w, h)
+        assert np.abs(dec * 255.0 - oracle_lib.bc7_ldr(sub)).max() <= 24.0
+
+
+def test_emulator_bc7_quick_flag_uses_mode6_only(emul):
+    img = synth.photo_rgba32f(32, 32, 3)
+    he, blocks = emul.compress(img, 32, 32, 2, 98, F.TEX_COMPRESS_BC7_QUICK)
+    assert he == 0
+    first = blocks.reshape(-1, 16)[:, 0]
+    assert np.all((first & 0x7F) == 0x40)      # mode 6: six zero bits then a one

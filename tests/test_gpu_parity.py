@@ -1,0 +1,186 @@
+"""GPU suite: the CUDA path (through the C ABI) against the oracle = the unmodified reference sources.
+Bit-exact for BC1-BC5, Convert and the mip filters; BC7 within the stated MSE tolerance and bit-identical
+to the host lock-step emulator of the same source."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from directxtex_b200 import capi, formats as F, synth
+from tests import golden_util, oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    assert capi.lib.dxb200_init(0) == 0
+
+
+def test_bc15_golden():
+    n0 = capi.launch_count()
+    for name, src, meta, exp in golden_util.cases("compress_"):
+        w, h, sf, df, flags = (int(v) for v in meta)
+        got = capi.compress(src, w, h, sf, df, flags)
+        assert np.array_equal(got, exp), name
+    assert capi.launch_count() > n0          # the CUDA kernels really ran
+
+
+def test_config1_bc1_matches_reference_hash():
+    img = synth.c1_rgba8(256, 256)
+    got = capi.compress(img, 256, 256, 28, 71)
+    assert np.array_equal(got, golden_util.load()["config1_bc1_out"])
+
+
+@pytest.mark.parametrize("df", [71, 74, 77, 80, 81, 83, 84])
+def test_bc15_vs_oracle_random(oracle, df):
+    rng = np.random.default_rng(200 + df)
+    for (w, h, sf) in [(256, 128, 28), (31, 17, 28), (1, 1, 28), (2, 3, 28), (5, 7, 2), (64, 64, 2), (48, 24, 10),
+                       (128, 32, 61), (16, 16, 31), (20, 12, 41), (36, 20, 87), (12, 12, 11)]:
+        src = oracle_lib.random_image(sf, w, h, rng)
+        for flags in (0, F.TEX_COMPRESS_UNIFORM, F.TEX_COMPRESS_DITHER, F.TEX_COMPRESS_PARALLEL):
+            hr, want = oracle.compress(src, w, h, sf, df, flags & ~F.TEX_COMPRESS_PARALLEL)
+            got = capi.compress(src, w, h, sf, df, flags)
+            assert hr == 0 and np.array_equal(got, want), (w, h, sf, df, hex(flags))
+
+
+def test_bc1_threshold_and_structured(oracle):
+    img = synth.c1_rgba8(128, 128, seed=5)
+    for thr in (0.0, 0.25, 0.5, 0.75, 1.0):
+        hr, want = oracle.compress(img, 128, 128, 28, 71, 0, threshold=thr)
+        got = capi.compress(img, 128, 128, 28, 71, 0, threshold=thr)
+        assert hr == 0 and np.array_equal(got, want), thr
+
+
+def test_compress_array_batch(oracle):
+    rng = np.random.default_rng(9)
+    srcs = [oracle_lib.random_image(28, 40, 24, rng) for _ in range(7)]
+    outs = capi.compress_array(srcs, 40, 24, 28, 77)
+    for s, o in zip(srcs, outs):
+        hr, want = oracle.compress(s, 40, 24, 28, 77)
+        assert hr == 0 and np.array_equal(o, want)
+
+
+def test_convert_golden_and_random(oracle):
+    for name, src, meta, exp in golden_util.cases("convert_"):
+        w, h, sf, df, fl = (int(v) for v in meta)
+        got = capi.convert(src, w, h, sf, df, fl)
+        assert np.array_equal(got, exp), name
+    rng = np.random.default_rng(4)
+    for (sf, df) in [(61, 41), (41, 61), (28, 2), (2, 28), (10, 28), (2, 10), (28, 87)]:
+        src = oracle_lib.random_image(sf, 257, 63, rng)
+        hr, want = oracle.convert(src, 257, 63, sf, df)
+        got = capi.convert(src, 257, 63, sf, df)
+        assert hr == 0 and np.array_equal(got, want), (sf, df)
+
+
+def test_convert_srgb_within_one_code(oracle):
+    rng = np.random.default_rng(5)
+    src = oracle_lib.random_image(29, 64, 16, rng)
+    hr, want = oracle.convert(src, 64, 16, 29, 28)
+    got = capi.convert(src, 64, 16, 29, 28)
+    assert hr == 0 and np.abs(got.astype(int) - want.astype(int)).max() <= 1
+
+
+def test_mips_golden():
+    for name, src, meta, exp in golden_util.cases("mips_"):
+        w, h, fmt, fl = (int(v) for v in meta)
+        if h == 1 and (fl & 0xF00000) == F.TEX_FILTER_BOX:
+            continue
+        got, _ = capi.generate_mipmaps(src, w, h, fmt, fl)
+        assert np.array_equal(got, exp), name
+
+
+@pytest.mark.parametrize("fl", [F.TEX_FILTER_BOX, F.TEX_FILTER_LINEAR, F.TEX_FILTER_CUBIC, F.TEX_FILTER_TRIANGLE, F.TEX_FILTER_POINT, 0])
+def test_mips_vs_oracle(oracle, fl):
+    rng = np.random.default_rng(6)
+    for (fmt, w, h) in [(28, 256, 256), (10, 128, 64), (2, 64, 64), (61, 256, 64), (28, 100, 60)]:
+        if (fl == F.TEX_FILTER_BOX) and (w & (w - 1) or h & (h - 1)):
+            continue
+        src = oracle_lib.random_image(fmt, w, h, rng)
+        hr, want = oracle.generate_mipmaps(src, w, h, fmt, fl)
+        got, _ = capi.generate_mipmaps(src, w, h, fmt, fl)
+        assert hr == 0 and np.array_equal(got, want), (fmt, w, h, hex(fl))
+
+
+def test_bc7_equals_emulator_and_quality(oracle, emul):
+    """GPU BC7 == host lock-step emulator (same source, explicit fmaf, -fmad=false) bit for bit, and
+    MSE <= 1.02 x the reference CPU encoder's MSE (golden anchor) on each test image."""
+    z = golden_util.load()
+    for j in range(3):
+        w, h, seed = (int(v) for v in z["bc7_%d_meta" % j])
+        kind = bytes(z["bc7_%d_kind" % j]).decode()
+        img = synth.c2_rgba32f(w, h, seed) if kind == "c2" else synth.photo_rgba32f(w, h, seed, alpha=(kind == "alpha"))
+        got = capi.compress(img, w, h, 2, 98)
+        he, em = emul.compress(img, w, h, 2, 98)
+        assert he == 0
+        nd = int((got.reshape(-1, 16) != em.reshape(-1, 16)).any(1).sum())
+        mse = oracle_lib.mse255(oracle.decode_blocks(98, got, w, h), img)
+        ref_mse = float(z["bc7_%d_refmse" % j][0])
+        assert mse <= ref_mse * 1.02, (kind, mse, ref_mse)
+        assert nd == 0, "%d of %d blocks differ from the emulator" % (nd, got.size // 16)
+
+
+def test_bc7_rgba8_source_partial_blocks_and_quick(oracle, emul):
+    rng = np.random.default_rng(8)
+    for (w, h) in [(5, 7), (1, 1), (30, 18)]:
+        src = oracle_lib.random_image(28, w, h, rng)
+        for flags in (0, F.TEX_COMPRESS_BC7_QUICK):
+            got = capi.compress(src, w, h, 28, 98, flags)
+            he, em = emul.compress(src, w, h, 28, 98, flags)
+            assert he == 0 and np.array_equal(got, em), (w, h, flags)
+            dec = oracle.decode_blocks(98, got, w, h)      # decodable by the reference decoder
+            assert np.isfinite(dec).all()
+
+
+def test_device_api_with_torch_pointers(oracle):
+    torch = pytest.importorskip("torch")
+    img = synth.c1_rgba8(128, 64, seed=2)
+    d_in = torch.from_numpy(img.reshape(-1)).cuda()
+    row, sl = F.compute_pitch(77, 128, 64)
+    d_out = torch.zeros(sl, dtype=torch.uint8, device="cuda")
+    s = capi.images([capi.Image(128, 64, 28, 128 * 4, 128 * 64 * 4, d_in.data_ptr())])
+    d = capi.images([capi.Image(128, 64, 77, row, sl, d_out.data_ptr())])
+    st = torch.cuda.current_stream()
+    assert capi.lib.dxb200_compress_device(s, 1, 77, 0, 0.5, 1.0, d, C.c_void_p(st.cuda_stream)) == 0
+    torch.cuda.synchronize()
+    hr, want = oracle.compress(img, 128, 64, 28, 77)
+    assert hr == 0 and np.array_equal(d_out.cpu().numpy(), want)
+
+
+def test_full_size_c2_bc7_properties(oracle, emul):
+    """BASELINE configs[1] at full size (4096^2 RGBA32F -> BC7): size-independent properties.
+    determinism; locality (the blocks of an aligned crop are identical to the same blocks of the full image);
+    the crop equals the emulator; whole-image MSE sane (PSNR > 30 dB)."""
+    img = synth.c2_rgba32f(4096, 4096)
+    a = capi.compress(img, 4096, 4096, 2, 98)
+    b = capi.compress(img, 4096, 4096, 2, 98)
+    assert np.array_equal(a, b)
+    y0, x0, s = 1024, 2048, 128
+    crop = np.ascontiguousarray(img[y0:y0 + s, x0:x0 + s])
+    cb = capi.compress(crop, s, s, 2, 98).reshape(s // 4, s // 4, 16)
+    full = a.reshape(1024, 1024, 16)[y0 // 4:(y0 + s) // 4, x0 // 4:(x0 + s) // 4]
+    assert np.array_equal(cb, full)
+    he, em = emul.compress(crop, s, s, 2, 98)
+    assert he == 0 and np.array_equal(cb.reshape(-1), em)
+    step = 8
+    sub = a.reshape(1024, 1024, 16)[::step, ::step].reshape(-1, 16).copy()
+    dec = np.zeros((sub.shape[0], 16, 4), np.float32)
+    assert oracle.L.ref_decode_blocks(98, sub.ctypes.data, sub.shape[0], dec.ctypes.data) == 0
+    src_blocks = img.reshape(1024, 4, 1024, 4, 4).transpose(0, 2, 1, 3, 4)[::step, ::step].reshape(-1, 16, 4)
+    mse = float(((dec.astype(np.float64) * 255.0 - oracle_lib.bc7_ldr(src_blocks)) ** 2).mean())
+    assert oracle_lib.psnr(mse) > 30.0, mse
+
+
+def test_full_size_c5_bc4_and_convert_roundtrip(oracle):
+    """BASELINE configs[4]: 8192^2 R8 -> BC4 bit-exact on sampled block rows; R8 -> R32F -> R8 is the identity."""
+    img = synth.c5_r8(8192, 8192)
+    got = capi.compress(img, 8192, 8192, 61, 80).reshape(2048, 2048, 8)
+    for by in (0, 777, 2047):
+        rows = np.ascontiguousarray(img[by * 4:by * 4 + 4])
+        hr, want = oracle.compress(rows, 8192, 4, 61, 80)
+        assert hr == 0 and np.array_equal(got[by].reshape(-1), want), by
+    f = capi.convert(img, 8192, 8192, 61, 41)
+    assert np.array_equal(f.view(np.float32), (img.reshape(-1).astype(np.float32) / np.float32(255.0)))
+    back = capi.convert(f, 8192, 8192, 41, 61)
+    assert np.array_equal(back, img.reshape(-1))
