@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 OUT = os.path.join(OUT_DIR, "libdxtex_b200.so")
-SOURCES = [os.path.join(CSRC, "dxb_api.cu")]
+SOURCES = [os.path.join(CSRC, f) for f in ("dxb_api.cu", "dxb_k_bc7.cu", "dxb_k_bc15.cu", "dxb_k_rows.cu")]
 HOST_SOURCES = [os.path.join(HERE, "host", "DirectXTexB200.cpp")]
 
 
@@ -38,27 +38,62 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in _deps() if os.path.exists(d))
 
 
+def _flags():
+    return ["-std=c++17", "-O3", "-lineinfo",
+            "-gencode", "arch=compute_100a,code=sm_100a",
+            "-fmad=false",
+            "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
+            "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
+            "-I", os.path.join(HERE, "..", "include"), "-I", CSRC, "-DDXB_BUILDING_LIB"]
+
+
 def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return OUT
+    """Compile each translation unit (in parallel, only the stale ones) and link libdxtex_b200.so."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(OUT_DIR, exist_ok=True)
     srcs = SOURCES + [s for s in HOST_SOURCES if os.path.exists(s)]
-    cmd = [_nvcc(), "-std=c++17", "-O3", "-lineinfo",
-           "-gencode", "arch=compute_100a,code=sm_100a",
-           "-fmad=false",
-           "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=hidden",
-           "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
-           "-cudart", "static", "-shared",
-           "-I", os.path.join(HERE, "..", "include"), "-I", CSRC,
-           "-DDXB_BUILDING_LIB",
-           "-o", OUT] + srcs
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
+    import re
+
+    def dep_time(path, seen=None):
+        """newest mtime of `path` and every local header it includes (recursively)"""
+        seen = seen if seen is not None else set()
+        if path in seen or not os.path.exists(path):
+            return 0.0
+        seen.add(path)
+        t = os.path.getmtime(path)
+        for inc in re.findall(r'#include\s+"([^"]+)"', open(path).read()):
+            for base in (os.path.dirname(path), CSRC, os.path.join(HERE, "..", "include")):
+                cand = os.path.normpath(os.path.join(base, inc))
+                if os.path.exists(cand):
+                    t = max(t, dep_time(cand, seen))
+                    break
+        return t
+    objs, todo = [], []
+    for src in srcs:
+        obj = os.path.join(OUT_DIR, os.path.splitext(os.path.basename(src))[0] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < dep_time(src):
+            todo.append((src, obj))
+    if not todo and os.path.exists(OUT) and not force:
+        return OUT
+    nvcc = _nvcc()
+
+    def cc(job):
+        src, obj = job
+        cmd = [nvcc] + _flags() + (["-Xptxas=-v"] if verbose else []) + ["-c", src, "-o", obj]
+        return src, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        for src, r in ex.map(cc, todo):
+            if verbose or r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed on " + src)
+    r = subprocess.run([nvcc, "-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++",
+                        "-o", OUT] + objs, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libdxtex_b200.so")
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
     return OUT
 
 

@@ -16,7 +16,8 @@
 #include <algorithm>
 
 #include "../../include/dxtex_b200.h"
-#include "dxb_kernels.cuh"
+#include "dxb_formats.h"
+#include "dxb_launch.h"
 #include "dxb_host_tri.h"
 
 namespace {
@@ -58,11 +59,8 @@ int32_t ensure_init_locked()
     DXB_CUDA(cudaGetDeviceProperties(&prop, g.device));
     g.numSMs = prop.multiProcessorCount;
     for (int i = 0; i < 2; ++i) DXB_CUDA(cudaStreamCreateWithFlags(&g.streams[i], cudaStreamNonBlocking));
-    int b = 0;
-    DXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc15, 128, 0));
-    g.gridBC15 = g.numSMs * std::max(b, 1);
-    DXB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc7, DXB_BC7_WARPS * 32, 0));
-    g.gridBC7 = g.numSMs * std::max(b, 1);
+    g.gridBC15 = g.numSMs * dxb_occupancy_bc15();
+    g.gridBC7 = g.numSMs * dxb_occupancy_bc7();
     g.gridRow = g.numSMs * 8;
     g.inited = true;
     return DXB_S_OK;
@@ -186,14 +184,14 @@ int32_t launch_compress(const CompressPlan& plan, const dxb200_image* src, const
     {
         const uint32_t need = (uint32_t)((total + DXB_BC7_WARPS - 1) / DXB_BC7_WARPS);
         const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridBC7 * 4u));
-        k_compress_bc7<<<grid, DXB_BC7_WARPS * 32, 0, stream>>>(dj.d, jobs[0], P);
+        dxb_launch_bc7(grid, stream, dj.d, jobs[0], P);
         hr = check_launch("k_compress_bc7");
     }
     else
     {
         const uint32_t need = (uint32_t)((total + 127) / 128);
         const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridBC15 * 4u));
-        k_compress_bc15<<<grid, 128, 0, stream>>>(dj.d, jobs[0], P);
+        dxb_launch_bc15(grid, stream, dj.d, jobs[0], P);
         hr = check_launch("k_compress_bc15");
     }
     dj.release();
@@ -290,7 +288,7 @@ int32_t launch_convert(dxb_convert_params P, const dxb200_image* src, const dxb2
     if (hr != DXB_S_OK) return hr;
     const uint32_t need = (uint32_t)((total + 255) / 256);
     const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridRow * 8u));
-    k_convert<<<grid, 256, 0, stream>>>(dj.d, jobs[0], P);
+    dxb_launch_convert(grid, stream, dj.d, jobs[0], P);
     hr = check_launch("k_convert");
     dj.release();
     return hr;
@@ -389,7 +387,7 @@ int32_t launch_mips(const dxb200_image* chain, size_t items, size_t levels, uint
         if (hr != DXB_S_OK) break;
         const uint32_t need = (uint32_t)((total + 255) / 256);
         const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridRow * 8u));
-        k_mip_level<<<grid, 256, 0, stream>>>(dj.d, jobs[0], P);
+        dxb_launch_mip(grid, stream, dj.d, jobs[0], P);
         hr = check_launch("k_mip_level");
         dj.release();
         if (mode == DXB_FILTER_TRIANGLE)

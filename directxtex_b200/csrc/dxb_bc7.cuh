@@ -28,7 +28,7 @@
 #include "dxb_bc67_tables.h"
 
 #ifndef DXB_BC7_ROUNDS
-#define DXB_BC7_ROUNDS 3          // endpoint evaluation rounds per task (1 = PCA only, each extra = one LS refit)
+#define DXB_BC7_ROUNDS 2          // endpoint evaluation rounds per task (1 = PCA only, each extra = one LS refit)
 #endif
 
 struct dxb_bc7_res { float err; uint32_t q0, q1, pbits; };
@@ -114,7 +114,7 @@ DXB_DEV float dxb_bc7_moments(const dxb_px* px, uint32_t mask, float* s, float* 
     for (int k = 0; k < 10; ++k) m[k] = 0.0f;
     for (int i = 0; i < 16; ++i)
     {
-        const float f = (float)((mask >> i) & 1u);
+        const float f = dxb_uint_as_float((0u - ((mask >> i) & 1u)) & 0x3F800000u);
         const dxb_px p = px[i];
         const float x = p.x * f, y = p.y * f, z = p.z * f, w = p.w * f;
         n += f;
@@ -138,32 +138,35 @@ DXB_DEV float dxb_bc7_shape_estimate(const dxb_px* px, uint32_t shape, float qf,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// endpoint quantisation for one channel value e (0..255 float)
-//   bits  : field bits without p-bit;  hasP : field is followed by a p-bit;  p : its value
-// returns the field (without p); *deq = the 8-bit value the decoder reconstructs
-DXB_DEV uint32_t dxb_bc7_quant1(float e, uint32_t bits, bool hasP, uint32_t p, float* deq)
+// branch-free helpers (every lane of the warp runs the same instruction stream whatever its mode)
+#define DXB_MAGIC 12582912.0f                      // 1.5 * 2^23: (x + MAGIC) - MAGIC == round-to-nearest-even(x), |x| < 2^22
+
+DXB_DEV float dxb_rne(float x) { const float t = x + DXB_MAGIC; return t - DXB_MAGIC; }
+DXB_DEV float dxb_bit_as_float(uint32_t mask, int i)       // (mask >> i) & 1 as 0.0f / 1.0f without an I2F
 {
+    return dxb_uint_as_float((0u - ((mask >> i) & 1u)) & 0x3F800000u);
+}
+// interpolation weight / 64 of (float) index k at nmax = 2^ib - 1: RNE(k * 64 / nmax) / 64 reproduces the
+// BC7 weight tables {0,21,43,64} {0,9,18,27,37,46,55,64} {0,4,9,...,60,64} exactly (no product is a tie)
+DXB_DEV float dxb_bc7_weightf(float k, float c64 /* 64 / nmax */) { return dxb_rne(k * c64) * (1.0f / 64.0f); }
+
+// endpoint quantisation for one channel value e (0..255 float), branch-free
+//   bits : field bits without p-bit; hasP (0/1): field is followed by a p-bit; p (0/1): its value
+// returns the field (without p); *deq = the 8-bit value the decoder reconstructs
+DXB_DEV uint32_t dxb_bc7_quant1(float e, uint32_t bits, uint32_t hasP, uint32_t p, float* deq)
+{
+    const uint32_t B = bits + hasP;
     const uint32_t qmax = (1u << bits) - 1u;
-    uint32_t q;
-    if (!hasP)
-    {
-        const float f = dxb_fma(e, (float)qmax * (1.0f / 255.0f), 0.5f);
-        int32_t qi = dxb_f2i(f);
-        qi = qi < 0 ? 0 : (qi > (int32_t)qmax ? (int32_t)qmax : qi);
-        q = (uint32_t)qi;
-        *deq = (float)dxb_bc7_unq(q, bits);
-    }
-    else
-    {
-        const uint32_t B = bits + 1u;
-        const float fmaxv = (float)((1u << B) - 1u);
-        const float f = e * (fmaxv * (1.0f / 255.0f));
-        const float h = dxb_fma(f - (float)p, 0.5f, 0.5f);
-        int32_t qi = dxb_f2i(floorf(h));
-        qi = qi < 0 ? 0 : (qi > (int32_t)qmax ? (int32_t)qmax : qi);
-        q = (uint32_t)qi;
-        *deq = (float)dxb_bc7_unq((q << 1) | p, B);
-    }
+    const float fmaxv = (float)((1u << B) - 1u);
+    const float f = e * (fmaxv * (1.0f / 255.0f));
+    // no p-bit: q = floor(f + 0.5);  p-bit: q = floor((f - p) / 2 + 0.5)
+    const float half = hasP ? 0.5f : 1.0f;
+    const float h = dxb_fma(f - (float)(p & hasP), half, 0.5f);
+    int32_t qi = dxb_f2i(floorf(h));
+    qi = qi < 0 ? 0 : (qi > (int32_t)qmax ? (int32_t)qmax : qi);
+    const uint32_t q = (uint32_t)qi;
+    const uint32_t full = hasP ? ((q << 1) | p) : q;
+    *deq = (float)dxb_bc7_unq(full, B);
     return q;
 }
 
@@ -171,109 +174,113 @@ struct dxb_bc7_modecfg { uint32_t cbits, abits, ptype /*0 none,1 unique,2 shared
 
 DXB_DEV dxb_bc7_modecfg dxb_bc7_cfg(int mode)
 {
+    // packed per mode: cbits | abits<<4 | ptype<<8 | ib<<12 | ib2<<16   (mode table BC6HBC7.cpp:1106-1124)
+    const uint32_t t1 = 6u | (0u << 4) | (2u << 8) | (3u << 12) | (0u << 16);
+    const uint32_t t3 = 7u | (0u << 4) | (1u << 8) | (2u << 12) | (0u << 16);
+    const uint32_t t4 = 5u | (6u << 4) | (0u << 8) | (2u << 12) | (3u << 16);
+    const uint32_t t5 = 7u | (8u << 4) | (0u << 8) | (2u << 12) | (2u << 16);
+    const uint32_t t6 = 7u | (7u << 4) | (1u << 8) | (4u << 12) | (0u << 16);
+    const uint32_t t7 = 5u | (5u << 4) | (1u << 8) | (2u << 12) | (0u << 16);
+    const uint32_t t = (mode == 1) ? t1 : (mode == 3) ? t3 : (mode == 4) ? t4 : (mode == 5) ? t5 : (mode == 6) ? t6 : t7;
     dxb_bc7_modecfg c;
-    switch (mode)
-    {
-    case 1: c.cbits = 6; c.abits = 0; c.ptype = 2; c.ib = 3; c.ib2 = 0; break;
-    case 3: c.cbits = 7; c.abits = 0; c.ptype = 1; c.ib = 2; c.ib2 = 0; break;
-    case 4: c.cbits = 5; c.abits = 6; c.ptype = 0; c.ib = 2; c.ib2 = 3; break;
-    case 5: c.cbits = 7; c.abits = 8; c.ptype = 0; c.ib = 2; c.ib2 = 2; break;
-    case 6: c.cbits = 7; c.abits = 7; c.ptype = 1; c.ib = 4; c.ib2 = 0; break;
-    default: c.cbits = 5; c.abits = 5; c.ptype = 1; c.ib = 2; c.ib2 = 0; break;   // mode 7
-    }
+    c.cbits = t & 15u; c.abits = (t >> 4) & 15u; c.ptype = (t >> 8) & 15u; c.ib = (t >> 12) & 15u; c.ib2 = (t >> 16) & 15u;
     return c;
 }
 
-// Quantise both endpoints of a subset (vector part, channels 0..nch-1), choosing p-bits.
+// Quantise both endpoints of a subset (vector part), choosing p-bits; branch-free over modes.
+//   use3 = 1.0f when channel 3 is part of the vector (modes 6/7) else 0.0f (its field then stays 0)
 //   pforce < 0 : choose p-bits by endpoint reconstruction error; else bit0/bit1 = forced p of endpoint 0/1
-// outputs: q0/q1 packed fields (8 bits per channel), pbits, D0/D1 dequantised floats
-DXB_DEV void dxb_bc7_quant_endpoints(const float* E0, const float* E1, uint32_t nch, uint32_t cbits, uint32_t abits,
+DXB_DEV void dxb_bc7_quant_endpoints(const float* E0, const float* E1, float use3, uint32_t cbits, uint32_t abits,
                                      uint32_t ptype, int pforce, uint32_t* q0, uint32_t* q1, uint32_t* pbits, float* D0, float* D1)
 {
+    const uint32_t hasP = (ptype != 0u) ? 1u : 0u;
     uint32_t Q0[2] = { 0, 0 }, Q1[2] = { 0, 0 };
     float d0[2][4], d1[2][4];
     float err0[2] = { 0.0f, 0.0f }, err1[2] = { 0.0f, 0.0f };
-    const int np = (ptype == 0) ? 1 : 2;
-    for (int p = 0; p < np; ++p)
+    for (int p = 0; p < 2; ++p)
     {
         for (uint32_t c = 0; c < 4; ++c)
         {
-            if (c < nch)
-            {
-                const uint32_t bits = (c == 3) ? abits : cbits;
-                float a, b;
-                const uint32_t f0 = dxb_bc7_quant1(E0[c], bits, ptype != 0, (uint32_t)p, &a);
-                const uint32_t f1 = dxb_bc7_quant1(E1[c], bits, ptype != 0, (uint32_t)p, &b);
-                Q0[p] |= f0 << (8 * c); Q1[p] |= f1 << (8 * c);
-                d0[p][c] = a; d1[p][c] = b;
-                const float ea = a - E0[c], eb = b - E1[c];
-                err0[p] = dxb_fma(ea, ea, err0[p]); err1[p] = dxb_fma(eb, eb, err1[p]);
-            }
-            else { d0[p][c] = 0.0f; d1[p][c] = 0.0f; }
+            const uint32_t bits = (c == 3) ? (abits ? abits : 1u) : cbits;
+            const float wgt = (c == 3) ? use3 : 1.0f;
+            float a, b;
+            uint32_t f0 = dxb_bc7_quant1(E0[c], bits, hasP, (uint32_t)p, &a);
+            uint32_t f1 = dxb_bc7_quant1(E1[c], bits, hasP, (uint32_t)p, &b);
+            if (c == 3) { const uint32_t keep = (use3 != 0.0f) ? 0xFFu : 0u; f0 &= keep; f1 &= keep; a *= wgt; b *= wgt; }
+            Q0[p] |= f0 << (8 * c); Q1[p] |= f1 << (8 * c);
+            d0[p][c] = a; d1[p][c] = b;
+            const float ea = (a - E0[c]) * wgt, eb = (b - E1[c]) * wgt;
+            err0[p] = dxb_fma(ea, ea, err0[p]); err1[p] = dxb_fma(eb, eb, err1[p]);
         }
     }
-    uint32_t p0 = 0, p1 = 0;
-    if (ptype == 1)
-    {
-        if (pforce >= 0) { p0 = (uint32_t)pforce & 1u; p1 = ((uint32_t)pforce >> 1) & 1u; }
-        else { p0 = (err0[1] < err0[0]) ? 1u : 0u; p1 = (err1[1] < err1[0]) ? 1u : 0u; }
-    }
-    else if (ptype == 2)
-    {
-        if (pforce >= 0) { p0 = p1 = (uint32_t)pforce & 1u; }
-        else { p0 = p1 = ((err0[1] + err1[1]) < (err0[0] + err1[0])) ? 1u : 0u; }
-    }
-    *q0 = Q0[p0]; *q1 = Q1[p1]; *pbits = p0 | (p1 << 1);
-    for (int c = 0; c < 4; ++c) { D0[c] = d0[p0][c]; D1[c] = d1[p1][c]; }
+    // heuristic choice, then overrides; all selects
+    uint32_t p0 = (err0[1] < err0[0]) ? 1u : 0u;
+    uint32_t p1 = (err1[1] < err1[0]) ? 1u : 0u;
+    const uint32_t ps = ((err0[1] + err1[1]) < (err0[0] + err1[0])) ? 1u : 0u;
+    if (ptype == 2u) { p0 = ps; p1 = ps; }
+    if (pforce >= 0) { p0 = (uint32_t)pforce & 1u; p1 = (ptype == 2u) ? p0 : (((uint32_t)pforce >> 1) & 1u); }
+    if (ptype == 0u) { p0 = 0u; p1 = 0u; }
+    *q0 = p0 ? Q0[1] : Q0[0]; *q1 = p1 ? Q1[1] : Q1[0]; *pbits = p0 | (p1 << 1);
+    for (int c = 0; c < 4; ++c) { D0[c] = p0 ? d0[1][c] : d0[0][c]; D1[c] = p1 ? d1[1][c] : d1[0][c]; }
 }
 
 // ---------------------------------------------------------------------------------------------------
 // stage 2: one lane task.  px = 16 LDR pixels (floats 0..255).
 //   mode 1/3/7: subset `mask` of a 2-subset shape;  mode 6: whole block, forced p-bit pair;
 //   mode 4/5 : whole block, rotation `rot`, index selector `idxMode` (mode 4)
+// Written so that all 32 lanes execute ONE instruction stream for the vector part (mode differences are
+// data: bit counts, channel weight, p-bit type); only the separate-alpha part of modes 4/5 is a
+// divergent section.  Idle lanes (mode < 0) run the same code on dummy parameters.
 DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, uint32_t mask, int mode, int rot, int idxMode, int pforce)
 {
-    dxb_bc7_res R;
-    R.err = 3.0e38f; R.q0 = 0; R.q1 = 0; R.pbits = 0;
-    if (mode < 0) return R;
-
+    const bool idle = (mode < 0);
+    if (idle) { mode = 6; mask = 0xFFFFu; }
     const dxb_bc7_modecfg cfg = dxb_bc7_cfg(mode);
     const bool sep = (mode == 4 || mode == 5);
-    const uint32_t nch = (mode == 6 || mode == 7) ? 4u : 3u;
+    const float use3 = (mode == 6 || mode == 7) ? 1.0f : 0.0f;
     const uint32_t ibc = (mode == 4 && idxMode) ? 3u : cfg.ib;           // colour index bits
     const uint32_t iba = (mode == 4) ? (idxMode ? 2u : 3u) : cfg.ib2;    // alpha index bits (modes 4/5)
-    const float wch3 = (nch == 4) ? 1.0f : 0.0f;
+    const bool r1 = (rot == 1), r2 = (rot == 2), r3 = (rot == 3);
+
+    // rotated pixel: the colour vector is (x,y,z, use3*w); `a` is the rotated alpha slot
+#define DXB_BC7_FETCH(i, X, Y, Z, Wv, A) \
+    float X, Y, Z, Wv, A; \
+    { const dxb_px p_ = px[i]; \
+      X = r1 ? p_.w : p_.x; Y = r2 ? p_.w : p_.y; Z = r3 ? p_.w : p_.z; \
+      A = r1 ? p_.x : (r2 ? p_.y : (r3 ? p_.z : p_.w)); Wv = A * use3; }
 
     // ---- vector part: moments
-    float n = 0.0f, s[4] = { 0, 0, 0, 0 }, m[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    float n = 0.0f, s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+    float m00 = 0.0f, m01 = 0.0f, m02 = 0.0f, m03 = 0.0f, m11 = 0.0f, m12 = 0.0f, m13 = 0.0f, m22 = 0.0f, m23 = 0.0f, m33 = 0.0f;
     for (int i = 0; i < 16; ++i)
     {
-        const float f = (float)((mask >> i) & 1u);
-        dxb_px p = dxb_bc7_rotate(px[i], rot);
-        p.w *= wch3;
-        const float x = p.x * f, y = p.y * f, z = p.z * f, w = p.w * f;
+        const float f = dxb_bit_as_float(mask, i);
+        DXB_BC7_FETCH(i, X, Y, Z, Wv, A)
+        (void)A;
+        const float x = X * f, y = Y * f, z = Z * f, w = Wv * f;
         n += f;
-        s[0] += x; s[1] += y; s[2] += z; s[3] += w;
-        m[0] = dxb_fma(x, p.x, m[0]); m[1] = dxb_fma(x, p.y, m[1]); m[2] = dxb_fma(x, p.z, m[2]); m[3] = dxb_fma(x, p.w, m[3]);
-        m[4] = dxb_fma(y, p.y, m[4]); m[5] = dxb_fma(y, p.z, m[5]); m[6] = dxb_fma(y, p.w, m[6]);
-        m[7] = dxb_fma(z, p.z, m[7]); m[8] = dxb_fma(z, p.w, m[8]); m[9] = dxb_fma(w, p.w, m[9]);
+        s0 += x; s1 += y; s2 += z; s3 += w;
+        m00 = dxb_fma(x, X, m00); m01 = dxb_fma(x, Y, m01); m02 = dxb_fma(x, Z, m02); m03 = dxb_fma(x, Wv, m03);
+        m11 = dxb_fma(y, Y, m11); m12 = dxb_fma(y, Z, m12); m13 = dxb_fma(y, Wv, m13);
+        m22 = dxb_fma(z, Z, m22); m23 = dxb_fma(z, Wv, m23); m33 = dxb_fma(w, Wv, m33);
     }
-    if (n < 0.5f) { R.err = 0.0f; return R; }
-    const float inv = 1.0f / n;
-    float mean[4] = { s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv };
-    const float c00 = dxb_fma(-mean[0], s[0], m[0]), c01 = dxb_fma(-mean[0], s[1], m[1]), c02 = dxb_fma(-mean[0], s[2], m[2]), c03 = dxb_fma(-mean[0], s[3], m[3]);
-    const float c11 = dxb_fma(-mean[1], s[1], m[4]), c12 = dxb_fma(-mean[1], s[2], m[5]), c13 = dxb_fma(-mean[1], s[3], m[6]);
-    const float c22 = dxb_fma(-mean[2], s[2], m[7]), c23 = dxb_fma(-mean[2], s[3], m[8]), c33 = dxb_fma(-mean[3], s[3], m[9]);
+    const float inv = 1.0f / fmaxf(n, 1.0f);
+    const float mean[4] = { s0 * inv, s1 * inv, s2 * inv, s3 * inv };
+    const float c00 = dxb_fma(-mean[0], s0, m00), c01 = dxb_fma(-mean[0], s1, m01), c02 = dxb_fma(-mean[0], s2, m02), c03 = dxb_fma(-mean[0], s3, m03);
+    const float c11 = dxb_fma(-mean[1], s1, m11), c12 = dxb_fma(-mean[1], s2, m12), c13 = dxb_fma(-mean[1], s3, m13);
+    const float c22 = dxb_fma(-mean[2], s2, m22), c23 = dxb_fma(-mean[2], s3, m23), c33 = dxb_fma(-mean[3], s3, m33);
     const float tr = (c00 + c11) + (c22 + c33);
 
-    float ax[4] = { 0, 0, 0, 0 };
-    if (tr > 1e-3f)
+    // principal axis: power iteration from the row with the largest diagonal (selects, no branches)
+    float ax[4];
     {
-        float v0, v1, v2, v3;
-        if (c00 >= c11 && c00 >= c22 && c00 >= c33) { v0 = c00; v1 = c01; v2 = c02; v3 = c03; }
-        else if (c11 >= c22 && c11 >= c33) { v0 = c01; v1 = c11; v2 = c12; v3 = c13; }
-        else if (c22 >= c33) { v0 = c02; v1 = c12; v2 = c22; v3 = c23; }
-        else { v0 = c03; v1 = c13; v2 = c23; v3 = c33; }
+        const bool b0 = (c00 >= c11 && c00 >= c22 && c00 >= c33);
+        const bool b1 = !b0 && (c11 >= c22 && c11 >= c33);
+        const bool b2 = !b0 && !b1 && (c22 >= c33);
+        float v0 = b0 ? c00 : (b1 ? c01 : (b2 ? c02 : c03));
+        float v1 = b0 ? c01 : (b1 ? c11 : (b2 ? c12 : c13));
+        float v2 = b0 ? c02 : (b1 ? c12 : (b2 ? c22 : c23));
+        float v3 = b0 ? c03 : (b1 ? c13 : (b2 ? c23 : c33));
         for (int it = 0; it < 4; ++it)
         {
             const float w0 = dxb_fma(c00, v0, dxb_fma(c01, v1, dxb_fma(c02, v2, c03 * v3)));
@@ -281,30 +288,25 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, uint32_t mask, int mode, int 
             const float w2 = dxb_fma(c02, v0, dxb_fma(c12, v1, dxb_fma(c22, v2, c23 * v3)));
             const float w3 = dxb_fma(c03, v0, dxb_fma(c13, v1, dxb_fma(c23, v2, c33 * v3)));
             const float mx = fmaxf(fmaxf(fabsf(w0), fabsf(w1)), fmaxf(fabsf(w2), fabsf(w3)));
-            if (!(mx > 0.0f)) break;
-            const float r = 1.0f / mx;
+            const float r = (mx > 1e-30f) ? 1.0f / mx : 0.0f;
             v0 = w0 * r; v1 = w1 * r; v2 = w2 * r; v3 = w3 * r;
         }
         const float vv = dxb_fma(v0, v0, dxb_fma(v1, v1, dxb_fma(v2, v2, v3 * v3)));
-        if (vv > 0.0f)
-        {
-            const float r = 1.0f / sqrtf(vv);
-            ax[0] = v0 * r; ax[1] = v1 * r; ax[2] = v2 * r; ax[3] = v3 * r;
-        }
+        const float r = (vv > 1e-30f && tr > 1e-3f) ? 1.0f / sqrtf(vv) : 0.0f;
+        ax[0] = v0 * r; ax[1] = v1 * r; ax[2] = v2 * r; ax[3] = v3 * r;
     }
 
     // ---- projection extents -> initial endpoints
     float tmin = 3.0e38f, tmax = -3.0e38f;
     for (int i = 0; i < 16; ++i)
     {
-        if ((mask >> i) & 1u)
-        {
-            dxb_px p = dxb_bc7_rotate(px[i], rot);
-            p.w *= wch3;
-            const float t = dxb_fma(p.x - mean[0], ax[0], dxb_fma(p.y - mean[1], ax[1], dxb_fma(p.z - mean[2], ax[2], (p.w - mean[3]) * ax[3])));
-            tmin = fminf(tmin, t); tmax = fmaxf(tmax, t);
-        }
+        DXB_BC7_FETCH(i, X, Y, Z, Wv, A)
+        (void)A;
+        const float t = dxb_fma(X - mean[0], ax[0], dxb_fma(Y - mean[1], ax[1], dxb_fma(Z - mean[2], ax[2], (Wv - mean[3]) * ax[3])));
+        const bool in = ((mask >> i) & 1u) != 0u;
+        tmin = in ? fminf(tmin, t) : tmin; tmax = in ? fmaxf(tmax, t) : tmax;
     }
+    if (!(tmin <= tmax)) { tmin = 0.0f; tmax = 0.0f; }          // empty subset (cannot happen for valid shapes)
     float E0[4], E1[4];
     for (int c = 0; c < 4; ++c)
     {
@@ -315,51 +317,55 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, uint32_t mask, int mode, int 
     // ---- evaluation rounds (vector part)
     float bestErr = 3.0e38f; uint32_t bq0 = 0, bq1 = 0, bpb = 0;
     const float nmaxc = (float)((1u << ibc) - 1u);
+    const float c64c = 64.0f / nmaxc;
+    bool live = true;                                            // false once this lane has converged (keeps running, results ignored)
     for (int round = 0; round < DXB_BC7_ROUNDS; ++round)
     {
+        dxb_warp_sync();
         uint32_t q0, q1, pb; float D0[4], D1[4];
-        dxb_bc7_quant_endpoints(E0, E1, nch, cfg.cbits, cfg.abits, cfg.ptype, pforce, &q0, &q1, &pb, D0, D1);
+        dxb_bc7_quant_endpoints(E0, E1, use3, cfg.cbits, cfg.abits, cfg.ptype, pforce, &q0, &q1, &pb, D0, D1);
         const float dx = D1[0] - D0[0], dy = D1[1] - D0[1], dz = D1[2] - D0[2], dw = D1[3] - D0[3];
         const float dd = dxb_fma(dx, dx, dxb_fma(dy, dy, dxb_fma(dz, dz, dw * dw)));
         const float idd = (dd > 0.0f) ? 1.0f / dd : 0.0f;
+        const float B0 = D0[0] + (1.0f / 128.0f), B1 = D0[1] + (1.0f / 128.0f), B2 = D0[2] + (1.0f / 128.0f), B3 = D0[3] + (1.0f / 128.0f);
         float err = 0.0f;
         float la = 0.0f, lb = 0.0f, lc = 0.0f;                     // sum (1-s)^2, s(1-s), s^2
-        float u[4] = { 0, 0, 0, 0 }, v[4] = { 0, 0, 0, 0 };         // sum (1-s) p, sum s p
+        float u0 = 0, u1 = 0, u2 = 0, u3 = 0, v0 = 0, v1 = 0, v2 = 0, v3 = 0;     // sum (1-s) p, sum s p
         for (int i = 0; i < 16; ++i)
         {
             if ((mask >> i) & 1u)
             {
-                dxb_px p = dxb_bc7_rotate(px[i], rot);
-                p.w *= wch3;
-                const float t = dxb_fma(p.x - D0[0], dx, dxb_fma(p.y - D0[1], dy, dxb_fma(p.z - D0[2], dz, (p.w - D0[3]) * dw))) * idd;
-                float xk = fminf(fmaxf(t * nmaxc, 0.0f), nmaxc - 1.0f);
-                const uint32_t k0 = (uint32_t)dxb_f2i(xk);
-                const float s0 = (float)dxb_bc7_weight(ibc, k0) * (1.0f / 64.0f);
-                const float s1 = (float)dxb_bc7_weight(ibc, k0 + 1u) * (1.0f / 64.0f);
-                const float sk = ((t - s0) > (s1 - t)) ? s1 : s0;
-                const float cx = floorf(dxb_fma(dx, sk, D0[0]) + 0.5f), cy = floorf(dxb_fma(dy, sk, D0[1]) + 0.5f);
-                const float cz = floorf(dxb_fma(dz, sk, D0[2]) + 0.5f), cw = floorf(dxb_fma(dw, sk, D0[3]) + 0.5f);
-                const float ex = p.x - cx, ey = p.y - cy, ez = p.z - cz, ew = p.w - cw;
+                DXB_BC7_FETCH(i, X, Y, Z, Wv, A)
+                (void)A;
+                const float t = dxb_fma(X - D0[0], dx, dxb_fma(Y - D0[1], dy, dxb_fma(Z - D0[2], dz, (Wv - D0[3]) * dw))) * idd;
+                const float xk = fminf(fmaxf(t * nmaxc, 0.0f), nmaxc - 1.0f);
+                const float k0 = dxb_rne(xk - 0.5f);            // lower bracket index without an XU-pipe FRND
+                const float w0 = dxb_bc7_weightf(k0, c64c), w1 = dxb_bc7_weightf(k0 + 1.0f, c64c);
+                const float sk = ((t - w0) > (w1 - t)) ? w1 : w0;
+                // palette entry: floor(v/64 + 0.5) == RNE(v/64 + 1/128) because v/64 is a multiple of 1/64
+                const float cx = dxb_rne(dxb_fma(dx, sk, B0)), cy = dxb_rne(dxb_fma(dy, sk, B1));
+                const float cz = dxb_rne(dxb_fma(dz, sk, B2)), cw = dxb_rne(dxb_fma(dw, sk, B3));
+                const float ex = X - cx, ey = Y - cy, ez = Z - cz, ew = Wv - cw;
                 err += dxb_fma(ex, ex, dxb_fma(ey, ey, dxb_fma(ez, ez, ew * ew)));
                 const float os = 1.0f - sk;
                 la = dxb_fma(os, os, la); lb = dxb_fma(os, sk, lb); lc = dxb_fma(sk, sk, lc);
-                u[0] = dxb_fma(os, p.x, u[0]); u[1] = dxb_fma(os, p.y, u[1]); u[2] = dxb_fma(os, p.z, u[2]); u[3] = dxb_fma(os, p.w, u[3]);
-                v[0] = dxb_fma(sk, p.x, v[0]); v[1] = dxb_fma(sk, p.y, v[1]); v[2] = dxb_fma(sk, p.z, v[2]); v[3] = dxb_fma(sk, p.w, v[3]);
+                u0 = dxb_fma(os, X, u0); u1 = dxb_fma(os, Y, u1); u2 = dxb_fma(os, Z, u2); u3 = dxb_fma(os, Wv, u3);
+                v0 = dxb_fma(sk, X, v0); v1 = dxb_fma(sk, Y, v1); v2 = dxb_fma(sk, Z, v2); v3 = dxb_fma(sk, Wv, v3);
             }
         }
-        if (err < bestErr) { bestErr = err; bq0 = q0; bq1 = q1; bpb = pb; }
-        if (round + 1 < DXB_BC7_ROUNDS)
+        const bool better = live && (err < bestErr);
+        bestErr = better ? err : bestErr; bq0 = better ? q0 : bq0; bq1 = better ? q1 : bq1; bpb = better ? pb : bpb;
+        // least-squares refit for the next round (skipped lanes keep their endpoints)
+        const float det = dxb_fma(la, lc, -(lb * lb));
+        live = live && (det > 1e-4f) && (bestErr > 0.0f);
+        const float id = live ? 1.0f / det : 0.0f;
+        const float uu[4] = { u0, u1, u2, u3 }, vv[4] = { v0, v1, v2, v3 };
+        for (int c = 0; c < 4; ++c)
         {
-            const float det = dxb_fma(la, lc, -(lb * lb));
-            if (!(det > 1e-4f) || bestErr <= 0.0f) break;
-            const float id = 1.0f / det;
-            for (int c = 0; c < 4; ++c)
-            {
-                const float a = dxb_fma(lc, u[c], -(lb * v[c])) * id;
-                const float b = dxb_fma(la, v[c], -(lb * u[c])) * id;
-                E0[c] = fminf(fmaxf(a, 0.0f), 255.0f);
-                E1[c] = fminf(fmaxf(b, 0.0f), 255.0f);
-            }
+            const float a = dxb_fma(lc, uu[c], -(lb * vv[c])) * id;
+            const float b = dxb_fma(la, vv[c], -(lb * uu[c])) * id;
+            E0[c] = live ? fminf(fmaxf(a, 0.0f), 255.0f) : E0[c];
+            E1[c] = live ? fminf(fmaxf(b, 0.0f), 255.0f) : E1[c];
         }
     }
 
@@ -369,52 +375,57 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, uint32_t mask, int mode, int 
         float amin = 3.0e38f, amax = -3.0e38f;
         for (int i = 0; i < 16; ++i)
         {
-            const float a = dxb_bc7_rotate(px[i], rot).w;
-            amin = fminf(amin, a); amax = fmaxf(amax, a);
+            DXB_BC7_FETCH(i, X, Y, Z, Wv, A)
+            (void)X; (void)Y; (void)Z; (void)Wv;
+            amin = fminf(amin, A); amax = fmaxf(amax, A);
         }
         float A0 = amin, A1 = amax;
         float bestA = 3.0e38f; uint32_t ba0 = 0, ba1 = 0;
         const float nmaxa = (float)((1u << iba) - 1u);
+        const float c64a = 64.0f / nmaxa;
+        bool liveA = true;
         for (int round = 0; round < DXB_BC7_ROUNDS; ++round)
         {
             float d0, d1;
-            const uint32_t f0 = dxb_bc7_quant1(A0, cfg.abits, false, 0, &d0);
-            const uint32_t f1 = dxb_bc7_quant1(A1, cfg.abits, false, 0, &d1);
+            const uint32_t f0 = dxb_bc7_quant1(A0, cfg.abits, 0u, 0u, &d0);
+            const uint32_t f1 = dxb_bc7_quant1(A1, cfg.abits, 0u, 0u, &d1);
             const float da = d1 - d0;
             const float ida = (da != 0.0f) ? 1.0f / da : 0.0f;
+            const float Ba = d0 + (1.0f / 128.0f);
             float err = 0.0f, la = 0.0f, lb = 0.0f, lc = 0.0f, ua = 0.0f, va = 0.0f;
             for (int i = 0; i < 16; ++i)
             {
-                const float a = dxb_bc7_rotate(px[i], rot).w;
-                const float t = (a - d0) * ida;
-                float xk = fminf(fmaxf(t * nmaxa, 0.0f), nmaxa - 1.0f);
-                const uint32_t k0 = (uint32_t)dxb_f2i(xk);
-                const float s0 = (float)dxb_bc7_weight(iba, k0) * (1.0f / 64.0f);
-                const float s1 = (float)dxb_bc7_weight(iba, k0 + 1u) * (1.0f / 64.0f);
-                const float sk = ((t - s0) > (s1 - t)) ? s1 : s0;
-                const float ca = floorf(dxb_fma(da, sk, d0) + 0.5f);
-                const float ea = a - ca;
+                DXB_BC7_FETCH(i, X, Y, Z, Wv, A)
+                (void)X; (void)Y; (void)Z; (void)Wv;
+                const float t = (A - d0) * ida;
+                const float xk = fminf(fmaxf(t * nmaxa, 0.0f), nmaxa - 1.0f);
+                const float k0 = dxb_rne(xk - 0.5f);            // lower bracket index without an XU-pipe FRND
+                const float w0 = dxb_bc7_weightf(k0, c64a), w1 = dxb_bc7_weightf(k0 + 1.0f, c64a);
+                const float sk = ((t - w0) > (w1 - t)) ? w1 : w0;
+                const float ca = dxb_rne(dxb_fma(da, sk, Ba));
+                const float ea = A - ca;
                 err = dxb_fma(ea, ea, err);
                 const float os = 1.0f - sk;
                 la = dxb_fma(os, os, la); lb = dxb_fma(os, sk, lb); lc = dxb_fma(sk, sk, lc);
-                ua = dxb_fma(os, a, ua); va = dxb_fma(sk, a, va);
+                ua = dxb_fma(os, A, ua); va = dxb_fma(sk, A, va);
             }
-            if (err < bestA) { bestA = err; ba0 = f0; ba1 = f1; }
-            if (round + 1 < DXB_BC7_ROUNDS)
-            {
-                const float det = dxb_fma(la, lc, -(lb * lb));
-                if (!(det > 1e-4f) || bestA <= 0.0f) break;
-                const float id = 1.0f / det;
-                A0 = fminf(fmaxf(dxb_fma(lc, ua, -(lb * va)) * id, 0.0f), 255.0f);
-                A1 = fminf(fmaxf(dxb_fma(la, va, -(lb * ua)) * id, 0.0f), 255.0f);
-            }
+            const bool better = liveA && (err < bestA);
+            bestA = better ? err : bestA; ba0 = better ? f0 : ba0; ba1 = better ? f1 : ba1;
+            const float det = dxb_fma(la, lc, -(lb * lb));
+            liveA = liveA && (det > 1e-4f) && (bestA > 0.0f);
+            const float id = liveA ? 1.0f / det : 0.0f;
+            const float na = dxb_fma(lc, ua, -(lb * va)) * id, nb = dxb_fma(la, va, -(lb * ua)) * id;
+            A0 = liveA ? fminf(fmaxf(na, 0.0f), 255.0f) : A0;
+            A1 = liveA ? fminf(fmaxf(nb, 0.0f), 255.0f) : A1;
         }
         bestErr += bestA;
         bq0 = (bq0 & 0x00FFFFFFu) | (ba0 << 24);
         bq1 = (bq1 & 0x00FFFFFFu) | (ba1 << 24);
     }
+#undef DXB_BC7_FETCH
 
-    R.err = bestErr; R.q0 = bq0; R.q1 = bq1; R.pbits = bpb;
+    dxb_bc7_res R;
+    R.err = idle ? 3.0e38f : bestErr; R.q0 = bq0; R.q1 = bq1; R.pbits = bpb;
     return R;
 }
 

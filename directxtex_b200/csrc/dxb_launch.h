@@ -1,0 +1,64 @@
+// dxb_launch.h — job/parameter structs shared by the kernels' translation units and the host API, plus the
+// host-callable launchers each kernel TU exports (hidden visibility; not part of the C ABI).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <cuda_runtime.h>
+#include "dxb_mipjob.h"
+
+struct dxb_job
+{
+    const uint8_t* src; uint8_t* dst;
+    size_t srcPitch, dstPitch;
+    uint32_t width, height;
+    uint32_t nbx, nby;
+    uint32_t firstUnit;
+    uint32_t pad;
+};
+
+struct dxb_compress_params
+{
+    uint32_t srcFormat, dstFormat;
+    uint32_t inF, outF, cflags, bcflags;
+    float threshold;
+    uint32_t totalUnits, njobs;
+};
+
+struct dxb_convert_params
+{
+    uint32_t srcFormat, dstFormat, inF, outF, flags;
+    uint32_t totalUnits, njobs;
+};
+
+struct dxb_mip_params
+{
+    uint32_t format, mode /*DXB_FILTER_* mode bits*/, filter, lflags;
+    uint32_t totalUnits, njobs;
+    dxb_tri_axis triX, triY;       // triangle filter only
+};
+
+#define DXB_BC7_WARPS 8
+
+// launchers: `grid` CTAs on `stream`; jobs == nullptr -> `single` is used
+void dxb_launch_bc15(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job& single, const dxb_compress_params& P);
+void dxb_launch_bc7(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job& single, const dxb_compress_params& P);
+void dxb_launch_convert(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job& single, const dxb_convert_params& P);
+void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs, const dxb_mip_job& single, const dxb_mip_params& P);
+// resident CTAs per SM of each kernel at its block size
+int dxb_occupancy_bc15();
+int dxb_occupancy_bc7();
+
+#ifdef __CUDACC__
+template <typename J>
+__device__ __forceinline__ const J& dxb_find_job(const J* jobs, uint32_t njobs, const J& single, uint32_t unit)
+{
+    if (jobs == nullptr) return single;
+    uint32_t lo = 0, hi = njobs;            // last job with firstUnit <= unit
+    while (hi - lo > 1)
+    {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (jobs[mid].firstUnit <= unit) lo = mid; else hi = mid;
+    }
+    return jobs[lo];
+}
+#endif

@@ -13,18 +13,7 @@
 #pragma once
 #include "dxb_pixel.cuh"
 
-struct dxb_mip_job
-{
-    const uint8_t* src; uint8_t* dst;
-    size_t srcPitch, dstPitch;
-    uint32_t sw, sh, dw, dh;          // source / destination size
-    uint32_t firstUnit;               // prefix sum of destination pixels over the batch
-    const uint8_t* stale; size_t stalePitch;   // box filter only: see dxb_mip_box
-};
-
-// triangle filter gather lists for one axis (CSR): contributions of destination index d are
-// entries [off[d], off[d+1]) with ascending source index
-struct dxb_tri_axis { const uint32_t* off; const uint32_t* src; const float* w; };
+#include "dxb_mipjob.h"
 
 DXB_DEV dxb_px dxb_load_linear(uint32_t fmt, const uint8_t* base, size_t pitch, uint32_t x, uint32_t y, uint32_t lflags)
 {
