@@ -1,0 +1,365 @@
+// DirectXTexB200.cpp — implementation of the C++ mirror (DirectXTexB200.h): validation and destination
+// allocation as the reference's entry points do them, compute through the C ABI (include/dxtex_b200.h).
+// Reference behaviour restated (not copied): Compress/CompressEx DirectXTexCompress.cpp:632-845, Convert/ConvertEx
+// DirectXTexConvert.cpp:5091-5404, GenerateMipMaps DirectXTexMipmaps.cpp:2828-3247 + Setup2DMips :851-904,
+// ScratchImage DirectXTexImage.cpp:300-455, TexMetadata::ComputeIndex DirectXTexUtil.cpp:1695-1741.
+#include "DirectXTexB200.h"
+#include "../../include/dxtex_b200.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace
+{
+    inline dxb200_image to_c(const DirectX::Image& im)
+    {
+        dxb200_image c; c.width = im.width; c.height = im.height; c.format = static_cast<uint32_t>(im.format);
+        c.rowPitch = im.rowPitch; c.slicePitch = im.slicePitch; c.pixels = im.pixels;
+        return c;
+    }
+    inline bool implemented_pixel_format(DXGI_FORMAT f)
+    {
+        size_t r = 0, s = 0;
+        return dxb200_compute_pitch(static_cast<uint32_t>(f), 1, 1, &r, &s) == 0;
+    }
+}
+
+namespace DirectX
+{
+
+bool IsCompressed(DXGI_FORMAT fmt) noexcept
+{
+    switch (fmt)
+    {
+    case DXGI_FORMAT_BC1_UNORM: case DXGI_FORMAT_BC1_UNORM_SRGB: case DXGI_FORMAT_BC2_UNORM: case DXGI_FORMAT_BC2_UNORM_SRGB:
+    case DXGI_FORMAT_BC3_UNORM: case DXGI_FORMAT_BC3_UNORM_SRGB: case DXGI_FORMAT_BC4_UNORM: case DXGI_FORMAT_BC4_SNORM:
+    case DXGI_FORMAT_BC5_UNORM: case DXGI_FORMAT_BC5_SNORM: case DXGI_FORMAT_BC6H_UF16: case DXGI_FORMAT_BC6H_SF16:
+    case DXGI_FORMAT_BC7_UNORM: case DXGI_FORMAT_BC7_UNORM_SRGB: return true;
+    default: return false;
+    }
+}
+
+bool IsSRGB(DXGI_FORMAT fmt) noexcept
+{
+    switch (fmt)
+    {
+    case DXGI_FORMAT_R8G8B8A8_UNORM_SRGB: case DXGI_FORMAT_BC1_UNORM_SRGB: case DXGI_FORMAT_BC2_UNORM_SRGB: case DXGI_FORMAT_BC3_UNORM_SRGB:
+    case DXGI_FORMAT_B8G8R8A8_UNORM_SRGB: case DXGI_FORMAT_B8G8R8X8_UNORM_SRGB: case DXGI_FORMAT_BC7_UNORM_SRGB: return true;
+    default: return false;
+    }
+}
+
+size_t BitsPerPixel(DXGI_FORMAT fmt) noexcept
+{
+    if (IsCompressed(fmt))
+    {
+        size_t r = 0, s = 0;
+        dxb200_compute_pitch(static_cast<uint32_t>(fmt), 4, 4, &r, &s);
+        return r / 2;                     // 8-byte blocks: 4 bpp, 16-byte blocks: 8 bpp
+    }
+    size_t r = 0, s = 0;
+    if (dxb200_compute_pitch(static_cast<uint32_t>(fmt), 1, 1, &r, &s) != 0) return 0;
+    return r * 8;
+}
+
+HRESULT ComputePitch(DXGI_FORMAT fmt, size_t width, size_t height, size_t& rowPitch, size_t& slicePitch, CP_FLAGS) noexcept
+{
+    return dxb200_compute_pitch(static_cast<uint32_t>(fmt), width, height, &rowPitch, &slicePitch);
+}
+
+bool CalculateMipLevels(size_t width, size_t height, size_t& mipLevels) noexcept
+{
+    return dxb200_calculate_mip_levels(width, height, &mipLevels) == 0;
+}
+
+size_t TexMetadata::ComputeIndex(size_t mip, size_t item, size_t slice) const noexcept
+{
+    if (mip >= mipLevels || dimension == TEX_DIMENSION_TEXTURE3D) return size_t(-1);
+    if (slice > 0 || item >= arraySize) return size_t(-1);
+    return item * mipLevels + mip;
+}
+
+// ---------------------------------------------------------------------------------------------------
+ScratchImage& ScratchImage::operator=(ScratchImage&& o) noexcept
+{
+    if (this != &o)
+    {
+        Release();
+        m_nimages = o.m_nimages; m_size = o.m_size; m_metadata = o.m_metadata; m_image = o.m_image; m_memory = o.m_memory;
+        o.m_nimages = 0; o.m_size = 0; o.m_image = nullptr; o.m_memory = nullptr;
+    }
+    return *this;
+}
+
+void ScratchImage::Release() noexcept
+{
+    m_nimages = 0; m_size = 0;
+    delete[] m_image; m_image = nullptr;
+    if (m_memory) { std::free(m_memory); m_memory = nullptr; }
+    std::memset(&m_metadata, 0, sizeof(m_metadata));
+}
+
+HRESULT ScratchImage::Initialize(const TexMetadata& mdata, CP_FLAGS) noexcept
+{
+    if (mdata.dimension != TEX_DIMENSION_TEXTURE2D && mdata.dimension != TEX_DIMENSION_TEXTURE1D) return HRESULT_E_NOT_SUPPORTED;   // no volume maps on this path
+    if (!mdata.width || !mdata.height || mdata.depth != 1 || !mdata.arraySize) return E_INVALIDARG;
+    size_t mipLevels = mdata.mipLevels;
+    if (!CalculateMipLevels(mdata.width, mdata.height, mipLevels)) return E_INVALIDARG;
+    Release();
+    // item-major, mip-minor; every image occupies slicePitch bytes; one zero-filled 16-byte aligned block
+    size_t total = 0;
+    {
+        size_t w = mdata.width, h = mdata.height;
+        for (size_t l = 0; l < mipLevels; ++l)
+        {
+            size_t row = 0, slice = 0;
+            const HRESULT hr = ComputePitch(mdata.format, w, h, row, slice);
+            if (FAILED(hr)) return hr;
+            total += slice;
+            if (h > 1) h >>= 1;
+            if (w > 1) w >>= 1;
+        }
+        total *= mdata.arraySize;
+    }
+    const size_t nimages = mdata.arraySize * mipLevels;
+    m_image = new (std::nothrow) Image[nimages];
+    if (!m_image) return E_OUTOFMEMORY;
+    m_memory = static_cast<uint8_t*>(std::aligned_alloc(16, (total + 15) & ~size_t(15)));
+    if (!m_memory) { Release(); return E_OUTOFMEMORY; }
+    std::memset(m_memory, 0, total);
+    m_nimages = nimages; m_size = total;
+    m_metadata = mdata; m_metadata.mipLevels = mipLevels; m_metadata.depth = 1;
+    uint8_t* p = m_memory;
+    size_t idx = 0;
+    for (size_t item = 0; item < mdata.arraySize; ++item)
+    {
+        size_t w = mdata.width, h = mdata.height;
+        for (size_t l = 0; l < mipLevels; ++l, ++idx)
+        {
+            size_t row = 0, slice = 0;
+            ComputePitch(mdata.format, w, h, row, slice);
+            Image& im = m_image[idx];
+            im.width = w; im.height = h; im.format = mdata.format; im.rowPitch = row; im.slicePitch = slice; im.pixels = p;
+            p += slice;
+            if (h > 1) h >>= 1;
+            if (w > 1) w >>= 1;
+        }
+    }
+    return S_OK;
+}
+
+HRESULT ScratchImage::Initialize2D(DXGI_FORMAT fmt, size_t width, size_t height, size_t arraySize, size_t mipLevels, CP_FLAGS flags) noexcept
+{
+    TexMetadata m{};
+    m.width = width; m.height = height; m.depth = 1; m.arraySize = arraySize; m.mipLevels = mipLevels;
+    m.format = fmt; m.dimension = TEX_DIMENSION_TEXTURE2D;
+    return Initialize(m, flags);
+}
+
+HRESULT ScratchImage::InitializeFromImage(const Image& src, bool, CP_FLAGS flags) noexcept
+{
+    if (!src.pixels) return E_POINTER;
+    HRESULT hr = Initialize2D(src.format, src.width, src.height, 1, 1, flags);
+    if (FAILED(hr)) return hr;
+    const size_t rows = IsCompressed(src.format) ? (src.height + 3) / 4 : src.height;
+    const size_t n = m_image[0].rowPitch < src.rowPitch ? m_image[0].rowPitch : src.rowPitch;
+    for (size_t y = 0; y < rows; ++y) std::memcpy(m_image[0].pixels + y * m_image[0].rowPitch, src.pixels + y * src.rowPitch, n);
+    return S_OK;
+}
+
+const Image* ScratchImage::GetImage(size_t mip, size_t item, size_t slice) const noexcept
+{
+    const size_t i = m_metadata.ComputeIndex(mip, item, slice);
+    return (i < m_nimages) ? &m_image[i] : nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Compress
+HRESULT Compress(const Image& src, DXGI_FORMAT format, TEX_COMPRESS_FLAGS compress, float threshold, ScratchImage& image) noexcept
+{
+    CompressOptions o{ compress, threshold, TEX_ALPHA_WEIGHT_DEFAULT };
+    try { return CompressEx(src, format, o, image, nullptr); } catch (...) { return E_FAIL; }
+}
+
+HRESULT Compress(const Image* srcImages, size_t nimages, const TexMetadata& metadata, DXGI_FORMAT format, TEX_COMPRESS_FLAGS compress, float threshold, ScratchImage& cImages) noexcept
+{
+    CompressOptions o{ compress, threshold, TEX_ALPHA_WEIGHT_DEFAULT };
+    try { return CompressEx(srcImages, nimages, metadata, format, o, cImages, nullptr); } catch (...) { return E_FAIL; }
+}
+
+HRESULT CompressEx(const Image& src, DXGI_FORMAT format, const CompressOptions& options, ScratchImage& image, std::function<bool(size_t, size_t)> cb)
+{
+    if (IsCompressed(src.format) || !IsCompressed(format)) return E_INVALIDARG;
+    if (!implemented_pixel_format(src.format)) return HRESULT_E_NOT_SUPPORTED;
+    HRESULT hr = image.Initialize2D(format, src.width, src.height, 1, 1);
+    if (FAILED(hr)) return hr;
+    const Image* img = image.GetImage(0, 0, 0);
+    if (!img) { image.Release(); return E_POINTER; }
+    if (cb && !cb(0, img->height)) { image.Release(); return E_ABORT; }
+    const dxb200_image s = to_c(src), d = to_c(*img);
+    hr = dxb200_compress(&s, 1, static_cast<uint32_t>(format), static_cast<uint32_t>(options.flags), options.threshold, options.alphaWeight, &d);
+    if (FAILED(hr)) { image.Release(); return hr; }
+    if (cb && !cb(img->height, img->height)) { image.Release(); return E_ABORT; }
+    return S_OK;
+}
+
+HRESULT CompressEx(const Image* srcImages, size_t nimages, const TexMetadata& metadata, DXGI_FORMAT format, const CompressOptions& options,
+                   ScratchImage& cImages, std::function<bool(size_t, size_t)> cb)
+{
+    if (!srcImages || !nimages) return E_INVALIDARG;
+    if (IsCompressed(metadata.format) || !IsCompressed(format)) return E_INVALIDARG;
+    if (!implemented_pixel_format(metadata.format)) return HRESULT_E_NOT_SUPPORTED;
+    cImages.Release();
+    if (cb && nimages == 1 && !metadata.IsVolumemap() && metadata.mipLevels == 1 && metadata.arraySize == 1)
+        return CompressEx(srcImages[0], format, options, cImages, cb);
+    TexMetadata m2 = metadata; m2.format = format;
+    HRESULT hr = cImages.Initialize(m2);
+    if (FAILED(hr)) return hr;
+    if (nimages != cImages.GetImageCount()) { cImages.Release(); return E_FAIL; }
+    const Image* dest = cImages.GetImages();
+    if (cb && !cb(0, nimages)) { cImages.Release(); return E_ABORT; }
+    // images of one mip level share a size; the C ABI takes arbitrary per-image sizes in one batch
+    std::vector<dxb200_image> s(nimages), d(nimages);
+    for (size_t i = 0; i < nimages; ++i)
+    {
+        if (srcImages[i].width != dest[i].width || srcImages[i].height != dest[i].height) { cImages.Release(); return E_FAIL; }
+        s[i] = to_c(srcImages[i]); d[i] = to_c(dest[i]);
+    }
+    hr = dxb200_compress(s.data(), nimages, static_cast<uint32_t>(format), static_cast<uint32_t>(options.flags), options.threshold, options.alphaWeight, d.data());
+    if (FAILED(hr)) { cImages.Release(); return hr; }
+    if (cb && !cb(nimages, nimages)) { cImages.Release(); return E_ABORT; }
+    return S_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Decompress
+HRESULT Decompress(const Image& cImage, DXGI_FORMAT format, ScratchImage& image) noexcept
+{
+    if (!IsCompressed(cImage.format) || IsCompressed(format)) return E_INVALIDARG;
+    if (format == DXGI_FORMAT_UNKNOWN)
+    {
+        switch (cImage.format)         // DefaultDecompress, DirectXTexCompress.cpp:377-421
+        {
+        case DXGI_FORMAT_BC4_UNORM: format = DXGI_FORMAT_R8_UNORM; break;
+        case DXGI_FORMAT_BC4_SNORM: format = DXGI_FORMAT_R8_SNORM; break;
+        case DXGI_FORMAT_BC5_UNORM: format = DXGI_FORMAT_R8G8_UNORM; break;
+        case DXGI_FORMAT_BC5_SNORM: format = DXGI_FORMAT_R8G8_SNORM; break;
+        case DXGI_FORMAT_BC6H_UF16: case DXGI_FORMAT_BC6H_SF16: format = DXGI_FORMAT_R32G32B32A32_FLOAT; break;
+        default: format = IsSRGB(cImage.format) ? DXGI_FORMAT_R8G8B8A8_UNORM_SRGB : DXGI_FORMAT_R8G8B8A8_UNORM; break;
+        }
+    }
+    HRESULT hr = image.Initialize2D(format, cImage.width, cImage.height, 1, 1);
+    if (FAILED(hr)) return hr;
+    const dxb200_image s = to_c(cImage), d = to_c(*image.GetImage(0, 0, 0));
+    hr = dxb200_decompress(&s, 1, static_cast<uint32_t>(format), &d);
+    if (FAILED(hr)) image.Release();
+    return hr;
+}
+
+HRESULT Decompress(const Image* cImages, size_t nimages, const TexMetadata& metadata, DXGI_FORMAT format, ScratchImage& images) noexcept
+{
+    if (!cImages || !nimages) return E_INVALIDARG;
+    if (!IsCompressed(metadata.format) || IsCompressed(format) || format == DXGI_FORMAT_UNKNOWN) return E_INVALIDARG;
+    images.Release();
+    TexMetadata m2 = metadata; m2.format = format;
+    HRESULT hr = images.Initialize(m2);
+    if (FAILED(hr)) return hr;
+    if (nimages != images.GetImageCount()) { images.Release(); return E_FAIL; }
+    std::vector<dxb200_image> s(nimages), d(nimages);
+    for (size_t i = 0; i < nimages; ++i) { s[i] = to_c(cImages[i]); d[i] = to_c(images.GetImages()[i]); }
+    hr = dxb200_decompress(s.data(), nimages, static_cast<uint32_t>(format), d.data());
+    if (FAILED(hr)) images.Release();
+    return hr;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Convert
+HRESULT Convert(const Image& src, DXGI_FORMAT format, TEX_FILTER_FLAGS filter, float threshold, ScratchImage& image) noexcept
+{
+    ConvertOptions o{ filter, threshold };
+    try { return ConvertEx(src, format, o, image, nullptr); } catch (...) { return E_FAIL; }
+}
+
+HRESULT Convert(const Image* srcImages, size_t nimages, const TexMetadata& metadata, DXGI_FORMAT format, TEX_FILTER_FLAGS filter, float threshold, ScratchImage& result) noexcept
+{
+    ConvertOptions o{ filter, threshold };
+    try { return ConvertEx(srcImages, nimages, metadata, format, o, result, nullptr); } catch (...) { return E_FAIL; }
+}
+
+HRESULT ConvertEx(const Image& src, DXGI_FORMAT format, const ConvertOptions& options, ScratchImage& image, std::function<bool(size_t, size_t)> cb)
+{
+    if (src.format == format || IsCompressed(src.format) || IsCompressed(format)) return E_INVALIDARG;
+    if (!implemented_pixel_format(src.format) || !implemented_pixel_format(format)) return HRESULT_E_NOT_SUPPORTED;
+    if (src.width > 0xFFFFFFFFull || src.height > 0xFFFFFFFFull) return E_INVALIDARG;
+    HRESULT hr = image.Initialize2D(format, src.width, src.height, 1, 1);
+    if (FAILED(hr)) return hr;
+    const Image* rimage = image.GetImage(0, 0, 0);
+    if (!rimage) { image.Release(); return E_POINTER; }
+    if (cb && !cb(0, rimage->height)) { image.Release(); return E_ABORT; }
+    const dxb200_image s = to_c(src), d = to_c(*rimage);
+    hr = dxb200_convert(&s, 1, static_cast<uint32_t>(format), static_cast<uint32_t>(options.filter), options.threshold, &d);
+    if (FAILED(hr)) { image.Release(); return hr; }
+    if (cb && !cb(rimage->height, rimage->height)) { image.Release(); return E_ABORT; }
+    return S_OK;
+}
+
+HRESULT ConvertEx(const Image* srcImages, size_t nimages, const TexMetadata& metadata, DXGI_FORMAT format, const ConvertOptions& options,
+                  ScratchImage& result, std::function<bool(size_t, size_t)> cb)
+{
+    if (!srcImages || !nimages || metadata.format == format) return E_INVALIDARG;
+    if (IsCompressed(metadata.format) || IsCompressed(format)) return E_INVALIDARG;
+    if (!implemented_pixel_format(metadata.format) || !implemented_pixel_format(format)) return HRESULT_E_NOT_SUPPORTED;
+    TexMetadata m2 = metadata; m2.format = format;
+    HRESULT hr = result.Initialize(m2);
+    if (FAILED(hr)) return hr;
+    if (nimages != result.GetImageCount()) { result.Release(); return E_FAIL; }
+    if (cb && !cb(0, nimages)) { result.Release(); return E_ABORT; }
+    std::vector<dxb200_image> s(nimages), d(nimages);
+    for (size_t i = 0; i < nimages; ++i) { s[i] = to_c(srcImages[i]); d[i] = to_c(result.GetImages()[i]); }
+    hr = dxb200_convert(s.data(), nimages, static_cast<uint32_t>(format), static_cast<uint32_t>(options.filter), options.threshold, d.data());
+    if (FAILED(hr)) { result.Release(); return hr; }
+    if (cb && !cb(nimages, nimages)) { result.Release(); return E_ABORT; }
+    return S_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GenerateMipMaps
+HRESULT GenerateMipMaps(const Image& baseImage, TEX_FILTER_FLAGS filter, size_t levels, ScratchImage& mipChain, bool) noexcept
+{
+    TexMetadata m{};
+    m.width = baseImage.width; m.height = baseImage.height; m.depth = 1; m.arraySize = 1; m.mipLevels = 1;
+    m.format = baseImage.format; m.dimension = TEX_DIMENSION_TEXTURE2D;
+    try { return GenerateMipMaps(&baseImage, 1, m, filter, levels, mipChain); } catch (...) { return E_FAIL; }
+}
+
+HRESULT GenerateMipMaps(const Image* srcImages, size_t nimages, const TexMetadata& metadata, TEX_FILTER_FLAGS filter, size_t levels, ScratchImage& mipChain)
+{
+    if (!srcImages || !nimages || !metadata.width || !metadata.height) return E_INVALIDARG;
+    if (metadata.IsVolumemap() || IsCompressed(metadata.format)) return HRESULT_E_NOT_SUPPORTED;
+    if (!CalculateMipLevels(metadata.width, metadata.height, levels)) return E_INVALIDARG;
+    if (levels <= 1) return E_INVALIDARG;
+    if (nimages != metadata.arraySize) return E_FAIL;          // this path takes the base image of every array item
+    if (!implemented_pixel_format(metadata.format)) return HRESULT_E_NOT_SUPPORTED;
+    TexMetadata m2 = metadata; m2.mipLevels = levels;
+    HRESULT hr = mipChain.Initialize(m2);
+    if (FAILED(hr)) return hr;
+    // copy the base image of each item to the top of its chain (Setup2DMips)
+    for (size_t item = 0; item < nimages; ++item)
+    {
+        const Image& src = srcImages[item];
+        const Image* dest = mipChain.GetImage(0, item, 0);
+        if (!dest || !src.pixels) { mipChain.Release(); return E_POINTER; }
+        if (src.format != dest->format || src.width != dest->width || src.height != dest->height) { mipChain.Release(); return E_FAIL; }
+        const size_t n = dest->rowPitch < src.rowPitch ? dest->rowPitch : src.rowPitch;
+        for (size_t y = 0; y < src.height; ++y) std::memcpy(dest->pixels + y * dest->rowPitch, src.pixels + y * src.rowPitch, n);
+    }
+    std::vector<dxb200_image> chain(mipChain.GetImageCount());
+    for (size_t i = 0; i < chain.size(); ++i) chain[i] = to_c(mipChain.GetImages()[i]);
+    hr = dxb200_generate_mipmaps(chain.data(), nimages, levels, static_cast<uint32_t>(filter));
+    if (FAILED(hr)) mipChain.Release();
+    return hr;
+}
+
+} // namespace DirectX

@@ -1,0 +1,161 @@
+// DirectXTexB200.h — C++ host-side mirror of the part of the DirectXTex public API that the B200 backend
+// accelerates.  A program written against the reference's DirectXTex.h for this path
+//     ScratchImage out;  HRESULT hr = DirectX::Compress(img, DXGI_FORMAT_BC7_UNORM, TEX_COMPRESS_DEFAULT, 0.5f, out);
+// compiles against this header unchanged and links libdxtex_b200.so instead of libDirectXTex.  Names, argument
+// meaning, memory layout, ownership and HRESULTs follow the reference (citations: DirectXTex/DirectXTex.h of
+// microsoft/DirectXTex @ 0bb96f0); the implementation (DirectXTexB200.cpp) is new code that validates,
+// allocates the destination exactly like the reference and forwards to the C ABI in include/dxtex_b200.h.
+// Not provided (out of the hot path): file I/O, WIC, D3D interop, Resize, normal maps, ...
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <functional>
+
+#if defined(__GNUC__)
+#define DXTEXB200_API __attribute__((visibility("default")))
+#else
+#define DXTEXB200_API
+#endif
+
+typedef int32_t HRESULT;
+#ifndef S_OK
+#define S_OK            static_cast<HRESULT>(0)
+#define E_NOTIMPL       static_cast<HRESULT>(0x80004001)
+#define E_POINTER       static_cast<HRESULT>(0x80004003)
+#define E_ABORT         static_cast<HRESULT>(0x80004004)
+#define E_FAIL          static_cast<HRESULT>(0x80004005)
+#define E_OUTOFMEMORY   static_cast<HRESULT>(0x8007000E)
+#define E_INVALIDARG    static_cast<HRESULT>(0x80070057)
+#define SUCCEEDED(hr)   (static_cast<HRESULT>(hr) >= 0)
+#define FAILED(hr)      (static_cast<HRESULT>(hr) < 0)
+#endif
+#define HRESULT_E_NOT_SUPPORTED static_cast<HRESULT>(0x80070032)
+
+// DXGI_FORMAT values of the formats this backend implements (public D3D ABI)
+enum DXGI_FORMAT : uint32_t
+{
+    DXGI_FORMAT_UNKNOWN = 0,
+    DXGI_FORMAT_R32G32B32A32_FLOAT = 2, DXGI_FORMAT_R32G32B32_FLOAT = 6,
+    DXGI_FORMAT_R16G16B16A16_FLOAT = 10, DXGI_FORMAT_R16G16B16A16_UNORM = 11, DXGI_FORMAT_R16G16B16A16_SNORM = 13,
+    DXGI_FORMAT_R32G32_FLOAT = 16, DXGI_FORMAT_R10G10B10A2_UNORM = 24,
+    DXGI_FORMAT_R8G8B8A8_UNORM = 28, DXGI_FORMAT_R8G8B8A8_UNORM_SRGB = 29, DXGI_FORMAT_R8G8B8A8_SNORM = 31,
+    DXGI_FORMAT_R16G16_FLOAT = 34, DXGI_FORMAT_R16G16_UNORM = 35, DXGI_FORMAT_R16G16_SNORM = 37,
+    DXGI_FORMAT_R32_FLOAT = 41, DXGI_FORMAT_R8G8_UNORM = 49, DXGI_FORMAT_R8G8_SNORM = 51,
+    DXGI_FORMAT_R16_FLOAT = 54, DXGI_FORMAT_R16_UNORM = 56, DXGI_FORMAT_R16_SNORM = 58,
+    DXGI_FORMAT_R8_UNORM = 61, DXGI_FORMAT_R8_SNORM = 63, DXGI_FORMAT_A8_UNORM = 65,
+    DXGI_FORMAT_BC1_UNORM = 71, DXGI_FORMAT_BC1_UNORM_SRGB = 72, DXGI_FORMAT_BC2_UNORM = 74, DXGI_FORMAT_BC2_UNORM_SRGB = 75,
+    DXGI_FORMAT_BC3_UNORM = 77, DXGI_FORMAT_BC3_UNORM_SRGB = 78, DXGI_FORMAT_BC4_UNORM = 80, DXGI_FORMAT_BC4_SNORM = 81,
+    DXGI_FORMAT_BC5_UNORM = 83, DXGI_FORMAT_BC5_SNORM = 84,
+    DXGI_FORMAT_B8G8R8A8_UNORM = 87, DXGI_FORMAT_B8G8R8X8_UNORM = 88, DXGI_FORMAT_B8G8R8A8_UNORM_SRGB = 91, DXGI_FORMAT_B8G8R8X8_UNORM_SRGB = 93,
+    DXGI_FORMAT_BC6H_UF16 = 95, DXGI_FORMAT_BC6H_SF16 = 96, DXGI_FORMAT_BC7_UNORM = 98, DXGI_FORMAT_BC7_UNORM_SRGB = 99,
+};
+
+namespace DirectX
+{
+    // ---- format utilities (DirectXTex.h:72-99) for the implemented formats
+    DXTEXB200_API bool IsCompressed(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API bool IsSRGB(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API size_t BitsPerPixel(DXGI_FORMAT fmt) noexcept;
+
+    enum CP_FLAGS : uint32_t { CP_FLAGS_NONE = 0 };
+    DXTEXB200_API HRESULT ComputePitch(DXGI_FORMAT fmt, size_t width, size_t height, size_t& rowPitch, size_t& slicePitch, CP_FLAGS flags = CP_FLAGS_NONE) noexcept;   // DirectXTex.h:141-143
+    DXTEXB200_API bool CalculateMipLevels(size_t width, size_t height, size_t& mipLevels) noexcept;                                                                   // DirectXTex.h:147
+
+    // ---- metadata (DirectXTex.h:160-216)
+    enum TEX_DIMENSION : uint32_t { TEX_DIMENSION_TEXTURE1D = 2, TEX_DIMENSION_TEXTURE2D = 3, TEX_DIMENSION_TEXTURE3D = 4 };
+
+    struct TexMetadata
+    {
+        size_t width, height, depth, arraySize, mipLevels;
+        uint32_t miscFlags, miscFlags2;
+        DXGI_FORMAT format;
+        TEX_DIMENSION dimension;
+        size_t ComputeIndex(size_t mip, size_t item, size_t slice) const noexcept;     // DirectXTexUtil.cpp:1695-1741 (2D only)
+        bool IsVolumemap() const noexcept { return dimension == TEX_DIMENSION_TEXTURE3D; }
+    };
+
+    // ---- flags (DirectXTex.h:741-797, 887-917)
+    enum TEX_FILTER_FLAGS : uint32_t
+    {
+        TEX_FILTER_DEFAULT = 0,
+        TEX_FILTER_WRAP_U = 0x1, TEX_FILTER_WRAP_V = 0x2, TEX_FILTER_WRAP_W = 0x4, TEX_FILTER_WRAP = 0x7,
+        TEX_FILTER_MIRROR_U = 0x10, TEX_FILTER_MIRROR_V = 0x20, TEX_FILTER_MIRROR_W = 0x40, TEX_FILTER_MIRROR = 0x70,
+        TEX_FILTER_SEPARATE_ALPHA = 0x100, TEX_FILTER_FLOAT_X2BIAS = 0x200,
+        TEX_FILTER_RGB_COPY_RED = 0x1000, TEX_FILTER_RGB_COPY_GREEN = 0x2000, TEX_FILTER_RGB_COPY_BLUE = 0x4000, TEX_FILTER_RGB_COPY_ALPHA = 0x8000,
+        TEX_FILTER_DITHER = 0x10000, TEX_FILTER_DITHER_DIFFUSION = 0x20000,
+        TEX_FILTER_POINT = 0x100000, TEX_FILTER_LINEAR = 0x200000, TEX_FILTER_CUBIC = 0x300000, TEX_FILTER_BOX = 0x400000,
+        TEX_FILTER_FANT = 0x400000, TEX_FILTER_TRIANGLE = 0x500000,
+        TEX_FILTER_SRGB_IN = 0x1000000, TEX_FILTER_SRGB_OUT = 0x2000000, TEX_FILTER_SRGB = 0x3000000,
+    };
+    enum TEX_COMPRESS_FLAGS : uint32_t
+    {
+        TEX_COMPRESS_DEFAULT = 0,
+        TEX_COMPRESS_RGB_DITHER = 0x10000, TEX_COMPRESS_A_DITHER = 0x20000, TEX_COMPRESS_DITHER = 0x30000,
+        TEX_COMPRESS_UNIFORM = 0x40000, TEX_COMPRESS_BC7_USE_3SUBSETS = 0x80000, TEX_COMPRESS_BC7_QUICK = 0x100000,
+        TEX_COMPRESS_SRGB_IN = 0x1000000, TEX_COMPRESS_SRGB_OUT = 0x2000000, TEX_COMPRESS_SRGB = 0x3000000,
+        TEX_COMPRESS_PARALLEL = 0x10000000,
+    };
+    constexpr TEX_FILTER_FLAGS operator|(TEX_FILTER_FLAGS a, TEX_FILTER_FLAGS b) noexcept { return static_cast<TEX_FILTER_FLAGS>(static_cast<uint32_t>(a) | static_cast<uint32_t>(b)); }
+    constexpr TEX_COMPRESS_FLAGS operator|(TEX_COMPRESS_FLAGS a, TEX_COMPRESS_FLAGS b) noexcept { return static_cast<TEX_COMPRESS_FLAGS>(static_cast<uint32_t>(a) | static_cast<uint32_t>(b)); }
+
+    constexpr float TEX_THRESHOLD_DEFAULT = 0.5f;
+    constexpr float TEX_ALPHA_WEIGHT_DEFAULT = 1.0f;
+
+    struct ConvertOptions { TEX_FILTER_FLAGS filter; float threshold; };
+    struct CompressOptions { TEX_COMPRESS_FLAGS flags; float threshold; float alphaWeight; };
+
+    // ---- bitmap container (DirectXTex.h:437-498): same members, same layout, same ownership
+    struct Image
+    {
+        size_t width, height;
+        DXGI_FORMAT format;
+        size_t rowPitch, slicePitch;
+        uint8_t* pixels;
+    };
+
+    class DXTEXB200_API ScratchImage
+    {
+    public:
+        ScratchImage() noexcept : m_nimages(0), m_size(0), m_metadata{}, m_image(nullptr), m_memory(nullptr) {}
+        ScratchImage(ScratchImage&& moveFrom) noexcept : ScratchImage() { *this = static_cast<ScratchImage&&>(moveFrom); }
+        ~ScratchImage() { Release(); }
+        ScratchImage& operator=(ScratchImage&& moveFrom) noexcept;
+        ScratchImage(const ScratchImage&) = delete;
+        ScratchImage& operator=(const ScratchImage&) = delete;
+
+        HRESULT Initialize(const TexMetadata& mdata, CP_FLAGS flags = CP_FLAGS_NONE) noexcept;
+        HRESULT Initialize2D(DXGI_FORMAT fmt, size_t width, size_t height, size_t arraySize, size_t mipLevels, CP_FLAGS flags = CP_FLAGS_NONE) noexcept;
+        HRESULT InitializeFromImage(const Image& srcImage, bool allow1D = false, CP_FLAGS flags = CP_FLAGS_NONE) noexcept;
+        void Release() noexcept;
+
+        const TexMetadata& GetMetadata() const noexcept { return m_metadata; }
+        const Image* GetImage(size_t mip, size_t item, size_t slice) const noexcept;
+        const Image* GetImages() const noexcept { return m_image; }
+        size_t GetImageCount() const noexcept { return m_nimages; }
+        uint8_t* GetPixels() const noexcept { return m_memory; }
+        size_t GetPixelsSize() const noexcept { return m_size; }
+
+    private:
+        size_t m_nimages, m_size;
+        TexMetadata m_metadata;
+        Image* m_image;
+        uint8_t* m_memory;
+    };
+
+    // ---- the accelerated operations: same signatures as DirectXTex.h:818-832, 841-846, 929-944, 965-968
+    DXTEXB200_API HRESULT Convert(const Image& srcImage, DXGI_FORMAT format, TEX_FILTER_FLAGS filter, float threshold, ScratchImage& image) noexcept;
+    DXTEXB200_API HRESULT Convert(const Image* srcImages, size_t nimages, const TexMetadata& metadata, DXGI_FORMAT format, TEX_FILTER_FLAGS filter, float threshold, ScratchImage& result) noexcept;
+    DXTEXB200_API HRESULT ConvertEx(const Image& srcImage, DXGI_FORMAT format, const ConvertOptions& options, ScratchImage& image, std::function<bool(size_t, size_t)> statusCallBack = nullptr);
+    DXTEXB200_API HRESULT ConvertEx(const Image* srcImages, size_t nimages, const TexMetadata& metadata, DXGI_FORMAT format, const ConvertOptions& options, ScratchImage& result, std::function<bool(size_t, size_t)> statusCallBack = nullptr);
+
+    DXTEXB200_API HRESULT GenerateMipMaps(const Image& baseImage, TEX_FILTER_FLAGS filter, size_t levels, ScratchImage& mipChain, bool allow1D = false) noexcept;
+    DXTEXB200_API HRESULT GenerateMipMaps(const Image* srcImages, size_t nimages, const TexMetadata& metadata, TEX_FILTER_FLAGS filter, size_t levels, ScratchImage& mipChain);
+
+    DXTEXB200_API HRESULT Compress(const Image& srcImage, DXGI_FORMAT format, TEX_COMPRESS_FLAGS compress, float threshold, ScratchImage& cImage) noexcept;
+    DXTEXB200_API HRESULT Compress(const Image* srcImages, size_t nimages, const TexMetadata& metadata, DXGI_FORMAT format, TEX_COMPRESS_FLAGS compress, float threshold, ScratchImage& cImages) noexcept;
+    DXTEXB200_API HRESULT CompressEx(const Image& srcImage, DXGI_FORMAT format, const CompressOptions& options, ScratchImage& cImage, std::function<bool(size_t, size_t)> statusCallBack = nullptr);
+    DXTEXB200_API HRESULT CompressEx(const Image* srcImages, size_t nimages, const TexMetadata& metadata, DXGI_FORMAT format, const CompressOptions& options, ScratchImage& cImages, std::function<bool(size_t, size_t)> statusCallBack = nullptr);
+
+    DXTEXB200_API HRESULT Decompress(const Image& cImage, DXGI_FORMAT format, ScratchImage& image) noexcept;
+    DXTEXB200_API HRESULT Decompress(const Image* cImages, size_t nimages, const TexMetadata& metadata, DXGI_FORMAT format, ScratchImage& images) noexcept;
+}

@@ -1,0 +1,68 @@
+"""GPU suite: the C++ `namespace DirectX` mirror (directxtex_b200/host) driven by a caller written like a DirectXTex
+user's program (tests/cpp/texconv_mini.cpp); outputs compared with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from directxtex_b200 import formats as F, synth
+from tests import oracle_lib
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "directxtex_b200", "_lib")
+
+
+@pytest.fixture(scope="module")
+def exe(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("cpp") / "texconv_mini")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "directxtex_b200", "host"),
+                    os.path.join(ROOT, "tests", "cpp", "texconv_mini.cpp"), "-L", LIBDIR, "-ldxtex_b200",
+                    "-Wl,-rpath," + LIBDIR, "-o", out], check=True)
+    return out
+
+
+def run(exe, tmp_path, op, src, w, h, sf, arg, flags=0, items=1, expect_fail=False):
+    fin, fout = str(tmp_path / "in.raw"), str(tmp_path / "out.raw")
+    np.ascontiguousarray(src).tofile(fin)
+    r = subprocess.run([exe, op, fin, fout, str(w), str(h), str(sf), str(arg), str(flags), str(items)], capture_output=True, text=True)
+    if expect_fail:
+        return r
+    assert r.returncode == 0, r.stdout + r.stderr
+    return np.fromfile(fout, np.uint8)
+
+
+def test_cpp_compress_matches_oracle(exe, tmp_path, oracle):
+    img = synth.c1_rgba8(96, 64, seed=4)
+    for fmt in (71, 77, 83):
+        got = run(exe, tmp_path, "compress", img, 96, 64, 28, fmt)
+        hr, want = oracle.compress(img, 96, 64, 28, fmt)
+        assert hr == 0 and np.array_equal(got, want)
+    got = run(exe, tmp_path, "compress_cb", img, 96, 64, 28, 71)       # status callback: called (0,h) and (h,h)
+    hr, want = oracle.compress(img, 96, 64, 28, 71)
+    assert np.array_equal(got, want)
+
+
+def test_cpp_compress_array_and_errors(exe, tmp_path, oracle):
+    rng = np.random.default_rng(3)
+    imgs = np.stack([oracle_lib.random_image(28, 32, 16, rng) for _ in range(5)])
+    got = run(exe, tmp_path, "compress", imgs, 32, 16, 28, 77, 0, 5)
+    want = np.concatenate([oracle.compress(imgs[i], 32, 16, 28, 77)[1] for i in range(5)])
+    assert np.array_equal(got, want)
+    r = run(exe, tmp_path, "compress", imgs[0], 32, 16, 28, 28, expect_fail=True)          # destination not BC -> E_INVALIDARG
+    assert "hr=0x80070057" in r.stdout and r.returncode == 1
+
+
+def test_cpp_convert_and_mips(exe, tmp_path, oracle):
+    rng = np.random.default_rng(5)
+    src = oracle_lib.random_image(61, 128, 32, rng)
+    got = run(exe, tmp_path, "convert", src, 128, 32, 61, 41)
+    hr, want = oracle.convert(src, 128, 32, 61, 41)
+    assert hr == 0 and np.array_equal(got, want)
+    src = oracle_lib.random_image(28, 64, 64, rng)
+    for fl in (F.TEX_FILTER_BOX, F.TEX_FILTER_CUBIC, 0):
+        got = run(exe, tmp_path, "mips", src, 64, 64, 28, fl)
+        hr, want = oracle.generate_mipmaps(src, 64, 64, 28, fl)
+        assert hr == 0 and np.array_equal(got, want), hex(fl)
