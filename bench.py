@@ -132,7 +132,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from directxtex_b200 import capi, formats as F, synth
+    from directxtex_b200 import capi, dist as D, formats as F, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -150,7 +150,6 @@ def main():
     row_out, slice_out = F.compute_pitch(DST_FMT, W, H)
     d_in = torch.from_numpy(img.reshape(-1).view(np.uint8)).cuda()
     d_out = torch.zeros(slice_out, dtype=torch.uint8, device="cuda")
-    d_all = torch.zeros(slice_out * world, dtype=torch.uint8, device="cuda") if world > 1 else None
     src = capi.images([capi.Image(W, H, SRC_FMT, row_in, slice_in, d_in.data_ptr())])
     dst = capi.images([capi.Image(W, H, DST_FMT, row_out, slice_out, d_out.data_ptr())])
     stream = torch.cuda.current_stream()
@@ -160,7 +159,7 @@ def main():
         if hr != 0:
             raise capi.DxTexError(hr, "dxb200_compress_device")
         if world > 1:
-            dist.all_gather_into_tensor(d_all, d_out)
+            D.all_gather_blocks(d_out, world, slice_out, world, rank, dist, torch)
 
     def barrier():
         if world > 1:
@@ -186,7 +185,7 @@ def main():
         if hr != 0:
             raise capi.DxTexError(hr, "dxb200_compress_device")
         if world > 1:
-            dist.all_gather_into_tensor(d_all, d_out)
+            gathered = D.all_gather_blocks(d_out, world, slice_out, world, rank, dist, torch)
     e1.record()
     barrier()
     launches = capi.launch_count() - launches0
