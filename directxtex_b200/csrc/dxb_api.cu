@@ -288,7 +288,7 @@ int32_t launch_convert(dxb_convert_params P, const dxb200_image* src, const dxb2
     if (hr != DXB_S_OK) return hr;
     const uint32_t need = (uint32_t)((total + 255) / 256);
     const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridRow * 8u));
-    dxb_launch_convert(grid, stream, dj.d, jobs[0], P);
+    dxb_launch_convert(grid, stream, dj.d, jobs.data(), P);
     hr = check_launch("k_convert");
     dj.release();
     return hr;
@@ -338,12 +338,56 @@ int32_t launch_mips(const dxb200_image* chain, size_t items, size_t levels, uint
     P.format = fmt; P.mode = mode; P.filter = filter;
     P.lflags = dxb_resolve_srgb_linear(filter & DXB_FILTER_SRGB_MASK, fmt);
     int32_t hr = DXB_S_OK;
+    // job records of every level, built once and uploaded with ONE copy (a per-level upload left the GPU idle
+    // between the small launches of the tail of the chain)
     std::vector<const dxb200_image*> stale(items, nullptr);
+    std::vector<dxb_mip_job> all(items * (levels - 1));
+    std::vector<uint64_t> totals(levels, 0);
+    for (size_t l = 1; l < levels; ++l)
+    {
+        uint64_t total = 0;
+        for (size_t it = 0; it < items; ++it)
+        {
+            const dxb200_image& s = chain[it * levels + l - 1]; const dxb200_image& d = chain[it * levels + l];
+            dxb_mip_job& j = all[(l - 1) * items + it];
+            j.src = s.pixels; j.dst = d.pixels; j.srcPitch = s.rowPitch; j.dstPitch = d.rowPitch;
+            j.sw = (uint32_t)s.width; j.sh = (uint32_t)s.height; j.dw = (uint32_t)d.width; j.dh = (uint32_t)d.height;
+            j.firstUnit = (uint32_t)total; total += (uint64_t)j.dw * j.dh;
+            if (s.height == 2) stale[it] = &s;          // box filter quirk, see dxb_mip_box
+            j.stale = nullptr; j.stalePitch = 0;
+            if (mode == DXB_FILTER_BOX && s.height <= 1 && s.width > 1 && stale[it])
+            {
+                j.stale = stale[it]->pixels + stale[it]->rowPitch;      // row 1 of that level
+                j.stalePitch = stale[it]->rowPitch;
+            }
+        }
+        totals[l] = total;
+    }
+    dxb_mip_job* dAll = nullptr;
+    // first level whose SOURCE is at most 64x64: from there on one CTA per item finishes the chain in one launch
+    size_t tailStart = levels;
+    for (size_t l = 1; l < levels; ++l)
+        if (chain[l - 1].width <= 64 && chain[l - 1].height <= 64) { tailStart = l; break; }
+    const bool wantTail = (mode == DXB_FILTER_BOX || mode == DXB_FILTER_LINEAR || mode == DXB_FILTER_CUBIC) && (levels - tailStart) >= 2 && items <= 0x7FFFFFFFull;
+    if (items > 1 || wantTail)
+    {
+        DXB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dAll), all.size() * sizeof(dxb_mip_job), stream));
+        DXB_CUDA(cudaMemcpyAsync(dAll, all.data(), all.size() * sizeof(dxb_mip_job), cudaMemcpyHostToDevice, stream));
+    }
     for (size_t l = 1; l < levels && hr == DXB_S_OK; ++l)
     {
+        if (wantTail && l == tailStart)
+        {
+            P.njobs = (uint32_t)items;
+            if (dxb_launch_mip_tail(stream, dAll + (l - 1) * items, (uint32_t)items, (uint32_t)(levels - tailStart), P))
+            {
+                hr = check_launch("k_mip_tail");
+                break;
+            }
+        }
         if (mode == DXB_FILTER_TRIANGLE)
         {
-            // one launch per item: the gather lists are per (level) and shared by all items, uploaded once
+            // gather lists are per level and shared by all items
             const dxb200_image& s0 = chain[l - 1]; const dxb200_image& d0 = chain[l];
             TriLists tx, ty;
             build_triangle_axis(s0.width, d0.width, (filter & DXB_FILTER_WRAP_U) != 0, tx);
@@ -364,38 +408,19 @@ int32_t launch_mips(const dxb200_image* chain, size_t items, size_t levels, uint
             P.triX.src = dU + nOff; P.triY.src = dU + nOff + tx.src.size();
             P.triX.w = dW; P.triY.w = dW + tx.w.size();
         }
-        std::vector<dxb_mip_job> jobs(items);
-        uint64_t total = 0;
-        for (size_t it = 0; it < items; ++it)
-        {
-            const dxb200_image& s = chain[it * levels + l - 1]; const dxb200_image& d = chain[it * levels + l];
-            dxb_mip_job& j = jobs[it];
-            j.src = s.pixels; j.dst = d.pixels; j.srcPitch = s.rowPitch; j.dstPitch = d.rowPitch;
-            j.sw = (uint32_t)s.width; j.sh = (uint32_t)s.height; j.dw = (uint32_t)d.width; j.dh = (uint32_t)d.height;
-            j.firstUnit = (uint32_t)total; total += (uint64_t)j.dw * j.dh;
-            if (s.height == 2) stale[it] = &s;          // box filter quirk, see dxb_mip_box
-            j.stale = nullptr; j.stalePitch = 0;
-            if (mode == DXB_FILTER_BOX && s.height <= 1 && s.width > 1 && stale[it])
-            {
-                j.stale = stale[it]->pixels + stale[it]->rowPitch;      // row 1 of that level
-                j.stalePitch = stale[it]->rowPitch;
-            }
-        }
+        const uint64_t total = totals[l];
         P.totalUnits = (uint32_t)total; P.njobs = (uint32_t)items;
-        DeviceJobs<dxb_mip_job> dj;
-        hr = dj.upload(jobs, stream);
-        if (hr != DXB_S_OK) break;
         const uint32_t need = (uint32_t)((total + 255) / 256);
         const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridRow * 8u));
-        dxb_launch_mip(grid, stream, dj.d, jobs[0], P);
+        dxb_launch_mip(grid, stream, (dAll && items > 1) ? dAll + (l - 1) * items : nullptr, all.data() + (l - 1) * items, P);
         hr = check_launch("k_mip_level");
-        dj.release();
         if (mode == DXB_FILTER_TRIANGLE)
         {
             cudaFreeAsync(const_cast<uint32_t*>(P.triX.off), stream);
             cudaFreeAsync(const_cast<float*>(P.triX.w), stream);
         }
     }
+    if (dAll) cudaFreeAsync(dAll, stream);
     return hr;
 }
 

@@ -92,7 +92,9 @@ enum
 #define DXB_E_NOT_SUPPORTED ((int32_t)0x80070032)
 
 #if defined(__CUDACC__)
-#define DXB_FMT_FN __host__ __device__ inline
+#define DXB_FMT_FN __host__ __device__ constexpr
+#elif defined(__cplusplus)
+#define DXB_FMT_FN static constexpr
 #else
 #define DXB_FMT_FN static inline
 #endif

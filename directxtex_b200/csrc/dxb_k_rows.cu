@@ -1,8 +1,16 @@
-// dxb_k_rows.cu — row kernels: k_convert (Load -> Convert -> Store per pixel) and k_mip_level (one mip level of a batch)
+// dxb_k_rows.cu — row kernels (HBM-bound side of the path):
+//   k_convert            generic: one thread per pixel, any implemented format pair, heterogeneous batches
+//   k_convert_vec<SF,DF> hot pairs: compile-time formats, 16-byte vector access on the wider side, uniform batches
+//   k_mip_level          generic: one thread per destination pixel, any format / filter
+//   k_mip_tile<FMT,MODE> hot formats x {BOX,LINEAR,CUBIC}: compile-time format and filter, 2D thread tiles,
+//                        grid.z = array item (all items of a level have the same size), no integer division
+// The arithmetic is the same inline code in all variants (dxb_pixel.cuh / dxb_mips.cuh), so all of them are
+// bit-exact against the oracle; only the memory access pattern differs.
 #include "dxb_launch.h"
 #include "dxb_pixel.cuh"
 #include "dxb_mips.cuh"
 
+// ------------------------------------------------------------------------------------------------ generic
 __global__ void __launch_bounds__(256) k_convert(const dxb_job* __restrict__ jobs, dxb_job single, dxb_convert_params P)
 {
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -16,7 +24,6 @@ __global__ void __launch_bounds__(256) k_convert(const dxb_job* __restrict__ job
         dxb_store_pixel(P.dstFormat, j.dst + (size_t)y * j.dstPitch, x, v);
     }
 }
-
 
 __global__ void __launch_bounds__(256) k_mip_level(const dxb_mip_job* __restrict__ jobs, dxb_mip_job single, dxb_mip_params P)
 {
@@ -42,11 +49,224 @@ __global__ void __launch_bounds__(256) k_mip_level(const dxb_mip_job* __restrict
     }
 }
 
-void dxb_launch_convert(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job& single, const dxb_convert_params& P)
+// ------------------------------------------------------------------------------------------------ vector convert
+template <int BYTES> struct dxb_vec;
+template <> struct dxb_vec<1> { typedef uint8_t T; };
+template <> struct dxb_vec<2> { typedef uint16_t T; };
+template <> struct dxb_vec<4> { typedef uint32_t T; };
+template <> struct dxb_vec<8> { typedef uint2 T; };
+template <> struct dxb_vec<16> { typedef uint4 T; };
+
+template <int BYTES> __device__ __forceinline__ typename dxb_vec<BYTES>::T dxb_ld_stream(const void* p)
 {
-    k_convert<<<grid, 256, 0, stream>>>(jobs, single, P);
+    return __ldcs(reinterpret_cast<const typename dxb_vec<BYTES>::T*>(p));
 }
-void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs, const dxb_mip_job& single, const dxb_mip_params& P)
+template <int BYTES> __device__ __forceinline__ void dxb_st_stream(void* p, typename dxb_vec<BYTES>::T v)
 {
-    k_mip_level<<<grid, 256, 0, stream>>>(jobs, single, P);
+    __stcs(reinterpret_cast<typename dxb_vec<BYTES>::T*>(p), v);
+}
+
+// One thread converts PPT consecutive pixels of a row: PPT*max(bpp) == 16 bytes, so the wider side moves as one
+// 128-bit access and a warp touches one contiguous 512-byte span on that side.
+// grid = (ceil(chunksPerRow / (256*UNR)), rows, jobs): no integer division anywhere; a thread takes UNR chunks of its
+// row spaced 256 chunks apart and issues all its vector loads before the first store.
+#define DXB_CONV_UNR 4
+template <uint32_t SF, uint32_t DF>
+__global__ void __launch_bounds__(256) k_convert_vec(const dxb_job* __restrict__ jobs, dxb_job single, dxb_convert_params P)
+{
+    constexpr int SB = (int)dxb_bytes_per_pixel(SF), DB = (int)dxb_bytes_per_pixel(DF);
+    constexpr int PPT = 16 / (SB > DB ? SB : DB);
+    constexpr int SBY = SB * PPT, DBY = DB * PPT;
+    constexpr uint32_t inF = dxb_convert_flags(SF), outF = dxb_convert_flags(DF);
+    constexpr int UNR = DXB_CONV_UNR;
+    const dxb_job& j = (jobs == nullptr) ? single : jobs[blockIdx.z];
+    const uint32_t y = blockIdx.y;
+    const uint8_t* srow = j.src + (size_t)y * j.srcPitch;
+    uint8_t* drow = j.dst + (size_t)y * j.dstPitch;
+    const uint32_t width = j.width;
+    const uint32_t c0 = blockIdx.x * (UNR * 256u) + threadIdx.x;
+    __align__(16) uint8_t sbuf[UNR][SBY];
+    #pragma unroll
+    for (int u = 0; u < UNR; ++u)
+    {
+        const uint32_t x0 = (c0 + u * 256u) * PPT;
+        if (x0 + PPT <= width)
+            *reinterpret_cast<typename dxb_vec<SBY>::T*>(sbuf[u]) = dxb_ld_stream<SBY>(srow + (size_t)x0 * SB);
+    }
+    #pragma unroll
+    for (int u = 0; u < UNR; ++u)
+    {
+        const uint32_t x0 = (c0 + u * 256u) * PPT;
+        if (x0 + PPT <= width)
+        {
+            __align__(16) uint8_t dbuf[DBY];
+            #pragma unroll
+            for (int p = 0; p < PPT; ++p)
+            {
+                dxb_px v = dxb_load_pixel(SF, sbuf[u], p);
+                v = dxb_convert_pixel(v, inF, outF, P.flags);
+                dxb_store_pixel(DF, dbuf, p, v);
+            }
+            dxb_st_stream<DBY>(drow + (size_t)x0 * DB, *reinterpret_cast<const typename dxb_vec<DBY>::T*>(dbuf));
+        }
+        else
+        {
+            for (uint32_t x = x0; x < width; ++x)        // ragged end of the row
+            {
+                dxb_px v = dxb_load_pixel(SF, srow, x);
+                v = dxb_convert_pixel(v, inF, outF, P.flags);
+                dxb_store_pixel(DF, drow, x, v);
+            }
+        }
+    }
+}
+
+#define DXB_CONVERT_PAIRS(X) \
+    X(61, 41) X(41, 61) X(28, 2) X(2, 28) X(10, 2) X(2, 10) X(28, 10) X(10, 28) X(28, 87) X(87, 28) \
+    X(61, 28) X(28, 61) X(11, 2) X(2, 11) X(41, 2) X(2, 41) X(29, 2) X(2, 29) X(29, 28) X(28, 29)
+
+static bool convert_vec_ok(const dxb_job* hostJobs, uint32_t njobs, uint32_t SB, uint32_t DB)
+{
+    const uint32_t ppt = 16u / (SB > DB ? SB : DB);
+    const size_t sby = (size_t)SB * ppt, dby = (size_t)DB * ppt;
+    if (njobs > 65535u || hostJobs[0].height > 65535u) return false;
+    for (uint32_t i = 0; i < njobs; ++i)
+    {
+        const dxb_job& j = hostJobs[i];
+        if (j.width != hostJobs[0].width || j.height != hostJobs[0].height) return false;
+        if (((uintptr_t)j.src % sby) || ((uintptr_t)j.dst % dby) || (j.srcPitch % sby) || (j.dstPitch % dby)) return false;
+    }
+    return true;
+}
+
+void dxb_launch_convert(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job* hostJobs, const dxb_convert_params& P)
+{
+    const uint32_t SB = dxb_bytes_per_pixel(P.srcFormat), DB = dxb_bytes_per_pixel(P.dstFormat);
+    if (convert_vec_ok(hostJobs, P.njobs, SB, DB))
+    {
+        const uint32_t ppt = 16u / (SB > DB ? SB : DB);
+        const uint32_t chunksPerRow = (hostJobs[0].width + ppt - 1) / ppt;
+        const dim3 g((chunksPerRow + 256u * DXB_CONV_UNR - 1) / (256u * DXB_CONV_UNR), hostJobs[0].height, P.njobs);
+#define DXB_X(SF, DF) if (P.srcFormat == SF && P.dstFormat == DF) { k_convert_vec<SF, DF><<<g, 256, 0, stream>>>(jobs, hostJobs[0], P); return; }
+        DXB_CONVERT_PAIRS(DXB_X)
+#undef DXB_X
+    }
+    k_convert<<<grid, 256, 0, stream>>>(jobs, hostJobs[0], P);
+}
+
+// ------------------------------------------------------------------------------------------------ tiled mips
+template <uint32_t FMT, uint32_t MODE>
+__device__ __forceinline__ dxb_px dxb_mip_eval(const dxb_mip_job& j, uint32_t x, uint32_t y, const dxb_mip_params& P)
+{
+    if (MODE == DXB_FILTER_BOX) return dxb_mip_box(FMT, j, x, y, P.lflags);
+    if (MODE == DXB_FILTER_LINEAR) return dxb_mip_linear(FMT, j, x, y, P.filter, P.lflags);
+    return dxb_mip_cubic(FMT, j, x, y, P.filter, P.lflags);
+}
+
+// grid = (ceil(dw/32), ceil(dh/8), items); jobs[z] describes item z (all items share the level's size).
+// VEC: source rows are aligned for one vector load of two adjacent pixels (BOX only).
+template <uint32_t FMT, uint32_t MODE, bool VEC>
+__global__ void __launch_bounds__(256) k_mip_tile(const dxb_mip_job* __restrict__ jobs, dxb_mip_job single, dxb_mip_params P)
+{
+    const dxb_mip_job& j = (jobs == nullptr) ? single : jobs[blockIdx.z];
+    const uint32_t x = blockIdx.x * 32u + threadIdx.x, y = blockIdx.y * 8u + threadIdx.y;
+    if (x >= j.dw || y >= j.dh) return;
+    dxb_px v;
+    constexpr int B = (int)dxb_bytes_per_pixel(FMT);
+    constexpr uintptr_t VA = (B * 2 <= 16) ? B * 2 : 16;
+    // VEC = every item is aligned; otherwise decide per item (uniform within the CTA: blockIdx.z selects the item)
+    const bool vecOK = VEC || ((((uintptr_t)j.src % VA) == 0) && ((j.srcPitch % VA) == 0));
+    if (MODE == DXB_FILTER_BOX && vecOK && j.sw > 1 && j.sh > 1)
+    {
+        // two horizontally adjacent source pixels per row in one vector load: ((p00 + p10) + p01) + p11) * 0.25
+        constexpr int VB = (B * 2 <= 16) ? B * 2 : 16;
+        __align__(16) uint8_t r0[B * 2], r1[B * 2];
+        const uint8_t* s0 = j.src + (size_t)(2u * y) * j.srcPitch + (size_t)(2u * x) * B;
+        #pragma unroll
+        for (int k = 0; k < B * 2; k += VB)
+        {
+            *reinterpret_cast<typename dxb_vec<VB>::T*>(r0 + k) = __ldg(reinterpret_cast<const typename dxb_vec<VB>::T*>(s0 + k));
+            *reinterpret_cast<typename dxb_vec<VB>::T*>(r1 + k) = __ldg(reinterpret_cast<const typename dxb_vec<VB>::T*>(s0 + j.srcPitch + k));
+        }
+        dxb_px p00 = dxb_load_pixel(FMT, r0, 0), p01 = dxb_load_pixel(FMT, r0, 1);
+        dxb_px p10 = dxb_load_pixel(FMT, r1, 0), p11 = dxb_load_pixel(FMT, r1, 1);
+        if (P.lflags & DXB_FILTER_SRGB_IN) { p00 = dxb_srgb_to_linear(p00); p01 = dxb_srgb_to_linear(p01); p10 = dxb_srgb_to_linear(p10); p11 = dxb_srgb_to_linear(p11); }
+        v = dxb_px_add(p00, p10);
+        v = dxb_px_add(v, p01);
+        v = dxb_px_add(v, p11);
+        v = dxb_px_scale(v, 0.25f);
+    }
+    else v = dxb_mip_eval<FMT, MODE>(j, x, y, P);
+    dxb_store_linear(FMT, j.dst, j.dstPitch, x, y, v, P.lflags);
+}
+
+// Tail of the chain: one CTA per item computes levels [first, first+count) back to back (each level reads the
+// previous one from global memory after a block barrier), replacing `count` tiny launches by one.
+// jobs is laid out [level][item]: jobs[l * items + item].
+template <uint32_t FMT, uint32_t MODE>
+__global__ void __launch_bounds__(256) k_mip_tail(const dxb_mip_job* __restrict__ jobs, uint32_t items, uint32_t count, dxb_mip_params P)
+{
+    for (uint32_t l = 0; l < count; ++l)
+    {
+        const dxb_mip_job& j = jobs[(size_t)l * items + blockIdx.x];
+        const uint32_t n = j.dw * j.dh;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const uint32_t y = i / j.dw, x = i - y * j.dw;
+            const dxb_px v = dxb_mip_eval<FMT, MODE>(j, x, y, P);
+            dxb_store_linear(FMT, j.dst, j.dstPitch, x, y, v, P.lflags);
+        }
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
+#define DXB_MIP_FORMATS(X, MODE) X(28, MODE) X(29, MODE) X(10, MODE) X(2, MODE) X(61, MODE) X(41, MODE) X(87, MODE)
+
+static bool mip_uniform(const dxb_mip_job* hostJobs, uint32_t njobs, uint32_t bpp, bool* vec)
+{
+    if (njobs > 65535u) return false;
+    *vec = true;
+    const uint32_t va = (2 * bpp <= 16) ? 2 * bpp : 16;
+    for (uint32_t i = 0; i < njobs; ++i)
+    {
+        const dxb_mip_job& j = hostJobs[i];
+        if (j.dw != hostJobs[0].dw || j.dh != hostJobs[0].dh || j.sw != hostJobs[0].sw || j.sh != hostJobs[0].sh) return false;
+        if (((uintptr_t)j.src % va) || (j.srcPitch % va)) *vec = false;
+    }
+    return true;
+}
+
+void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs, const dxb_mip_job* hostJobs, const dxb_mip_params& P)
+{
+    bool vec = false;
+    if (mip_uniform(hostJobs, P.njobs, dxb_bytes_per_pixel(P.format), &vec) &&
+        (P.mode == DXB_FILTER_BOX || P.mode == DXB_FILTER_LINEAR || P.mode == DXB_FILTER_CUBIC))
+    {
+        const dim3 blk(32, 8, 1);
+        const dim3 g((hostJobs[0].dw + 31) / 32, (hostJobs[0].dh + 7) / 8, P.njobs);
+        if (g.y <= 65535u)
+        {
+#define DXB_X(FMT, MODE) if (P.format == FMT && P.mode == MODE) { \
+                if (vec) k_mip_tile<FMT, MODE, true><<<g, blk, 0, stream>>>(jobs, hostJobs[0], P); \
+                else k_mip_tile<FMT, MODE, false><<<g, blk, 0, stream>>>(jobs, hostJobs[0], P); \
+                return; }
+            DXB_MIP_FORMATS(DXB_X, DXB_FILTER_BOX)
+            DXB_MIP_FORMATS(DXB_X, DXB_FILTER_LINEAR)
+            DXB_MIP_FORMATS(DXB_X, DXB_FILTER_CUBIC)
+#undef DXB_X
+        }
+    }
+    k_mip_level<<<grid, 256, 0, stream>>>(jobs, hostJobs[0], P);
+}
+
+// levels [first, first+count) of every item in ONE launch; returns false when the format/filter has no tail kernel
+bool dxb_launch_mip_tail(cudaStream_t stream, const dxb_mip_job* jobsDev, uint32_t items, uint32_t count, const dxb_mip_params& P)
+{
+#define DXB_X(FMT, MODE) if (P.format == FMT && P.mode == MODE) { k_mip_tail<FMT, MODE><<<items, 256, 0, stream>>>(jobsDev, items, count, P); return true; }
+    DXB_MIP_FORMATS(DXB_X, DXB_FILTER_BOX)
+    DXB_MIP_FORMATS(DXB_X, DXB_FILTER_LINEAR)
+    DXB_MIP_FORMATS(DXB_X, DXB_FILTER_CUBIC)
+#undef DXB_X
+    return false;
 }

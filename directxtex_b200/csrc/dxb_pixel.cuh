@@ -14,6 +14,17 @@ struct dxb_px { float x, y, z, w; };
 
 DXB_DEV dxb_px dxb_make_px(float x, float y, float z, float w) { dxb_px p; p.x = x; p.y = y; p.z = z; p.w = w; return p; }
 
+// a / b for an INTEGER-valued a and a literal b in {255, 127, 65535, 32767}: q = a*(1/b); q += fma(-q,b,a)*(1/b) equals the
+// correctly rounded IEEE quotient for every value of the 8/16-bit input domains (checked exhaustively on the CPU and in
+// tests/test_gpu_parity.py::test_convert_exhaustive_small_domains); 3 FP ops instead of a ~15-instruction division.
+DXB_DEV float dxb_div_small(float a, float b)
+{
+    const float rcp = 1.0f / b;
+    const float q = a * rcp;
+    const float r = dxb_fma(-q, b, a);
+    return dxb_fma(r, rcp, q);
+}
+
 DXB_DEV float dxb_snorm_load(int32_t v, float rcp) { return dxb_ssemax((float)v * rcp, -1.0f); }
 DXB_DEV float dxb_clamp(float v, float lo, float hi) { return dxb_ssemin(dxb_ssemax(v, lo), hi); }
 
@@ -122,15 +133,15 @@ DXB_DEV dxb_px dxb_load_pixel(uint32_t fmt, const uint8_t* row, size_t i)
     case DXB_FMT_R16_FLOAT:
         return dxb_make_px(dxb_half_to_float(((const uint16_t*)row)[i]), 0.0f, 0.0f, 1.0f);
     case DXB_FMT_R16_UNORM:      // true division: DirectXTexConvert.cpp:1062
-        return dxb_make_px((float)((const uint16_t*)row)[i] / 65535.0f, 0.0f, 0.0f, 1.0f);
+        return dxb_make_px(dxb_div_small((float)((const uint16_t*)row)[i], 65535.0f), 0.0f, 0.0f, 1.0f);
     case DXB_FMT_R16_SNORM:      // :1088 (no clamp of -32768)
-        return dxb_make_px((float)((const int16_t*)row)[i] / 32767.0f, 0.0f, 0.0f, 1.0f);
+        return dxb_make_px(dxb_div_small((float)((const int16_t*)row)[i], 32767.0f), 0.0f, 0.0f, 1.0f);
     case DXB_FMT_R8_UNORM:       // :1113
-        return dxb_make_px((float)row[i] / 255.0f, 0.0f, 0.0f, 1.0f);
+        return dxb_make_px(dxb_div_small((float)row[i], 255.0f), 0.0f, 0.0f, 1.0f);
     case DXB_FMT_R8_SNORM:       // :1139
-        return dxb_make_px((float)((const int8_t*)row)[i] / 127.0f, 0.0f, 0.0f, 1.0f);
+        return dxb_make_px(dxb_div_small((float)((const int8_t*)row)[i], 127.0f), 0.0f, 0.0f, 1.0f);
     case DXB_FMT_A8_UNORM:       // :1165
-        return dxb_make_px(0.0f, 0.0f, 0.0f, (float)row[i] / 255.0f);
+        return dxb_make_px(0.0f, 0.0f, 0.0f, dxb_div_small((float)row[i], 255.0f));
     default:
         return dxb_make_px(0.0f, 0.0f, 0.0f, 1.0f);
     }

@@ -67,6 +67,18 @@ def test_emulator_convert_bit_exact(oracle, emul):
         assert he == 0 and np.array_equal(out, exp), name
 
 
+def test_emulator_convert_exhaustive_small_domains(oracle, emul):
+    """all values of the 8/16-bit scalar formats: the 3-op exact division equals the reference's IEEE divide"""
+    for sf, dtype, n in ((61, np.uint8, 256), (63, np.int8, 256), (65, np.uint8, 256), (56, np.uint16, 65536), (58, np.int16, 65536)):
+        vals = np.arange(n, dtype=np.int64).astype(dtype) if dtype in (np.uint8, np.uint16) else (np.arange(n, dtype=np.int64) - n // 2).astype(dtype)
+        w, h = (256, n // 256)
+        src = vals.reshape(h, w)
+        for df in (2, 41):
+            hr, want = oracle.convert(src, w, h, sf, df)
+            he, got = emul.convert(src, w, h, sf, df)
+            assert hr == 0 and he == 0 and np.array_equal(got, want), (sf, df)
+
+
 def test_emulator_mips_bit_exact(oracle, emul):
     for name, src, meta, exp in golden_util.cases("mips_"):
         w, h, fmt, fl = (int(v) for v in meta)

@@ -74,6 +74,18 @@ def test_convert_golden_and_random(oracle):
         assert hr == 0 and np.array_equal(got, want), (sf, df)
 
 
+def test_convert_exhaustive_small_domains(oracle):
+    """every value of the 8/16-bit scalar formats (they use a 3-op exact division instead of an IEEE divide)"""
+    for sf, dtype, n in ((61, np.uint8, 256), (63, np.int8, 256), (65, np.uint8, 256), (56, np.uint16, 65536), (58, np.int16, 65536)):
+        vals = np.arange(n, dtype=np.int64).astype(dtype) if dtype in (np.uint8, np.uint16) else (np.arange(n, dtype=np.int64) - n // 2).astype(dtype)
+        w, h = (256, n // 256)
+        src = vals.reshape(h, w)
+        for df in (2, 41):
+            hr, want = oracle.convert(src, w, h, sf, df)
+            got = capi.convert(src, w, h, sf, df)
+            assert hr == 0 and np.array_equal(got, want), (sf, df)
+
+
 def test_convert_srgb_within_one_code(oracle):
     rng = np.random.default_rng(5)
     src = oracle_lib.random_image(29, 64, 16, rng)

@@ -73,6 +73,7 @@ if what in ("rows", "all"):
     # C4-like: 64 x (1024^2 RGBA8) box mip chains
     items, w, h = 64, 1024, 1024
     layout, total = F.mip_chain_layout(28, w, h)
+    total = (total + 255) & ~255          # item stride padded so that every item is vector-aligned (as the host-staged path does)
     chain = torch.zeros(total * items, dtype=torch.uint8, device="cuda")
     base = dev(synth.c1_rgba8(w, h))
     imgs = []
