@@ -34,7 +34,7 @@ struct State
     cudaStream_t streams[2] = { nullptr, nullptr };
     void* dIn[2] = { nullptr, nullptr };  size_t dInCap[2] = { 0, 0 };
     void* dOut[2] = { nullptr, nullptr }; size_t dOutCap[2] = { 0, 0 };
-    int gridBC15 = 0, gridBC7 = 0, gridRow = 0;
+    int gridBC15 = 0, gridBC7 = 0, gridBC6H = 0, gridRow = 0;
 } g;
 
 int32_t cuda_hr(cudaError_t e, const char* what)
@@ -61,6 +61,7 @@ int32_t ensure_init_locked()
     for (int i = 0; i < 2; ++i) DXB_CUDA(cudaStreamCreateWithFlags(&g.streams[i], cudaStreamNonBlocking));
     g.gridBC15 = g.numSMs * dxb_occupancy_bc15();
     g.gridBC7 = g.numSMs * dxb_occupancy_bc7();
+    g.gridBC6H = g.numSMs * dxb_occupancy_bc6h();
     g.gridRow = g.numSMs * 8;
     g.inited = true;
     return DXB_S_OK;
@@ -126,7 +127,7 @@ int32_t check_launch(const char* name)
 }
 
 // ---- Compress ---------------------------------------------------------------------------------
-struct CompressPlan { dxb_compress_params P; bool bc7; };
+struct CompressPlan { dxb_compress_params P; bool bc7, bc6h; };
 
 // validation + flag resolution shared by host and device variants (DirectXTexCompress.cpp:664-676, 732-749, 72-107)
 int32_t plan_compress(const dxb200_image* src, size_t n, uint32_t dstFormat, uint32_t flags, float threshold,
@@ -136,7 +137,6 @@ int32_t plan_compress(const dxb200_image* src, size_t n, uint32_t dstFormat, uin
     const uint32_t srcFormat = src[0].format;
     if (is_compressed(srcFormat) || !is_compressed(dstFormat)) return DXB_E_INVALIDARG;
     if (!is_supported_pixel_format(srcFormat)) return DXB_E_NOT_SUPPORTED;        // no CPU fallback for other formats
-    if (dstFormat == DXB_FMT_BC6H_UF16 || dstFormat == DXB_FMT_BC6H_SF16) return DXB_E_NOT_SUPPORTED;   // round 2
     for (size_t i = 0; i < n; ++i)
     {
         if (!src[i].pixels || !dst[i].pixels) return DXB_E_POINTER;
@@ -156,6 +156,7 @@ int32_t plan_compress(const dxb200_image* src, size_t n, uint32_t dstFormat, uin
                          DXB_BC_FLAGS_USE_3SUBSETS | DXB_BC_FLAGS_FORCE_BC7_MODE6);                 // GetBCFlags :26-35
     P.threshold = threshold;
     plan->bc7 = (dstFormat == DXB_FMT_BC7_UNORM || dstFormat == DXB_FMT_BC7_UNORM_SRGB);
+    plan->bc6h = (dstFormat == DXB_FMT_BC6H_UF16 || dstFormat == DXB_FMT_BC6H_SF16);
     return DXB_S_OK;
 }
 
@@ -180,7 +181,14 @@ int32_t launch_compress(const CompressPlan& plan, const dxb200_image* src, const
     DeviceJobs<dxb_job> dj;
     int32_t hr = dj.upload(jobs, stream);
     if (hr != DXB_S_OK) return hr;
-    if (plan.bc7)
+    if (plan.bc6h)
+    {
+        const uint32_t need = (uint32_t)((total + DXB_BC7_WARPS - 1) / DXB_BC7_WARPS);
+        const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridBC6H * 4u));
+        dxb_launch_bc6h(grid, stream, dj.d, jobs[0], P);
+        hr = check_launch("k_compress_bc6h");
+    }
+    else if (plan.bc7)
     {
         const uint32_t need = (uint32_t)((total + DXB_BC7_WARPS - 1) / DXB_BC7_WARPS);
         const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridBC7 * 4u));

@@ -1,0 +1,573 @@
+// dxb_bc6h.cuh — BC6H (UF16 / SF16) block encoder, ONE WARP PER 4x4 BLOCK (single-source SPMD, dxb_warp.cuh).
+//
+// Replaces D3DXEncodeBC6HU/S -> D3DX_BC6H::Encode (BC6HBC7.cpp:3624-3639, 1817-1859).  Parity contract as for BC7:
+// a valid stream for the reference decoder (D3DX_BC6H::Decode, :1658-1813) whose error — in the reference
+// encoder's own metric, the squared difference of half-float bit patterns over RGB (Norm / MapColorsQuantized,
+// :1167-1173, 2044-2077) — stays within the tolerance stated in DESIGN.md of the reference CPU encoder's error.
+//
+// Pixel domain = the reference's INTColor domain: F16ToINT(half(rgb)) (:534-552): unsigned -> half bits with
+// negatives clamped to 0; signed -> sign-magnitude integer, magnitude clamped to 0x7BFF.
+//   stage 1  the 32 two-region shapes ranked by a line-fit residual (one shape per lane), 15 best kept
+//   stage 2  lanes 0..29 = 15 shapes x 2 regions, lane 30 = the one-region fit: PCA axis + least-squares refit
+//            of continuous endpoints (3-bit / 4-bit interpolation weights)
+//   stage 3  region pairs exchange endpoints (__shfl_xor) and pick the format mode: the highest base precision
+//            whose delta fields can hold the endpoint differences (modes 3,4,5 > 1 > 6 > 7,8,9 > 2 > 10 for two
+//            regions; 13 > 12 > 11 for one region; BC6HBC7.cpp:1051-1067); endpoints quantised exactly as the
+//            reference does (Quantize :1864-1889) and the exact decoder palette (Unquantize / interpolate /
+//            FinishUnquantize :1893-1940) gives each lane its region's true error
+//   stage 4  winner by integer-key warp min; 16 lanes = 16 pixels choose indices against the exact palette, every
+//            lane deposits its header bits / index field into a 128-bit word, warp OR-reduction, one store
+#pragma once
+#include "dxb_warp.cuh"
+#include "dxb_pixel.cuh"
+#include "dxb_bc7.cuh"            // moments / estimate helpers, dxb_rne, dxb_u128, dxb_put_bits
+#include "dxb_bc6h_tables.h"
+
+#ifndef DXB_BC6H_ROUNDS
+#define DXB_BC6H_ROUNDS 3
+#endif
+
+// half bits -> INTColor component (F16ToINT, BC6HBC7.cpp:534-552), as float
+DXB_DEV float dxb_bc6h_to_int(float v, bool bSigned)
+{
+    const uint32_t h = dxb_float_to_half(v);
+    int32_t out;
+    if (bSigned)
+    {
+        const int32_t m = (int32_t)(h & 0x7FFFu);
+        out = (m > 0x7BFF) ? 0x7BFF : m;
+        out = (h & 0x8000u) ? -out : out;
+    }
+    else out = (h & 0x8000u) ? 0 : (int32_t)h;
+    return (float)out;
+}
+
+// D3DX_BC6H::Quantize (BC6HBC7.cpp:1864-1889)
+DXB_DEV int32_t dxb_bc6h_quantize(int32_t v, int32_t prec, bool bSigned)
+{
+    if (bSigned)
+    {
+        const int32_t a = v < 0 ? -v : v;
+        const int32_t q = (prec >= 16) ? a : ((a << (prec - 1)) / (0x7BFF + 1));
+        return v < 0 ? -q : q;
+    }
+    return (prec >= 15) ? v : ((v << prec) / (0x7BFF + 1));
+}
+// D3DX_BC6H::Unquantize (BC6HBC7.cpp:1893-1929)
+DXB_DEV int32_t dxb_bc6h_unquantize(int32_t comp, int32_t bits, bool bSigned)
+{
+    if (bSigned)
+    {
+        if (bits >= 16) return comp;
+        const bool neg = comp < 0;
+        const int32_t c = neg ? -comp : comp;
+        int32_t unq;
+        if (c == 0) unq = 0;
+        else if (c >= ((1 << (bits - 1)) - 1)) unq = 0x7FFF;
+        else unq = ((c << 15) + 0x4000) >> (bits - 1);
+        return neg ? -unq : unq;
+    }
+    if (bits >= 15) return comp;
+    if (comp == 0) return 0;
+    if (comp == ((1 << bits) - 1)) return 0xFFFF;
+    return ((comp << 16) + 0x8000) >> bits;
+}
+// D3DX_BC6H::FinishUnquantize (BC6HBC7.cpp:1932-1942)
+DXB_DEV int32_t dxb_bc6h_finish(int32_t comp, bool bSigned)
+{
+    if (bSigned) return (comp < 0) ? -(((-comp) * 31) >> 5) : ((comp * 31) >> 5);
+    return (comp * 31) >> 6;
+}
+// decoder palette entry k (3 or 4 index bits) for unquantised endpoints ua, ub (Decode :1771-1779)
+DXB_DEV int32_t dxb_bc6h_palette(int32_t ua, int32_t ub, int32_t w, bool bSigned)
+{
+    return dxb_bc6h_finish((ua * (64 - w) + ub * w + 32) >> 6, bSigned);
+}
+
+// does signed delta d fit in n bits (NBits(d, true) <= n, BC6HBC7.cpp:1176-1194)
+DXB_DEV bool dxb_fits_signed(int32_t d, int32_t n) { return d >= -(1 << (n - 1)) && d <= ((1 << (n - 1)) - 1); }
+
+// ---------------------------------------------------------------------------------------------------
+// stage 2: continuous endpoint fit of one region in the INT domain (3 channels), centred on `ctr`.
+//   ib = index bits (3 two-region, 4 one-region); anchor = the region's fix-up pixel
+// outputs E0/E1 (absolute INT-domain floats), ordered so that the anchor pixel projects into the first half
+DXB_DEV void dxb_bc6h_fit(const dxb_px* px, uint32_t mask, uint32_t ib, int anchor, const float* ctr, float lo, float hi, float* E0, float* E1)
+{
+    float n = 0, s0 = 0, s1 = 0, s2 = 0, m00 = 0, m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0;
+    for (int i = 0; i < 16; ++i)
+    {
+        const float f = dxb_bit_as_float(mask, i);
+        const dxb_px p = px[i];
+        const float X = p.x - ctr[0], Y = p.y - ctr[1], Z = p.z - ctr[2];
+        const float x = X * f, y = Y * f, z = Z * f;
+        n += f; s0 += x; s1 += y; s2 += z;
+        m00 = dxb_fma(x, X, m00); m01 = dxb_fma(x, Y, m01); m02 = dxb_fma(x, Z, m02);
+        m11 = dxb_fma(y, Y, m11); m12 = dxb_fma(y, Z, m12); m22 = dxb_fma(z, Z, m22);
+    }
+    const float inv = 1.0f / fmaxf(n, 1.0f);
+    const float mean[3] = { s0 * inv, s1 * inv, s2 * inv };
+    const float c00 = dxb_fma(-mean[0], s0, m00), c01 = dxb_fma(-mean[0], s1, m01), c02 = dxb_fma(-mean[0], s2, m02);
+    const float c11 = dxb_fma(-mean[1], s1, m11), c12 = dxb_fma(-mean[1], s2, m12), c22 = dxb_fma(-mean[2], s2, m22);
+    float ax[3];
+    {
+        const bool b0 = (c00 >= c11 && c00 >= c22), b1 = !b0 && (c11 >= c22);
+        float v0 = b0 ? c00 : (b1 ? c01 : c02), v1 = b0 ? c01 : (b1 ? c11 : c12), v2 = b0 ? c02 : (b1 ? c12 : c22);
+        for (int it = 0; it < 4; ++it)
+        {
+            const float w0 = dxb_fma(c00, v0, dxb_fma(c01, v1, c02 * v2));
+            const float w1 = dxb_fma(c01, v0, dxb_fma(c11, v1, c12 * v2));
+            const float w2 = dxb_fma(c02, v0, dxb_fma(c12, v1, c22 * v2));
+            const float mx = fmaxf(fabsf(w0), fmaxf(fabsf(w1), fabsf(w2)));
+            const float r = (mx > 1e-20f) ? 1.0f / mx : 0.0f;
+            v0 = w0 * r; v1 = w1 * r; v2 = w2 * r;
+        }
+        const float vv = dxb_fma(v0, v0, dxb_fma(v1, v1, v2 * v2));
+        const float r = (vv > 1e-20f) ? 1.0f / sqrtf(vv) : 0.0f;
+        ax[0] = v0 * r; ax[1] = v1 * r; ax[2] = v2 * r;
+    }
+    float tmin = 3.0e38f, tmax = -3.0e38f;
+    for (int i = 0; i < 16; ++i)
+    {
+        const dxb_px p = px[i];
+        const float t = dxb_fma(p.x - ctr[0] - mean[0], ax[0], dxb_fma(p.y - ctr[1] - mean[1], ax[1], (p.z - ctr[2] - mean[2]) * ax[2]));
+        const bool in = ((mask >> i) & 1u) != 0u;
+        tmin = in ? fminf(tmin, t) : tmin; tmax = in ? fmaxf(tmax, t) : tmax;
+    }
+    if (!(tmin <= tmax)) { tmin = 0.0f; tmax = 0.0f; }
+    float A[3], B[3];      // centred endpoints
+    for (int c = 0; c < 3; ++c) { A[c] = dxb_fma(tmin, ax[c], mean[c]); B[c] = dxb_fma(tmax, ax[c], mean[c]); }
+
+    const float nmax = (float)((1u << ib) - 1u);
+    const float c64 = 64.0f / nmax;
+    bool live = true;
+    for (int round = 0; round + 1 < DXB_BC6H_ROUNDS; ++round)
+    {
+        dxb_warp_sync();
+        const float dx = B[0] - A[0], dy = B[1] - A[1], dz = B[2] - A[2];
+        const float dd = dxb_fma(dx, dx, dxb_fma(dy, dy, dz * dz));
+        const float idd = (dd > 0.0f) ? 1.0f / dd : 0.0f;
+        float la = 0, lb = 0, lc = 0, u0 = 0, u1 = 0, u2 = 0, v0 = 0, v1 = 0, v2 = 0;
+        for (int i = 0; i < 16; ++i)
+        {
+            if ((mask >> i) & 1u)
+            {
+                const dxb_px p = px[i];
+                const float X = p.x - ctr[0], Y = p.y - ctr[1], Z = p.z - ctr[2];
+                const float t = dxb_fma(X - A[0], dx, dxb_fma(Y - A[1], dy, (Z - A[2]) * dz)) * idd;
+                const float xk = fminf(fmaxf(t * nmax, 0.0f), nmax - 1.0f);
+                const float k0 = dxb_rne(xk - 0.5f);
+                const float w0 = dxb_bc7_weightf(k0, c64), w1 = dxb_bc7_weightf(k0 + 1.0f, c64);
+                const float sk = ((t - w0) > (w1 - t)) ? w1 : w0;
+                const float os = 1.0f - sk;
+                la = dxb_fma(os, os, la); lb = dxb_fma(os, sk, lb); lc = dxb_fma(sk, sk, lc);
+                u0 = dxb_fma(os, X, u0); u1 = dxb_fma(os, Y, u1); u2 = dxb_fma(os, Z, u2);
+                v0 = dxb_fma(sk, X, v0); v1 = dxb_fma(sk, Y, v1); v2 = dxb_fma(sk, Z, v2);
+            }
+        }
+        const float det = dxb_fma(la, lc, -(lb * lb));
+        live = live && (det > 1e-4f);
+        const float id = live ? 1.0f / det : 0.0f;
+        const float uu[3] = { u0, u1, u2 }, vv[3] = { v0, v1, v2 };
+        for (int c = 0; c < 3; ++c)
+        {
+            const float a = dxb_fma(lc, uu[c], -(lb * vv[c])) * id, b = dxb_fma(la, vv[c], -(lb * uu[c])) * id;
+            A[c] = live ? a : A[c]; B[c] = live ? b : B[c];
+        }
+    }
+    // order: anchor pixel closer to E0
+    {
+        const dxb_px p = px[anchor];
+        const float dx = B[0] - A[0], dy = B[1] - A[1], dz = B[2] - A[2];
+        const float dd = dxb_fma(dx, dx, dxb_fma(dy, dy, dz * dz));
+        const float t = dxb_fma(p.x - ctr[0] - A[0], dx, dxb_fma(p.y - ctr[1] - A[1], dy, (p.z - ctr[2] - A[2]) * dz));
+        const bool sw = (t * 2.0f > dd);
+        for (int c = 0; c < 3; ++c)
+        {
+            const float a = fminf(fmaxf(A[c] + ctr[c], lo), hi), b = fminf(fmaxf(B[c] + ctr[c], lo), hi);
+            E0[c] = sw ? b : a; E1[c] = sw ? a : b;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 3: pick the mode for a set of endpoints (ep[4][3]: A0 B0 A1 B1, INT domain) and quantise them.
+//   two = two regions.  Returns the mode index (0..13); q[4][3] = quantised endpoints (not yet delta-transformed).
+DXB_DEV int dxb_bc6h_pick_mode(const int32_t ep[4][3], bool two, bool bSigned, int32_t q[4][3])
+{
+    // candidates in decreasing base precision; the last of each list has no delta restriction (always fits)
+    const int order2[10] = { 2, 3, 4, 0, 5, 6, 7, 8, 1, 9 };
+    const int order1[3] = { 12, 11, 10 };
+    const int ncand = two ? 10 : 3;
+    const int nep = two ? 4 : 2;
+    int chosen = two ? 9 : 10;
+    for (int ci = 0; ci < ncand; ++ci)
+    {
+        const int m = two ? order2[ci] : order1[ci];
+        const uint32_t info = dxb_bc6h_info[m];
+        const int32_t prec = (int32_t)((info >> 8) & 31u);
+        const bool transformed = ((info >> 6) & 1u) != 0u;
+        const int32_t db[3] = { (int32_t)((info >> 16) & 15u), (int32_t)((info >> 20) & 15u), (int32_t)((info >> 24) & 15u) };
+        int32_t t[4][3];
+        bool ok = true;
+        const int32_t qhi = bSigned ? ((1 << (prec - 1)) - 1) : ((1 << prec) - 1);
+        for (int e = 0; e < nep; ++e)
+            for (int c = 0; c < 3; ++c)
+                t[e][c] = dxb_bc6h_quantize(ep[e][c], prec, bSigned);
+        // a region whose two endpoints quantise to the same code wastes its interpolation levels: open the pair by one
+        // code so that the 8/16 palette entries subdivide the quantisation step (what the reference's perturbation finds)
+        for (int r = 0; r < nep; r += 2)
+            for (int c = 0; c < 3; ++c)
+                if (t[r][c] == t[r + 1][c])
+                {
+                    if (t[r + 1][c] < qhi) t[r + 1][c] += 1; else t[r][c] -= 1;
+                }
+        for (int e = 1; e < nep; ++e)
+            for (int c = 0; c < 3; ++c)
+                if (transformed) ok = ok && dxb_fits_signed(t[e][c] - t[0][c], db[c]);
+        if (ok)
+        {
+            chosen = m;
+            for (int e = 0; e < nep; ++e) for (int c = 0; c < 3; ++c) q[e][c] = t[e][c];
+            break;
+        }
+    }
+    return chosen;
+}
+
+// exact error of one region against the decoder palette of quantised endpoints qa/qb at `prec` bits
+template <int NIDX>
+DXB_DEV float dxb_bc6h_region_error(const dxb_px* px, uint32_t mask, const int32_t* qa, const int32_t* qb, int32_t prec, bool bSigned)
+{
+    const uint32_t ib = (NIDX == 8) ? 3u : 4u;
+    float pal[NIDX][3];
+    int32_t ua[3], ub[3];
+    for (int c = 0; c < 3; ++c) { ua[c] = dxb_bc6h_unquantize(qa[c], prec, bSigned); ub[c] = dxb_bc6h_unquantize(qb[c], prec, bSigned); }
+    for (int k = 0; k < NIDX; ++k)
+    {
+        const int32_t w = (int32_t)dxb_bc7_weight(ib, (uint32_t)k);
+        for (int c = 0; c < 3; ++c) pal[k][c] = (float)dxb_bc6h_palette(ua[c], ub[c], w, bSigned);
+    }
+    float tot = 0.0f;
+    for (int i = 0; i < 16; ++i)
+    {
+        if ((mask >> i) & 1u)
+        {
+            const dxb_px p = px[i];
+            float best = 3.0e38f;
+            for (int k = 0; k < NIDX; ++k)
+            {
+                const float dx = p.x - pal[k][0], dy = p.y - pal[k][1], dz = p.z - pal[k][2];
+                const float e = dxb_fma(dx, dx, dxb_fma(dy, dy, dz * dz));
+                best = fminf(best, e);
+            }
+            tot += best;
+        }
+    }
+    return tot;
+}
+
+// +-1 code refinement of one region's quantised endpoints for modes without delta coding (mode 10 / mode 11, where a
+// code is 1/64 resp. 1/1024 of the range): alternate exact index assignment and, with indices fixed, an independent
+// 3x3 search per channel (the error is separable per channel once the indices are fixed).
+template <int NIDX>
+DXB_DEV void dxb_bc6h_refine_region(const dxb_px* px, uint32_t mask, int32_t* qa, int32_t* qb, int32_t prec, bool bSigned)
+{
+    const uint32_t ib = (NIDX == 8) ? 3u : 4u;
+    const int32_t qlo = bSigned ? -((1 << (prec - 1)) - 1) : 0, qhi = bSigned ? ((1 << (prec - 1)) - 1) : ((1 << prec) - 1);
+    for (int iter = 0; iter < 2; ++iter)
+    {
+        // exact nearest indices, 4 bits per pixel
+        uint64_t idxs = 0;
+        {
+            float pal[NIDX][3];
+            for (int k = 0; k < NIDX; ++k)
+            {
+                const int32_t w = (int32_t)dxb_bc7_weight(ib, (uint32_t)k);
+                for (int c = 0; c < 3; ++c)
+                    pal[k][c] = (float)dxb_bc6h_palette(dxb_bc6h_unquantize(qa[c], prec, bSigned), dxb_bc6h_unquantize(qb[c], prec, bSigned), w, bSigned);
+            }
+            for (int i = 0; i < 16; ++i)
+            {
+                const dxb_px p = px[i];
+                float best = 3.0e38f; uint32_t bk = 0;
+                for (int k = 0; k < NIDX; ++k)
+                {
+                    const float dx = p.x - pal[k][0], dy = p.y - pal[k][1], dz = p.z - pal[k][2];
+                    const float e = dxb_fma(dx, dx, dxb_fma(dy, dy, dz * dz));
+                    if (e < best) { best = e; bk = (uint32_t)k; }
+                }
+                idxs |= (uint64_t)bk << (4 * i);
+            }
+        }
+        for (int c = 0; c < 3; ++c)
+        {
+            float bestE = 3.0e38f; int32_t ba = qa[c], bb = qb[c];
+            for (int da = -1; da <= 1; ++da)
+                for (int dbb = -1; dbb <= 1; ++dbb)
+                {
+                    const int32_t a = qa[c] + da, b = qb[c] + dbb;
+                    if (a < qlo || a > qhi || b < qlo || b > qhi) continue;
+                    const int32_t ua = dxb_bc6h_unquantize(a, prec, bSigned), ub = dxb_bc6h_unquantize(b, prec, bSigned);
+                    float e = 0.0f;
+                    for (int i = 0; i < 16; ++i)
+                    {
+                        if ((mask >> i) & 1u)
+                        {
+                            const int32_t w = (int32_t)dxb_bc7_weight(ib, (uint32_t)((idxs >> (4 * i)) & 15u));
+                            const float v = (c == 0) ? px[i].x : (c == 1) ? px[i].y : px[i].z;
+                            const float d = v - (float)dxb_bc6h_palette(ua, ub, w, bSigned);
+                            e = dxb_fma(d, d, e);
+                        }
+                    }
+                    if (e < bestE) { bestE = e; ba = a; bb = b; }
+                }
+            qa[c] = ba; qb[c] = bb;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// whole block, SPMD over the warp.  spx = 16 pixels in the INT domain (x,y,z; w unused), out = 16 bytes.
+DXB_DEV void dxb_bc6h_encode_warp(const dxb_px* spx, bool bSigned, uint8_t* out)
+{
+    const float lo = bSigned ? -31743.0f : 0.0f, hi = 31743.0f;
+    // block centre (keeps the fp32 moments well conditioned: values are up to 3e4, squares 1e9)
+    float ctr[3] = { 0, 0, 0 };
+    for (int i = 0; i < 16; ++i) { ctr[0] += spx[i].x; ctr[1] += spx[i].y; ctr[2] += spx[i].z; }
+    ctr[0] *= (1.0f / 16.0f); ctr[1] *= (1.0f / 16.0f); ctr[2] *= (1.0f / 16.0f);
+
+    // ---- stage 1: one shape per lane (BC6H uses the first 32 two-subset shapes)
+    uint32_t key[DXB_NL];
+    DXB_LANES_BEGIN
+        // centred moments of subset 1 and of the whole block
+        float n1 = 0, s[3] = { 0, 0, 0 }, m[6] = { 0, 0, 0, 0, 0, 0 }, ts[3] = { 0, 0, 0 }, tm[6] = { 0, 0, 0, 0, 0, 0 };
+        const uint32_t mask1 = dxb_part2[lane];
+        for (int i = 0; i < 16; ++i)
+        {
+            const float f = dxb_bit_as_float(mask1, i);
+            const dxb_px p = spx[i];
+            const float X = p.x - ctr[0], Y = p.y - ctr[1], Z = p.z - ctr[2];
+            const float x = X * f, y = Y * f, z = Z * f;
+            n1 += f; s[0] += x; s[1] += y; s[2] += z;
+            m[0] = dxb_fma(x, X, m[0]); m[1] = dxb_fma(x, Y, m[1]); m[2] = dxb_fma(x, Z, m[2]);
+            m[3] = dxb_fma(y, Y, m[3]); m[4] = dxb_fma(y, Z, m[4]); m[5] = dxb_fma(z, Z, m[5]);
+            ts[0] += X; ts[1] += Y; ts[2] += Z;
+            tm[0] = dxb_fma(X, X, tm[0]); tm[1] = dxb_fma(X, Y, tm[1]); tm[2] = dxb_fma(X, Z, tm[2]);
+            tm[3] = dxb_fma(Y, Y, tm[3]); tm[4] = dxb_fma(Y, Z, tm[4]); tm[5] = dxb_fma(Z, Z, tm[5]);
+        }
+        float s4[4] = { s[0], s[1], s[2], 0.0f }, m10[10] = { m[0], m[1], m[2], 0.0f, m[3], m[4], 0.0f, m[5], 0.0f, 0.0f };
+        float s40[4] = { ts[0] - s[0], ts[1] - s[1], ts[2] - s[2], 0.0f };
+        float m100[10] = { tm[0] - m[0], tm[1] - m[1], tm[2] - m[2], 0.0f, tm[3] - m[3], tm[4] - m[4], 0.0f, tm[5] - m[5], 0.0f, 0.0f };
+        const float est = dxb_bc7_subset_estimate(16.0f - n1, s40, m100, 1.0f / 49.0f) + dxb_bc7_subset_estimate(n1, s4, m10, 1.0f / 49.0f);
+        key[L] = (dxb_float_as_uint(fmaxf(est, 0.0f)) & 0xFFFFFFE0u) | (uint32_t)lane;
+    DXB_LANES_END
+    uint32_t sel[15];
+    for (int r = 0; r < 15; ++r)
+    {
+        const uint32_t win = dxb_warp_min_u32(key);
+        sel[r] = win & 31u;
+        DXB_LANES_BEGIN
+            if (key[L] == win) key[L] = 0xFFFFFFFFu;
+        DXB_LANES_END
+    }
+
+    // ---- stage 2: continuous fits.  lanes 0..29: (shape sel[lane>>1], region lane&1); lane 30: one region; lane 31 idles on a copy
+    float e0x[DXB_NL], e0y[DXB_NL], e0z[DXB_NL], e1x[DXB_NL], e1y[DXB_NL], e1z[DXB_NL];
+    uint32_t tShape[DXB_NL], tMask[DXB_NL];
+    DXB_LANES_BEGIN
+        const bool one = (lane >= 30);
+        const uint32_t shape = one ? 0u : sel[lane >> 1];
+        const uint32_t m1 = dxb_part2[shape];
+        const uint32_t mask = one ? 0xFFFFu : ((lane & 1) ? m1 : (~m1 & 0xFFFFu));
+        const int anchor = one ? 0 : ((lane & 1) ? (int)dxb_anchor2[shape] : 0);
+        float E0[3], E1[3];
+        dxb_bc6h_fit(spx, mask, one ? 4u : 3u, anchor, ctr, lo, hi, E0, E1);
+        e0x[L] = E0[0]; e0y[L] = E0[1]; e0z[L] = E0[2]; e1x[L] = E1[0]; e1y[L] = E1[1]; e1z[L] = E1[2];
+        tShape[L] = shape; tMask[L] = mask;
+    DXB_LANES_END
+
+    // ---- stage 3: partner exchange, mode choice, exact region error
+    float p0x[DXB_NL], p0y[DXB_NL], p0z[DXB_NL], p1x[DXB_NL], p1y[DXB_NL], p1z[DXB_NL];
+    dxb_xchg_xor_f32(e0x, p0x, 1); dxb_xchg_xor_f32(e0y, p0y, 1); dxb_xchg_xor_f32(e0z, p0z, 1);
+    dxb_xchg_xor_f32(e1x, p1x, 1); dxb_xchg_xor_f32(e1y, p1y, 1); dxb_xchg_xor_f32(e1z, p1z, 1);
+    uint32_t rErr[DXB_NL], rMode[DXB_NL];
+    uint32_t rq[DXB_NL][12];            // quantised endpoints A0 B0 A1 B1 (two's complement ints)
+    uint32_t mine[6][DXB_NL], theirs[6][DXB_NL];      // refined endpoints of this lane's region / of the partner's
+    DXB_LANES_BEGIN
+        const bool one = (lane >= 30);
+        const bool second = !one && (lane & 1);
+        int32_t ep[4][3];
+        // region 0 endpoints come from the even lane, region 1 from the odd lane
+        const float mine0[3] = { e0x[L], e0y[L], e0z[L] }, mine1[3] = { e1x[L], e1y[L], e1z[L] };
+        const float oth0[3] = { p0x[L], p0y[L], p0z[L] }, oth1[3] = { p1x[L], p1y[L], p1z[L] };
+        for (int c = 0; c < 3; ++c)
+        {
+            const float a0 = second ? oth0[c] : mine0[c], b0 = second ? oth1[c] : mine1[c];
+            const float a1 = second ? mine0[c] : oth0[c], b1 = second ? mine1[c] : oth1[c];
+            ep[0][c] = dxb_f2i(dxb_rne(a0)); ep[1][c] = dxb_f2i(dxb_rne(b0));
+            ep[2][c] = dxb_f2i(dxb_rne(a1)); ep[3][c] = dxb_f2i(dxb_rne(b1));
+        }
+        int32_t q[4][3];
+        for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) q[e][c] = 0;
+        const int mode = dxb_bc6h_pick_mode(ep, !one, bSigned, q);
+        const int32_t prec = (int32_t)((dxb_bc6h_info[mode] >> 8) & 31u);
+        // +-1 code refinement of this lane's own region
+        int32_t qa[3], qb[3];
+        for (int c = 0; c < 3; ++c) { qa[c] = second ? q[2][c] : q[0][c]; qb[c] = second ? q[3][c] : q[1][c]; }
+        if (one) dxb_bc6h_refine_region<16>(spx, 0xFFFFu, qa, qb, prec, bSigned);
+        else dxb_bc6h_refine_region<8>(spx, tMask[L], qa, qb, prec, bSigned);
+        for (int c = 0; c < 3; ++c) { mine[c][L] = (uint32_t)qa[c]; mine[3 + c][L] = (uint32_t)qb[c]; }
+        rMode[L] = (uint32_t)mode;
+        for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) rq[L][e * 3 + c] = (uint32_t)q[e][c];
+    DXB_LANES_END
+    for (int k = 0; k < 6; ++k) dxb_xchg_xor_u32(mine[k], theirs[k], 1);
+    DXB_LANES_BEGIN
+        const bool one = (lane >= 30);
+        const bool second = !one && (lane & 1);
+        const int mode = (int)rMode[L];
+        const uint32_t info = dxb_bc6h_info[mode];
+        const int32_t prec = (int32_t)((info >> 8) & 31u);
+        const bool transformed = ((info >> 6) & 1u) != 0u;
+        const int32_t db[3] = { (int32_t)((info >> 16) & 15u), (int32_t)((info >> 20) & 15u), (int32_t)((info >> 24) & 15u) };
+        // refined set of all endpoints (identical on both lanes of a pair): keep it only if the deltas still fit
+        int32_t r[4][3];
+        for (int c = 0; c < 3; ++c)
+        {
+            const int32_t ma = (int32_t)mine[c][L], mb = (int32_t)mine[3 + c][L];
+            const int32_t ta = one ? 0 : (int32_t)theirs[c][L], tb = one ? 0 : (int32_t)theirs[3 + c][L];
+            r[0][c] = second ? ta : ma; r[1][c] = second ? tb : mb;
+            r[2][c] = second ? ma : ta; r[3][c] = second ? mb : tb;
+        }
+        bool ok = true;
+        if (transformed)
+            for (int e = 1; e < (one ? 2 : 4); ++e)
+                for (int c = 0; c < 3; ++c) ok = ok && dxb_fits_signed(r[e][c] - r[0][c], db[c]);
+        int32_t q[4][3];
+        for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) q[e][c] = ok ? r[e][c] : (int32_t)rq[L][e * 3 + c];
+        float err;
+        if (one) err = dxb_bc6h_region_error<16>(spx, 0xFFFFu, q[0], q[1], prec, bSigned);
+        else err = dxb_bc6h_region_error<8>(spx, tMask[L], second ? q[2] : q[0], second ? q[3] : q[1], prec, bSigned);
+        // errors are sums of squared differences of 15-bit integers: scale into 27 bits for the integer key
+        rErr[L] = (lane == 31) ? 0x07FFFFFFu : (uint32_t)dxb_f2i(fminf(err * (1.0f / 1024.0f), 6.0e7f));
+        for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) rq[L][e * 3 + c] = (uint32_t)q[e][c];
+    DXB_LANES_END
+    uint32_t partner[DXB_NL];
+    dxb_xchg_xor_u32(rErr, partner, 1);
+    uint32_t wkeys[DXB_NL];
+    DXB_LANES_BEGIN
+        uint32_t e = rErr[L];
+        if (lane < 30) e += partner[L];
+        e = (e > 0x07FFFFFFu) ? 0x07FFFFFFu : e;
+        wkeys[L] = (e << 5) | (uint32_t)lane;
+        if (lane == 31) wkeys[L] = 0xFFFFFFFFu;
+    DXB_LANES_END
+    const uint32_t wkey = dxb_warp_min_u32(wkeys);
+    const int wl = (int)(wkey & 31u) & ~1;                  // even lane of the winning pair (lane 30 for one region)
+    const bool two = (wl < 30);
+    const uint32_t wMode = dxb_bcast_u32(rMode, wl);
+    const uint32_t wShape = two ? dxb_bcast_u32(tShape, wl) : 0u;
+    int32_t wq[4][3];
+    for (int e = 0; e < 4; ++e)
+        for (int c = 0; c < 3; ++c)
+        {
+            uint32_t col[DXB_NL];
+            DXB_LANES_BEGIN
+                col[L] = rq[L][e * 3 + c];
+            DXB_LANES_END
+            wq[e][c] = (int32_t)dxb_bcast_u32(col, wl);
+        }
+
+    // ---- stage 4: indices against the exact palette, header + index packing
+    const uint32_t info = dxb_bc6h_info[wMode];
+    const int32_t prec = (int32_t)((info >> 8) & 31u);
+    const bool transformed = ((info >> 6) & 1u) != 0u;
+    const uint32_t ib = two ? 3u : 4u;
+    const uint32_t part = two ? dxb_part2[wShape] : 0u;
+    const uint32_t anchor1 = two ? dxb_anchor2[wShape] : 0u;
+    int32_t ua[2][3], ub[2][3];
+    for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 3; ++c)
+        {
+            ua[r][c] = dxb_bc6h_unquantize(wq[r * 2][c], prec, bSigned);
+            ub[r][c] = dxb_bc6h_unquantize(wq[r * 2 + 1][c], prec, bSigned);
+        }
+    uint32_t idx[DXB_NL];
+    DXB_LANES_BEGIN
+        idx[L] = 0;
+        if (lane < 16)
+        {
+            const int r = (int)((part >> lane) & 1u);
+            const dxb_px p = spx[lane];
+            const bool isAnchor = (lane == 0) || (two && (uint32_t)lane == anchor1);
+            const uint32_t nk = isAnchor ? (1u << (ib - 1u)) : (1u << ib);       // anchors only have ib-1 bits
+            float best = 3.0e38f; uint32_t bk = 0;
+            for (uint32_t k = 0; k < nk; ++k)
+            {
+                const int32_t w = (int32_t)dxb_bc7_weight(ib, k);
+                const float dx = p.x - (float)dxb_bc6h_palette(ua[r][0], ub[r][0], w, bSigned);
+                const float dy = p.y - (float)dxb_bc6h_palette(ua[r][1], ub[r][1], w, bSigned);
+                const float dz = p.z - (float)dxb_bc6h_palette(ua[r][2], ub[r][2], w, bSigned);
+                const float e = dxb_fma(dx, dx, dxb_fma(dy, dy, dz * dz));
+                if (e < best) { best = e; bk = k; }
+            }
+            idx[L] = bk;
+        }
+    DXB_LANES_END
+
+    // header fields: endpoint 0 A as is, the others as deltas in transformed modes, masked to their field widths
+    const int32_t db[3] = { (int32_t)((info >> 16) & 15u), (int32_t)((info >> 20) & 15u), (int32_t)((info >> 24) & 15u) };
+    uint32_t field[15];
+    field[0] = 0; field[1] = info & 31u; field[2] = wShape;
+    for (int c = 0; c < 3; ++c)
+    {
+        const uint32_t m0 = (prec >= 32) ? 0xFFFFFFFFu : ((1u << prec) - 1u);
+        const uint32_t md = transformed ? ((1u << db[c]) - 1u) : m0;
+        const int32_t a0 = wq[0][c];
+        field[3 + 4 * c + 0] = (uint32_t)a0 & m0;
+        field[3 + 4 * c + 1] = (uint32_t)(transformed ? wq[1][c] - a0 : wq[1][c]) & md;
+        field[3 + 4 * c + 2] = (uint32_t)(transformed ? wq[2][c] - a0 : wq[2][c]) & md;
+        field[3 + 4 * c + 3] = (uint32_t)(transformed ? wq[3][c] - a0 : wq[3][c]) & md;
+    }
+    const uint32_t hdrBits = two ? 82u : 65u;
+    uint32_t w0[DXB_NL], w1[DXB_NL], w2[DXB_NL], w3[DXB_NL];
+    DXB_LANES_BEGIN
+        dxb_u128 bits; bits.lo = 0; bits.hi = 0;
+        // header: lane l deposits bits l, l+32, l+64
+        for (uint32_t b = (uint32_t)lane; b < hdrBits; b += 32u)
+        {
+            const uint32_t d = dxb_bc6h_desc[wMode][b];
+            uint32_t f = 0;
+            // field[] is indexed with a lane-varying value: select chain keeps it in registers
+            const uint32_t fi = d >> 4;
+            for (uint32_t k = 1; k < 15; ++k) f = (fi == k) ? field[k] : f;
+            dxb_put_bits(&bits, b, 1, (f >> (d & 15u)) & 1u);
+        }
+        if (lane < 16)
+        {
+            const uint32_t i = (uint32_t)lane;
+            const uint32_t before = (i > 0 ? 1u : 0u) + ((two && i > anchor1) ? 1u : 0u);
+            const bool isAnchor = (i == 0) || (two && i == anchor1);
+            dxb_put_bits(&bits, hdrBits + i * ib - before, isAnchor ? ib - 1u : ib, idx[L]);
+        }
+        w0[L] = (uint32_t)bits.lo; w1[L] = (uint32_t)(bits.lo >> 32); w2[L] = (uint32_t)bits.hi; w3[L] = (uint32_t)(bits.hi >> 32);
+    DXB_LANES_END
+    const uint32_t o0 = dxb_warp_or_u32(w0), o1 = dxb_warp_or_u32(w1), o2 = dxb_warp_or_u32(w2), o3 = dxb_warp_or_u32(w3);
+    DXB_LANES_BEGIN
+        if (lane == 0)
+        {
+            uint32_t* o = (uint32_t*)out;
+            o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
+        }
+    DXB_LANES_END
+}
+
+#if !DXB_ON_DEVICE
+// emulator entry: px = 16 RGBA fp32 pixels after ConvertScanline
+static inline void dxb_bc6h_encode_block_emul(const dxb_px* px, bool bSigned, uint8_t* out)
+{
+    dxb_px ip[16];
+    for (int i = 0; i < 16; ++i)
+        ip[i] = dxb_make_px(dxb_bc6h_to_int(px[i].x, bSigned), dxb_bc6h_to_int(px[i].y, bSigned), dxb_bc6h_to_int(px[i].z, bSigned), 0.0f);
+    dxb_bc6h_encode_warp(ip, bSigned, out);
+}
+#endif

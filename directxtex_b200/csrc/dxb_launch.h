@@ -42,6 +42,7 @@ struct dxb_mip_params
 // launchers: `grid` CTAs on `stream`; jobs == nullptr -> `single` is used
 void dxb_launch_bc15(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job& single, const dxb_compress_params& P);
 void dxb_launch_bc7(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job& single, const dxb_compress_params& P);
+void dxb_launch_bc6h(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job& single, const dxb_compress_params& P);
 // hostJobs = the same records on the host (njobs of them); jobs = device copy or nullptr when njobs == 1
 void dxb_launch_convert(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job* hostJobs, const dxb_convert_params& P);
 void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs, const dxb_mip_job* hostJobs, const dxb_mip_params& P);
@@ -50,6 +51,7 @@ bool dxb_launch_mip_tail(cudaStream_t stream, const dxb_mip_job* jobsDev, uint32
 // resident CTAs per SM of each kernel at its block size
 int dxb_occupancy_bc15();
 int dxb_occupancy_bc7();
+int dxb_occupancy_bc6h();
 
 #ifdef __CUDACC__
 template <typename J>

@@ -22,6 +22,7 @@
 #include "dxb_bc15.cuh"
 #ifdef DXB_EMUL_BC7
 #include "dxb_bc7.cuh"
+#include "dxb_bc6h.cuh"
 #endif
 
 extern "C" {
@@ -51,6 +52,8 @@ int32_t emul_compress(const uint8_t* src, size_t w, size_t h, uint32_t srcFmt, s
 #ifdef DXB_EMUL_BC7
             if (dstFmt == DXB_FMT_BC7_UNORM || dstFmt == DXB_FMT_BC7_UNORM_SRGB)
                 dxb_bc7_encode_block_emul(px, bcflags, blk);
+            else if (dstFmt == DXB_FMT_BC6H_UF16 || dstFmt == DXB_FMT_BC6H_SF16)
+                dxb_bc6h_encode_block_emul(px, dstFmt == DXB_FMT_BC6H_SF16, blk);
             else
 #endif
                 dxb_encode_block_bc15(dstFmt, px, bcflags, threshold, blk);

@@ -169,3 +169,39 @@ def random_image(fmt, w, h, rng):
     if fmt in (10, 34, 54):
         return (rng.random(n // 2) * 1.4 - 0.2).astype(np.float16).view(np.uint8)
     return rng.integers(0, 256, n, dtype=np.uint8)
+
+
+def bc6h_to_int(img_f, signed=False):
+    """the reference's INTColor domain (F16ToINT, BC6HBC7.cpp:534-552) of an RGB(A) float image"""
+    h = np.asarray(img_f, np.float32).astype(np.float16).view(np.uint16).astype(np.int64)
+    if signed:
+        m = np.minimum(h & 0x7FFF, 0x7BFF)
+        return np.where(h & 0x8000, -m, m)
+    return np.where(h & 0x8000, 0, h)
+
+
+def bc6h_int_mse(decoded, src_f32, signed=False):
+    """mean squared difference of half-float bit patterns over RGB: the reference encoder's own error metric"""
+    a = bc6h_to_int(decoded[..., :3], signed)
+    b = bc6h_to_int(np.clip(src_f32[..., :3], -65504 if signed else 0, 65504), signed)
+    return float(((a - b).astype(np.float64) ** 2).mean())
+
+
+def bc6h_test_image(kind, w, h, seed):
+    from directxtex_b200 import synth
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    if kind == "c3":
+        return np.ascontiguousarray(synth.c3_rgba16f(w, h, seed=seed).astype(np.float32))
+    smooth = np.stack([np.exp2(4 * np.sin(x * 0.05) + 2 * np.cos(y * 0.03)), np.exp2(3 * np.cos(x * 0.02 + y * 0.04)),
+                       np.exp2(2 * np.sin(y * 0.06)), np.ones_like(x)], -1).astype(np.float32)
+    if kind == "smooth":
+        return np.ascontiguousarray((smooth * (1 + 0.02 * rng.normal(size=smooth.shape))).astype(np.float32))
+    if kind == "edges":
+        e = np.where(((x // 4 + y // 4) % 3 == 0)[..., None] & ((x % 4) < 2)[..., None], np.float32(50.0), smooth)
+        return np.ascontiguousarray(e.astype(np.float32))
+    if kind == "signed":
+        v = smooth - np.float32(3.0)
+        v[..., 3] = 1
+        return np.ascontiguousarray(v.astype(np.float32))
+    raise ValueError(kind)

@@ -149,3 +149,37 @@ def test_emulator_bc7_quick_flag_uses_mode6_only(emul):
     assert he == 0
     first = blocks.reshape(-1, 16)[:, 0]
     assert np.all((first & 0x7F) == 0x40)      # mode 6: six zero bits then a one
+
+
+def test_emulator_bc6h_quality_vs_reference(oracle, emul):
+    """BC6H tolerance: error in the reference encoder's own metric (squared half-float bit-pattern
+    differences over RGB) <= 1.05 x the reference CPU encoder's on the same input; decodable by the reference decoder."""
+    z = golden_util.load()
+    for j in range(4):
+        w, h, seed, fmt = (int(v) for v in z["bc6h_%d_meta" % j])
+        kind = bytes(z["bc6h_%d_kind" % j]).decode()
+        img = oracle_lib.bc6h_test_image(kind, w, h, seed)
+        ref_err = float(z["bc6h_%d_referr" % j][0])
+        assert abs(oracle_lib.bc6h_int_mse(oracle.decode_blocks(fmt, z["bc6h_%d_blocks" % j], w, h), img, fmt == 96) - ref_err) <= 1e-6 * max(ref_err, 1)
+        he, blocks = emul.compress(img, w, h, 2, fmt, 0)
+        assert he == 0
+        err = oracle_lib.bc6h_int_mse(oracle.decode_blocks(fmt, blocks, w, h), img, fmt == 96)
+        assert err <= ref_err * 1.05, (kind, fmt, err, ref_err)
+
+
+def test_emulator_bc6h_special_blocks(oracle, emul):
+    img = np.zeros((12, 16, 4), np.float32)
+    img[..., 3] = 1
+    img[0:4, 0:4, :3] = 0.0
+    img[0:4, 4:8, :3] = 65504.0
+    img[0:4, 8:12, :3] = [1.0, 0.5, 0.25]
+    img[4:8, :, :3] = np.exp2(np.linspace(-8, 8, 16))[None, :, None]
+    img[8:12, :, 0] = 1000.0
+    for (w, h) in [(16, 12), (5, 7), (1, 1)]:
+        sub = np.ascontiguousarray(img[:h, :w])
+        he, blocks = emul.compress(sub, w, h, 2, 95, 0)
+        assert he == 0
+        dec = oracle.decode_blocks(95, blocks, w, h)
+        assert np.isfinite(dec).all()
+        rel = np.abs(dec[..., :3] - sub[..., :3]) / np.maximum(np.abs(sub[..., :3]), 1e-3)
+        assert rel[:4, :min(w, 12)].max() <= 0.02 if h >= 4 and w >= 12 else True      # solid blocks are near exact

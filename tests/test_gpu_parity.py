@@ -196,3 +196,34 @@ def test_full_size_c5_bc4_and_convert_roundtrip(oracle):
     assert np.array_equal(f.view(np.float32), (img.reshape(-1).astype(np.float32) / np.float32(255.0)))
     back = capi.convert(f, 8192, 8192, 41, 61)
     assert np.array_equal(back, img.reshape(-1))
+
+
+def test_bc6h_equals_emulator_and_quality(oracle, emul):
+    """GPU BC6H == host lock-step emulator bit for bit; error (reference metric) <= 1.05 x the reference CPU encoder's."""
+    z = golden_util.load()
+    for j in range(4):
+        w, h, seed, fmt = (int(v) for v in z["bc6h_%d_meta" % j])
+        kind = bytes(z["bc6h_%d_kind" % j]).decode()
+        img = oracle_lib.bc6h_test_image(kind, w, h, seed)
+        got = capi.compress(img, w, h, 2, fmt)
+        he, em = emul.compress(img, w, h, 2, fmt)
+        assert he == 0
+        err = oracle_lib.bc6h_int_mse(oracle.decode_blocks(fmt, got, w, h), img, fmt == 96)
+        assert err <= float(z["bc6h_%d_referr" % j][0]) * 1.05, (kind, err)
+        nd = int((got.reshape(-1, 16) != em.reshape(-1, 16)).any(1).sum())
+        assert nd == 0, "%d blocks differ from the emulator" % nd
+
+
+def test_config3_rgba16f_cubic_chain_bc6h(oracle, emul):
+    """BASELINE configs[2] at reduced size: RGBA16F -> full CUBIC mip chain (bit-exact vs oracle) -> BC6H_UF16 of every
+    level (== emulator; top level within tolerance of the reference encoder)."""
+    w = h = 256
+    img = synth.c3_rgba16f(w, h)
+    chain, layout = capi.generate_mipmaps(img, w, h, 10, F.TEX_FILTER_CUBIC)
+    hr, want = oracle.generate_mipmaps(img, w, h, 10, F.TEX_FILTER_CUBIC)
+    assert hr == 0 and np.array_equal(chain, want)
+    for (off, lw, lh, row, sl) in layout[:4]:
+        level = chain[off:off + sl]
+        got = capi.compress(level, lw, lh, 10, 95)
+        he, em = emul.compress(level, lw, lh, 10, 95)
+        assert he == 0 and np.array_equal(got, em)
