@@ -141,3 +141,15 @@ def generate_mipmaps(src, w, h, fmt, filter=0, levels=0):
     if hr != 0:
         raise DxTexError(hr, "dxb200_generate_mipmaps")
     return chain, layout
+
+
+def decompress(blocks, w, h, bc_fmt, dst_fmt):
+    blocks = np.ascontiguousarray(blocks)
+    row, sl = F.compute_pitch(dst_fmt, w, h) if dst_fmt in F.BYTES_PER_PIXEL else (0, 0)
+    out = np.zeros(max(sl, 1), np.uint8)
+    s = images([make_image(_np_ptr(blocks), w, h, bc_fmt) if bc_fmt in F.BLOCK_BYTES else Image(w, h, bc_fmt, 0, 0, _np_ptr(blocks))])
+    d = images([Image(w, h, dst_fmt, row, sl, _np_ptr(out))])
+    hr = lib.dxb200_decompress(s, 1, dst_fmt, d)
+    if hr != 0:
+        raise DxTexError(hr, "dxb200_decompress")
+    return out[:sl]

@@ -525,9 +525,76 @@ int32_t dxb200_compress(const dxb200_image* src, size_t nimages, uint32_t dstFor
         [&](const dxb200_image* ds, const dxb200_image* dd, size_t cnt, cudaStream_t st) { return launch_compress(plan, ds, dd, cnt, st); });
 }
 
-// ---- Decompress (lands after the encode path) ------------------------------------
-int32_t dxb200_decompress_device(const dxb200_image*, size_t, uint32_t, const dxb200_image*, void*) { return DXB_E_NOTIMPL; }
-int32_t dxb200_decompress(const dxb200_image*, size_t, uint32_t, const dxb200_image*) { return DXB_E_NOTIMPL; }
+// ---- Decompress (DirectXTexCompress.cpp:852-979; DecompressBC :425-535) ---------------------------------
+static int32_t plan_decompress(const dxb200_image* src, size_t n, uint32_t dstFormat, const dxb200_image* dst, dxb_compress_params* P)
+{
+    if (!src || !dst || !n) return DXB_E_INVALIDARG;
+    const uint32_t srcFormat = src[0].format;
+    if (!is_compressed(srcFormat) || is_compressed(dstFormat)) return DXB_E_INVALIDARG;
+    if (!is_supported_pixel_format(dstFormat)) return DXB_E_NOT_SUPPORTED;
+    for (size_t i = 0; i < n; ++i)
+    {
+        if (!src[i].pixels || !dst[i].pixels) return DXB_E_POINTER;
+        if (src[i].format != srcFormat || dst[i].format != dstFormat) return DXB_E_INVALIDARG;
+        if (src[i].width != dst[i].width || src[i].height != dst[i].height) return DXB_E_FAIL;
+        if (!src[i].width || !src[i].height || src[i].width > 0xFFFFFFFFull || src[i].height > 0xFFFFFFFFull) return DXB_E_INVALIDARG;
+    }
+    memset(P, 0, sizeof(*P));
+    P->srcFormat = srcFormat; P->dstFormat = dstFormat;
+    P->inF = dxb_convert_flags(srcFormat); P->outF = dxb_convert_flags(dstFormat);
+    P->cflags = dxb_resolve_srgb_convert(0, srcFormat, dstFormat);          // ConvertScanline(..., TEX_FILTER_DEFAULT) (:500)
+    return DXB_S_OK;
+}
+
+static int32_t launch_decompress(dxb_compress_params P, const dxb200_image* src, const dxb200_image* dst, size_t n, cudaStream_t stream)
+{
+    std::vector<dxb_job> jobs(n);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; ++i)
+    {
+        dxb_job& j = jobs[i];
+        j.src = src[i].pixels; j.dst = dst[i].pixels; j.srcPitch = src[i].rowPitch; j.dstPitch = dst[i].rowPitch;
+        j.width = (uint32_t)src[i].width; j.height = (uint32_t)src[i].height;
+        j.nbx = (j.width + 3) / 4; j.nby = (j.height + 3) / 4; j.pad = 0;
+        j.firstUnit = (uint32_t)total; total += (uint64_t)j.nbx * j.nby;
+        if (total > 0x7FFFFFFFull) return DXB_E_INVALIDARG;
+    }
+    P.totalUnits = (uint32_t)total; P.njobs = (uint32_t)n;
+    DeviceJobs<dxb_job> dj;
+    int32_t hr = dj.upload(jobs, stream);
+    if (hr != DXB_S_OK) return hr;
+    const uint32_t need = (uint32_t)((total + 127) / 128);
+    const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridBC15 * 8u));
+    dxb_launch_decompress(grid, stream, dj.d, jobs[0], P);
+    hr = check_launch("k_decompress");
+    dj.release();
+    return hr;
+}
+
+int32_t dxb200_decompress_device(const dxb200_image* src, size_t nimages, uint32_t dstFormat, const dxb200_image* dst, void* stream)
+{
+    dxb_compress_params P;
+    int32_t hr = plan_decompress(src, nimages, dstFormat, dst, &P);
+    if (hr != DXB_S_OK) return hr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        hr = ensure_init_locked();
+    }
+    if (hr != DXB_S_OK) return hr;
+    return launch_decompress(P, src, dst, nimages, static_cast<cudaStream_t>(stream));
+}
+
+int32_t dxb200_decompress(const dxb200_image* src, size_t nimages, uint32_t dstFormat, const dxb200_image* dst)
+{
+    dxb_compress_params P;
+    int32_t hr = plan_decompress(src, nimages, dstFormat, dst, &P);
+    if (hr != DXB_S_OK) return hr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    hr = ensure_init_locked();
+    if (hr != DXB_S_OK) return hr;
+    return run_staged(src, dst, nimages, true, true,
+        [&](const dxb200_image* ds, const dxb200_image* dd, size_t cnt, cudaStream_t st) { return launch_decompress(P, ds, dd, cnt, st); });
+}
 
 // ---- Convert ------------------------------------------------------------------------------------
 int32_t dxb200_convert_device(const dxb200_image* src, size_t nimages, uint32_t dstFormat, uint32_t filter, float threshold,

@@ -135,3 +135,26 @@ extern "C" int32_t emul_generate_mipmaps(uint8_t* chainBase, const size_t* offse
     }
     return DXB_S_OK;
 }
+
+// ---- Decompress emulation (DecompressBC, DirectXTexCompress.cpp:425-535) -----------------------------------
+#include "dxb_decode.cuh"
+extern "C" int32_t emul_decompress(const uint8_t* blocks, size_t w, size_t h, uint32_t bcFmt, uint32_t dstFmt, uint8_t* dst)
+{
+    const uint32_t bs = dxb_bc_block_bytes(bcFmt), bpp = dxb_bytes_per_pixel(dstFmt);
+    if (!bs || !bpp) return DXB_E_NOT_SUPPORTED;
+    const uint32_t inF = dxb_convert_flags(bcFmt), outF = dxb_convert_flags(dstFmt);
+    const uint32_t cflags = dxb_resolve_srgb_convert(0, bcFmt, dstFmt);
+    const size_t nbx = (w + 3) / 4, nby = (h + 3) / 4, dpitch = w * bpp;
+    for (size_t by = 0; by < nby; ++by)
+        for (size_t bx = 0; bx < nbx; ++bx)
+        {
+            dxb_px px[16];
+            alignas(16) uint8_t blk[16];
+            memcpy(blk, blocks + (by * nbx + bx) * bs, bs);
+            dxb_decode_block(bcFmt, blk, px);
+            for (size_t t = 0; t < 4 && by * 4 + t < h; ++t)
+                for (size_t s2 = 0; s2 < 4 && bx * 4 + s2 < w; ++s2)
+                    dxb_store_pixel(dstFmt, dst + (by * 4 + t) * dpitch, bx * 4 + s2, dxb_convert_pixel(px[(t << 2) | s2], inF, outF, cflags));
+        }
+    return DXB_S_OK;
+}

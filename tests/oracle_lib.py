@@ -87,6 +87,13 @@ class Ref:
         hr = self.L.ref_generate_mipmaps(src.ctypes.data, w, h, fmt, 0, filter, levels, out.ctypes.data, total, nl, nb)
         return F.hr_u32(hr), out
 
+    def decompress(self, blocks, w, h, bc_fmt, dst_fmt):
+        blocks = np.ascontiguousarray(blocks)
+        n = w * h * F.BYTES_PER_PIXEL[dst_fmt]
+        out = np.zeros(n, np.uint8)
+        hr = self.L.ref_decompress(blocks.ctypes.data, w, h, bc_fmt, dst_fmt, out.ctypes.data, n)
+        return F.hr_u32(hr), out
+
     def decode_blocks(self, fmt, blocks, w, h):
         """BC blocks (row-major block order) -> float32 image (h4*4, w4*4, 4) via D3DXDecodeBC*."""
         nbx, nby = (w + 3) // 4, (h + 3) // 4
@@ -111,6 +118,7 @@ class Emul:
         L.emul_compress.argtypes = [vp, sz, sz, u32, sz, u32, u32, f32, vp]
         L.emul_convert.argtypes = [vp, sz, sz, u32, sz, u32, sz, u32, vp]
         L.emul_generate_mipmaps.argtypes = [vp] + [C.POINTER(sz)] * 4 + [sz, u32, u32]
+        L.emul_decompress.argtypes = [vp, sz, sz, u32, u32, vp]
 
     def compress(self, src, w, h, src_fmt, dst_fmt, flags=0, threshold=0.5):
         src = np.ascontiguousarray(src)
@@ -123,6 +131,12 @@ class Emul:
         src = np.ascontiguousarray(src)
         out = np.zeros(w * h * F.BYTES_PER_PIXEL[dst_fmt], np.uint8)
         hr = self.L.emul_convert(src.ctypes.data, w, h, src_fmt, 0, dst_fmt, 0, filter, out.ctypes.data)
+        return F.hr_u32(hr), out
+
+    def decompress(self, blocks, w, h, bc_fmt, dst_fmt):
+        blocks = np.ascontiguousarray(blocks)
+        out = np.zeros(w * h * F.BYTES_PER_PIXEL[dst_fmt], np.uint8)
+        hr = self.L.emul_decompress(blocks.ctypes.data, w, h, bc_fmt, dst_fmt, out.ctypes.data)
         return F.hr_u32(hr), out
 
     def generate_mipmaps(self, src, w, h, fmt, filter=0, levels=0):

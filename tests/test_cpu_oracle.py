@@ -183,3 +183,28 @@ def test_emulator_bc6h_special_blocks(oracle, emul):
         assert np.isfinite(dec).all()
         rel = np.abs(dec[..., :3] - sub[..., :3]) / np.maximum(np.abs(sub[..., :3]), 1e-3)
         assert rel[:4, :min(w, 12)].max() <= 0.02 if h >= 4 and w >= 12 else True      # solid blocks are near exact
+
+
+DECOMPRESS_CASES = ((71, (28, 2)), (74, (28,)), (77, (28, 2)), (80, (61, 41)), (81, (63, 41)), (83, (49, 16)), (84, (51,)),
+                    (98, (28, 2, 87)), (95, (2, 10)), (96, (2, 10)))
+
+
+def _bc_inputs(oracle, bc, w, h, rng):
+    """random bytes (every mode / invalid mode of the format) and a block stream produced by the reference encoder"""
+    nb = ((w + 3) // 4) * ((h + 3) // 4)
+    yield rng.integers(0, 256, nb * F.BLOCK_BYTES[bc], dtype=np.uint8)
+    src = rng.random((h, w, 4)).astype(np.float32) * (4.0 if bc in (95, 96) else 1.0) - (1.0 if bc in (81, 84, 96) else 0.0)
+    hr, blocks = oracle.compress(src, w, h, 2, bc, 0)
+    assert hr == 0
+    yield blocks
+
+
+def test_emulator_decompress_bit_exact(oracle, emul):
+    rng = np.random.default_rng(21)
+    for bc, dsts in DECOMPRESS_CASES:
+        for (w, h) in ((32, 32), (5, 7), (13, 9)):
+            for blocks in _bc_inputs(oracle, bc, w, h, rng):
+                for df in dsts:
+                    hr, want = oracle.decompress(blocks, w, h, bc, df)
+                    he, got = emul.decompress(blocks, w, h, bc, df)
+                    assert hr == 0 and he == 0 and np.array_equal(got, want), (bc, df, w, h)
