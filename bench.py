@@ -30,13 +30,11 @@ W = H = 4096
 SRC_FMT, DST_FMT = 2, 98                      # R32G32B32A32_FLOAT -> BC7_UNORM
 TEXELS = W * H
 ALGO_BYTES = W * H * 16 + (W // 4) * (H // 4) * 16      # 17 B/texel = 285,212,672 B per image
-def cpu_crop(cores):
-    """side of the centre crop the reference CPU encoder is timed on: sized so one call is a few seconds
-    (the reference needs ~7 ms per block per core): 256 at <=8 cores, 512 at 32, 1024 at >=128"""
-    side = 256
-    while side < 1024 and (side * 2) ** 2 / 16 * 7e-3 / cores <= 5.0:
-        side *= 2
-    return side
+def cpu_crop(cores, single_sample):
+    """side of the centre crop the reference CPU encoder is timed on (it needs ~7 ms per block per core and its OpenMP
+    loop scales poorly beyond ~32 threads): 512^2 for the one-off cpu_baseline sample on a many-core box, else 256^2 so
+    that `--impl reference --steps K` stays within minutes"""
+    return 512 if (single_sample and cores >= 32) else 256
 
 
 def peaks():
@@ -84,14 +82,14 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def reference_cpu_rate(img, threads=None):
+def reference_cpu_rate(img, threads=None, single_sample=False):
     """Mtexels/s of the reference CPU encoder (oracle/_ref) on the centre CPU_CROP^2 crop, all host threads."""
     from tests import oracle_lib
     ref = oracle_lib.load_ref()
     # torchrun exports OMP_NUM_THREADS=1: the reference arm must use all the host threads it can
     threads = threads or len(os.sched_getaffinity(0))
     ref.L.ref_omp_set_threads(threads)
-    side = cpu_crop(threads)
+    side = cpu_crop(threads, single_sample)
     y0 = (H - side) // 2
     crop = np.ascontiguousarray(img[y0:y0 + side, y0:y0 + side])
     sec = ref.compress_seconds(crop, side, side, SRC_FMT, DST_FMT, 0, 0.5, parallel=True)
@@ -238,7 +236,7 @@ def main():
     if rank == 0:
         pk, pk_kind = peaks()
         achieved = ALGO_BYTES / (kern_ms * 1e-3) / 1e9
-        cpu_rate, cores, cpu_sec, side = reference_cpu_rate(img)
+        cpu_rate, cores, cpu_sec, side = reference_cpu_rate(img, single_sample=True)
         out = {
             "metric": "Mtexels/s BC7 encode (4096^2 RGBA, default quality)", "value": value, "unit": "Mtexels/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,

@@ -31,9 +31,9 @@ struct State
     bool inited = false;
     int device = 0;
     int numSMs = 148;
-    cudaStream_t streams[2] = { nullptr, nullptr };
-    void* dIn[2] = { nullptr, nullptr };  size_t dInCap[2] = { 0, 0 };
-    void* dOut[2] = { nullptr, nullptr }; size_t dOutCap[2] = { 0, 0 };
+    cudaStream_t streams[3] = { nullptr, nullptr, nullptr };
+    void* dIn[3] = { nullptr, nullptr, nullptr };  size_t dInCap[3] = { 0, 0, 0 };
+    void* dOut[3] = { nullptr, nullptr, nullptr }; size_t dOutCap[3] = { 0, 0, 0 };
     int gridBC15 = 0, gridBC7 = 0, gridBC6H = 0, gridRow = 0;
 } g;
 
@@ -58,7 +58,7 @@ int32_t ensure_init_locked()
     cudaDeviceProp prop;
     DXB_CUDA(cudaGetDeviceProperties(&prop, g.device));
     g.numSMs = prop.multiProcessorCount;
-    for (int i = 0; i < 2; ++i) DXB_CUDA(cudaStreamCreateWithFlags(&g.streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) DXB_CUDA(cudaStreamCreateWithFlags(&g.streams[i], cudaStreamNonBlocking));
     g.gridBC15 = g.numSMs * dxb_occupancy_bc15();
     g.gridBC7 = g.numSMs * dxb_occupancy_bc7();
     g.gridBC6H = g.numSMs * dxb_occupancy_bc6h();
@@ -191,7 +191,9 @@ int32_t launch_compress(const CompressPlan& plan, const dxb200_image* src, const
     else if (plan.bc7)
     {
         const uint32_t need = (uint32_t)((total + DXB_BC7_WARPS - 1) / DXB_BC7_WARPS);
-        const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridBC7 * 4u));
+        // one CTA per DXB_BC7_WARPS blocks (no grid-stride cap): block costs differ (alpha blocks run the separate-alpha
+        // tasks), so the hardware CTA scheduler balances better than a static stride
+        const uint32_t grid = std::max(1u, need);
         dxb_launch_bc7(grid, stream, dj.d, jobs[0], P);
         hr = check_launch("k_compress_bc7");
     }
@@ -206,13 +208,46 @@ int32_t launch_compress(const CompressPlan& plan, const dxb200_image* src, const
     return hr;
 }
 
-// ---- host staging: run `fn(devSrc[], devDst[], count, stream)` over chunks of the batch -------------
-// Inputs are copied to the device, outputs copied back; two slots alternate so that the copies of one
-// chunk overlap the kernels of the other when the host memory is pinned.
-template <typename LaunchFn>
-int32_t run_staged(const dxb200_image* src, const dxb200_image* dst, size_t n, bool copyInput, bool copyAllOutput, LaunchFn fn)
+// ---- host staging -------------------------------------------------------------------------------------
+// Host images are cut into BANDS of whole work rows (4 pixel rows per block row on the BC side) of about 32 MiB, and the
+// bands are pushed through NSLOT (stream, device buffer) slots: H2D -> kernel -> D2H of one band overlaps the other
+// slots' copies and kernels (fully when the caller's memory is pinned, see dxb200_host_alloc).  Band boundaries fall on
+// block rows, so the result is identical to processing the whole image at once.
+constexpr int NSLOT = 3;
+
+struct BandSplit { std::vector<dxb200_image> src, dst; };
+
+// srcRows/dstRows: pixel (or block) rows of the source/destination image consumed/produced per work row
+void split_bands(const dxb200_image* src, const dxb200_image* dst, size_t n, size_t srcRows, size_t dstRows, bool srcIsBC, bool dstIsBC, BandSplit& out)
 {
-    const size_t CHUNK = size_t(1) << 30;
+    const size_t BAND = size_t(32) << 20;
+    for (size_t m = 0; m < n; ++m)
+    {
+        const size_t srcTotalRows = srcIsBC ? (src[m].height + 3) / 4 : src[m].height;
+        const size_t dstTotalRows = dstIsBC ? (dst[m].height + 3) / 4 : dst[m].height;
+        const size_t units = std::max<size_t>(1, (srcTotalRows + srcRows - 1) / srcRows);
+        const size_t bytesPerUnit = src[m].rowPitch * srcRows + dst[m].rowPitch * dstRows;
+        const size_t per = std::max<size_t>(1, BAND / std::max<size_t>(bytesPerUnit, 1));
+        for (size_t u0 = 0; u0 < units; u0 += per)
+        {
+            const size_t u1 = std::min(units, u0 + per);
+            dxb200_image s = src[m], d = dst[m];
+            const size_t sr0 = u0 * srcRows, sr1 = std::min(srcTotalRows, u1 * srcRows);
+            const size_t dr0 = u0 * dstRows, dr1 = std::min(dstTotalRows, u1 * dstRows);
+            s.pixels = src[m].pixels + sr0 * src[m].rowPitch; s.slicePitch = (sr1 - sr0) * src[m].rowPitch;
+            d.pixels = dst[m].pixels + dr0 * dst[m].rowPitch; d.slicePitch = (dr1 - dr0) * dst[m].rowPitch;
+            // pixel heights of the band (the uncompressed side counts pixel rows; the BC side the same pixel rows)
+            const size_t pixRows = srcIsBC ? std::min(src[m].height, sr1 * 4) - sr0 * 4 : (sr1 - sr0);
+            s.height = pixRows; d.height = pixRows;
+            out.src.push_back(s); out.dst.push_back(d);
+        }
+    }
+}
+
+template <typename LaunchFn>
+int32_t run_staged(const dxb200_image* src, const dxb200_image* dst, size_t n, LaunchFn fn)
+{
+    const size_t CHUNK = size_t(48) << 20;
     size_t i = 0; int slot = 0;
     int32_t hr = DXB_S_OK;
     while (i < n && hr == DXB_S_OK)
@@ -234,8 +269,7 @@ int32_t run_staged(const dxb200_image* src, const dxb200_image* dst, size_t n, b
         {
             ds[m - i].pixels = static_cast<uint8_t*>(g.dIn[slot]) + offIn;
             dd[m - i].pixels = static_cast<uint8_t*>(g.dOut[slot]) + offOut;
-            if (copyInput)
-                hr = cuda_hr(cudaMemcpyAsync(ds[m - i].pixels, src[m].pixels, src[m].slicePitch, cudaMemcpyHostToDevice, st), "H2D");
+            hr = cuda_hr(cudaMemcpyAsync(ds[m - i].pixels, src[m].pixels, src[m].slicePitch, cudaMemcpyHostToDevice, st), "H2D");
             offIn += (src[m].slicePitch + 255) & ~size_t(255);
             offOut += (dst[m].slicePitch + 255) & ~size_t(255);
         }
@@ -243,10 +277,9 @@ int32_t run_staged(const dxb200_image* src, const dxb200_image* dst, size_t n, b
         hr = fn(ds.data(), dd.data(), k - i, st); if (hr) break;
         for (size_t m = i; m < k && hr == DXB_S_OK; ++m)
             hr = cuda_hr(cudaMemcpyAsync(dst[m].pixels, dd[m - i].pixels, dst[m].slicePitch, cudaMemcpyDeviceToHost, st), "D2H");
-        (void)copyAllOutput;
-        i = k; slot ^= 1;
+        i = k; slot = (slot + 1) % NSLOT;
     }
-    for (int s = 0; s < 2; ++s)
+    for (int s = 0; s < NSLOT; ++s)
     {
         const int32_t h2 = cuda_hr(cudaStreamSynchronize(g.streams[s]), "final sync");
         if (hr == DXB_S_OK) hr = h2;
@@ -461,7 +494,7 @@ void dxb200_shutdown(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g.inited) return;
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 3; ++i)
     {
         if (g.streams[i]) { cudaStreamSynchronize(g.streams[i]); cudaStreamDestroy(g.streams[i]); g.streams[i] = nullptr; }
         if (g.dIn[i]) { cudaFree(g.dIn[i]); g.dIn[i] = nullptr; g.dInCap[i] = 0; }
@@ -521,7 +554,9 @@ int32_t dxb200_compress(const dxb200_image* src, size_t nimages, uint32_t dstFor
     std::lock_guard<std::mutex> lk(g_mu);
     hr = ensure_init_locked();
     if (hr != DXB_S_OK) return hr;
-    return run_staged(src, dst, nimages, true, true,
+    BandSplit bands;
+    split_bands(src, dst, nimages, 4, 1, false, true, bands);
+    return run_staged(bands.src.data(), bands.dst.data(), bands.src.size(),
         [&](const dxb200_image* ds, const dxb200_image* dd, size_t cnt, cudaStream_t st) { return launch_compress(plan, ds, dd, cnt, st); });
 }
 
@@ -592,7 +627,9 @@ int32_t dxb200_decompress(const dxb200_image* src, size_t nimages, uint32_t dstF
     std::lock_guard<std::mutex> lk(g_mu);
     hr = ensure_init_locked();
     if (hr != DXB_S_OK) return hr;
-    return run_staged(src, dst, nimages, true, true,
+    BandSplit bands;
+    split_bands(src, dst, nimages, 1, 4, true, false, bands);
+    return run_staged(bands.src.data(), bands.dst.data(), bands.src.size(),
         [&](const dxb200_image* ds, const dxb200_image* dd, size_t cnt, cudaStream_t st) { return launch_decompress(P, ds, dd, cnt, st); });
 }
 
@@ -621,7 +658,9 @@ int32_t dxb200_convert(const dxb200_image* src, size_t nimages, uint32_t dstForm
     std::lock_guard<std::mutex> lk(g_mu);
     hr = ensure_init_locked();
     if (hr != DXB_S_OK) return hr;
-    return run_staged(src, dst, nimages, true, true,
+    BandSplit bands;
+    split_bands(src, dst, nimages, 1, 1, false, false, bands);
+    return run_staged(bands.src.data(), bands.dst.data(), bands.src.size(),
         [&](const dxb200_image* ds, const dxb200_image* dd, size_t cnt, cudaStream_t st) { return launch_convert(P, ds, dd, cnt, st); });
 }
 

@@ -27,6 +27,9 @@
 #include "dxb_pixel.cuh"
 #include "dxb_bc67_tables.h"
 
+#ifndef DXB_BC7_KSHAPES_DBG
+#define DXB_BC7_KSHAPES_DBG 8       // experiment knob: evaluate only the K best-ranked shapes (8 = all lane slots distinct)
+#endif
 #ifndef DXB_BC7_ROUNDS
 #define DXB_BC7_ROUNDS 2          // endpoint evaluation rounds per task (1 = PCA only, each extra = one LS refit)
 #endif
@@ -319,8 +322,12 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, uint32_t mask, int mode, int 
     const float nmaxc = (float)((1u << ibc) - 1u);
     const float c64c = 64.0f / nmaxc;
     bool live = true;                                            // false once this lane has converged (keeps running, results ignored)
+#if DXB_ON_DEVICE
+    #pragma unroll
+#endif
     for (int round = 0; round < DXB_BC7_ROUNDS; ++round)
     {
+        const bool last = (round + 1 == DXB_BC7_ROUNDS);       // compile-time after unrolling: the refit sums vanish from the last round
         dxb_warp_sync();
         uint32_t q0, q1, pb; float D0[4], D1[4];
         dxb_bc7_quant_endpoints(E0, E1, use3, cfg.cbits, cfg.abits, cfg.ptype, pforce, &q0, &q1, &pb, D0, D1);
@@ -347,14 +354,18 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, uint32_t mask, int mode, int 
                 const float cz = dxb_rne(dxb_fma(dz, sk, B2)), cw = dxb_rne(dxb_fma(dw, sk, B3));
                 const float ex = X - cx, ey = Y - cy, ez = Z - cz, ew = Wv - cw;
                 err += dxb_fma(ex, ex, dxb_fma(ey, ey, dxb_fma(ez, ez, ew * ew)));
-                const float os = 1.0f - sk;
-                la = dxb_fma(os, os, la); lb = dxb_fma(os, sk, lb); lc = dxb_fma(sk, sk, lc);
-                u0 = dxb_fma(os, X, u0); u1 = dxb_fma(os, Y, u1); u2 = dxb_fma(os, Z, u2); u3 = dxb_fma(os, Wv, u3);
-                v0 = dxb_fma(sk, X, v0); v1 = dxb_fma(sk, Y, v1); v2 = dxb_fma(sk, Z, v2); v3 = dxb_fma(sk, Wv, v3);
+                if (!last)
+                {
+                    const float os = 1.0f - sk;
+                    la = dxb_fma(os, os, la); lb = dxb_fma(os, sk, lb); lc = dxb_fma(sk, sk, lc);
+                    u0 = dxb_fma(os, X, u0); u1 = dxb_fma(os, Y, u1); u2 = dxb_fma(os, Z, u2); u3 = dxb_fma(os, Wv, u3);
+                    v0 = dxb_fma(sk, X, v0); v1 = dxb_fma(sk, Y, v1); v2 = dxb_fma(sk, Z, v2); v3 = dxb_fma(sk, Wv, v3);
+                }
             }
         }
         const bool better = live && (err < bestErr);
         bestErr = better ? err : bestErr; bq0 = better ? q0 : bq0; bq1 = better ? q1 : bq1; bpb = better ? pb : bpb;
+        if (last) break;
         // least-squares refit for the next round (skipped lanes keep their endpoints)
         const float det = dxb_fma(la, lc, -(lb * lb));
         live = live && (det > 1e-4f) && (bestErr > 0.0f);
@@ -528,7 +539,7 @@ DXB_DEV void dxb_bc7_encode_warp(const dxb_px* spx, uint32_t bcflags, uint8_t* o
         {
             if (lane < 28)
             {
-                shape = sel[lane >> 2];
+                shape = sel[(lane >> 2) % DXB_BC7_KSHAPES_DBG];
                 const uint32_t m1 = dxb_part2[shape];
                 mask = ((lane >> 1) & 1) ? m1 : (~m1 & 0xFFFFu);
                 mode = (lane & 1) ? 3 : 1;
@@ -540,7 +551,7 @@ DXB_DEV void dxb_bc7_encode_warp(const dxb_px* spx, uint32_t bcflags, uint8_t* o
         {
             if (lane < 16)
             {
-                shape = sel[lane >> 1];
+                shape = sel[(lane >> 1) % DXB_BC7_KSHAPES_DBG];
                 const uint32_t m1 = dxb_part2[shape];
                 mask = (lane & 1) ? m1 : (~m1 & 0xFFFFu);
                 mode = quick ? -1 : 7;
