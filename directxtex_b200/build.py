@@ -47,6 +47,33 @@ def _flags():
             "-I", os.path.join(HERE, "..", "include"), "-I", CSRC, "-DDXB_BUILDING_LIB"]
 
 
+def build_variant(tag, defines, only=("dxb_k_bc7.cu",)):
+    """Experiment helper: rebuild the TUs in `only` with extra -D flags and link _lib/variants/libdxtex_b200_<tag>.so
+    (all other objects are reused from the main build)."""
+    vdir = os.path.join(OUT_DIR, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    build()
+    nvcc = _nvcc()
+    objs = []
+    for src in SOURCES + [s for s in HOST_SOURCES if os.path.exists(s)]:
+        base = os.path.splitext(os.path.basename(src))[0]
+        if os.path.basename(src) in only:
+            obj = os.path.join(vdir, base + "_" + tag + ".o")
+            r = subprocess.run([nvcc] + _flags() + list(defines) + ["-c", src, "-o", obj], capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                raise RuntimeError("variant build failed")
+        else:
+            obj = os.path.join(OUT_DIR, base + ".o")
+        objs.append(obj)
+    out = os.path.join(vdir, "libdxtex_b200_%s.so" % tag)
+    r = subprocess.run([nvcc, "-shared", "-cudart", "static", "-ccbin", "/usr/bin/g++", "-o", out] + objs, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("variant link failed")
+    return out
+
+
 def build(force=False, verbose=False):
     """Compile each translation unit (in parallel, only the stale ones) and link libdxtex_b200.so."""
     from concurrent.futures import ThreadPoolExecutor

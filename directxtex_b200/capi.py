@@ -6,7 +6,7 @@ import numpy as np
 from . import formats as F
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libdxtex_b200.so")
+LIB_PATH = os.environ.get("DXTEX_B200_LIB") or os.path.join(_HERE, "_lib", "libdxtex_b200.so")     # env override: kernel-variant experiments
 
 SYMBOLS = [
     "dxb200_version", "dxb200_init", "dxb200_shutdown", "dxb200_device_count", "dxb200_launch_count", "dxb200_last_error",
