@@ -27,9 +27,6 @@
 #include "dxb_pixel.cuh"
 #include "dxb_bc67_tables.h"
 
-#ifndef DXB_BC7_KSHAPES_DBG
-#define DXB_BC7_KSHAPES_DBG 8       // experiment knob: evaluate only the K best-ranked shapes (8 = all lane slots distinct)
-#endif
 #ifndef DXB_BC7_ROUNDS
 #define DXB_BC7_ROUNDS 2          // endpoint evaluation rounds per task (1 = PCA only, each extra = one LS refit)
 #endif
@@ -109,35 +106,140 @@ DXB_DEV float dxb_bc7_subset_estimate(float n, const float* s, const float* m, f
     return dxb_fma(lam, qf, resid);
 }
 
-// moments of the pixels selected by `mask`: s[4] sums, m[10] upper-triangular products, returns count
-DXB_DEV float dxb_bc7_moments(const dxb_px* px, uint32_t mask, float* s, float* m)
+// ---- stage 1 moment table -------------------------------------------------------------------------
+// For every two-subset shape s the 14 moments of subset 1 (sum of x,y,z,w and of the 10 products
+// xx,xy,xz,xw,yy,yz,yw,zz,zw,ww over the pixels whose bit is set in dxb_part2[s]) are one matrix product
+//     M[65 x 14] = S[65 x 16] * F[16 x 14],   S = 0/1 membership (row 64 = all ones -> whole-block totals).
+// LDR pixel values are integers 0..255, so every entry is an integer < 2^24: exact in fp32 in any order.
+// On sm_100a the product runs on the tensor cores (mma.sync m16n8k16, bf16 in / fp32 out): products up to
+// 255^2 are split into two 8-bit halves (hi*256 + lo), each exactly representable in bf16, giving 24
+// feature columns = three n-tiles; 5 m-tiles x 3 n-tiles = 15 MMAs per block instead of ~1100 FFMA per lane.
+// The host emulator computes the same integers with plain loops, so device and emulator agree bit for bit.
+#define DXB_BC7_MT_ROWS 65
+#define DXB_BC7_MT_FLOATS (DXB_BC7_MT_ROWS * 16)
+
+struct dxb_bc7_scratch
 {
-    float n = 0.0f;
-    for (int k = 0; k < 4; ++k) s[k] = 0.0f;
-    for (int k = 0; k < 10; ++k) m[k] = 0.0f;
-    for (int i = 0; i < 16; ++i)
-    {
-        const float f = dxb_uint_as_float((0u - ((mask >> i) & 1u)) & 0x3F800000u);
-        const dxb_px p = px[i];
-        const float x = p.x * f, y = p.y * f, z = p.z * f, w = p.w * f;
-        n += f;
-        s[0] += x; s[1] += y; s[2] += z; s[3] += w;
-        m[0] = dxb_fma(x, p.x, m[0]); m[1] = dxb_fma(x, p.y, m[1]); m[2] = dxb_fma(x, p.z, m[2]); m[3] = dxb_fma(x, p.w, m[3]);
-        m[4] = dxb_fma(y, p.y, m[4]); m[5] = dxb_fma(y, p.z, m[5]); m[6] = dxb_fma(y, p.w, m[6]);
-        m[7] = dxb_fma(z, p.z, m[7]); m[8] = dxb_fma(z, p.w, m[8]); m[9] = dxb_fma(w, p.w, m[9]);
-    }
-    return n;
+    dxb_px   px[32];                          // LDR pixels (floats 0..255) of the warp's two blocks: half h -> px[16h ..]
+    float    mt[2][DXB_BC7_MT_FLOATS];        // moment tables: row = shape, 16-float rows, 16-byte chunks XOR-swizzled
+    uint16_t feat[2][24][16];                 // bf16 feature matrix F^T (device only)
+};
+
+// float offset of 16-byte chunk c (0..3) of table row `row`; the swizzle makes both the MMA-fragment
+// stores and the row-per-lane loads bank-conflict free
+DXB_DEV int dxb_bc7_mt_chunk(int row, int c) { return row * 16 + (((c ^ (row >> 1)) & 3) << 2); }
+
+// columns: 0..3 = sums, 4..13 = products.  v[14] <- row
+DXB_DEV void dxb_bc7_mt_load(const float* mt, int row, float* v)
+{
+#if DXB_ON_DEVICE
+    const float4 a = *(const float4*)(mt + dxb_bc7_mt_chunk(row, 0));
+    const float4 b = *(const float4*)(mt + dxb_bc7_mt_chunk(row, 1));
+    const float4 c = *(const float4*)(mt + dxb_bc7_mt_chunk(row, 2));
+    const float2 d = *(const float2*)(mt + dxb_bc7_mt_chunk(row, 3));
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w; v[12] = d.x; v[13] = d.y;
+#else
+    for (int k = 0; k < 14; ++k) v[k] = mt[dxb_bc7_mt_chunk(row, k >> 2) + (k & 3)];
+#endif
 }
 
-// estimate for a whole 2-subset shape; tot* = moments of all 16 pixels
-DXB_DEV float dxb_bc7_shape_estimate(const dxb_px* px, uint32_t shape, float qf, const float* totS, const float* totM)
+#if DXB_ON_DEVICE
+DXB_DEV uint16_t dxb_bc7_bf16_of_byte(uint32_t n)          // bf16 bits of the integer n (0..255), no I2F
 {
-    const uint32_t mask1 = dxb_part2[shape];
-    float s1[4], m1[10], s0[4], m0[10];
-    const float n1 = dxb_bc7_moments(px, mask1, s1, m1);
-    for (int k = 0; k < 4; ++k) s0[k] = totS[k] - s1[k];
-    for (int k = 0; k < 10; ++k) m0[k] = totM[k] - m1[k];
-    return dxb_bc7_subset_estimate(16.0f - n1, s0, m0, qf) + dxb_bc7_subset_estimate(n1, s1, m1, qf);
+    const float f = __uint_as_float(0x4B000000u | n) - 8388608.0f;
+    return (uint16_t)(__float_as_uint(f) >> 16);
+}
+#endif
+
+// Fills S->mt[0..1] from S->px (both blocks of the warp).  Collective over the warp.
+DXB_DEV void dxb_bc7_build_moments(dxb_bc7_scratch* S)
+{
+#if DXB_ON_DEVICE
+    const uint32_t lane = threadIdx.x & 31u, h = lane >> 4, hl = lane & 15u;
+    {
+        const dxb_px p = S->px[lane];
+        uint16_t* F = &S->feat[h][0][hl];                 // feature n of this pixel = F[16 * n]
+        F[0] = (uint16_t)(__float_as_uint(p.x) >> 16); F[16] = (uint16_t)(__float_as_uint(p.y) >> 16);
+        F[32] = (uint16_t)(__float_as_uint(p.z) >> 16); F[48] = (uint16_t)(__float_as_uint(p.w) >> 16);
+        const float P[10] = { p.x * p.x, p.x * p.y, p.x * p.z, p.x * p.w, p.y * p.y, p.y * p.z, p.y * p.w, p.z * p.z, p.z * p.w, p.w * p.w };
+        #pragma unroll
+        for (int k = 0; k < 10; ++k)
+        {
+            const uint32_t b = __float_as_uint(P[k] + 8388608.0f);            // low 23 bits = the integer product
+            const uint16_t hi = dxb_bc7_bf16_of_byte((b >> 8) & 0xFFu), lo = dxb_bc7_bf16_of_byte(b & 0xFFu);
+            // n-tile 0 = {s0,s1,s2,s3, hi8,lo8, hi9,lo9}; n-tile 1 = hi0..7; n-tile 2 = lo0..7
+            const int nh = (k < 8) ? 8 + k : 4 + 2 * (k - 8), nl = (k < 8) ? 16 + k : 5 + 2 * (k - 8);
+            F[16 * nh] = hi; F[16 * nl] = lo;
+        }
+    }
+    __syncwarp();
+    const uint32_t g = lane >> 2, q = lane & 3u;
+    uint32_t B[2][3][2];
+    #pragma unroll
+    for (int hb = 0; hb < 2; ++hb)
+        #pragma unroll
+        for (int t = 0; t < 3; ++t)
+        {
+            const uint32_t* w = (const uint32_t*)&S->feat[hb][t * 8 + g][0];
+            B[hb][t][0] = w[q]; B[hb][t][1] = w[q + 4];
+        }
+    #pragma unroll
+    for (int tile = 0; tile < 5; ++tile)
+    {
+        const uint4 A = ((const uint4*)dxb_bc7_afrag)[tile * 32 + lane];
+        #pragma unroll
+        for (int hb = 0; hb < 2; ++hb)
+        {
+            float d[3][4];
+            #pragma unroll
+            for (int t = 0; t < 3; ++t)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                             : "=f"(d[t][0]), "=f"(d[t][1]), "=f"(d[t][2]), "=f"(d[t][3])
+                             : "r"(A.x), "r"(A.y), "r"(A.z), "r"(A.w), "r"(B[hb][t][0]), "r"(B[hb][t][1]), "f"(0.0f));
+            float* mt = S->mt[hb];
+            #pragma unroll
+            for (int rr = 0; rr < 2; ++rr)                // fragment rows g and g + 8
+            {
+                if (tile == 4 && (rr == 1 || g != 0)) continue;
+                const int row = tile * 16 + (int)g + 8 * rr;
+                // products 2q, 2q+1 (columns 4+2q, 5+2q)
+                const float2 pp = make_float2(fmaf(d[1][2 * rr], 256.0f, d[2][2 * rr]), fmaf(d[1][2 * rr + 1], 256.0f, d[2][2 * rr + 1]));
+                *(float2*)(mt + dxb_bc7_mt_chunk(row, 1 + (int)(q >> 1)) + 2 * (int)(q & 1u)) = pp;
+                if (q < 2) *(float2*)(mt + dxb_bc7_mt_chunk(row, 0) + 2 * (int)q) = make_float2(d[0][2 * rr], d[0][2 * rr + 1]);
+                else mt[dxb_bc7_mt_chunk(row, 3) + (int)q - 2] = fmaf(d[0][2 * rr], 256.0f, d[0][2 * rr + 1]);
+            }
+        }
+    }
+    __syncwarp();
+#else
+    for (int hb = 0; hb < 2; ++hb)
+        for (int row = 0; row < DXB_BC7_MT_ROWS; ++row)
+        {
+            const uint32_t mask = (row < 64) ? dxb_part2[row] : 0xFFFFu;
+            float v[14];
+            for (int k = 0; k < 14; ++k) v[k] = 0.0f;
+            for (int i = 0; i < 16; ++i)
+                if ((mask >> i) & 1u)
+                {
+                    const dxb_px p = S->px[16 * hb + i];
+                    v[0] += p.x; v[1] += p.y; v[2] += p.z; v[3] += p.w;
+                    v[4] += p.x * p.x; v[5] += p.x * p.y; v[6] += p.x * p.z; v[7] += p.x * p.w; v[8] += p.y * p.y;
+                    v[9] += p.y * p.z; v[10] += p.y * p.w; v[11] += p.z * p.z; v[12] += p.z * p.w; v[13] += p.w * p.w;
+                }
+            for (int k = 0; k < 14; ++k) S->mt[hb][dxb_bc7_mt_chunk(row, k >> 2) + (k & 3)] = v[k];
+        }
+#endif
+}
+
+// estimate for a whole 2-subset shape from the moment table; tot = row 64
+DXB_DEV float dxb_bc7_shape_estimate(const float* mt, uint32_t shape, float qf, const float* tot)
+{
+    float v1[14], v0[14];
+    dxb_bc7_mt_load(mt, (int)shape, v1);
+    for (int k = 0; k < 14; ++k) v0[k] = tot[k] - v1[k];
+    const float n1 = (float)dxb_popc16(dxb_part2[shape]);
+    return dxb_bc7_subset_estimate(16.0f - n1, v0, v0 + 4, qf) + dxb_bc7_subset_estimate(n1, v1, v1 + 4, qf);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -234,7 +336,7 @@ DXB_DEV void dxb_bc7_quant_endpoints(const float* E0, const float* E1, float use
 // Written so that all 32 lanes execute ONE instruction stream for the vector part (mode differences are
 // data: bit counts, channel weight, p-bit type); only the separate-alpha part of modes 4/5 is a
 // divergent section.  Idle lanes (mode < 0) run the same code on dummy parameters.
-DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, uint32_t mask, int mode, int rot, int idxMode, int pforce)
+DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t shape, uint32_t mask, int mode, int rot, int idxMode, int pforce)
 {
     const bool idle = (mode < 0);
     if (idle) { mode = 6; mask = 0xFFFFu; }
@@ -252,20 +354,31 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, uint32_t mask, int mode, int 
       X = r1 ? p_.w : p_.x; Y = r2 ? p_.w : p_.y; Z = r3 ? p_.w : p_.z; \
       A = r1 ? p_.x : (r2 ? p_.y : (r3 ? p_.z : p_.w)); Wv = A * use3; }
 
-    // ---- vector part: moments
-    float n = 0.0f, s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
-    float m00 = 0.0f, m01 = 0.0f, m02 = 0.0f, m03 = 0.0f, m11 = 0.0f, m12 = 0.0f, m13 = 0.0f, m22 = 0.0f, m23 = 0.0f, m33 = 0.0f;
-    for (int i = 0; i < 16; ++i)
+    // ---- vector part: moments of the subset, from the stage-1 table (exact integers): subset 1 = row `shape`,
+    // subset 0 = totals - row, whole block = totals; then the rotation's channel swap and the use3 mask
+    float s0, s1, s2, s3, m00, m01, m02, m03, m11, m12, m13, m22, m23, m33;
+    const float n = (float)dxb_popc16(mask);
     {
-        const float f = dxb_bit_as_float(mask, i);
-        DXB_BC7_FETCH(i, X, Y, Z, Wv, A)
-        (void)A;
-        const float x = X * f, y = Y * f, z = Z * f, w = Wv * f;
-        n += f;
-        s0 += x; s1 += y; s2 += z; s3 += w;
-        m00 = dxb_fma(x, X, m00); m01 = dxb_fma(x, Y, m01); m02 = dxb_fma(x, Z, m02); m03 = dxb_fma(x, Wv, m03);
-        m11 = dxb_fma(y, Y, m11); m12 = dxb_fma(y, Z, m12); m13 = dxb_fma(y, Wv, m13);
-        m22 = dxb_fma(z, Z, m22); m23 = dxb_fma(z, Wv, m23); m33 = dxb_fma(w, Wv, m33);
+        const bool whole = (mask == 0xFFFFu);
+        const bool sub0 = !whole && ((mask & 1u) != 0u);        // pixel 0 always belongs to subset 0
+        float R[14], T[14];
+        dxb_bc7_mt_load(mt, whole ? 64 : (int)shape, R);
+        dxb_bc7_mt_load(mt, 64, T);
+        for (int k = 0; k < 14; ++k) R[k] = sub0 ? T[k] - R[k] : R[k];
+        // channel swap c <-> 3 (c = rot - 1) applied to the symmetric moment matrix
+        s0 = r1 ? R[3] : R[0]; s1 = r2 ? R[3] : R[1]; s2 = r3 ? R[3] : R[2];
+        s3 = r1 ? R[0] : (r2 ? R[1] : (r3 ? R[2] : R[3]));
+        m00 = r1 ? R[13] : R[4];                         // xx
+        m01 = r1 ? R[10] : (r2 ? R[7] : R[5]);           // xy: r1 -> wy, r2 -> xw
+        m02 = r1 ? R[12] : (r3 ? R[7] : R[6]);           // xz: r1 -> wz, r3 -> xw
+        m03 = r2 ? R[5] : (r3 ? R[6] : R[7]);            // xw: r1 -> wx (same), r2 -> xy, r3 -> xz
+        m11 = r2 ? R[13] : R[8];                         // yy
+        m12 = r2 ? R[12] : (r3 ? R[10] : R[9]);          // yz: r2 -> wz, r3 -> yw
+        m13 = r1 ? R[5] : (r3 ? R[9] : R[10]);           // yw: r1 -> yx, r2 -> wy (same), r3 -> yz
+        m22 = r3 ? R[13] : R[11];                        // zz
+        m23 = r1 ? R[6] : (r2 ? R[9] : R[12]);           // zw: r1 -> zx, r2 -> zy, r3 -> wz (same)
+        m33 = r1 ? R[4] : (r2 ? R[8] : (r3 ? R[11] : R[13]));
+        s3 *= use3; m03 *= use3; m13 *= use3; m23 *= use3; m33 *= use3;
     }
     const float inv = 1.0f / fmaxf(n, 1.0f);
     const float mean[4] = { s0 * inv, s1 * inv, s2 * inv, s3 * inv };
@@ -484,266 +597,271 @@ DXB_DEV void dxb_put_bits(dxb_u128* b, uint32_t pos, uint32_t nbits, uint32_t va
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The whole-block encoder, SPMD over the 32 lanes of one warp.
-//   spx   : 16 LDR pixels (floats 0..255), warp-shared (device: shared memory; emulator: plain array)
-//   out   : 16 output bytes (written by lane 0)
-DXB_DEV void dxb_bc7_encode_warp(const dxb_px* spx, uint32_t bcflags, uint8_t* out)
+// The encoder proper, SPMD over the 32 lanes of one warp: TWO blocks per warp, one per 16-lane half.
+//   S->px : LDR pixels of both blocks (floats 0..255): S->px[16 h + i] = pixel i of the half-h block
+//   out0/out1 : 16 output bytes of the half-0 / half-1 block (nullptr = that half carries no block)
+// Everything "per block" below is a lane-private value that is uniform inside a half.
+struct dxb_bc7_win { uint32_t mode, shape, rot, idx, q0[2], q1[2], pb[2]; };
+
+DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* out0, uint8_t* out1)
 {
     const bool quick = (bcflags & DXB_BC_FLAGS_FORCE_BC7_MODE6) != 0;
 
-    // ---- block-wide facts (every lane computes them redundantly from the shared pixels)
-    bool hasAlpha = false;
-    float totS[4], totM[10];
-    dxb_bc7_moments(spx, 0xFFFFu, totS, totM);
-    for (int i = 0; i < 16; ++i) hasAlpha = hasAlpha || (spx[i].w != 255.0f);
-
-    // ---- stage 1: rank the 64 two-subset shapes (2 per lane), select the 8 best
-    uint32_t keyA[DXB_NL], keyB[DXB_NL];
-    uint32_t sel[8];
-    if (!quick)
+    // ---- stage 1: moment table (tensor cores), 4 shapes per lane ranked, 3 best kept per block
+    dxb_bc7_build_moments(S);
+    uint32_t hasA[DXB_NL], sel[3][DXB_NL];
     {
-        // index quantisation factor 1/(2^b-1)^2: 3-bit for mode 1 (opaque), 2-bit for mode 7 (alpha)
-        const float qf = hasAlpha ? (1.0f / 9.0f) : (1.0f / 49.0f);
+        uint32_t key[4][DXB_NL];
         DXB_LANES_BEGIN
-            const float ea = dxb_bc7_shape_estimate(spx, (uint32_t)lane, qf, totS, totM);
-            const float eb = dxb_bc7_shape_estimate(spx, (uint32_t)lane + 32u, qf, totS, totM);
-            keyA[L] = (dxb_float_as_uint(ea) & 0xFFFFFFC0u) | (uint32_t)lane;
-            keyB[L] = (dxb_float_as_uint(eb) & 0xFFFFFFC0u) | ((uint32_t)lane + 32u);
+            const float* mt = S->mt[lane >> 4];
+            float tot[14];
+            dxb_bc7_mt_load(mt, 64, tot);
+            hasA[L] = (tot[3] != 4080.0f) ? 1u : 0u;             // 16 * 255: every alpha is 255
+            // index quantisation factor 1/(2^b-1)^2: 3-bit for mode 1 (opaque), 2-bit for mode 7 (alpha)
+            const float qf = hasA[L] ? (1.0f / 9.0f) : (1.0f / 49.0f);
+            for (int j = 0; j < 4; ++j)
+            {
+                const uint32_t shape = (uint32_t)(lane & 15) + 16u * (uint32_t)j;
+                const float e = quick ? 0.0f : dxb_bc7_shape_estimate(mt, shape, qf, tot);
+                key[j][L] = (dxb_float_as_uint(e) & 0xFFFFFFC0u) | shape;
+            }
         DXB_LANES_END
-        for (int r = 0; r < 8; ++r)
+        for (int r = 0; r < 3; ++r)
         {
-            uint32_t cand[DXB_NL];
+            uint32_t cand[DXB_NL], win[DXB_NL];
             DXB_LANES_BEGIN
-                cand[L] = (keyA[L] < keyB[L]) ? keyA[L] : keyB[L];
+                const uint32_t a = (key[0][L] < key[1][L]) ? key[0][L] : key[1][L];
+                const uint32_t b = (key[2][L] < key[3][L]) ? key[2][L] : key[3][L];
+                cand[L] = (a < b) ? a : b;
             DXB_LANES_END
-            const uint32_t win = dxb_warp_min_u32(cand);
-            sel[r] = win & 63u;
+            dxb_half_min_u32(cand, win);
             DXB_LANES_BEGIN
-                if (keyA[L] == win) keyA[L] = 0xFFFFFFFFu;
-                if (keyB[L] == win) keyB[L] = 0xFFFFFFFFu;
+                sel[r][L] = win[L] & 63u;
+                for (int j = 0; j < 4; ++j) if (key[j][L] == win[L]) key[j][L] = 0xFFFFFFFFu;
             DXB_LANES_END
         }
-    }
-    else
-    {
-        for (int r = 0; r < 8; ++r) sel[r] = 0;
     }
 
     // ---- stage 2: one task per lane
-    uint32_t tMode[DXB_NL], tShape[DXB_NL], tRot[DXB_NL], tIdx[DXB_NL];
-    uint32_t rErr[DXB_NL], rQ0[DXB_NL], rQ1[DXB_NL], rPb[DXB_NL];
+    //   opaque block: 3 best shapes x 2 subsets x {mode 1, mode 3} (lanes 0-11), mode 6 x 4 p-bit pairs (12-15)
+    //   alpha block : 3 best shapes x 2 subsets x mode 7 (0-5), mode 6 x 4 p-bit pairs (6-9),
+    //                 mode 5 x 4 rotations (10-13), mode 4 x 2 index selectors (14-15)
+    uint32_t tMeta[DXB_NL], rErr[DXB_NL], rQ0[DXB_NL], rQ1[DXB_NL];
     DXB_LANES_BEGIN
+        const int hl = lane & 15;
         int mode = -1, rot = 0, idxMode = 0, pforce = -1;
         uint32_t mask = 0xFFFFu, shape = 0;
-        if (!hasAlpha)
+        if (!hasA[L])
         {
-            if (lane < 28)
+            if (hl < 12)
             {
-                shape = sel[(lane >> 2) % DXB_BC7_KSHAPES_DBG];
+                const int k = hl >> 2;
+                shape = (k == 0) ? sel[0][L] : (k == 1) ? sel[1][L] : sel[2][L];
                 const uint32_t m1 = dxb_part2[shape];
-                mask = ((lane >> 1) & 1) ? m1 : (~m1 & 0xFFFFu);
-                mode = (lane & 1) ? 3 : 1;
-                if (quick) mode = -1;
+                mask = ((hl >> 1) & 1) ? m1 : (~m1 & 0xFFFFu);
+                mode = quick ? -1 : ((hl & 1) ? 3 : 1);
             }
-            else { mode = 6; pforce = lane & 3; }
+            else { mode = 6; pforce = hl & 3; }
         }
         else
         {
-            if (lane < 16)
+            if (hl < 6)
             {
-                shape = sel[(lane >> 1) % DXB_BC7_KSHAPES_DBG];
+                const int k = hl >> 1;
+                shape = (k == 0) ? sel[0][L] : (k == 1) ? sel[1][L] : sel[2][L];
                 const uint32_t m1 = dxb_part2[shape];
-                mask = (lane & 1) ? m1 : (~m1 & 0xFFFFu);
+                mask = (hl & 1) ? m1 : (~m1 & 0xFFFFu);
                 mode = quick ? -1 : 7;
             }
-            else if (lane < 20) { mode = 6; pforce = lane & 3; }
-            else if (lane < 24) { mode = quick ? -1 : 5; rot = lane & 3; }
-            else { mode = quick ? -1 : 4; rot = lane & 3; idxMode = (lane >> 2) & 1; }
+            else if (hl < 10) { mode = 6; pforce = hl - 6; }
+            else if (hl < 14) { mode = quick ? -1 : 5; rot = hl - 10; }
+            else { mode = quick ? -1 : 4; idxMode = hl & 1; }
         }
-        const dxb_bc7_res res = dxb_bc7_eval(spx, mask, mode, rot, idxMode, pforce);
-        tMode[L] = (uint32_t)mode; tShape[L] = shape; tRot[L] = (uint32_t)rot; tIdx[L] = (uint32_t)idxMode;
+        const dxb_bc7_res res = dxb_bc7_eval(S->px + (lane & 16), S->mt[lane >> 4], shape, mask, mode, rot, idxMode, pforce);
+        // meta word: mode(3) | shape(6) << 3 | rot(2) << 9 | idx(1) << 11 | pbits(2) << 12
+        tMeta[L] = ((uint32_t)mode & 7u) | (shape << 3) | ((uint32_t)rot << 9) | ((uint32_t)idxMode << 11) | (res.pbits << 12);
         rErr[L] = (mode < 0) ? 0x03FFFFFFu : (uint32_t)dxb_f2i(fminf(res.err, 6.0e7f));
-        rQ0[L] = res.q0; rQ1[L] = res.q1; rPb[L] = res.pbits;
+        rQ0[L] = res.q0; rQ1[L] = res.q1;
     DXB_LANES_END
 
-    // ---- stage 3: combine subset errors, pick the winner
-    uint32_t partner[DXB_NL];
-    dxb_xchg_xor_u32(rErr, partner, hasAlpha ? 1 : 2);
-    uint32_t key[DXB_NL];
+    // ---- stage 3: combine subset errors, pick the winner of each half
+    dxb_bc7_win W[DXB_NL];
+    {
+        uint32_t part1[DXB_NL], part2v[DXB_NL], key[DXB_NL], wkey[DXB_NL], src[DXB_NL], src1[DXB_NL], wm[DXB_NL];
+        uint32_t g0[DXB_NL], g1[DXB_NL], g2[DXB_NL], h0[DXB_NL], h1[DXB_NL], h2[DXB_NL];
+        dxb_xchg_xor_u32(rErr, part1, 1);
+        dxb_xchg_xor_u32(rErr, part2v, 2);
+        DXB_LANES_BEGIN
+            uint32_t e = rErr[L];
+            const uint32_t md = tMeta[L] & 7u;
+            if (md == 1u || md == 3u || md == 7u) e += hasA[L] ? part1[L] : part2v[L];
+            e = (e > 0x03FFFFFFu) ? 0x03FFFFFFu : e;
+            key[L] = (e << 5) | (uint32_t)(lane & 15);
+        DXB_LANES_END
+        dxb_half_min_u32(key, wkey);
+        DXB_LANES_BEGIN
+            src[L] = wkey[L] & 15u;
+        DXB_LANES_END
+        dxb_half_gather_u32(tMeta, src, wm);
+        DXB_LANES_BEGIN
+            const uint32_t md = wm[L] & 7u;
+            const bool two = (md == 1u || md == 3u || md == 7u);
+            const uint32_t subBit = hasA[L] ? 1u : 2u;
+            src1[L] = two ? (src[L] | subBit) : src[L];
+            src[L] = two ? (src[L] & ~subBit) : src[L];
+        DXB_LANES_END
+        dxb_half_gather_u32(rQ0, src, g0); dxb_half_gather_u32(rQ1, src, g1); dxb_half_gather_u32(tMeta, src, g2);
+        dxb_half_gather_u32(rQ0, src1, h0); dxb_half_gather_u32(rQ1, src1, h1); dxb_half_gather_u32(tMeta, src1, h2);
+        DXB_LANES_BEGIN
+            W[L].mode = wm[L] & 7u; W[L].shape = (wm[L] >> 3) & 63u; W[L].rot = (wm[L] >> 9) & 3u; W[L].idx = (wm[L] >> 11) & 1u;
+            W[L].q0[0] = g0[L]; W[L].q1[0] = g1[L]; W[L].pb[0] = (g2[L] >> 12) & 3u;
+            W[L].q0[1] = h0[L]; W[L].q1[1] = h1[L]; W[L].pb[1] = (h2[L] >> 12) & 3u;
+        DXB_LANES_END
+    }
+
+    // ---- stage 4: every lane = one pixel of its block: exhaustive nearest palette entry
+    uint32_t idxC[DXB_NL], idxA[DXB_NL], anchorSrc[DXB_NL], zeroSrc[DXB_NL];
     DXB_LANES_BEGIN
-        uint32_t e = rErr[L];
-        const uint32_t md = tMode[L];
-        if (md == 1u || md == 3u || md == 7u) e += partner[L];
-        e = (e > 0x03FFFFFFu) ? 0x03FFFFFFu : e;
-        key[L] = (e << 5) | (uint32_t)lane;
-    DXB_LANES_END
-    const uint32_t wkey = dxb_warp_min_u32(key);
-    const int wl = (int)(wkey & 31u);
-    const uint32_t wMode = dxb_bcast_u32(tMode, wl);
-    const uint32_t wShape = dxb_bcast_u32(tShape, wl);
-    const uint32_t wRot = dxb_bcast_u32(tRot, wl);
-    const uint32_t wIdx = dxb_bcast_u32(tIdx, wl);
-    const bool two = (wMode == 1u || wMode == 3u || wMode == 7u);
-    const int subBit = hasAlpha ? 1 : 2;
-    const int l0 = two ? (wl & ~subBit) : wl;
-    const int l1 = two ? (wl | subBit) : wl;
-    // endpoints of subset 0 and subset 1 (single-subset modes: both = the winner lane)
-    uint32_t q0s[2], q1s[2], pbs[2];
-    q0s[0] = dxb_bcast_u32(rQ0, l0); q1s[0] = dxb_bcast_u32(rQ1, l0); pbs[0] = dxb_bcast_u32(rPb, l0);
-    q0s[1] = dxb_bcast_u32(rQ0, l1); q1s[1] = dxb_bcast_u32(rQ1, l1); pbs[1] = dxb_bcast_u32(rPb, l1);
-
-    // ---- stage 4: indices, anchor fix-up, packing
-    const dxb_bc7_modecfg cfg = dxb_bc7_cfg((int)wMode);
-    const uint32_t ibc = (wMode == 4u && wIdx) ? 3u : cfg.ib;
-    const uint32_t iba = (wMode == 4u) ? (wIdx ? 2u : 3u) : cfg.ib2;
-    const uint32_t part = two ? dxb_part2[wShape] : 0u;
-    const uint32_t anchor1 = two ? dxb_anchor2[wShape] : 0u;
-    const bool vec4 = (wMode == 6u || wMode == 7u);
-
-    // dequantised endpoints per subset
-    int32_t e0[2][4], e1[2][4];
-    for (int sb = 0; sb < 2; ++sb)
+        const int hl = lane & 15;
+        const uint32_t wMode = W[L].mode;
+        const dxb_bc7_modecfg cfg = dxb_bc7_cfg((int)wMode);
+        const bool two = (wMode == 1u || wMode == 3u || wMode == 7u);
+        const bool sepA = (wMode == 4u || wMode == 5u);
+        const uint32_t ibc = (wMode == 4u && W[L].idx) ? 3u : cfg.ib;
+        const uint32_t iba = (wMode == 4u) ? (W[L].idx ? 2u : 3u) : cfg.ib2;
+        const uint32_t part = two ? dxb_part2[W[L].shape] : 0u;
+        const int sb = (int)((part >> hl) & 1u);
+        const uint32_t q0 = sb ? W[L].q0[1] : W[L].q0[0], q1 = sb ? W[L].q1[1] : W[L].q1[0], pb = sb ? W[L].pb[1] : W[L].pb[0];
+        const uint32_t hasP = (cfg.ptype != 0 && !sepA) ? 1u : 0u;
+        int32_t e0[4], e1[4];
         for (uint32_t c = 0; c < 4; ++c)
         {
             const uint32_t bits = (c == 3) ? cfg.abits : cfg.cbits;
             const bool coded = (c < 3) || (cfg.abits != 0);
-            const bool hasP = (cfg.ptype != 0) && !(wMode == 4u || wMode == 5u);
-            e0[sb][c] = coded ? (int32_t)dxb_bc7_deq_field((q0s[sb] >> (8 * c)) & 0xFF, bits, hasP ? 1u : 0u, pbs[sb] & 1u) : 255;
-            e1[sb][c] = coded ? (int32_t)dxb_bc7_deq_field((q1s[sb] >> (8 * c)) & 0xFF, bits, hasP ? 1u : 0u, (pbs[sb] >> 1) & 1u) : 255;
+            e0[c] = coded ? (int32_t)dxb_bc7_deq_field((q0 >> (8 * c)) & 0xFF, bits, hasP, pb & 1u) : 255;
+            e1[c] = coded ? (int32_t)dxb_bc7_deq_field((q1 >> (8 * c)) & 0xFF, bits, hasP, (pb >> 1) & 1u) : 255;
         }
-
-    uint32_t idxC[DXB_NL], idxA[DXB_NL];
-    DXB_LANES_BEGIN
-        idxC[L] = 0; idxA[L] = 0;
-        if (lane < 16)
+        const dxb_px pr = dxb_bc7_rotate(S->px[lane], (int)W[L].rot);
+        const int32_t p[4] = { dxb_f2i(pr.x), dxb_f2i(pr.y), dxb_f2i(pr.z), dxb_f2i(pr.w) };
+        idxA[L] = 0;
+        if (sepA)
         {
-            const dxb_px pr = dxb_bc7_rotate(spx[lane], (int)wRot);
-            int32_t p[4] = { dxb_f2i(pr.x), dxb_f2i(pr.y), dxb_f2i(pr.z), dxb_f2i(pr.w) };
-            const int sb = (int)((part >> lane) & 1u);
-            if (wMode == 4u || wMode == 5u)
-            {
-                idxC[L] = dxb_bc7_nearest(p, e0[sb], e1[sb], 0, 3, ibc);
-                idxA[L] = dxb_bc7_nearest(p, e0[sb], e1[sb], 3, 4, iba);
-            }
-            else
-                idxC[L] = dxb_bc7_nearest(p, e0[sb], e1[sb], 0, vec4 ? 4 : 3, ibc);
+            idxC[L] = dxb_bc7_nearest(p, e0, e1, 0, 3, ibc);
+            idxA[L] = dxb_bc7_nearest(p, e0, e1, 3, 4, iba);
         }
+        else
+            idxC[L] = dxb_bc7_nearest(p, e0, e1, 0, (wMode == 6u || wMode == 7u) ? 4 : 3, ibc);
+        anchorSrc[L] = two ? dxb_anchor2[W[L].shape] : 0u;
+        zeroSrc[L] = 0u;
     DXB_LANES_END
 
     // anchor fix-up: the anchor index of each subset must have its MSB clear; otherwise swap that
     // subset's endpoints and mirror its indices (weights are symmetric: w[n-k] = 64 - w[k])
-    const uint32_t aC0 = dxb_bcast_u32(idxC, 0);
-    const uint32_t aC1 = dxb_bcast_u32(idxC, (int)anchor1);
-    const uint32_t aA0 = dxb_bcast_u32(idxA, 0);
-    const bool flipC[2] = { ((aC0 >> (ibc - 1u)) & 1u) != 0, two && (((aC1 >> (ibc - 1u)) & 1u) != 0) };
-    const bool flipA = (iba != 0) && (((aA0 >> (iba - 1u)) & 1u) != 0);
-    DXB_LANES_BEGIN
-        if (lane < 16)
-        {
-            const int sb = (int)((part >> lane) & 1u);
-            if (flipC[sb]) idxC[L] = ((1u << ibc) - 1u) - idxC[L];
-            if (flipA) idxA[L] = ((1u << iba) - 1u) - idxA[L];
-        }
-    DXB_LANES_END
-    // endpoint fields after the swaps.  Colour channels follow flipC[subset]; in modes 4/5 the alpha
-    // channel has its own index set and follows flipA.
-    uint32_t f0[2], f1[2], pb0[2], pb1[2];
-    for (int sb = 0; sb < 2; ++sb)
-    {
-        uint32_t a = q0s[sb], b = q1s[sb];
-        uint32_t pa = pbs[sb] & 1u, pbv = (pbs[sb] >> 1) & 1u;
-        if (wMode == 4u || wMode == 5u)
-        {
-            uint32_t ca = a & 0x00FFFFFFu, cb = b & 0x00FFFFFFu, aa = a >> 24, ab = b >> 24;
-            if (flipC[sb]) { const uint32_t t = ca; ca = cb; cb = t; }
-            if (flipA) { const uint32_t t = aa; aa = ab; ab = t; }
-            a = ca | (aa << 24); b = cb | (ab << 24);
-        }
-        else if (flipC[sb])
-        {
-            const uint32_t t = a; a = b; b = t;
-            const uint32_t tp = pa; pa = pbv; pbv = tp;
-        }
-        f0[sb] = a; f1[sb] = b; pb0[sb] = pa; pb1[sb] = pbv;
-    }
+    uint32_t aC0[DXB_NL], aC1[DXB_NL], aA0[DXB_NL];
+    dxb_half_gather_u32(idxC, zeroSrc, aC0);
+    dxb_half_gather_u32(idxC, anchorSrc, aC1);
+    dxb_half_gather_u32(idxA, zeroSrc, aA0);
 
     // bit layout (D3DX_BC7::Decode, BC6HBC7.cpp:2566-2780): mode (unary), partition, rotation, index
     // selector, then R of every endpoint, G, B, A, p-bits, colour indices, alpha indices.
-    const uint32_t nsub = two ? 2u : 1u;
-    const uint32_t partBits = two ? 6u : 0u;
-    const uint32_t rotBits = (wMode == 4u || wMode == 5u) ? 2u : 0u;
-    const uint32_t imBits = (wMode == 4u) ? 1u : 0u;
-    const uint32_t hdr = (wMode + 1u) + partBits + rotBits + imBits;
-    const uint32_t epBits = nsub * 2u * (3u * cfg.cbits + cfg.abits);
-    const uint32_t npb = (cfg.ptype == 1) ? nsub * 2u : (cfg.ptype == 2) ? nsub : 0u;
-    const uint32_t idxStart = hdr + epBits + npb;
-    // Mode 4: the first index block is always the 2-bit set, the second the 3-bit set (:2727-2757)
-    const bool swapSets = (wMode == 4u) && (wIdx != 0u);
-    const uint32_t ib1 = swapSets ? iba : ibc;                 // bits of the first index block
-    const uint32_t ib2v = swapSets ? ibc : iba;                // bits of the second index block
-    const uint32_t firstLen = 16u * ib1 - nsub;
-    const uint32_t secondStart = idxStart + firstLen;
-
+    // Every lane contributes its pixel's index fields AND one endpoint field (lane = 4 * channel + endpoint);
+    // lanes 0..3 add the p-bits, lane 0 the header.
     uint32_t w0[DXB_NL], w1[DXB_NL], w2[DXB_NL], w3[DXB_NL];
     DXB_LANES_BEGIN
-        dxb_u128 bits; bits.lo = 0; bits.hi = 0;
-        if (lane < 16)
+        const uint32_t hl = (uint32_t)(lane & 15);
+        const uint32_t wMode = W[L].mode, wIdx = W[L].idx;
+        const dxb_bc7_modecfg cfg = dxb_bc7_cfg((int)wMode);
+        const bool two = (wMode == 1u || wMode == 3u || wMode == 7u);
+        const bool sepA = (wMode == 4u || wMode == 5u);
+        const uint32_t ibc = (wMode == 4u && wIdx) ? 3u : cfg.ib;
+        const uint32_t iba = (wMode == 4u) ? (wIdx ? 2u : 3u) : cfg.ib2;
+        const uint32_t part = two ? dxb_part2[W[L].shape] : 0u;
+        const uint32_t anchor1 = anchorSrc[L];
+        const bool flipC0 = ((aC0[L] >> (ibc - 1u)) & 1u) != 0;
+        const bool flipC1 = two && (((aC1[L] >> (ibc - 1u)) & 1u) != 0);
+        const bool flipA = (iba != 0) && (((aA0[L] >> (iba - 1u)) & 1u) != 0);
+        uint32_t iC = idxC[L], iA = idxA[L];
         {
-            const uint32_t i = (uint32_t)lane;
-            const uint32_t first = swapSets ? idxA[L] : idxC[L];
-            const uint32_t second = swapSets ? idxC[L] : idxA[L];
-            // number of anchors strictly before pixel i in the first index block (anchors: 0 and anchor1)
-            const uint32_t before = (i > 0 ? 1u : 0u) + ((two && i > anchor1) ? 1u : 0u);
-            const bool isAnchor = (i == 0) || (two && i == anchor1);
-            dxb_put_bits(&bits, idxStart + i * ib1 - before, isAnchor ? ib1 - 1u : ib1, first);
-            if (ib2v)
-                dxb_put_bits(&bits, secondStart + (i ? i * ib2v - 1u : 0u), i ? ib2v : ib2v - 1u, second);
+            const bool fl = ((part >> hl) & 1u) ? flipC1 : flipC0;
+            if (fl) iC = ((1u << ibc) - 1u) - iC;
+            if (flipA) iA = ((1u << iba) - 1u) - iA;
         }
-        else if (lane == 16)
+        const uint32_t nsub = two ? 2u : 1u;
+        const uint32_t partBits = two ? 6u : 0u;
+        const uint32_t rotBits = sepA ? 2u : 0u;
+        const uint32_t imBits = (wMode == 4u) ? 1u : 0u;
+        const uint32_t hdr = (wMode + 1u) + partBits + rotBits + imBits;
+        const uint32_t epBits = nsub * 2u * (3u * cfg.cbits + cfg.abits);
+        const uint32_t npb = (cfg.ptype == 1) ? nsub * 2u : (cfg.ptype == 2) ? nsub : 0u;
+        const uint32_t idxStart = hdr + epBits + npb;
+        // Mode 4: the first index block is always the 2-bit set, the second the 3-bit set (:2727-2757)
+        const bool swapSets = (wMode == 4u) && (wIdx != 0u);
+        const uint32_t ib1 = swapSets ? iba : ibc;                 // bits of the first index block
+        const uint32_t ib2v = swapSets ? ibc : iba;                // bits of the second index block
+        const uint32_t secondStart = idxStart + 16u * ib1 - nsub;
+
+        dxb_u128 bits; bits.lo = 0; bits.hi = 0;
         {
-            uint32_t pos = 0;
-            dxb_put_bits(&bits, wMode, 1, 1u); pos = wMode + 1u;
-            dxb_put_bits(&bits, pos, partBits, wShape); pos += partBits;
-            dxb_put_bits(&bits, pos, rotBits, wRot); pos += rotBits;
-            dxb_put_bits(&bits, pos, imBits, wIdx); pos += imBits;
-            for (uint32_t c = 0; c < 4; ++c)
-            {
-                const uint32_t nb = (c == 3) ? cfg.abits : cfg.cbits;
-                if (nb == 0) continue;
-                for (uint32_t sb = 0; sb < nsub; ++sb)
-                {
-                    dxb_put_bits(&bits, pos, nb, (f0[sb] >> (8 * c)) & 0xFF); pos += nb;
-                    dxb_put_bits(&bits, pos, nb, (f1[sb] >> (8 * c)) & 0xFF); pos += nb;
-                }
-            }
-            if (cfg.ptype == 1)
-                for (uint32_t sb = 0; sb < nsub; ++sb)
-                {
-                    dxb_put_bits(&bits, pos, 1, pb0[sb]); pos += 1;
-                    dxb_put_bits(&bits, pos, 1, pb1[sb]); pos += 1;
-                }
-            else if (cfg.ptype == 2)
-                for (uint32_t sb = 0; sb < nsub; ++sb) { dxb_put_bits(&bits, pos, 1, pb0[sb]); pos += 1; }
+            // index fields of pixel hl
+            const uint32_t first = swapSets ? iA : iC, second = swapSets ? iC : iA;
+            const uint32_t before = (hl > 0 ? 1u : 0u) + ((two && hl > anchor1) ? 1u : 0u);   // anchors before this pixel
+            const bool isAnchor = (hl == 0) || (two && hl == anchor1);
+            dxb_put_bits(&bits, idxStart + hl * ib1 - before, isAnchor ? ib1 - 1u : ib1, first);
+            dxb_put_bits(&bits, secondStart + (hl ? hl * ib2v - 1u : 0u), ib2v ? (hl ? ib2v : ib2v - 1u) : 0u, second);
+        }
+        {
+            // endpoint field: channel c, endpoint e = 2 * subset + which.  Colour channels follow the colour
+            // flip of their subset; in modes 4/5 the alpha channel has its own index set and follows flipA.
+            const uint32_t c = hl >> 2, e = hl & 3u, sub = e >> 1, which = e & 1u;
+            const bool fl = (sepA && c == 3u) ? flipA : (sub ? flipC1 : flipC0);
+            const uint32_t qa = sub ? W[L].q0[1] : W[L].q0[0], qb = sub ? W[L].q1[1] : W[L].q1[0];
+            const uint32_t field = (((which != 0u) != fl) ? qb : qa) >> (8u * c);
+            const uint32_t nb = (c == 3u) ? cfg.abits : cfg.cbits;
+            const uint32_t pos = hdr + ((c == 3u) ? 3u * 2u * nsub * cfg.cbits + e * cfg.abits : (c * 2u * nsub + e) * cfg.cbits);
+            dxb_put_bits(&bits, pos, (e < 2u * nsub) ? nb : 0u, field & 0xFFu);
+        }
+        if (hl < npb)
+        {
+            // p-bits: unique (ptype 1): endpoint order; shared (ptype 2): one per subset
+            const uint32_t sub = (cfg.ptype == 2) ? hl : (hl >> 1), which = (cfg.ptype == 2) ? 0u : (hl & 1u);
+            const bool fl = sub ? flipC1 : flipC0;
+            const uint32_t pbv = sub ? W[L].pb[1] : W[L].pb[0];
+            const uint32_t bit = (cfg.ptype == 2) ? (pbv & 1u) : ((pbv >> (((which != 0u) != fl) ? 1u : 0u)) & 1u);
+            dxb_put_bits(&bits, hdr + epBits + hl, 1, bit);
+        }
+        if (hl == 0)
+        {
+            dxb_put_bits(&bits, wMode, 1, 1u);
+            dxb_put_bits(&bits, wMode + 1u, partBits, W[L].shape);
+            dxb_put_bits(&bits, wMode + 1u + partBits, rotBits, W[L].rot);
+            dxb_put_bits(&bits, wMode + 1u + partBits + rotBits, imBits, wIdx);
         }
         w0[L] = (uint32_t)bits.lo; w1[L] = (uint32_t)(bits.lo >> 32); w2[L] = (uint32_t)bits.hi; w3[L] = (uint32_t)(bits.hi >> 32);
     DXB_LANES_END
-    const uint32_t o0 = dxb_warp_or_u32(w0), o1 = dxb_warp_or_u32(w1), o2 = dxb_warp_or_u32(w2), o3 = dxb_warp_or_u32(w3);
+    uint32_t o0[DXB_NL], o1[DXB_NL], o2[DXB_NL], o3[DXB_NL];
+    dxb_half_or_u32(w0, o0); dxb_half_or_u32(w1, o1); dxb_half_or_u32(w2, o2); dxb_half_or_u32(w3, o3);
     DXB_LANES_BEGIN
-        if (lane == 0)
+        uint8_t* out = (lane & 16) ? out1 : out0;
+        if ((lane & 15) == 0 && out)
         {
             uint32_t* o = (uint32_t*)out;
-            o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
+            o[0] = o0[L]; o[1] = o1[L]; o[2] = o2[L]; o[3] = o3[L];
         }
     DXB_LANES_END
 }
 
 #if !DXB_ON_DEVICE
-// emulator entry: px = 16 RGBA fp32 pixels after ConvertScanline (values clamped to [0,1])
-static inline void dxb_bc7_encode_block_emul(const dxb_px* px, uint32_t bcflags, uint8_t* out)
+// emulator entry: pxA / pxB = 16 RGBA fp32 pixels each after ConvertScanline (values clamped to [0,1]);
+// pxB / outB may be null (odd block count)
+static inline void dxb_bc7_encode_pair_emul(const dxb_px* pxA, const dxb_px* pxB, uint32_t bcflags, uint8_t* outA, uint8_t* outB)
 {
-    dxb_px ldr[16];
+    static thread_local dxb_bc7_scratch S;
     for (int i = 0; i < 16; ++i)
-        ldr[i] = dxb_make_px(dxb_bc7_ldr(px[i].x), dxb_bc7_ldr(px[i].y), dxb_bc7_ldr(px[i].z), dxb_bc7_ldr(px[i].w));
-    dxb_bc7_encode_warp(ldr, bcflags, out);
+    {
+        S.px[i] = dxb_make_px(dxb_bc7_ldr(pxA[i].x), dxb_bc7_ldr(pxA[i].y), dxb_bc7_ldr(pxA[i].z), dxb_bc7_ldr(pxA[i].w));
+        S.px[16 + i] = pxB ? dxb_make_px(dxb_bc7_ldr(pxB[i].x), dxb_bc7_ldr(pxB[i].y), dxb_bc7_ldr(pxB[i].z), dxb_bc7_ldr(pxB[i].w))
+                           : dxb_make_px(0.0f, 0.0f, 0.0f, 255.0f);
+    }
+    dxb_bc7_encode_pair(&S, bcflags, outA, pxB ? outB : nullptr);
 }
 #endif

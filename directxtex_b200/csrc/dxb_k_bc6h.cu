@@ -2,13 +2,13 @@
 #include "dxb_launch.h"
 #include "dxb_bc6h.cuh"
 
-__global__ void __launch_bounds__(DXB_BC7_WARPS * 32) k_compress_bc6h(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
+__global__ void __launch_bounds__(DXB_BC6H_WARPS * 32) k_compress_bc6h(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
 {
-    __shared__ dxb_px spx[DXB_BC7_WARPS][16];
+    __shared__ dxb_px spx[DXB_BC6H_WARPS][16];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t stride = gridDim.x * DXB_BC7_WARPS;
+    const uint32_t stride = gridDim.x * DXB_BC6H_WARPS;
     const bool bSigned = (P.dstFormat == DXB_FMT_BC6H_SF16);
-    for (uint32_t unit = blockIdx.x * DXB_BC7_WARPS + warp; unit < P.totalUnits; unit += stride)
+    for (uint32_t unit = blockIdx.x * DXB_BC6H_WARPS + warp; unit < P.totalUnits; unit += stride)
     {
         const dxb_job& j = dxb_find_job(jobs, P.njobs, single, unit);
         const uint32_t local = unit - j.firstUnit;
@@ -35,11 +35,11 @@ __global__ void __launch_bounds__(DXB_BC7_WARPS * 32) k_compress_bc6h(const dxb_
 
 void dxb_launch_bc6h(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job& single, const dxb_compress_params& P)
 {
-    k_compress_bc6h<<<grid, DXB_BC7_WARPS * 32, 0, stream>>>(jobs, single, P);
+    k_compress_bc6h<<<grid, DXB_BC6H_WARPS * 32, 0, stream>>>(jobs, single, P);
 }
 int dxb_occupancy_bc6h()
 {
     int b = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc6h, DXB_BC7_WARPS * 32, 0) != cudaSuccess) { (void)cudaGetLastError(); b = 1; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc6h, DXB_BC6H_WARPS * 32, 0) != cudaSuccess) { (void)cudaGetLastError(); b = 1; }
     return b > 0 ? b : 1;
 }

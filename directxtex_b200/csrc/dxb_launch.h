@@ -37,7 +37,13 @@ struct dxb_mip_params
     dxb_tri_axis triX, triY;       // triangle filter only
 };
 
-#define DXB_BC7_WARPS 8
+#ifndef DXB_BC7_WARPS
+#define DXB_BC7_WARPS 4       // warps per CTA of k_compress_bc7 (two blocks per warp, ~10 KB shared per warp)
+#endif
+#ifndef DXB_BC7_MINB
+#define DXB_BC7_MINB 5        // __launch_bounds__ min CTAs per SM of k_compress_bc7
+#endif
+#define DXB_BC6H_WARPS 8      // warps per CTA of k_compress_bc6h (one block per warp)
 
 // launchers: `grid` CTAs on `stream`; jobs == nullptr -> `single` is used
 void dxb_launch_bc15(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job& single, const dxb_compress_params& P);

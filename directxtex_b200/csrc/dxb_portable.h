@@ -69,6 +69,14 @@ DXB_DEV uint32_t dxb_float_as_uint(float f)
     uint32_t u; memcpy(&u, &f, 4); return u;
 #endif
 }
+DXB_DEV uint32_t dxb_popc16(uint32_t v)
+{
+#if DXB_ON_DEVICE
+    return (uint32_t)__popc(v & 0xFFFFu);
+#else
+    return (uint32_t)__builtin_popcount(v & 0xFFFFu);
+#endif
+}
 DXB_DEV float dxb_uint_as_float(uint32_t u)
 {
 #if DXB_ON_DEVICE

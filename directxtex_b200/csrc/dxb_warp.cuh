@@ -98,3 +98,48 @@ DXB_DEV void dxb_warp_sync()
     __syncwarp();
 #endif
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Half-warp (16-lane group) collectives: the BC7 encoder runs TWO blocks per warp, one per half.
+// Results are lane-private (uniform inside a half, different between halves).
+
+// out[lane] = min / OR over the 16-lane half that contains `lane`
+DXB_DEV void dxb_half_min_u32(const uint32_t* v, uint32_t* out)
+{
+#if DXB_ON_DEVICE
+    const uint32_t hm = 0xFFFFu << (threadIdx.x & 16u);
+    out[0] = __reduce_min_sync(hm, v[0]);
+#else
+    for (int h = 0; h < 32; h += 16)
+    {
+        uint32_t m = v[h];
+        for (int l = 1; l < 16; ++l) m = (v[h + l] < m) ? v[h + l] : m;
+        for (int l = 0; l < 16; ++l) out[h + l] = m;
+    }
+#endif
+}
+DXB_DEV void dxb_half_or_u32(const uint32_t* v, uint32_t* out)
+{
+#if DXB_ON_DEVICE
+    const uint32_t hm = 0xFFFFu << (threadIdx.x & 16u);
+    out[0] = __reduce_or_sync(hm, v[0]);
+#else
+    for (int h = 0; h < 32; h += 16)
+    {
+        uint32_t m = 0;
+        for (int l = 0; l < 16; ++l) m |= v[h + l];
+        for (int l = 0; l < 16; ++l) out[h + l] = m;
+    }
+#endif
+}
+// out[lane] = v[lane of the same half whose index inside the half is src[lane] & 15]
+DXB_DEV void dxb_half_gather_u32(const uint32_t* v, const uint32_t* src, uint32_t* out)
+{
+#if DXB_ON_DEVICE
+    out[0] = __shfl_sync(DXB_FULLMASK, v[0], (int)(src[0] & 15u), 16);
+#else
+    uint32_t tmp[32];
+    for (int l = 0; l < 32; ++l) tmp[l] = v[(l & 16) | (int)(src[l] & 15u)];
+    for (int l = 0; l < 32; ++l) out[l] = tmp[l];
+#endif
+}

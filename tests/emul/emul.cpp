@@ -42,6 +42,26 @@ int32_t emul_compress(const uint8_t* src, size_t w, size_t h, uint32_t srcFmt, s
     const uint32_t bcflags = flags & (DXB_BC_FLAGS_DITHER_RGB | DXB_BC_FLAGS_DITHER_A | DXB_BC_FLAGS_UNIFORM | DXB_BC_FLAGS_USE_3SUBSETS | DXB_BC_FLAGS_FORCE_BC7_MODE6);
     dxb_image_desc img; img.pixels = src; img.rowPitch = rowPitch; img.width = (uint32_t)w; img.height = (uint32_t)h; img.format = srcFmt;
     const uint32_t nbx = (uint32_t)((w + 3) / 4), nby = (uint32_t)((h + 3) / 4);
+#ifdef DXB_EMUL_BC7
+    if (dstFmt == DXB_FMT_BC7_UNORM || dstFmt == DXB_FMT_BC7_UNORM_SRGB)
+    {
+        // the device kernel encodes two consecutive blocks (raster order) per warp; so does the emulator
+        const long total = (long)nbx * (long)nby;
+        #pragma omp parallel for schedule(dynamic, 32)
+        for (long pair = 0; pair < (total + 1) / 2; ++pair)
+        {
+            dxb_px px[2][16];
+            alignas(16) uint8_t blk[2][16];
+            const long u0 = 2 * pair, u1 = u0 + 1;
+            dxb_gather_block(img, (uint32_t)(u0 % nbx), (uint32_t)(u0 / nbx), inF, outF, cflags, px[0]);
+            if (u1 < total) dxb_gather_block(img, (uint32_t)(u1 % nbx), (uint32_t)(u1 / nbx), inF, outF, cflags, px[1]);
+            dxb_bc7_encode_pair_emul(px[0], (u1 < total) ? px[1] : nullptr, bcflags, blk[0], blk[1]);
+            memcpy(dst + (size_t)u0 * bs, blk[0], bs);
+            if (u1 < total) memcpy(dst + (size_t)u1 * bs, blk[1], bs);
+        }
+        return DXB_S_OK;
+    }
+#endif
     #pragma omp parallel for schedule(dynamic, 8)
     for (long by = 0; by < (long)nby; ++by)
         for (uint32_t bx = 0; bx < nbx; ++bx)
@@ -50,9 +70,7 @@ int32_t emul_compress(const uint8_t* src, size_t w, size_t h, uint32_t srcFmt, s
             dxb_gather_block(img, bx, (uint32_t)by, inF, outF, cflags, px);
             alignas(16) uint8_t blk[16];
 #ifdef DXB_EMUL_BC7
-            if (dstFmt == DXB_FMT_BC7_UNORM || dstFmt == DXB_FMT_BC7_UNORM_SRGB)
-                dxb_bc7_encode_block_emul(px, bcflags, blk);
-            else if (dstFmt == DXB_FMT_BC6H_UF16 || dstFmt == DXB_FMT_BC6H_SF16)
+            if (dstFmt == DXB_FMT_BC6H_UF16 || dstFmt == DXB_FMT_BC6H_SF16)
                 dxb_bc6h_encode_block_emul(px, dstFmt == DXB_FMT_BC6H_SF16, blk);
             else
 #endif
