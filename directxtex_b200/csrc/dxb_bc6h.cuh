@@ -355,10 +355,12 @@ DXB_DEV void dxb_bc6h_encode_warp(const dxb_px* spx, bool bSigned, uint8_t* out)
             tm[0] = dxb_fma(X, X, tm[0]); tm[1] = dxb_fma(X, Y, tm[1]); tm[2] = dxb_fma(X, Z, tm[2]);
             tm[3] = dxb_fma(Y, Y, tm[3]); tm[4] = dxb_fma(Y, Z, tm[4]); tm[5] = dxb_fma(Z, Z, tm[5]);
         }
-        float s4[4] = { s[0], s[1], s[2], 0.0f }, m10[10] = { m[0], m[1], m[2], 0.0f, m[3], m[4], 0.0f, m[5], 0.0f, 0.0f };
-        float s40[4] = { ts[0] - s[0], ts[1] - s[1], ts[2] - s[2], 0.0f };
-        float m100[10] = { tm[0] - m[0], tm[1] - m[1], tm[2] - m[2], 0.0f, tm[3] - m[3], tm[4] - m[4], 0.0f, tm[5] - m[5], 0.0f, 0.0f };
-        const float est = dxb_bc7_subset_estimate(16.0f - n1, s40, m100, 1.0f / 49.0f) + dxb_bc7_subset_estimate(n1, s4, m10, 1.0f / 49.0f);
+        const float v1[14] = { s[0], s[1], s[2], 0.0f, m[0], m[1], m[2], 0.0f, m[3], m[4], 0.0f, m[5], 0.0f, 0.0f };
+        const float v0[14] = { ts[0] - s[0], ts[1] - s[1], ts[2] - s[2], 0.0f, tm[0] - m[0], tm[1] - m[1], tm[2] - m[2], 0.0f,
+                               tm[3] - m[3], tm[4] - m[4], 0.0f, tm[5] - m[5], 0.0f, 0.0f };
+        const uint32_t c1 = dxb_popc16(mask1);
+        (void)n1;
+        const float est = dxb_bc7_subset_estimate(16u - c1, v0, 1.0f / 49.0f) + dxb_bc7_subset_estimate(c1, v1, 1.0f / 49.0f);
         key[L] = (dxb_float_as_uint(fmaxf(est, 0.0f)) & 0xFFFFFFE0u) | (uint32_t)lane;
     DXB_LANES_END
     uint32_t sel[15];

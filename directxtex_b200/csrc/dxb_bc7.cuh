@@ -67,43 +67,51 @@ DXB_DEV dxb_px dxb_bc7_rotate(dxb_px p, int rot)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// stage 1: residual of the best line through one subset, from its moments (n*covariance form).
+// stage 1: residual of the best line through one subset, from its moments v[14] (4 sums, 10 products).
 // est = (trace - lambda_max) + lambda_max * qf  where qf models the index quantisation along the axis.
-DXB_DEV float dxb_bc7_subset_estimate(float n, const float* s, const float* m, float qf)
+// lambda_max: three power-iteration steps on the covariance scaled to unit trace (so nothing needs
+// renormalising between steps: the largest eigenvalue of the scaled matrix is >= 1/4), Rayleigh quotient
+// at the end.  n = pixel count of the subset (0..16).
+DXB_TABLE float dxb_rcp16[17] = { 1.0f, 1.0f, 1.0f / 2.0f, 1.0f / 3.0f, 1.0f / 4.0f, 1.0f / 5.0f, 1.0f / 6.0f, 1.0f / 7.0f, 1.0f / 8.0f,
+                                  1.0f / 9.0f, 1.0f / 10.0f, 1.0f / 11.0f, 1.0f / 12.0f, 1.0f / 13.0f, 1.0f / 14.0f, 1.0f / 15.0f, 1.0f / 16.0f };
+
+DXB_DEV float dxb_bc7_subset_estimate(uint32_t n, const float* v, float qf)
 {
-    if (n < 1.5f) return 0.0f;
-    const float inv = 1.0f / n;
-    const float c00 = dxb_fma(-s[0] * inv, s[0], m[0]), c01 = dxb_fma(-s[0] * inv, s[1], m[1]);
-    const float c02 = dxb_fma(-s[0] * inv, s[2], m[2]), c03 = dxb_fma(-s[0] * inv, s[3], m[3]);
-    const float c11 = dxb_fma(-s[1] * inv, s[1], m[4]), c12 = dxb_fma(-s[1] * inv, s[2], m[5]);
-    const float c13 = dxb_fma(-s[1] * inv, s[3], m[6]), c22 = dxb_fma(-s[2] * inv, s[2], m[7]);
-    const float c23 = dxb_fma(-s[2] * inv, s[3], m[8]), c33 = dxb_fma(-s[3] * inv, s[3], m[9]);
-    const float tr = (c00 + c11) + (c22 + c33);
-    if (!(tr > 1e-3f)) return 0.0f;
-    // power iteration from the row with the largest diagonal
-    float v0, v1, v2, v3;
-    if (c00 >= c11 && c00 >= c22 && c00 >= c33) { v0 = c00; v1 = c01; v2 = c02; v3 = c03; }
-    else if (c11 >= c22 && c11 >= c33) { v0 = c01; v1 = c11; v2 = c12; v3 = c13; }
-    else if (c22 >= c33) { v0 = c02; v1 = c12; v2 = c22; v3 = c23; }
-    else { v0 = c03; v1 = c13; v2 = c23; v3 = c33; }
-    float lam = 0.0f;
+    const float inv = dxb_rcp16[n];
+    const float* s = v; const float* m = v + 4;
+    const float a00 = dxb_fma(-s[0] * inv, s[0], m[0]), a01 = dxb_fma(-s[0] * inv, s[1], m[1]);
+    const float a02 = dxb_fma(-s[0] * inv, s[2], m[2]), a03 = dxb_fma(-s[0] * inv, s[3], m[3]);
+    const float a11 = dxb_fma(-s[1] * inv, s[1], m[4]), a12 = dxb_fma(-s[1] * inv, s[2], m[5]);
+    const float a13 = dxb_fma(-s[1] * inv, s[3], m[6]), a22 = dxb_fma(-s[2] * inv, s[2], m[7]);
+    const float a23 = dxb_fma(-s[2] * inv, s[3], m[8]), a33 = dxb_fma(-s[3] * inv, s[3], m[9]);
+    const float tr = (a00 + a11) + (a22 + a33);
+    const bool flat = !(tr > 1e-3f) || (n < 2u);
+    const float sc = flat ? 0.0f : 1.0f / tr;
+    const float c00 = a00 * sc, c01 = a01 * sc, c02 = a02 * sc, c03 = a03 * sc, c11 = a11 * sc;
+    const float c12 = a12 * sc, c13 = a13 * sc, c22 = a22 * sc, c23 = a23 * sc, c33 = a33 * sc;
+    // start from the row with the largest diagonal
+    const bool b0 = (c00 >= c11 && c00 >= c22 && c00 >= c33);
+    const bool b1 = !b0 && (c11 >= c22 && c11 >= c33);
+    const bool b2 = !b0 && !b1 && (c22 >= c33);
+    float v0 = b0 ? c00 : (b1 ? c01 : (b2 ? c02 : c03));
+    float v1 = b0 ? c01 : (b1 ? c11 : (b2 ? c12 : c13));
+    float v2 = b0 ? c02 : (b1 ? c12 : (b2 ? c22 : c23));
+    float v3 = b0 ? c03 : (b1 ? c13 : (b2 ? c23 : c33));
+    float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
     for (int it = 0; it < 3; ++it)
     {
-        const float w0 = dxb_fma(c00, v0, dxb_fma(c01, v1, dxb_fma(c02, v2, c03 * v3)));
-        const float w1 = dxb_fma(c01, v0, dxb_fma(c11, v1, dxb_fma(c12, v2, c13 * v3)));
-        const float w2 = dxb_fma(c02, v0, dxb_fma(c12, v1, dxb_fma(c22, v2, c23 * v3)));
-        const float w3 = dxb_fma(c03, v0, dxb_fma(c13, v1, dxb_fma(c23, v2, c33 * v3)));
-        const float vv = dxb_fma(v0, v0, dxb_fma(v1, v1, dxb_fma(v2, v2, v3 * v3)));
-        const float vw = dxb_fma(v0, w0, dxb_fma(v1, w1, dxb_fma(v2, w2, v3 * w3)));
-        lam = (vv > 0.0f) ? vw / vv : 0.0f;
-        const float mx = fmaxf(fmaxf(fabsf(w0), fabsf(w1)), fmaxf(fabsf(w2), fabsf(w3)));
-        if (!(mx > 0.0f)) break;
-        const float r = 1.0f / mx;
-        v0 = w0 * r; v1 = w1 * r; v2 = w2 * r; v3 = w3 * r;
+        w0 = dxb_fma(c00, v0, dxb_fma(c01, v1, dxb_fma(c02, v2, c03 * v3)));
+        w1 = dxb_fma(c01, v0, dxb_fma(c11, v1, dxb_fma(c12, v2, c13 * v3)));
+        w2 = dxb_fma(c02, v0, dxb_fma(c12, v1, dxb_fma(c22, v2, c23 * v3)));
+        w3 = dxb_fma(c03, v0, dxb_fma(c13, v1, dxb_fma(c23, v2, c33 * v3)));
+        if (it < 2) { v0 = w0; v1 = w1; v2 = w2; v3 = w3; }
     }
-    lam = fminf(lam, tr);
-    const float resid = fmaxf(tr - lam, 0.0f);
-    return dxb_fma(lam, qf, resid);
+    const float vv = dxb_fma(v0, v0, dxb_fma(v1, v1, dxb_fma(v2, v2, v3 * v3)));
+    const float vw = dxb_fma(v0, w0, dxb_fma(v1, w1, dxb_fma(v2, w2, v3 * w3)));
+    const float lam = (vv > 0.0f) ? fminf(vw / vv, 1.0f) : 0.0f;        // of the unit-trace matrix
+    // tr * ((1 - lam) + lam * qf)
+    const float e = tr * dxb_fma(lam, qf, fmaxf(1.0f - lam, 0.0f));
+    return flat ? 0.0f : e;
 }
 
 // ---- stage 1 moment table -------------------------------------------------------------------------
@@ -238,8 +246,8 @@ DXB_DEV float dxb_bc7_shape_estimate(const float* mt, uint32_t shape, float qf, 
     float v1[14], v0[14];
     dxb_bc7_mt_load(mt, (int)shape, v1);
     for (int k = 0; k < 14; ++k) v0[k] = tot[k] - v1[k];
-    const float n1 = (float)dxb_popc16(dxb_part2[shape]);
-    return dxb_bc7_subset_estimate(16.0f - n1, v0, v0 + 4, qf) + dxb_bc7_subset_estimate(n1, v1, v1 + 4, qf);
+    const uint32_t n1 = dxb_popc16(dxb_part2[shape]);
+    return dxb_bc7_subset_estimate(16u - n1, v0, qf) + dxb_bc7_subset_estimate(n1, v1, qf);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -255,23 +263,34 @@ DXB_DEV float dxb_bit_as_float(uint32_t mask, int i)       // (mask >> i) & 1 as
 // BC7 weight tables {0,21,43,64} {0,9,18,27,37,46,55,64} {0,4,9,...,60,64} exactly (no product is a tie)
 DXB_DEV float dxb_bc7_weightf(float k, float c64 /* 64 / nmax */) { return dxb_rne(k * c64) * (1.0f / 64.0f); }
 
-// endpoint quantisation for one channel value e (0..255 float), branch-free
-//   bits : field bits without p-bit; hasP (0/1): field is followed by a p-bit; p (0/1): its value
-// returns the field (without p); *deq = the 8-bit value the decoder reconstructs
-DXB_DEV uint32_t dxb_bc7_quant1(float e, uint32_t bits, uint32_t hasP, uint32_t p, float* deq)
+// ---- endpoint quantisation, float-only (no F2I / I2F / integer shifts in the per-round path) -----------
+// A field of `bits` bits, optionally followed by a p-bit (hasP), B = bits + hasP total bits:
+//   f = e * (2^B - 1) / 255;  no p-bit: q = round(f);  p-bit p: q = round((f - p) / 2);  q clamped to the field
+//   full = 2 q + p (or q);  the decoder reconstructs  deq = (full << (8 - B)) | (full >> (2 B - 8))
+// round() is the magic-number RNE; the ">>" is floor(full * 2^(8-2B)) = RNE(full * 2^(8-2B) - (1/2 - 2^-9)),
+// exact because the product is a multiple of 2^-8.  All per-mode numbers are lane constants.
+struct dxb_bc7_qconst { float scaleH, half, qmax, mul, c8, c2; };
+
+DXB_DEV dxb_bc7_qconst dxb_bc7_make_qconst(uint32_t bits, uint32_t hasP)
 {
     const uint32_t B = bits + hasP;
-    const uint32_t qmax = (1u << bits) - 1u;
-    const float fmaxv = (float)((1u << B) - 1u);
-    const float f = e * (fmaxv * (1.0f / 255.0f));
-    // no p-bit: q = floor(f + 0.5);  p-bit: q = floor((f - p) / 2 + 0.5)
-    const float half = hasP ? 0.5f : 1.0f;
-    const float h = dxb_fma(f - (float)(p & hasP), half, 0.5f);
-    int32_t qi = dxb_f2i(floorf(h));
-    qi = qi < 0 ? 0 : (qi > (int32_t)qmax ? (int32_t)qmax : qi);
-    const uint32_t q = (uint32_t)qi;
-    const uint32_t full = hasP ? ((q << 1) | p) : q;
-    *deq = (float)dxb_bc7_unq(full, B);
+    dxb_bc7_qconst k;
+    k.half = hasP ? 0.5f : 1.0f;
+    k.scaleH = (float)((1u << B) - 1u) * (1.0f / 255.0f) * k.half;
+    k.qmax = (float)((1u << bits) - 1u);
+    k.mul = hasP ? 2.0f : 1.0f;
+    k.c8 = dxb_uint_as_float((127u + 8u - B) << 23);            // 2^(8-B)
+    k.c2 = dxb_uint_as_float((127u + 8u - 2u * B) << 23);       // 2^(8-2B)
+    return k;
+}
+// pE = p * hasP as float.  Returns the field q (float integer); *deq = reconstructed 8-bit value (float integer)
+DXB_DEV float dxb_bc7_quant1f(float e, const dxb_bc7_qconst& k, float pE, float* deq)
+{
+    const float h = dxb_fma(e, k.scaleH, -(pE * k.half));
+    const float q = fminf(fmaxf(dxb_rne(h), 0.0f), k.qmax);
+    const float full = dxb_fma(q, k.mul, pE);
+    const float r = dxb_rne(dxb_fma(full, k.c2, -(0.5f - 1.0f / 512.0f)));
+    *deq = dxb_fma(full, k.c8, r);
     return q;
 }
 
@@ -292,72 +311,32 @@ DXB_DEV dxb_bc7_modecfg dxb_bc7_cfg(int mode)
     return c;
 }
 
-// Quantise both endpoints of a subset (vector part), choosing p-bits; branch-free over modes.
-//   use3 = 1.0f when channel 3 is part of the vector (modes 6/7) else 0.0f (its field then stays 0)
-//   pforce < 0 : choose p-bits by endpoint reconstruction error; else bit0/bit1 = forced p of endpoint 0/1
-DXB_DEV void dxb_bc7_quant_endpoints(const float* E0, const float* E1, float use3, uint32_t cbits, uint32_t abits,
-                                     uint32_t ptype, int pforce, uint32_t* q0, uint32_t* q1, uint32_t* pbits, float* D0, float* D1)
-{
-    const uint32_t hasP = (ptype != 0u) ? 1u : 0u;
-    uint32_t Q0[2] = { 0, 0 }, Q1[2] = { 0, 0 };
-    float d0[2][4], d1[2][4];
-    float err0[2] = { 0.0f, 0.0f }, err1[2] = { 0.0f, 0.0f };
-    for (int p = 0; p < 2; ++p)
-    {
-        for (uint32_t c = 0; c < 4; ++c)
-        {
-            const uint32_t bits = (c == 3) ? (abits ? abits : 1u) : cbits;
-            const float wgt = (c == 3) ? use3 : 1.0f;
-            float a, b;
-            uint32_t f0 = dxb_bc7_quant1(E0[c], bits, hasP, (uint32_t)p, &a);
-            uint32_t f1 = dxb_bc7_quant1(E1[c], bits, hasP, (uint32_t)p, &b);
-            if (c == 3) { const uint32_t keep = (use3 != 0.0f) ? 0xFFu : 0u; f0 &= keep; f1 &= keep; a *= wgt; b *= wgt; }
-            Q0[p] |= f0 << (8 * c); Q1[p] |= f1 << (8 * c);
-            d0[p][c] = a; d1[p][c] = b;
-            const float ea = (a - E0[c]) * wgt, eb = (b - E1[c]) * wgt;
-            err0[p] = dxb_fma(ea, ea, err0[p]); err1[p] = dxb_fma(eb, eb, err1[p]);
-        }
-    }
-    // heuristic choice, then overrides; all selects
-    uint32_t p0 = (err0[1] < err0[0]) ? 1u : 0u;
-    uint32_t p1 = (err1[1] < err1[0]) ? 1u : 0u;
-    const uint32_t ps = ((err0[1] + err1[1]) < (err0[0] + err1[0])) ? 1u : 0u;
-    if (ptype == 2u) { p0 = ps; p1 = ps; }
-    if (pforce >= 0) { p0 = (uint32_t)pforce & 1u; p1 = (ptype == 2u) ? p0 : (((uint32_t)pforce >> 1) & 1u); }
-    if (ptype == 0u) { p0 = 0u; p1 = 0u; }
-    *q0 = p0 ? Q0[1] : Q0[0]; *q1 = p1 ? Q1[1] : Q1[0]; *pbits = p0 | (p1 << 1);
-    for (int c = 0; c < 4; ++c) { D0[c] = p0 ? d0[1][c] : d0[0][c]; D1[c] = p1 ? d1[1][c] : d1[0][c]; }
-}
-
 // ---------------------------------------------------------------------------------------------------
-// stage 2: one lane task.  px = 16 LDR pixels (floats 0..255).
-//   mode 1/3/7: subset `mask` of a 2-subset shape;  mode 6: whole block, forced p-bit pair;
+// stage 2: one lane task.  px = the block's 16 LDR pixels (floats 0..255), mt = its moment table.
+//   mode 1/3/7: subset `mask` of 2-subset shape `shape`;  mode 6: whole block, forced p-bit pair;
 //   mode 4/5 : whole block, rotation `rot`, index selector `idxMode` (mode 4)
-// Written so that all 32 lanes execute ONE instruction stream for the vector part (mode differences are
-// data: bit counts, channel weight, p-bit type); only the separate-alpha part of modes 4/5 is a
-// divergent section.  Idle lanes (mode < 0) run the same code on dummy parameters.
+// Everything works on pixels in their NATURAL channel order.  A rotation only decides which channel is
+// the separately coded scalar (channel rot-1, or alpha when rot = 0); vm[c] = 1 for the channels that form
+// the endpoint vector, 0 otherwise (the scalar of modes 4/5; alpha in modes 1/3).  Masked channels have zero
+// moments, axis and endpoints, so one instruction stream serves every mode; only the scalar part of
+// modes 4/5 is a divergent section.  Idle lanes (mode < 0) run the same code on dummy parameters.
+// The result's q0/q1 bytes are in the bit stream's slot order (byte 3 = the scalar / alpha slot).
 DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t shape, uint32_t mask, int mode, int rot, int idxMode, int pforce)
 {
     const bool idle = (mode < 0);
     if (idle) { mode = 6; mask = 0xFFFFu; }
     const dxb_bc7_modecfg cfg = dxb_bc7_cfg(mode);
     const bool sep = (mode == 4 || mode == 5);
-    const float use3 = (mode == 6 || mode == 7) ? 1.0f : 0.0f;
-    const uint32_t ibc = (mode == 4 && idxMode) ? 3u : cfg.ib;           // colour index bits
-    const uint32_t iba = (mode == 4) ? (idxMode ? 2u : 3u) : cfg.ib2;    // alpha index bits (modes 4/5)
-    const bool r1 = (rot == 1), r2 = (rot == 2), r3 = (rot == 3);
+    const uint32_t ibc = (mode == 4 && idxMode) ? 3u : cfg.ib;           // vector index bits
+    const uint32_t iba = (mode == 4) ? (idxMode ? 2u : 3u) : cfg.ib2;    // scalar index bits (modes 4/5)
+    const int sc = rot ? rot - 1 : 3;                                    // natural channel of the scalar / alpha slot
+    float vm[4];
+    for (int c = 0; c < 4; ++c) vm[c] = (c == sc && (sep || mode == 1 || mode == 3)) ? 0.0f : 1.0f;
 
-    // rotated pixel: the colour vector is (x,y,z, use3*w); `a` is the rotated alpha slot
-#define DXB_BC7_FETCH(i, X, Y, Z, Wv, A) \
-    float X, Y, Z, Wv, A; \
-    { const dxb_px p_ = px[i]; \
-      X = r1 ? p_.w : p_.x; Y = r2 ? p_.w : p_.y; Z = r3 ? p_.w : p_.z; \
-      A = r1 ? p_.x : (r2 ? p_.y : (r3 ? p_.z : p_.w)); Wv = A * use3; }
-
-    // ---- vector part: moments of the subset, from the stage-1 table (exact integers): subset 1 = row `shape`,
-    // subset 0 = totals - row, whole block = totals; then the rotation's channel swap and the use3 mask
-    float s0, s1, s2, s3, m00, m01, m02, m03, m11, m12, m13, m22, m23, m33;
+    // ---- moments of the subset from the stage-1 table (exact integers): subset 1 = row `shape`,
+    // subset 0 = totals - row, whole block = totals; masked channels zeroed
     const float n = (float)dxb_popc16(mask);
+    float s[4], m00, m01, m02, m03, m11, m12, m13, m22, m23, m33;
     {
         const bool whole = (mask == 0xFFFFu);
         const bool sub0 = !whole && ((mask & 1u) != 0u);        // pixel 0 always belongs to subset 0
@@ -365,26 +344,16 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
         dxb_bc7_mt_load(mt, whole ? 64 : (int)shape, R);
         dxb_bc7_mt_load(mt, 64, T);
         for (int k = 0; k < 14; ++k) R[k] = sub0 ? T[k] - R[k] : R[k];
-        // channel swap c <-> 3 (c = rot - 1) applied to the symmetric moment matrix
-        s0 = r1 ? R[3] : R[0]; s1 = r2 ? R[3] : R[1]; s2 = r3 ? R[3] : R[2];
-        s3 = r1 ? R[0] : (r2 ? R[1] : (r3 ? R[2] : R[3]));
-        m00 = r1 ? R[13] : R[4];                         // xx
-        m01 = r1 ? R[10] : (r2 ? R[7] : R[5]);           // xy: r1 -> wy, r2 -> xw
-        m02 = r1 ? R[12] : (r3 ? R[7] : R[6]);           // xz: r1 -> wz, r3 -> xw
-        m03 = r2 ? R[5] : (r3 ? R[6] : R[7]);            // xw: r1 -> wx (same), r2 -> xy, r3 -> xz
-        m11 = r2 ? R[13] : R[8];                         // yy
-        m12 = r2 ? R[12] : (r3 ? R[10] : R[9]);          // yz: r2 -> wz, r3 -> yw
-        m13 = r1 ? R[5] : (r3 ? R[9] : R[10]);           // yw: r1 -> yx, r2 -> wy (same), r3 -> yz
-        m22 = r3 ? R[13] : R[11];                        // zz
-        m23 = r1 ? R[6] : (r2 ? R[9] : R[12]);           // zw: r1 -> zx, r2 -> zy, r3 -> wz (same)
-        m33 = r1 ? R[4] : (r2 ? R[8] : (r3 ? R[11] : R[13]));
-        s3 *= use3; m03 *= use3; m13 *= use3; m23 *= use3; m33 *= use3;
+        for (int c = 0; c < 4; ++c) s[c] = R[c] * vm[c];
+        m00 = R[4] * vm[0]; m01 = R[5] * (vm[0] * vm[1]); m02 = R[6] * (vm[0] * vm[2]); m03 = R[7] * (vm[0] * vm[3]);
+        m11 = R[8] * vm[1]; m12 = R[9] * (vm[1] * vm[2]); m13 = R[10] * (vm[1] * vm[3]);
+        m22 = R[11] * vm[2]; m23 = R[12] * (vm[2] * vm[3]); m33 = R[13] * vm[3];
     }
     const float inv = 1.0f / fmaxf(n, 1.0f);
-    const float mean[4] = { s0 * inv, s1 * inv, s2 * inv, s3 * inv };
-    const float c00 = dxb_fma(-mean[0], s0, m00), c01 = dxb_fma(-mean[0], s1, m01), c02 = dxb_fma(-mean[0], s2, m02), c03 = dxb_fma(-mean[0], s3, m03);
-    const float c11 = dxb_fma(-mean[1], s1, m11), c12 = dxb_fma(-mean[1], s2, m12), c13 = dxb_fma(-mean[1], s3, m13);
-    const float c22 = dxb_fma(-mean[2], s2, m22), c23 = dxb_fma(-mean[2], s3, m23), c33 = dxb_fma(-mean[3], s3, m33);
+    const float mean[4] = { s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv };
+    const float c00 = dxb_fma(-mean[0], s[0], m00), c01 = dxb_fma(-mean[0], s[1], m01), c02 = dxb_fma(-mean[0], s[2], m02), c03 = dxb_fma(-mean[0], s[3], m03);
+    const float c11 = dxb_fma(-mean[1], s[1], m11), c12 = dxb_fma(-mean[1], s[2], m12), c13 = dxb_fma(-mean[1], s[3], m13);
+    const float c22 = dxb_fma(-mean[2], s[2], m22), c23 = dxb_fma(-mean[2], s[3], m23), c33 = dxb_fma(-mean[3], s[3], m33);
     const float tr = (c00 + c11) + (c22 + c33);
 
     // principal axis: power iteration from the row with the largest diagonal (selects, no branches)
@@ -412,13 +381,15 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
         ax[0] = v0 * r; ax[1] = v1 * r; ax[2] = v2 * r; ax[3] = v3 * r;
     }
 
-    // ---- projection extents -> initial endpoints
+    // ---- projection extents -> initial endpoints (masked channels: axis 0, mean 0 -> endpoints 0)
     float tmin = 3.0e38f, tmax = -3.0e38f;
+#if DXB_ON_DEVICE
+    #pragma unroll 4
+#endif
     for (int i = 0; i < 16; ++i)
     {
-        DXB_BC7_FETCH(i, X, Y, Z, Wv, A)
-        (void)A;
-        const float t = dxb_fma(X - mean[0], ax[0], dxb_fma(Y - mean[1], ax[1], dxb_fma(Z - mean[2], ax[2], (Wv - mean[3]) * ax[3])));
+        const dxb_px p = px[i];
+        const float t = dxb_fma(p.x - mean[0], ax[0], dxb_fma(p.y - mean[1], ax[1], dxb_fma(p.z - mean[2], ax[2], (p.w - mean[3]) * ax[3])));
         const bool in = ((mask >> i) & 1u) != 0u;
         tmin = in ? fminf(tmin, t) : tmin; tmax = in ? fmaxf(tmax, t) : tmax;
     }
@@ -430,8 +401,10 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
         E1[c] = fminf(fmaxf(dxb_fma(tmax, ax[c], mean[c]), 0.0f), 255.0f);
     }
 
-    // ---- evaluation rounds (vector part)
-    float bestErr = 3.0e38f; uint32_t bq0 = 0, bq1 = 0, bpb = 0;
+    // ---- evaluation rounds (vector part).  Every vector channel has cbits bits (modes 6/7: abits == cbits).
+    const uint32_t hasP = (cfg.ptype != 0u) ? 1u : 0u;
+    const dxb_bc7_qconst qk = dxb_bc7_make_qconst(cfg.cbits, hasP);
+    float bestErr = 3.0e38f, bqa0 = 0.0f, bqa1 = 0.0f, bqb0 = 0.0f, bqb1 = 0.0f; uint32_t bpb = 0;
     const float nmaxc = (float)((1u << ibc) - 1u);
     const float c64c = 64.0f / nmaxc;
     bool live = true;                                            // false once this lane has converged (keeps running, results ignored)
@@ -442,42 +415,70 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
     {
         const bool last = (round + 1 == DXB_BC7_ROUNDS);       // compile-time after unrolling: the refit sums vanish from the last round
         dxb_warp_sync();
-        uint32_t q0, q1, pb; float D0[4], D1[4];
-        dxb_bc7_quant_endpoints(E0, E1, use3, cfg.cbits, cfg.abits, cfg.ptype, pforce, &q0, &q1, &pb, D0, D1);
+        // quantise both endpoints for p = 0 and p = 1; fields packed as float integers q0 + 256 q1 + 65536 q2, q3 apart
+        float qa[2][2], qb[2][2], d0[2][4], d1[2][4], err0[2] = { 0.0f, 0.0f }, err1[2] = { 0.0f, 0.0f };
+        for (int p = 0; p < 2; ++p)
+        {
+            const float pE = (p && hasP) ? 1.0f : 0.0f;
+            float f0[4], f1[4];
+            for (int c = 0; c < 4; ++c)
+            {
+                float a, b;
+                f0[c] = dxb_bc7_quant1f(E0[c], qk, pE, &a) * vm[c];
+                f1[c] = dxb_bc7_quant1f(E1[c], qk, pE, &b) * vm[c];
+                a *= vm[c]; b *= vm[c];
+                d0[p][c] = a; d1[p][c] = b;
+                const float ea = a - E0[c], eb = b - E1[c];      // masked channels: E = 0 and a = b = 0
+                err0[p] = dxb_fma(ea, ea, err0[p]); err1[p] = dxb_fma(eb, eb, err1[p]);
+            }
+            qa[p][0] = dxb_fma(f0[2], 65536.0f, dxb_fma(f0[1], 256.0f, f0[0])); qb[p][0] = f0[3];
+            qa[p][1] = dxb_fma(f1[2], 65536.0f, dxb_fma(f1[1], 256.0f, f1[0])); qb[p][1] = f1[3];
+        }
+        // p-bit choice: by endpoint reconstruction error, then the overrides; all selects
+        uint32_t p0 = (err0[1] < err0[0]) ? 1u : 0u;
+        uint32_t p1 = (err1[1] < err1[0]) ? 1u : 0u;
+        const uint32_t ps = ((err0[1] + err1[1]) < (err0[0] + err1[0])) ? 1u : 0u;
+        if (cfg.ptype == 2u) { p0 = ps; p1 = ps; }
+        if (pforce >= 0) { p0 = (uint32_t)pforce & 1u; p1 = (cfg.ptype == 2u) ? p0 : (((uint32_t)pforce >> 1) & 1u); }
+        if (cfg.ptype == 0u) { p0 = 0u; p1 = 0u; }
+        const float qa0 = p0 ? qa[1][0] : qa[0][0], qb0 = p0 ? qb[1][0] : qb[0][0];
+        const float qa1 = p1 ? qa[1][1] : qa[0][1], qb1 = p1 ? qb[1][1] : qb[0][1];
+        float D0[4], D1[4];
+        for (int c = 0; c < 4; ++c) { D0[c] = p0 ? d0[1][c] : d0[0][c]; D1[c] = p1 ? d1[1][c] : d1[0][c]; }
+
         const float dx = D1[0] - D0[0], dy = D1[1] - D0[1], dz = D1[2] - D0[2], dw = D1[3] - D0[3];
         const float dd = dxb_fma(dx, dx, dxb_fma(dy, dy, dxb_fma(dz, dz, dw * dw)));
-        const float idd = (dd > 0.0f) ? 1.0f / dd : 0.0f;
-        const float B0 = D0[0] + (1.0f / 128.0f), B1 = D0[1] + (1.0f / 128.0f), B2 = D0[2] + (1.0f / 128.0f), B3 = D0[3] + (1.0f / 128.0f);
+        const float idd = (dd > 0.0f) ? nmaxc / dd : 0.0f;          // index scale folded in
         float err = 0.0f;
         float la = 0.0f, lb = 0.0f, lc = 0.0f;                     // sum (1-s)^2, s(1-s), s^2
         float u0 = 0, u1 = 0, u2 = 0, u3 = 0, v0 = 0, v1 = 0, v2 = 0, v3 = 0;     // sum (1-s) p, sum s p
+#if DXB_ON_DEVICE
+        #pragma unroll 4
+#endif
         for (int i = 0; i < 16; ++i)
         {
-            if ((mask >> i) & 1u)
+            const float f = dxb_bit_as_float(mask, i);          // 1 if the pixel belongs to this lane's subset
+            const dxb_px p = px[i];
+            const float X = p.x * vm[0], Y = p.y * vm[1], Z = p.z * vm[2], Wv = p.w * vm[3];
+            const float tk = dxb_fma(X - D0[0], dx, dxb_fma(Y - D0[1], dy, dxb_fma(Z - D0[2], dz, (Wv - D0[3]) * dw))) * idd;
+            // index = nearest of the uniformly spaced positions; weight of that index (palette entries are not
+            // rounded here: this error only ranks candidates, stage 4 assigns the final indices exhaustively)
+            const float kk = dxb_rne(fminf(fmaxf(tk, 0.0f), nmaxc));
+            const float sk = dxb_bc7_weightf(kk, c64c);
+            const float ex = X - dxb_fma(dx, sk, D0[0]), ey = Y - dxb_fma(dy, sk, D0[1]);
+            const float ez = Z - dxb_fma(dz, sk, D0[2]), ew = Wv - dxb_fma(dw, sk, D0[3]);
+            err = dxb_fma(f, dxb_fma(ex, ex, dxb_fma(ey, ey, dxb_fma(ez, ez, ew * ew))), err);
+            if (!last)
             {
-                DXB_BC7_FETCH(i, X, Y, Z, Wv, A)
-                (void)A;
-                const float t = dxb_fma(X - D0[0], dx, dxb_fma(Y - D0[1], dy, dxb_fma(Z - D0[2], dz, (Wv - D0[3]) * dw))) * idd;
-                const float xk = fminf(fmaxf(t * nmaxc, 0.0f), nmaxc - 1.0f);
-                const float k0 = dxb_rne(xk - 0.5f);            // lower bracket index without an XU-pipe FRND
-                const float w0 = dxb_bc7_weightf(k0, c64c), w1 = dxb_bc7_weightf(k0 + 1.0f, c64c);
-                const float sk = ((t - w0) > (w1 - t)) ? w1 : w0;
-                // palette entry: floor(v/64 + 0.5) == RNE(v/64 + 1/128) because v/64 is a multiple of 1/64
-                const float cx = dxb_rne(dxb_fma(dx, sk, B0)), cy = dxb_rne(dxb_fma(dy, sk, B1));
-                const float cz = dxb_rne(dxb_fma(dz, sk, B2)), cw = dxb_rne(dxb_fma(dw, sk, B3));
-                const float ex = X - cx, ey = Y - cy, ez = Z - cz, ew = Wv - cw;
-                err += dxb_fma(ex, ex, dxb_fma(ey, ey, dxb_fma(ez, ez, ew * ew)));
-                if (!last)
-                {
-                    const float os = 1.0f - sk;
-                    la = dxb_fma(os, os, la); lb = dxb_fma(os, sk, lb); lc = dxb_fma(sk, sk, lc);
-                    u0 = dxb_fma(os, X, u0); u1 = dxb_fma(os, Y, u1); u2 = dxb_fma(os, Z, u2); u3 = dxb_fma(os, Wv, u3);
-                    v0 = dxb_fma(sk, X, v0); v1 = dxb_fma(sk, Y, v1); v2 = dxb_fma(sk, Z, v2); v3 = dxb_fma(sk, Wv, v3);
-                }
+                const float skf = sk * f, osf = f - skf, os = 1.0f - sk;
+                la = dxb_fma(osf, os, la); lb = dxb_fma(osf, sk, lb); lc = dxb_fma(skf, sk, lc);
+                u0 = dxb_fma(osf, X, u0); u1 = dxb_fma(osf, Y, u1); u2 = dxb_fma(osf, Z, u2); u3 = dxb_fma(osf, Wv, u3);
+                v0 = dxb_fma(skf, X, v0); v1 = dxb_fma(skf, Y, v1); v2 = dxb_fma(skf, Z, v2); v3 = dxb_fma(skf, Wv, v3);
             }
         }
         const bool better = live && (err < bestErr);
-        bestErr = better ? err : bestErr; bq0 = better ? q0 : bq0; bq1 = better ? q1 : bq1; bpb = better ? pb : bpb;
+        bestErr = better ? err : bestErr; bpb = better ? (p0 | (p1 << 1)) : bpb;
+        bqa0 = better ? qa0 : bqa0; bqa1 = better ? qa1 : bqa1; bqb0 = better ? qb0 : bqb0; bqb1 = better ? qb1 : bqb1;
         if (last) break;
         // least-squares refit for the next round (skipped lanes keep their endpoints)
         const float det = dxb_fma(la, lc, -(lb * lb));
@@ -492,41 +493,43 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
             E1[c] = live ? fminf(fmaxf(b, 0.0f), 255.0f) : E1[c];
         }
     }
+    // natural-order fields as integers: n0 / n1 byte c = field of natural channel c
+    // (x + 2^23 has x in its mantissa for 0 <= x < 2^23; colour fields have at most 7 bits, so the packed value fits)
+    uint32_t n0 = (dxb_float_as_uint(bqa0 + 8388608.0f) & 0x7FFFFFu) | ((dxb_float_as_uint(bqb0 + 8388608.0f) & 0xFFu) << 24);
+    uint32_t n1 = (dxb_float_as_uint(bqa1 + 8388608.0f) & 0x7FFFFFu) | ((dxb_float_as_uint(bqb1 + 8388608.0f) & 0xFFu) << 24);
 
-    // ---- scalar part (modes 4/5): the rotated alpha slot with its own endpoints and indices
+    // ---- scalar part (modes 4/5): channel `sc` with its own endpoints and indices
     if (sep)
     {
+        const float* pf = (const float*)px + sc;                  // scalar of pixel i = pf[4 i]
         float amin = 3.0e38f, amax = -3.0e38f;
-        for (int i = 0; i < 16; ++i)
-        {
-            DXB_BC7_FETCH(i, X, Y, Z, Wv, A)
-            (void)X; (void)Y; (void)Z; (void)Wv;
-            amin = fminf(amin, A); amax = fmaxf(amax, A);
-        }
+        for (int i = 0; i < 16; ++i) { const float A = pf[4 * i]; amin = fminf(amin, A); amax = fmaxf(amax, A); }
         float A0 = amin, A1 = amax;
-        float bestA = 3.0e38f; uint32_t ba0 = 0, ba1 = 0;
+        float bestA = 3.0e38f, ba0 = 0.0f, ba1 = 0.0f;
+        const dxb_bc7_qconst qa = dxb_bc7_make_qconst(cfg.abits, 0u);
         const float nmaxa = (float)((1u << iba) - 1u);
         const float c64a = 64.0f / nmaxa;
         bool liveA = true;
+#if DXB_ON_DEVICE
+        #pragma unroll 1
+#endif
         for (int round = 0; round < DXB_BC7_ROUNDS; ++round)
         {
             float d0, d1;
-            const uint32_t f0 = dxb_bc7_quant1(A0, cfg.abits, 0u, 0u, &d0);
-            const uint32_t f1 = dxb_bc7_quant1(A1, cfg.abits, 0u, 0u, &d1);
+            const float f0 = dxb_bc7_quant1f(A0, qa, 0.0f, &d0);
+            const float f1 = dxb_bc7_quant1f(A1, qa, 0.0f, &d1);
             const float da = d1 - d0;
-            const float ida = (da != 0.0f) ? 1.0f / da : 0.0f;
-            const float Ba = d0 + (1.0f / 128.0f);
+            const float ida = (da != 0.0f) ? nmaxa / da : 0.0f;
             float err = 0.0f, la = 0.0f, lb = 0.0f, lc = 0.0f, ua = 0.0f, va = 0.0f;
+#if DXB_ON_DEVICE
+            #pragma unroll 4
+#endif
             for (int i = 0; i < 16; ++i)
             {
-                DXB_BC7_FETCH(i, X, Y, Z, Wv, A)
-                (void)X; (void)Y; (void)Z; (void)Wv;
-                const float t = (A - d0) * ida;
-                const float xk = fminf(fmaxf(t * nmaxa, 0.0f), nmaxa - 1.0f);
-                const float k0 = dxb_rne(xk - 0.5f);            // lower bracket index without an XU-pipe FRND
-                const float w0 = dxb_bc7_weightf(k0, c64a), w1 = dxb_bc7_weightf(k0 + 1.0f, c64a);
-                const float sk = ((t - w0) > (w1 - t)) ? w1 : w0;
-                const float ca = dxb_rne(dxb_fma(da, sk, Ba));
+                const float A = pf[4 * i];
+                const float kk = dxb_rne(fminf(fmaxf((A - d0) * ida, 0.0f), nmaxa));
+                const float sk = dxb_bc7_weightf(kk, c64a);
+                const float ca = dxb_rne(dxb_fma(da, sk, d0 + (1.0f / 128.0f)));
                 const float ea = A - ca;
                 err = dxb_fma(ea, ea, err);
                 const float os = 1.0f - sk;
@@ -543,13 +546,22 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
             A1 = liveA ? fminf(fmaxf(nb, 0.0f), 255.0f) : A1;
         }
         bestErr += bestA;
-        bq0 = (bq0 & 0x00FFFFFFu) | (ba0 << 24);
-        bq1 = (bq1 & 0x00FFFFFFu) | (ba1 << 24);
+        // scalar fields into natural byte `sc`
+        const uint32_t sh = 8u * (uint32_t)sc;
+        n0 = (n0 & ~(0xFFu << sh)) | ((dxb_float_as_uint(ba0 + 8388608.0f) & 0xFFu) << sh);
+        n1 = (n1 & ~(0xFFu << sh)) | ((dxb_float_as_uint(ba1 + 8388608.0f) & 0xFFu) << sh);
     }
-#undef DXB_BC7_FETCH
+    // natural order -> slot order: a rotation swaps bytes rot-1 and 3
+    if (rot)
+    {
+        const uint32_t sh = 8u * (uint32_t)(rot - 1);
+        const uint32_t a0 = (n0 >> sh) & 0xFFu, b0 = n0 >> 24, a1 = (n1 >> sh) & 0xFFu, b1 = n1 >> 24;
+        n0 = (n0 & ~((0xFFu << sh) | 0xFF000000u)) | (b0 << sh) | (a0 << 24);
+        n1 = (n1 & ~((0xFFu << sh) | 0xFF000000u)) | (b1 << sh) | (a1 << 24);
+    }
 
     dxb_bc7_res R;
-    R.err = idle ? 3.0e38f : bestErr; R.q0 = bq0; R.q1 = bq1; R.pbits = bpb;
+    R.err = idle ? 3.0e38f : bestErr; R.q0 = n0; R.q1 = n1; R.pbits = bpb;
     return R;
 }
 
@@ -611,7 +623,7 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
     dxb_bc7_build_moments(S);
     uint32_t hasA[DXB_NL], sel[3][DXB_NL];
     {
-        uint32_t key[4][DXB_NL];
+        uint32_t k0[DXB_NL], k1[DXB_NL], k2[DXB_NL];             // each lane's three best keys, ascending
         DXB_LANES_BEGIN
             const float* mt = S->mt[lane >> 4];
             float tot[14];
@@ -619,25 +631,28 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
             hasA[L] = (tot[3] != 4080.0f) ? 1u : 0u;             // 16 * 255: every alpha is 255
             // index quantisation factor 1/(2^b-1)^2: 3-bit for mode 1 (opaque), 2-bit for mode 7 (alpha)
             const float qf = hasA[L] ? (1.0f / 9.0f) : (1.0f / 49.0f);
+            uint32_t a = 0xFFFFFFFFu, b = 0xFFFFFFFFu, c = 0xFFFFFFFFu;
+#if DXB_ON_DEVICE
+            #pragma unroll 1
+#endif
             for (int j = 0; j < 4; ++j)
             {
                 const uint32_t shape = (uint32_t)(lane & 15) + 16u * (uint32_t)j;
                 const float e = quick ? 0.0f : dxb_bc7_shape_estimate(mt, shape, qf, tot);
-                key[j][L] = (dxb_float_as_uint(e) & 0xFFFFFFC0u) | shape;
+                const uint32_t x = (dxb_float_as_uint(e) & 0xFFFFFFC0u) | shape;
+                const uint32_t lo = (x < a) ? x : a, hi = (x < a) ? a : x;               // sorted insert
+                const uint32_t lo2 = (hi < b) ? hi : b, hi2 = (hi < b) ? b : hi;
+                a = lo; b = lo2; c = (hi2 < c) ? hi2 : c;
             }
+            k0[L] = a; k1[L] = b; k2[L] = c;
         DXB_LANES_END
         for (int r = 0; r < 3; ++r)
         {
-            uint32_t cand[DXB_NL], win[DXB_NL];
-            DXB_LANES_BEGIN
-                const uint32_t a = (key[0][L] < key[1][L]) ? key[0][L] : key[1][L];
-                const uint32_t b = (key[2][L] < key[3][L]) ? key[2][L] : key[3][L];
-                cand[L] = (a < b) ? a : b;
-            DXB_LANES_END
-            dxb_half_min_u32(cand, win);
+            uint32_t win[DXB_NL];
+            dxb_half_min_u32(k0, win);
             DXB_LANES_BEGIN
                 sel[r][L] = win[L] & 63u;
-                for (int j = 0; j < 4; ++j) if (key[j][L] == win[L]) key[j][L] = 0xFFFFFFFFu;
+                if (k0[L] == win[L]) { k0[L] = k1[L]; k1[L] = k2[L]; k2[L] = 0xFFFFFFFFu; }
             DXB_LANES_END
         }
     }
