@@ -27,6 +27,10 @@
 #include "dxb_pixel.cuh"
 #include "dxb_bc67_tables.h"
 
+#ifndef DXB_BC7_PIXUNROLL
+#define DXB_BC7_PIXUNROLL 2       // unroll factor of the 16-pixel loops of a lane task (code size vs loop overhead)
+#endif
+static constexpr int dxb_bc7_pixunroll = DXB_BC7_PIXUNROLL;
 #ifndef DXB_BC7_ROUNDS
 #define DXB_BC7_ROUNDS 2          // endpoint evaluation rounds per task (1 = PCA only, each extra = one LS refit)
 #endif
@@ -130,7 +134,8 @@ struct dxb_bc7_scratch
 {
     dxb_px   px[32];                          // LDR pixels (floats 0..255) of the warp's two blocks: half h -> px[16h ..]
     float    mt[2][DXB_BC7_MT_FLOATS];        // moment tables: row = shape, 16-float rows, 16-byte chunks XOR-swizzled
-    uint16_t feat[2][24][16];                 // bf16 feature matrix F^T (device only)
+    // (device: the bf16 feature matrix F^T, uint16_t[2][24][16], lives in the first 1536 bytes of mt until the
+    //  MMA B fragments have been read into registers)
 };
 
 // float offset of 16-byte chunk c (0..3) of table row `row`; the swizzle makes both the MMA-fragment
@@ -167,7 +172,7 @@ DXB_DEV void dxb_bc7_build_moments(dxb_bc7_scratch* S)
     const uint32_t lane = threadIdx.x & 31u, h = lane >> 4, hl = lane & 15u;
     {
         const dxb_px p = S->px[lane];
-        uint16_t* F = &S->feat[h][0][hl];                 // feature n of this pixel = F[16 * n]
+        uint16_t* F = (uint16_t*)S->mt + (h * 24 * 16 + hl);   // feature n of this pixel = F[16 * n]
         F[0] = (uint16_t)(__float_as_uint(p.x) >> 16); F[16] = (uint16_t)(__float_as_uint(p.y) >> 16);
         F[32] = (uint16_t)(__float_as_uint(p.z) >> 16); F[48] = (uint16_t)(__float_as_uint(p.w) >> 16);
         const float P[10] = { p.x * p.x, p.x * p.y, p.x * p.z, p.x * p.w, p.y * p.y, p.y * p.z, p.y * p.w, p.z * p.z, p.z * p.w, p.w * p.w };
@@ -189,9 +194,10 @@ DXB_DEV void dxb_bc7_build_moments(dxb_bc7_scratch* S)
         #pragma unroll
         for (int t = 0; t < 3; ++t)
         {
-            const uint32_t* w = (const uint32_t*)&S->feat[hb][t * 8 + g][0];
+            const uint32_t* w = (const uint32_t*)((const uint16_t*)S->mt + ((hb * 24 + t * 8 + (int)g) * 16));
             B[hb][t][0] = w[q]; B[hb][t][1] = w[q + 4];
         }
+    __syncwarp();                                             // the feature bytes are dead from here: mt may be written
     #pragma unroll
     for (int tile = 0; tile < 5; ++tile)
     {
@@ -384,7 +390,7 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
     // ---- projection extents -> initial endpoints (masked channels: axis 0, mean 0 -> endpoints 0)
     float tmin = 3.0e38f, tmax = -3.0e38f;
 #if DXB_ON_DEVICE
-    #pragma unroll 4
+    #pragma unroll dxb_bc7_pixunroll
 #endif
     for (int i = 0; i < 16; ++i)
     {
@@ -408,13 +414,16 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
     const float nmaxc = (float)((1u << ibc) - 1u);
     const float c64c = 64.0f / nmaxc;
     bool live = true;                                            // false once this lane has converged (keeps running, results ignored)
-#if DXB_ON_DEVICE
+#if DXB_ON_DEVICE && defined(DXB_BC7_ROLLROUNDS)
+    #pragma unroll 1
+#elif DXB_ON_DEVICE
     #pragma unroll
 #endif
     for (int round = 0; round < DXB_BC7_ROUNDS; ++round)
     {
         const bool last = (round + 1 == DXB_BC7_ROUNDS);       // compile-time after unrolling: the refit sums vanish from the last round
         dxb_warp_sync();
+        dxb_phase_sync();
         // quantise both endpoints for p = 0 and p = 1; fields packed as float integers q0 + 256 q1 + 65536 q2, q3 apart
         float qa[2][2], qb[2][2], d0[2][4], d1[2][4], err0[2] = { 0.0f, 0.0f }, err1[2] = { 0.0f, 0.0f };
         for (int p = 0; p < 2; ++p)
@@ -453,7 +462,7 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
         float la = 0.0f, lb = 0.0f, lc = 0.0f;                     // sum (1-s)^2, s(1-s), s^2
         float u0 = 0, u1 = 0, u2 = 0, u3 = 0, v0 = 0, v1 = 0, v2 = 0, v3 = 0;     // sum (1-s) p, sum s p
 #if DXB_ON_DEVICE
-        #pragma unroll 4
+        #pragma unroll dxb_bc7_pixunroll
 #endif
         for (int i = 0; i < 16; ++i)
         {
@@ -522,7 +531,7 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
             const float ida = (da != 0.0f) ? nmaxa / da : 0.0f;
             float err = 0.0f, la = 0.0f, lb = 0.0f, lc = 0.0f, ua = 0.0f, va = 0.0f;
 #if DXB_ON_DEVICE
-            #pragma unroll 4
+            #pragma unroll dxb_bc7_pixunroll
 #endif
             for (int i = 0; i < 16; ++i)
             {
@@ -657,6 +666,7 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
         }
     }
 
+    dxb_phase_sync();
     // ---- stage 2: one task per lane
     //   opaque block: 3 best shapes x 2 subsets x {mode 1, mode 3} (lanes 0-11), mode 6 x 4 p-bit pairs (12-15)
     //   alpha block : 3 best shapes x 2 subsets x mode 7 (0-5), mode 6 x 4 p-bit pairs (6-9),
@@ -699,6 +709,7 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
         rQ0[L] = res.q0; rQ1[L] = res.q1;
     DXB_LANES_END
 
+    dxb_phase_sync();
     // ---- stage 3: combine subset errors, pick the winner of each half
     dxb_bc7_win W[DXB_NL];
     {

@@ -4,15 +4,18 @@
 
 __global__ void __launch_bounds__(DXB_BC7_WARPS * 32, DXB_BC7_MINB) k_compress_bc7(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
 {
-    __shared__ dxb_bc7_scratch scratch[DXB_BC7_WARPS];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    dxb_bc7_scratch* scratch = (dxb_bc7_scratch*)smem_raw;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, hl = lane & 15u;
     dxb_bc7_scratch* S = &scratch[warp];
     const uint32_t stride = gridDim.x * DXB_BC7_WARPS;
     const uint32_t npairs = (P.totalUnits + 1u) >> 1;
-    for (uint32_t pair = blockIdx.x * DXB_BC7_WARPS + warp; pair < npairs; pair += stride)
+    // every warp of the CTA runs the same number of iterations (a warp without a pair encodes dummy pixels and
+    // stores nothing), so CTA-wide barriers inside the encoder are legal
+    for (uint32_t base = blockIdx.x * DXB_BC7_WARPS; base < npairs; base += stride)
     {
         // lanes 0-15 stage block 2*pair, lanes 16-31 block 2*pair+1; lane = pixel
-        const uint32_t unit = 2u * pair + (lane >> 4);
+        const uint32_t unit = 2u * (base + warp) + (lane >> 4);
         uint8_t* out = nullptr;
         dxb_px ldr = dxb_make_px(0.0f, 0.0f, 0.0f, 255.0f);
         if (unit < P.totalUnits)
@@ -40,14 +43,21 @@ __global__ void __launch_bounds__(DXB_BC7_WARPS * 32, DXB_BC7_MINB) k_compress_b
     }
 }
 
+static const size_t kBC7Smem = sizeof(dxb_bc7_scratch) * DXB_BC7_WARPS;
+static bool bc7_attr_set()
+{
+    static const bool ok = (cudaFuncSetAttribute(k_compress_bc7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7Smem) == cudaSuccess);
+    return ok;
+}
 
 void dxb_launch_bc7(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job& single, const dxb_compress_params& P)
 {
-    k_compress_bc7<<<grid, DXB_BC7_WARPS * 32, 0, stream>>>(jobs, single, P);
+    bc7_attr_set();
+    k_compress_bc7<<<grid, DXB_BC7_WARPS * 32, kBC7Smem, stream>>>(jobs, single, P);
 }
 int dxb_occupancy_bc7()
 {
     int b = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc7, DXB_BC7_WARPS * 32, 0) != cudaSuccess) { (void)cudaGetLastError(); b = 1; }
+    if (!bc7_attr_set() || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc7, DXB_BC7_WARPS * 32, kBC7Smem) != cudaSuccess) { (void)cudaGetLastError(); b = 1; }
     return b > 0 ? b : 1;
 }

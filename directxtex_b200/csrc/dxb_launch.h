@@ -38,10 +38,10 @@ struct dxb_mip_params
 };
 
 #ifndef DXB_BC7_WARPS
-#define DXB_BC7_WARPS 4       // warps per CTA of k_compress_bc7 (two blocks per warp, ~10 KB shared per warp)
+#define DXB_BC7_WARPS 8       // warps per CTA of k_compress_bc7 (two blocks per warp, 8.6 KB dynamic shared per warp)
 #endif
 #ifndef DXB_BC7_MINB
-#define DXB_BC7_MINB 5        // __launch_bounds__ min CTAs per SM of k_compress_bc7
+#define DXB_BC7_MINB 3        // __launch_bounds__ min CTAs per SM of k_compress_bc7
 #endif
 #define DXB_BC6H_WARPS 8      // warps per CTA of k_compress_bc6h (one block per warp)
 

@@ -92,6 +92,14 @@ DXB_DEV uint64_t dxb_warp_min_u64(const uint64_t* v)
     return m;
 #endif
 }
+// CTA-wide phase alignment: keeps the warps of a CTA in the same code region so that they share instruction-cache
+// lines (the BC7 encoder is ~75 KB of straight-line code; measured 4.0 -> 3.8 ms).  -DDXB_BC7_NO_CTA_SYNC disables it.
+DXB_DEV void dxb_phase_sync()
+{
+#if DXB_ON_DEVICE && !defined(DXB_BC7_NO_CTA_SYNC)
+    __syncthreads();
+#endif
+}
 DXB_DEV void dxb_warp_sync()
 {
 #if DXB_ON_DEVICE
