@@ -31,6 +31,12 @@
 #define DXB_BC7_PIXUNROLL 2       // unroll factor of the 16-pixel loops of a lane task (code size vs loop overhead)
 #endif
 static constexpr int dxb_bc7_pixunroll = DXB_BC7_PIXUNROLL;
+#ifndef DXB_BC7_PCA_ITERS
+#define DXB_BC7_PCA_ITERS 2       // power-iteration steps for a task's principal axis
+#endif
+#ifndef DXB_BC7_EST_ITERS
+#define DXB_BC7_EST_ITERS 2       // power-iteration steps inside the stage-1 shape estimate
+#endif
 #ifndef DXB_BC7_ROUNDS
 #define DXB_BC7_ROUNDS 2          // endpoint evaluation rounds per task (1 = PCA only, each extra = one LS refit)
 #endif
@@ -102,13 +108,13 @@ DXB_DEV float dxb_bc7_subset_estimate(uint32_t n, const float* v, float qf)
     float v2 = b0 ? c02 : (b1 ? c12 : (b2 ? c22 : c23));
     float v3 = b0 ? c03 : (b1 ? c13 : (b2 ? c23 : c33));
     float w0 = 0.0f, w1 = 0.0f, w2 = 0.0f, w3 = 0.0f;
-    for (int it = 0; it < 3; ++it)
+    for (int it = 0; it < DXB_BC7_EST_ITERS; ++it)
     {
         w0 = dxb_fma(c00, v0, dxb_fma(c01, v1, dxb_fma(c02, v2, c03 * v3)));
         w1 = dxb_fma(c01, v0, dxb_fma(c11, v1, dxb_fma(c12, v2, c13 * v3)));
         w2 = dxb_fma(c02, v0, dxb_fma(c12, v1, dxb_fma(c22, v2, c23 * v3)));
         w3 = dxb_fma(c03, v0, dxb_fma(c13, v1, dxb_fma(c23, v2, c33 * v3)));
-        if (it < 2) { v0 = w0; v1 = w1; v2 = w2; v3 = w3; }
+        if (it < DXB_BC7_EST_ITERS - 1) { v0 = w0; v1 = w1; v2 = w2; v3 = w3; }
     }
     const float vv = dxb_fma(v0, v0, dxb_fma(v1, v1, dxb_fma(v2, v2, v3 * v3)));
     const float vw = dxb_fma(v0, w0, dxb_fma(v1, w1, dxb_fma(v2, w2, v3 * w3)));
@@ -362,28 +368,30 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
     const float c22 = dxb_fma(-mean[2], s[2], m22), c23 = dxb_fma(-mean[2], s[3], m23), c33 = dxb_fma(-mean[3], s[3], m33);
     const float tr = (c00 + c11) + (c22 + c33);
 
-    // principal axis: power iteration from the row with the largest diagonal (selects, no branches)
+    // principal axis: power iteration on the covariance scaled to unit trace (largest eigenvalue >= 1/4, so four
+    // un-normalised steps stay far inside the fp32 range), from the row with the largest diagonal; selects, no branches
     float ax[4];
     {
-        const bool b0 = (c00 >= c11 && c00 >= c22 && c00 >= c33);
-        const bool b1 = !b0 && (c11 >= c22 && c11 >= c33);
-        const bool b2 = !b0 && !b1 && (c22 >= c33);
-        float v0 = b0 ? c00 : (b1 ? c01 : (b2 ? c02 : c03));
-        float v1 = b0 ? c01 : (b1 ? c11 : (b2 ? c12 : c13));
-        float v2 = b0 ? c02 : (b1 ? c12 : (b2 ? c22 : c23));
-        float v3 = b0 ? c03 : (b1 ? c13 : (b2 ? c23 : c33));
-        for (int it = 0; it < 4; ++it)
+        const float sc = (tr > 1e-3f) ? 1.0f / tr : 0.0f;
+        const float k00 = c00 * sc, k01 = c01 * sc, k02 = c02 * sc, k03 = c03 * sc, k11 = c11 * sc;
+        const float k12 = c12 * sc, k13 = c13 * sc, k22 = c22 * sc, k23 = c23 * sc, k33 = c33 * sc;
+        const bool b0 = (k00 >= k11 && k00 >= k22 && k00 >= k33);
+        const bool b1 = !b0 && (k11 >= k22 && k11 >= k33);
+        const bool b2 = !b0 && !b1 && (k22 >= k33);
+        float v0 = b0 ? k00 : (b1 ? k01 : (b2 ? k02 : k03));
+        float v1 = b0 ? k01 : (b1 ? k11 : (b2 ? k12 : k13));
+        float v2 = b0 ? k02 : (b1 ? k12 : (b2 ? k22 : k23));
+        float v3 = b0 ? k03 : (b1 ? k13 : (b2 ? k23 : k33));
+        for (int it = 0; it < DXB_BC7_PCA_ITERS; ++it)
         {
-            const float w0 = dxb_fma(c00, v0, dxb_fma(c01, v1, dxb_fma(c02, v2, c03 * v3)));
-            const float w1 = dxb_fma(c01, v0, dxb_fma(c11, v1, dxb_fma(c12, v2, c13 * v3)));
-            const float w2 = dxb_fma(c02, v0, dxb_fma(c12, v1, dxb_fma(c22, v2, c23 * v3)));
-            const float w3 = dxb_fma(c03, v0, dxb_fma(c13, v1, dxb_fma(c23, v2, c33 * v3)));
-            const float mx = fmaxf(fmaxf(fabsf(w0), fabsf(w1)), fmaxf(fabsf(w2), fabsf(w3)));
-            const float r = (mx > 1e-30f) ? 1.0f / mx : 0.0f;
-            v0 = w0 * r; v1 = w1 * r; v2 = w2 * r; v3 = w3 * r;
+            const float w0 = dxb_fma(k00, v0, dxb_fma(k01, v1, dxb_fma(k02, v2, k03 * v3)));
+            const float w1 = dxb_fma(k01, v0, dxb_fma(k11, v1, dxb_fma(k12, v2, k13 * v3)));
+            const float w2 = dxb_fma(k02, v0, dxb_fma(k12, v1, dxb_fma(k22, v2, k23 * v3)));
+            const float w3 = dxb_fma(k03, v0, dxb_fma(k13, v1, dxb_fma(k23, v2, k33 * v3)));
+            v0 = w0; v1 = w1; v2 = w2; v3 = w3;
         }
         const float vv = dxb_fma(v0, v0, dxb_fma(v1, v1, dxb_fma(v2, v2, v3 * v3)));
-        const float r = (vv > 1e-30f && tr > 1e-3f) ? 1.0f / sqrtf(vv) : 0.0f;
+        const float r = (vv > 1e-30f) ? 1.0f / sqrtf(vv) : 0.0f;
         ax[0] = v0 * r; ax[1] = v1 * r; ax[2] = v2 * r; ax[3] = v3 * r;
     }
 
@@ -469,14 +477,22 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
             const float f = dxb_bit_as_float(mask, i);          // 1 if the pixel belongs to this lane's subset
             const dxb_px p = px[i];
             const float X = p.x * vm[0], Y = p.y * vm[1], Z = p.z * vm[2], Wv = p.w * vm[3];
-            const float tk = dxb_fma(X - D0[0], dx, dxb_fma(Y - D0[1], dy, dxb_fma(Z - D0[2], dz, (Wv - D0[3]) * dw))) * idd;
+            const float ax_ = X - D0[0], ay_ = Y - D0[1], az_ = Z - D0[2], aw_ = Wv - D0[3];
+            const float pr = dxb_fma(ax_, dx, dxb_fma(ay_, dy, dxb_fma(az_, dz, aw_ * dw)));
+            const float tk = pr * idd;
             // index = nearest of the uniformly spaced positions; weight of that index (palette entries are not
             // rounded here: this error only ranks candidates, stage 4 assigns the final indices exhaustively)
             const float kk = dxb_rne(fminf(fmaxf(tk, 0.0f), nmaxc));
             const float sk = dxb_bc7_weightf(kk, c64c);
+#ifndef DXB_BC7_NO_ALGERR
+            // |P - D0 - sk d|^2 = |P - D0|^2 - sk (2 (P - D0).d - sk |d|^2)
+            const float e2 = dxb_fma(-sk, dxb_fma(-sk, dd, pr + pr), dxb_fma(ax_, ax_, dxb_fma(ay_, ay_, dxb_fma(az_, az_, aw_ * aw_))));
+            err = dxb_fma(f, e2, err);
+#else
             const float ex = X - dxb_fma(dx, sk, D0[0]), ey = Y - dxb_fma(dy, sk, D0[1]);
             const float ez = Z - dxb_fma(dz, sk, D0[2]), ew = Wv - dxb_fma(dw, sk, D0[3]);
             err = dxb_fma(f, dxb_fma(ex, ex, dxb_fma(ey, ey, dxb_fma(ez, ez, ew * ew))), err);
+#endif
             if (!last)
             {
                 const float skf = sk * f, osf = f - skf, os = 1.0f - sk;
