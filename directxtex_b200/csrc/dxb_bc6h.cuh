@@ -145,24 +145,22 @@ DXB_DEV void dxb_bc6h_fit(const dxb_px* px, uint32_t mask, uint32_t ib, int anch
         dxb_warp_sync();
         const float dx = B[0] - A[0], dy = B[1] - A[1], dz = B[2] - A[2];
         const float dd = dxb_fma(dx, dx, dxb_fma(dy, dy, dz * dz));
-        const float idd = (dd > 0.0f) ? 1.0f / dd : 0.0f;
+        const float idd = (dd > 0.0f) ? nmax / dd : 0.0f;            // index scale folded in
         float la = 0, lb = 0, lc = 0, u0 = 0, u1 = 0, u2 = 0, v0 = 0, v1 = 0, v2 = 0;
+#if DXB_ON_DEVICE
+        #pragma unroll 4
+#endif
         for (int i = 0; i < 16; ++i)
         {
-            if ((mask >> i) & 1u)
-            {
-                const dxb_px p = px[i];
-                const float X = p.x - ctr[0], Y = p.y - ctr[1], Z = p.z - ctr[2];
-                const float t = dxb_fma(X - A[0], dx, dxb_fma(Y - A[1], dy, (Z - A[2]) * dz)) * idd;
-                const float xk = fminf(fmaxf(t * nmax, 0.0f), nmax - 1.0f);
-                const float k0 = dxb_rne(xk - 0.5f);
-                const float w0 = dxb_bc7_weightf(k0, c64), w1 = dxb_bc7_weightf(k0 + 1.0f, c64);
-                const float sk = ((t - w0) > (w1 - t)) ? w1 : w0;
-                const float os = 1.0f - sk;
-                la = dxb_fma(os, os, la); lb = dxb_fma(os, sk, lb); lc = dxb_fma(sk, sk, lc);
-                u0 = dxb_fma(os, X, u0); u1 = dxb_fma(os, Y, u1); u2 = dxb_fma(os, Z, u2);
-                v0 = dxb_fma(sk, X, v0); v1 = dxb_fma(sk, Y, v1); v2 = dxb_fma(sk, Z, v2);
-            }
+            const float f = dxb_bit_as_float(mask, i);
+            const dxb_px p = px[i];
+            const float X = p.x - ctr[0], Y = p.y - ctr[1], Z = p.z - ctr[2];
+            const float t = dxb_fma(X - A[0], dx, dxb_fma(Y - A[1], dy, (Z - A[2]) * dz)) * idd;
+            const float sk = dxb_bc7_weightf(dxb_rne(fminf(fmaxf(t, 0.0f), nmax)), c64);
+            const float skf = sk * f, osf = f - skf, os = 1.0f - sk;
+            la = dxb_fma(osf, os, la); lb = dxb_fma(osf, sk, lb); lc = dxb_fma(skf, sk, lc);
+            u0 = dxb_fma(osf, X, u0); u1 = dxb_fma(osf, Y, u1); u2 = dxb_fma(osf, Z, u2);
+            v0 = dxb_fma(skf, X, v0); v1 = dxb_fma(skf, Y, v1); v2 = dxb_fma(skf, Z, v2);
         }
         const float det = dxb_fma(la, lc, -(lb * lb));
         live = live && (det > 1e-4f);
@@ -200,6 +198,15 @@ DXB_DEV int dxb_bc6h_pick_mode(const int32_t ep[4][3], bool two, bool bSigned, i
     const int ncand = two ? 10 : 3;
     const int nep = two ? 4 : 2;
     int chosen = two ? 9 : 10;
+    int32_t q12[4][3]; bool neg[4][3];
+    for (int e = 0; e < 4; ++e)
+        for (int c = 0; c < 3; ++c)
+        {
+            const int32_t v = ep[e][c];
+            neg[e][c] = bSigned && (v < 0);
+            const int32_t a = neg[e][c] ? -v : v;
+            q12[e][c] = bSigned ? ((a << 11) / (0x7BFF + 1)) : ((a << 12) / (0x7BFF + 1));
+        }
     for (int ci = 0; ci < ncand; ++ci)
     {
         const int m = two ? order2[ci] : order1[ci];
@@ -210,9 +217,14 @@ DXB_DEV int dxb_bc6h_pick_mode(const int32_t ep[4][3], bool two, bool bSigned, i
         int32_t t[4][3];
         bool ok = true;
         const int32_t qhi = bSigned ? ((1 << (prec - 1)) - 1) : ((1 << prec) - 1);
+        // Quantize(v, prec) = floor(|v| 2^prec' / 31744) (:1864-1889) = the 12-bit quantisation shifted down, because
+        // nested floor divisions compose; magnitudes and signs are handled apart for the signed format
         for (int e = 0; e < nep; ++e)
             for (int c = 0; c < 3; ++c)
-                t[e][c] = dxb_bc6h_quantize(ep[e][c], prec, bSigned);
+            {
+                const int32_t mag = q12[e][c] >> (12 - prec);
+                t[e][c] = neg[e][c] ? -mag : mag;
+            }
         // a region whose two endpoints quantise to the same code wastes its interpolation levels: open the pair by one
         // code so that the 8/16 palette entries subdivide the quantisation step (what the reference's perturbation finds)
         for (int r = 0; r < nep; r += 2)
@@ -234,92 +246,98 @@ DXB_DEV int dxb_bc6h_pick_mode(const int32_t ep[4][3], bool two, bool bSigned, i
     return chosen;
 }
 
-// exact error of one region against the decoder palette of quantised endpoints qa/qb at `prec` bits
+// error of one region for quantised endpoints qa/qb at `prec` bits, used to RANK the candidate shapes: indices by
+// projection, decoded values modelled in float as in dxb_bc6h_refine_region (within 2 units of the decoder's integers;
+// the winner's indices are then chosen exhaustively against the exact palette in stage 4)
 template <int NIDX>
-DXB_DEV float dxb_bc6h_region_error(const dxb_px* px, uint32_t mask, const int32_t* qa, const int32_t* qb, int32_t prec, bool bSigned)
+DXB_DEV float dxb_bc6h_region_error(const dxb_px* px, uint32_t mask, const float* ctr, const int32_t* qa, const int32_t* qb, int32_t prec, bool bSigned)
 {
-    const uint32_t ib = (NIDX == 8) ? 3u : 4u;
-    float pal[NIDX][3];
-    int32_t ua[3], ub[3];
-    for (int c = 0; c < 3; ++c) { ua[c] = dxb_bc6h_unquantize(qa[c], prec, bSigned); ub[c] = dxb_bc6h_unquantize(qb[c], prec, bSigned); }
-    for (int k = 0; k < NIDX; ++k)
+    const float nmax = (float)(NIDX - 1), c64 = 64.0f / nmax;
+    const float fs = bSigned ? (31.0f / 32.0f) : (31.0f / 64.0f);
+    float A[3], D[3];
+    for (int c = 0; c < 3; ++c)
     {
-        const int32_t w = (int32_t)dxb_bc7_weight(ib, (uint32_t)k);
-        for (int c = 0; c < 3; ++c) pal[k][c] = (float)dxb_bc6h_palette(ua[c], ub[c], w, bSigned);
+        A[c] = dxb_fma((float)dxb_bc6h_unquantize(qa[c], prec, bSigned), fs, -ctr[c]);
+        D[c] = dxb_fma((float)dxb_bc6h_unquantize(qb[c], prec, bSigned), fs, -ctr[c]) - A[c];
     }
+    const float dd = dxb_fma(D[0], D[0], dxb_fma(D[1], D[1], D[2] * D[2]));
+    const float idd = (dd > 0.0f) ? nmax / dd : 0.0f;
     float tot = 0.0f;
+#if DXB_ON_DEVICE
+    #pragma unroll 4
+#endif
     for (int i = 0; i < 16; ++i)
     {
-        if ((mask >> i) & 1u)
-        {
-            const dxb_px p = px[i];
-            float best = 3.0e38f;
-            for (int k = 0; k < NIDX; ++k)
-            {
-                const float dx = p.x - pal[k][0], dy = p.y - pal[k][1], dz = p.z - pal[k][2];
-                const float e = dxb_fma(dx, dx, dxb_fma(dy, dy, dz * dz));
-                best = fminf(best, e);
-            }
-            tot += best;
-        }
+        const float f = dxb_bit_as_float(mask, i);
+        const dxb_px p = px[i];
+        const float X = p.x - ctr[0] - A[0], Y = p.y - ctr[1] - A[1], Z = p.z - ctr[2] - A[2];
+        const float t = dxb_fma(X, D[0], dxb_fma(Y, D[1], Z * D[2])) * idd;
+        const float sk = dxb_bc7_weightf(dxb_rne(fminf(fmaxf(t, 0.0f), nmax)), c64);
+        const float ex = dxb_fma(-sk, D[0], X), ey = dxb_fma(-sk, D[1], Y), ez = dxb_fma(-sk, D[2], Z);
+        tot = dxb_fma(f, dxb_fma(ex, ex, dxb_fma(ey, ey, ez * ez)), tot);
     }
     return tot;
 }
 
-// +-1 code refinement of one region's quantised endpoints for modes without delta coding (mode 10 / mode 11, where a
-// code is 1/64 resp. 1/1024 of the range): alternate exact index assignment and, with indices fixed, an independent
-// 3x3 search per channel (the error is separable per channel once the indices are fixed).
+// +-1 code refinement of one region's quantised endpoints: alternate (1) index assignment by projection onto the current
+// decoded segment and (2), with the interpolation weights s_i fixed, the best of the 3x3 neighbouring code pairs per
+// channel.  With fixed weights the error of a channel is the quadratic
+//     e(A, B) = A^2 sum(1-s)^2 + 2 A B sum s(1-s) + B^2 sum s^2 - 2 A sum (1-s) v - 2 B sum s v  (+ const)
+// in the decoded endpoints A, B, so one pass over the pixels gives five sums and every candidate costs a few FMAs.
+// Decoded values are modelled in float as unquantize(code) * 31/64 (31/32 signed), i.e. without the decoder's two
+// floor operations (< 2 units of 65536); the caller re-measures the result against the exact palette.
+// Everything is centred on `ctr` to keep the fp32 sums well conditioned.
 template <int NIDX>
-DXB_DEV void dxb_bc6h_refine_region(const dxb_px* px, uint32_t mask, int32_t* qa, int32_t* qb, int32_t prec, bool bSigned)
+DXB_DEV void dxb_bc6h_refine_region(const dxb_px* px, uint32_t mask, const float* ctr, int32_t* qa, int32_t* qb, int32_t prec, bool bSigned)
 {
-    const uint32_t ib = (NIDX == 8) ? 3u : 4u;
+    const float nmax = (float)(NIDX - 1), c64 = 64.0f / nmax;
+    const float fs = bSigned ? (31.0f / 32.0f) : (31.0f / 64.0f);
     const int32_t qlo = bSigned ? -((1 << (prec - 1)) - 1) : 0, qhi = bSigned ? ((1 << (prec - 1)) - 1) : ((1 << prec) - 1);
     for (int iter = 0; iter < 2; ++iter)
     {
-        // exact nearest indices, 4 bits per pixel
-        uint64_t idxs = 0;
-        {
-            float pal[NIDX][3];
-            for (int k = 0; k < NIDX; ++k)
-            {
-                const int32_t w = (int32_t)dxb_bc7_weight(ib, (uint32_t)k);
-                for (int c = 0; c < 3; ++c)
-                    pal[k][c] = (float)dxb_bc6h_palette(dxb_bc6h_unquantize(qa[c], prec, bSigned), dxb_bc6h_unquantize(qb[c], prec, bSigned), w, bSigned);
-            }
-            for (int i = 0; i < 16; ++i)
-            {
-                const dxb_px p = px[i];
-                float best = 3.0e38f; uint32_t bk = 0;
-                for (int k = 0; k < NIDX; ++k)
-                {
-                    const float dx = p.x - pal[k][0], dy = p.y - pal[k][1], dz = p.z - pal[k][2];
-                    const float e = dxb_fma(dx, dx, dxb_fma(dy, dy, dz * dz));
-                    if (e < best) { best = e; bk = (uint32_t)k; }
-                }
-                idxs |= (uint64_t)bk << (4 * i);
-            }
-        }
+        float A[3], D[3];
         for (int c = 0; c < 3; ++c)
         {
+            A[c] = dxb_fma((float)dxb_bc6h_unquantize(qa[c], prec, bSigned), fs, -ctr[c]);
+            D[c] = dxb_fma((float)dxb_bc6h_unquantize(qb[c], prec, bSigned), fs, -ctr[c]) - A[c];
+        }
+        const float dd = dxb_fma(D[0], D[0], dxb_fma(D[1], D[1], D[2] * D[2]));
+        const float idd = (dd > 0.0f) ? nmax / dd : 0.0f;
+        float soo = 0, sos = 0, sss = 0, u0 = 0, u1 = 0, u2 = 0, v0 = 0, v1 = 0, v2 = 0;
+#if DXB_ON_DEVICE
+        #pragma unroll 4
+#endif
+        for (int i = 0; i < 16; ++i)
+        {
+            const float f = dxb_bit_as_float(mask, i);
+            const dxb_px p = px[i];
+            const float X = p.x - ctr[0], Y = p.y - ctr[1], Z = p.z - ctr[2];
+            const float t = dxb_fma(X - A[0], D[0], dxb_fma(Y - A[1], D[1], (Z - A[2]) * D[2])) * idd;
+            const float sk = dxb_bc7_weightf(dxb_rne(fminf(fmaxf(t, 0.0f), nmax)), c64);
+            const float skf = sk * f, osf = f - skf, os = 1.0f - sk;
+            soo = dxb_fma(osf, os, soo); sos = dxb_fma(osf, sk, sos); sss = dxb_fma(skf, sk, sss);
+            u0 = dxb_fma(osf, X, u0); u1 = dxb_fma(osf, Y, u1); u2 = dxb_fma(osf, Z, u2);
+            v0 = dxb_fma(skf, X, v0); v1 = dxb_fma(skf, Y, v1); v2 = dxb_fma(skf, Z, v2);
+        }
+        const float U[3] = { u0, u1, u2 }, V[3] = { v0, v1, v2 };
+        for (int c = 0; c < 3; ++c)
+        {
+            float ca[3], cb[3];                                      // decoded, centred values of the 3 neighbouring codes
+            for (int k = 0; k < 3; ++k)
+            {
+                ca[k] = dxb_fma((float)dxb_bc6h_unquantize(qa[c] + k - 1, prec, bSigned), fs, -ctr[c]);
+                cb[k] = dxb_fma((float)dxb_bc6h_unquantize(qb[c] + k - 1, prec, bSigned), fs, -ctr[c]);
+            }
             float bestE = 3.0e38f; int32_t ba = qa[c], bb = qb[c];
-            for (int da = -1; da <= 1; ++da)
-                for (int dbb = -1; dbb <= 1; ++dbb)
+            for (int da = 0; da < 3; ++da)
+                for (int dbb = 0; dbb < 3; ++dbb)
                 {
-                    const int32_t a = qa[c] + da, b = qb[c] + dbb;
-                    if (a < qlo || a > qhi || b < qlo || b > qhi) continue;
-                    const int32_t ua = dxb_bc6h_unquantize(a, prec, bSigned), ub = dxb_bc6h_unquantize(b, prec, bSigned);
-                    float e = 0.0f;
-                    for (int i = 0; i < 16; ++i)
-                    {
-                        if ((mask >> i) & 1u)
-                        {
-                            const int32_t w = (int32_t)dxb_bc7_weight(ib, (uint32_t)((idxs >> (4 * i)) & 15u));
-                            const float v = (c == 0) ? px[i].x : (c == 1) ? px[i].y : px[i].z;
-                            const float d = v - (float)dxb_bc6h_palette(ua, ub, w, bSigned);
-                            e = dxb_fma(d, d, e);
-                        }
-                    }
-                    if (e < bestE) { bestE = e; ba = a; bb = b; }
+                    const int32_t a = qa[c] + da - 1, b = qb[c] + dbb - 1;
+                    const bool ok = !(a < qlo || a > qhi || b < qlo || b > qhi);
+                    const float Av = ca[da], Bv = cb[dbb];
+                    // A (A soo + 2 B sos - 2 U) + B (B sss - 2 V)
+                    const float e = dxb_fma(Av, dxb_fma(Av, soo, dxb_fma(Bv + Bv, sos, -(U[c] + U[c]))), Bv * dxb_fma(Bv, sss, -(V[c] + V[c])));
+                    if (ok && e < bestE) { bestE = e; ba = a; bb = b; }
                 }
             qa[c] = ba; qb[c] = bb;
         }
@@ -416,8 +434,8 @@ DXB_DEV void dxb_bc6h_encode_warp(const dxb_px* spx, bool bSigned, uint8_t* out)
         // +-1 code refinement of this lane's own region
         int32_t qa[3], qb[3];
         for (int c = 0; c < 3; ++c) { qa[c] = second ? q[2][c] : q[0][c]; qb[c] = second ? q[3][c] : q[1][c]; }
-        if (one) dxb_bc6h_refine_region<16>(spx, 0xFFFFu, qa, qb, prec, bSigned);
-        else dxb_bc6h_refine_region<8>(spx, tMask[L], qa, qb, prec, bSigned);
+        if (one) dxb_bc6h_refine_region<16>(spx, 0xFFFFu, ctr, qa, qb, prec, bSigned);
+        else dxb_bc6h_refine_region<8>(spx, tMask[L], ctr, qa, qb, prec, bSigned);
         for (int c = 0; c < 3; ++c) { mine[c][L] = (uint32_t)qa[c]; mine[3 + c][L] = (uint32_t)qb[c]; }
         rMode[L] = (uint32_t)mode;
         for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) rq[L][e * 3 + c] = (uint32_t)q[e][c];
@@ -447,8 +465,8 @@ DXB_DEV void dxb_bc6h_encode_warp(const dxb_px* spx, bool bSigned, uint8_t* out)
         int32_t q[4][3];
         for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) q[e][c] = ok ? r[e][c] : (int32_t)rq[L][e * 3 + c];
         float err;
-        if (one) err = dxb_bc6h_region_error<16>(spx, 0xFFFFu, q[0], q[1], prec, bSigned);
-        else err = dxb_bc6h_region_error<8>(spx, tMask[L], second ? q[2] : q[0], second ? q[3] : q[1], prec, bSigned);
+        if (one) err = dxb_bc6h_region_error<16>(spx, 0xFFFFu, ctr, q[0], q[1], prec, bSigned);
+        else err = dxb_bc6h_region_error<8>(spx, tMask[L], ctr, second ? q[2] : q[0], second ? q[3] : q[1], prec, bSigned);
         // errors are sums of squared differences of 15-bit integers: scale into 27 bits for the integer key
         rErr[L] = (lane == 31) ? 0x07FFFFFFu : (uint32_t)dxb_f2i(fminf(err * (1.0f / 1024.0f), 6.0e7f));
         for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) rq[L][e * 3 + c] = (uint32_t)q[e][c];

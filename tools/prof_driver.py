@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs each hot-path kernel a few times on device-resident data so that `ncu` can capture it
-(profiles/README.md lists the exact ncu command lines).  Usage: python tools/prof_driver.py [bc7|bc15|rows|all] [reps]"""
+(profiles/README.md lists the exact ncu command lines).  Usage: python tools/prof_driver.py [bc7|bc6h|bc15|rows|all] [reps]"""
 import ctypes as C
 import os
 import sys
@@ -43,6 +43,14 @@ if what in ("bc7", "all"):
     s = capi.images([capi.Image(w, h, 2, *F.compute_pitch(2, w, h), d_in.data_ptr())])
     d = capi.images([capi.Image(w, h, 98, *F.compute_pitch(98, w, h), d_out.data_ptr())])
     timed("bc7 4096^2 rgba32f", lambda: capi.lib.dxb200_compress_device(s, 1, 98, 0, 0.5, 1.0, d, st), w * h)
+
+if what in ("bc6h", "all"):
+    w = h = 2048
+    d_in = dev(synth.c3_rgba16f(w, h))
+    d_out = torch.zeros(F.compute_pitch(95, w, h)[1], dtype=torch.uint8, device="cuda")
+    s = capi.images([capi.Image(w, h, 10, *F.compute_pitch(10, w, h), d_in.data_ptr())])
+    d = capi.images([capi.Image(w, h, 95, *F.compute_pitch(95, w, h), d_out.data_ptr())])
+    timed("bc6h 2048^2 rgba16f (C3)", lambda: capi.lib.dxb200_compress_device(s, 1, 95, 0, 0.5, 1.0, d, st), w * h)
 
 if what in ("bc15", "all"):
     w = h = 8192
