@@ -59,6 +59,17 @@ int32_t ensure_init_locked()
     DXB_CUDA(cudaGetDeviceProperties(&prop, g.device));
     g.numSMs = prop.multiProcessorCount;
     for (int i = 0; i < 3; ++i) DXB_CUDA(cudaStreamCreateWithFlags(&g.streams[i], cudaStreamNonBlocking));
+    {
+        // job arrays use stream-ordered allocation: keep freed blocks in the pool across synchronisation points
+        // (the default release threshold of 0 returns them to the OS, which makes the next call's cudaMallocAsync slow)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, g.device) == cudaSuccess)
+        {
+            uint64_t keep = ~uint64_t(0);
+            (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+    }
     g.gridBC15 = g.numSMs * dxb_occupancy_bc15();
     g.gridBC7 = g.numSMs * dxb_occupancy_bc7();
     g.gridBC6H = g.numSMs * dxb_occupancy_bc6h();
@@ -410,17 +421,29 @@ int32_t launch_mips(const dxb200_image* chain, size_t items, size_t levels, uint
     for (size_t l = 1; l < levels; ++l)
         if (chain[l - 1].width <= 64 && chain[l - 1].height <= 64) { tailStart = l; break; }
     const bool wantTail = (mode == DXB_FILTER_BOX || mode == DXB_FILTER_LINEAR || mode == DXB_FILTER_CUBIC) && (levels - tailStart) >= 2 && items <= 0x7FFFFFFFull;
-    if (items > 1 || wantTail)
+    const bool wantFused = (mode == DXB_FILTER_BOX) && levels >= 4;
+    if (items > 1 || wantTail || wantFused)
     {
         DXB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dAll), all.size() * sizeof(dxb_mip_job), stream));
         DXB_CUDA(cudaMemcpyAsync(dAll, all.data(), all.size() * sizeof(dxb_mip_job), cudaMemcpyHostToDevice, stream));
     }
     for (size_t l = 1; l < levels && hr == DXB_S_OK; ++l)
     {
-        if (wantTail && l == tailStart)
+        // three BOX levels per launch while the source is larger than the tail kernel's 64x64 and divides by 8
+        if (wantFused && l + 2 < levels && (chain[l - 1].width > 64 || chain[l - 1].height > 64))
         {
             P.njobs = (uint32_t)items;
-            if (dxb_launch_mip_tail(stream, dAll + (l - 1) * items, (uint32_t)items, (uint32_t)(levels - tailStart), P))
+            if (dxb_launch_mip_box3(stream, dAll + (l - 1) * items, all.data() + (l - 1) * items, (uint32_t)items, P))
+            {
+                hr = check_launch("k_mip_box3");
+                l += 2;
+                continue;
+            }
+        }
+        if (wantTail && l >= tailStart)
+        {
+            P.njobs = (uint32_t)items;
+            if (dxb_launch_mip_tail(stream, dAll + (l - 1) * items, (uint32_t)items, (uint32_t)(levels - l), P))
             {
                 hr = check_launch("k_mip_tail");
                 break;

@@ -156,22 +156,28 @@ void dxb_launch_convert(unsigned grid, cudaStream_t stream, const dxb_job* jobs,
 
 // ------------------------------------------------------------------------------------------------ tiled mips
 template <uint32_t FMT, uint32_t MODE>
-__device__ __forceinline__ dxb_px dxb_mip_eval(const dxb_mip_job& j, uint32_t x, uint32_t y, const dxb_mip_params& P)
+__device__ __forceinline__ dxb_px dxb_mip_eval(const dxb_mip_job& j, uint32_t x, uint32_t y, const dxb_mip_params& P, uint32_t lflags)
 {
-    if (MODE == DXB_FILTER_BOX) return dxb_mip_box(FMT, j, x, y, P.lflags);
-    if (MODE == DXB_FILTER_LINEAR) return dxb_mip_linear(FMT, j, x, y, P.filter, P.lflags);
-    return dxb_mip_cubic(FMT, j, x, y, P.filter, P.lflags);
+    if (MODE == DXB_FILTER_BOX) return dxb_mip_box(FMT, j, x, y, lflags);
+    if (MODE == DXB_FILTER_LINEAR) return dxb_mip_linear(FMT, j, x, y, P.filter, lflags);
+    return dxb_mip_cubic(FMT, j, x, y, P.filter, lflags);
 }
+// The sRGB <-> linear steps are a COMPILE-TIME property of the specialised kernels (SRGB = both SRGB_IN and SRGB_OUT,
+// the only combination a mip chain produces; anything else takes the generic kernel): with a run-time flag every
+// instantiation carried the inlined powf code (26.5 k SASS instructions for the fused BOX kernel) and stalled on
+// instruction fetch.
+#define DXB_LF(SRGB) ((SRGB) ? (DXB_FILTER_SRGB_IN | DXB_FILTER_SRGB_OUT) : 0u)
 
 // grid = (ceil(dw/32), ceil(dh/8), items); jobs[z] describes item z (all items share the level's size).
 // VEC: source rows are aligned for one vector load of two adjacent pixels (BOX only).
-template <uint32_t FMT, uint32_t MODE, bool VEC>
+template <uint32_t FMT, uint32_t MODE, bool VEC, bool SRGB>
 __global__ void __launch_bounds__(256) k_mip_tile(const dxb_mip_job* __restrict__ jobs, dxb_mip_job single, dxb_mip_params P)
 {
     const dxb_mip_job& j = (jobs == nullptr) ? single : jobs[blockIdx.z];
     const uint32_t x = blockIdx.x * 32u + threadIdx.x, y = blockIdx.y * 8u + threadIdx.y;
     if (x >= j.dw || y >= j.dh) return;
     dxb_px v;
+    constexpr uint32_t LF = DXB_LF(SRGB);
     constexpr int B = (int)dxb_bytes_per_pixel(FMT);
     constexpr uintptr_t VA = (B * 2 <= 16) ? B * 2 : 16;
     // VEC = every item is aligned; otherwise decide per item (uniform within the CTA: blockIdx.z selects the item)
@@ -190,20 +196,20 @@ __global__ void __launch_bounds__(256) k_mip_tile(const dxb_mip_job* __restrict_
         }
         dxb_px p00 = dxb_load_pixel(FMT, r0, 0), p01 = dxb_load_pixel(FMT, r0, 1);
         dxb_px p10 = dxb_load_pixel(FMT, r1, 0), p11 = dxb_load_pixel(FMT, r1, 1);
-        if (P.lflags & DXB_FILTER_SRGB_IN) { p00 = dxb_srgb_to_linear(p00); p01 = dxb_srgb_to_linear(p01); p10 = dxb_srgb_to_linear(p10); p11 = dxb_srgb_to_linear(p11); }
+        if (LF & DXB_FILTER_SRGB_IN) { p00 = dxb_srgb_to_linear(p00); p01 = dxb_srgb_to_linear(p01); p10 = dxb_srgb_to_linear(p10); p11 = dxb_srgb_to_linear(p11); }
         v = dxb_px_add(p00, p10);
         v = dxb_px_add(v, p01);
         v = dxb_px_add(v, p11);
         v = dxb_px_scale(v, 0.25f);
     }
-    else v = dxb_mip_eval<FMT, MODE>(j, x, y, P);
-    dxb_store_linear(FMT, j.dst, j.dstPitch, x, y, v, P.lflags);
+    else v = dxb_mip_eval<FMT, MODE>(j, x, y, P, LF);
+    dxb_store_linear(FMT, j.dst, j.dstPitch, x, y, v, LF);
 }
 
 // Tail of the chain: one CTA per item computes levels [first, first+count) back to back (each level reads the
 // previous one from global memory after a block barrier), replacing `count` tiny launches by one.
 // jobs is laid out [level][item]: jobs[l * items + item].
-template <uint32_t FMT, uint32_t MODE>
+template <uint32_t FMT, uint32_t MODE, bool SRGB>
 __global__ void __launch_bounds__(256) k_mip_tail(const dxb_mip_job* __restrict__ jobs, uint32_t items, uint32_t count, dxb_mip_params P)
 {
     for (uint32_t l = 0; l < count; ++l)
@@ -213,8 +219,8 @@ __global__ void __launch_bounds__(256) k_mip_tail(const dxb_mip_job* __restrict_
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
         {
             const uint32_t y = i / j.dw, x = i - y * j.dw;
-            const dxb_px v = dxb_mip_eval<FMT, MODE>(j, x, y, P);
-            dxb_store_linear(FMT, j.dst, j.dstPitch, x, y, v, P.lflags);
+            const dxb_px v = dxb_mip_eval<FMT, MODE>(j, x, y, P, DXB_LF(SRGB));
+            dxb_store_linear(FMT, j.dst, j.dstPitch, x, y, v, DXB_LF(SRGB));
         }
         __threadfence_block();
         __syncthreads();
@@ -240,7 +246,8 @@ static bool mip_uniform(const dxb_mip_job* hostJobs, uint32_t njobs, uint32_t bp
 void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs, const dxb_mip_job* hostJobs, const dxb_mip_params& P)
 {
     bool vec = false;
-    if (mip_uniform(hostJobs, P.njobs, dxb_bytes_per_pixel(P.format), &vec) &&
+    const bool srgb = (P.lflags == (DXB_FILTER_SRGB_IN | DXB_FILTER_SRGB_OUT));
+    if ((srgb || P.lflags == 0) && mip_uniform(hostJobs, P.njobs, dxb_bytes_per_pixel(P.format), &vec) &&
         (P.mode == DXB_FILTER_BOX || P.mode == DXB_FILTER_LINEAR || P.mode == DXB_FILTER_CUBIC))
     {
         const dim3 blk(32, 8, 1);
@@ -248,8 +255,10 @@ void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs,
         if (g.y <= 65535u)
         {
 #define DXB_X(FMT, MODE) if (P.format == FMT && P.mode == MODE) { \
-                if (vec) k_mip_tile<FMT, MODE, true><<<g, blk, 0, stream>>>(jobs, hostJobs[0], P); \
-                else k_mip_tile<FMT, MODE, false><<<g, blk, 0, stream>>>(jobs, hostJobs[0], P); \
+                if (vec && srgb) k_mip_tile<FMT, MODE, true, true><<<g, blk, 0, stream>>>(jobs, hostJobs[0], P); \
+                else if (vec) k_mip_tile<FMT, MODE, true, false><<<g, blk, 0, stream>>>(jobs, hostJobs[0], P); \
+                else if (srgb) k_mip_tile<FMT, MODE, false, true><<<g, blk, 0, stream>>>(jobs, hostJobs[0], P); \
+                else k_mip_tile<FMT, MODE, false, false><<<g, blk, 0, stream>>>(jobs, hostJobs[0], P); \
                 return; }
             DXB_MIP_FORMATS(DXB_X, DXB_FILTER_BOX)
             DXB_MIP_FORMATS(DXB_X, DXB_FILTER_LINEAR)
@@ -260,10 +269,116 @@ void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs,
     k_mip_level<<<grid, 256, 0, stream>>>(jobs, hostJobs[0], P);
 }
 
+// ------------------------------------------------------------------------------------------------ fused BOX levels
+// Three consecutive BOX levels in one pass: a thread owns an 8x8 source patch, writes the 4x4 / 2x2 / 1 destination
+// pixels of levels l, l+1, l+2.  Each level is computed from the STORED representation of the previous one (pixels are
+// encoded to the format and decoded again in registers), exactly what three separate launches read back from memory,
+// so the result is bit-identical; the source is read once and the two intermediate levels are never re-read from HBM
+// (5.6 instead of 7.0 bytes moved per source texel-chain, one launch instead of three).
+// jobs: [level][item] records of the three levels; requires source width/height multiples of 8 and vector alignment.
+template <int N> __device__ __forceinline__ void dxb_copy_vec(uint8_t* dst, const uint8_t* src, bool streamLoad)
+{
+    constexpr int V = (N >= 16) ? 16 : N;
+    #pragma unroll
+    for (int k = 0; k < N; k += V)
+    {
+        typedef typename dxb_vec<V>::T T;
+        if (streamLoad) *reinterpret_cast<T*>(dst + k) = __ldcs(reinterpret_cast<const T*>(src + k));
+        else *reinterpret_cast<T*>(dst + k) = *reinterpret_cast<const T*>(src + k);
+    }
+}
+template <uint32_t FMT>
+__device__ __forceinline__ dxb_px dxb_box4(const uint8_t* r0, const uint8_t* r1, int k, uint32_t lflags)
+{
+    dxb_px p00 = dxb_load_pixel(FMT, r0, 2 * k), p01 = dxb_load_pixel(FMT, r0, 2 * k + 1);
+    dxb_px p10 = dxb_load_pixel(FMT, r1, 2 * k), p11 = dxb_load_pixel(FMT, r1, 2 * k + 1);
+    if (lflags & DXB_FILTER_SRGB_IN) { p00 = dxb_srgb_to_linear(p00); p01 = dxb_srgb_to_linear(p01); p10 = dxb_srgb_to_linear(p10); p11 = dxb_srgb_to_linear(p11); }
+    dxb_px v = dxb_px_add(p00, p10);
+    v = dxb_px_add(v, p01);
+    v = dxb_px_add(v, p11);
+    v = dxb_px_scale(v, 0.25f);
+    if (lflags & DXB_FILTER_SRGB_OUT) v = dxb_linear_to_srgb(v);
+    return v;
+}
+template <uint32_t FMT, bool SRGB>
+__global__ void __launch_bounds__(256) k_mip_box3(const dxb_mip_job* __restrict__ jobs, uint32_t items, dxb_mip_params P)
+{
+    constexpr int B = (int)dxb_bytes_per_pixel(FMT);
+    const uint32_t item = blockIdx.z;
+    const dxb_mip_job& jA = jobs[item];
+    const dxb_mip_job& jB = jobs[(size_t)items + item];
+    const dxb_mip_job& jC = jobs[2 * (size_t)items + item];
+    const uint32_t tx = blockIdx.x * 32u + threadIdx.x, ty = blockIdx.y * 8u + threadIdx.y;
+    if (tx >= jC.dw || ty >= jC.dh) return;
+    // all source rows of a group are loaded before the first store of that group (bytes in flight per thread =
+    // PRE rows x 8 pixels; 8 rows for <= 4-byte pixels, 4 for 8-byte, 2 for 16-byte keeps it at <= 64 registers)
+    constexpr int PRE = (B <= 4) ? 8 : (B == 8 ? 4 : 2);
+    const uint8_t* sbase = jA.src + (size_t)(8u * ty) * jA.srcPitch + (size_t)(8u * tx) * B;
+    __align__(16) uint8_t rowB[2][2 * B];
+    __align__(16) uint8_t rowA[2][4 * B];
+    #pragma unroll
+    for (int grp = 0; grp < 8 / PRE; ++grp)
+    {
+        __align__(16) uint8_t s[PRE][8 * B];
+        #pragma unroll
+        for (int k = 0; k < PRE; ++k) dxb_copy_vec<8 * B>(s[k], sbase + (size_t)(grp * PRE + k) * jA.srcPitch, true);
+        #pragma unroll
+        for (int pr = 0; pr < PRE / 2; ++pr)
+        {
+            const int arow = grp * (PRE / 2) + pr;                   // level-A row 0..3 of this thread
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) dxb_store_pixel(FMT, rowA[arow & 1], k, dxb_box4<FMT>(s[2 * pr], s[2 * pr + 1], k, DXB_LF(SRGB)));
+            dxb_copy_vec<4 * B>(jA.dst + (size_t)(4u * ty + arow) * jA.dstPitch + (size_t)(4u * tx) * B, rowA[arow & 1], false);
+            if (arow & 1)
+            {
+                const int half = arow >> 1;
+                #pragma unroll
+                for (int k = 0; k < 2; ++k) dxb_store_pixel(FMT, rowB[half], k, dxb_box4<FMT>(rowA[0], rowA[1], k, DXB_LF(SRGB)));
+                dxb_copy_vec<2 * B>(jB.dst + (size_t)(2u * ty + half) * jB.dstPitch + (size_t)(2u * tx) * B, rowB[half], false);
+            }
+        }
+    }
+    __align__(16) uint8_t pc[B];
+    dxb_store_pixel(FMT, pc, 0, dxb_box4<FMT>(rowB[0], rowB[1], 0, DXB_LF(SRGB)));
+    dxb_copy_vec<B>(jC.dst + (size_t)ty * jC.dstPitch + (size_t)tx * B, pc, false);
+}
+
+// hostJobs: [3][items] records of levels l, l+1, l+2.  Returns false when the fused kernel does not apply.
+bool dxb_launch_mip_box3(cudaStream_t stream, const dxb_mip_job* jobsDev, const dxb_mip_job* hostJobs, uint32_t items, const dxb_mip_params& P)
+{
+    if (P.mode != DXB_FILTER_BOX || items == 0 || items > 65535u || jobsDev == nullptr) return false;
+    const bool srgb = (P.lflags == (DXB_FILTER_SRGB_IN | DXB_FILTER_SRGB_OUT));
+    if (!srgb && P.lflags != 0) return false;
+    const uint32_t B = dxb_bytes_per_pixel(P.format);
+    const dxb_mip_job& a0 = hostJobs[0];
+    if (B == 0 || (a0.sw & 7u) || (a0.sh & 7u) || a0.sw < 8u || a0.sh < 8u) return false;
+    auto al = [](const void* p, size_t pitch, uint32_t bytes) { const uint32_t v = bytes >= 16 ? 16 : bytes; return ((uintptr_t)p % v) == 0 && (pitch % v) == 0; };
+    for (uint32_t i = 0; i < items; ++i)
+    {
+        const dxb_mip_job& a = hostJobs[i]; const dxb_mip_job& b = hostJobs[items + i]; const dxb_mip_job& c = hostJobs[2 * (size_t)items + i];
+        if (a.sw != a0.sw || a.sh != a0.sh || a.dw != a.sw / 2 || a.dh != a.sh / 2 || b.dw != a.sw / 4 || b.dh != a.sh / 4 || c.dw != a.sw / 8 || c.dh != a.sh / 8) return false;
+        if (b.src != a.dst || c.src != b.dst || b.srcPitch != a.dstPitch || c.srcPitch != b.dstPitch) return false;
+        if (!al(a.src, a.srcPitch, 8 * B) || !al(a.dst, a.dstPitch, 4 * B) || !al(b.dst, b.dstPitch, 2 * B) || !al(c.dst, c.dstPitch, B)) return false;
+    }
+    const dim3 blk(32, 8, 1);
+    const dim3 g((a0.sw / 8 + 31) / 32, (a0.sh / 8 + 7) / 8, items);
+    if (g.y > 65535u) return false;
+#define DXB_X(FMT, MODE) if (P.format == FMT) { \
+        if (srgb) k_mip_box3<FMT, true><<<g, blk, 0, stream>>>(jobsDev, items, P); else k_mip_box3<FMT, false><<<g, blk, 0, stream>>>(jobsDev, items, P); \
+        return true; }
+    DXB_MIP_FORMATS(DXB_X, 0)
+#undef DXB_X
+    return false;
+}
+
 // levels [first, first+count) of every item in ONE launch; returns false when the format/filter has no tail kernel
 bool dxb_launch_mip_tail(cudaStream_t stream, const dxb_mip_job* jobsDev, uint32_t items, uint32_t count, const dxb_mip_params& P)
 {
-#define DXB_X(FMT, MODE) if (P.format == FMT && P.mode == MODE) { k_mip_tail<FMT, MODE><<<items, 256, 0, stream>>>(jobsDev, items, count, P); return true; }
+    const bool srgb = (P.lflags == (DXB_FILTER_SRGB_IN | DXB_FILTER_SRGB_OUT));
+    if (!srgb && P.lflags != 0) return false;
+#define DXB_X(FMT, MODE) if (P.format == FMT && P.mode == MODE) { \
+        if (srgb) k_mip_tail<FMT, MODE, true><<<items, 256, 0, stream>>>(jobsDev, items, count, P); else k_mip_tail<FMT, MODE, false><<<items, 256, 0, stream>>>(jobsDev, items, count, P); \
+        return true; }
     DXB_MIP_FORMATS(DXB_X, DXB_FILTER_BOX)
     DXB_MIP_FORMATS(DXB_X, DXB_FILTER_LINEAR)
     DXB_MIP_FORMATS(DXB_X, DXB_FILTER_CUBIC)

@@ -25,7 +25,7 @@ DXB_DEV float dxb_div_small(float a, float b)
     return dxb_fma(r, rcp, q);
 }
 
-DXB_DEV float dxb_snorm_load(int32_t v, float rcp) { return dxb_ssemax((float)v * rcp, -1.0f); }
+DXB_DEV float dxb_snorm_load(int32_t v, float rcp) { return dxb_ssemax(dxb_i2f_small((int32_t)v) * rcp, -1.0f); }
 DXB_DEV float dxb_clamp(float v, float lo, float hi) { return dxb_ssemin(dxb_ssemax(v, lo), hi); }
 
 // ---------------------------------------------------------------------------------------------
@@ -53,7 +53,7 @@ DXB_DEV dxb_px dxb_load_pixel(uint32_t fmt, const uint8_t* row, size_t i)
     {
         const uint16_t* p = (const uint16_t*)row + i * 4;
         const float s = 1.0f / 65535.0f;
-        return dxb_make_px((float)p[0] * s, (float)p[1] * s, (float)p[2] * s, (float)p[3] * s);
+        return dxb_make_px(dxb_i2f_small((int32_t)p[0]) * s, dxb_i2f_small((int32_t)p[1]) * s, dxb_i2f_small((int32_t)p[2]) * s, dxb_i2f_small((int32_t)p[3]) * s);
     }
     case DXB_FMT_R16G16B16A16_SNORM:
     {
@@ -70,28 +70,28 @@ DXB_DEV dxb_px dxb_load_pixel(uint32_t fmt, const uint8_t* row, size_t i)
     {
         const uint32_t v = ((const uint32_t*)row)[i];
         const float s = 1.0f / 1023.0f;
-        return dxb_make_px((float)(v & 0x3FF) * s, (float)((v >> 10) & 0x3FF) * s, (float)((v >> 20) & 0x3FF) * s, (float)(v >> 30) * (1.0f / 3.0f));
+        return dxb_make_px(dxb_i2f_small((int32_t)(v & 0x3FF)) * s, dxb_i2f_small((int32_t)((v >> 10) & 0x3FF)) * s, dxb_i2f_small((int32_t)((v >> 20) & 0x3FF)) * s, dxb_i2f_small((int32_t)(v >> 30)) * (1.0f / 3.0f));
     }
     case DXB_FMT_R8G8B8A8_UNORM:
     case DXB_FMT_R8G8B8A8_UNORM_SRGB:
     {
         const uint32_t v = ((const uint32_t*)row)[i];
         const float s = 1.0f / 255.0f;
-        return dxb_make_px((float)(v & 0xFF) * s, (float)((v >> 8) & 0xFF) * s, (float)((v >> 16) & 0xFF) * s, (float)(v >> 24) * s);
+        return dxb_make_px(dxb_i2f_small((int32_t)(v & 0xFF)) * s, dxb_i2f_small((int32_t)((v >> 8) & 0xFF)) * s, dxb_i2f_small((int32_t)((v >> 16) & 0xFF)) * s, dxb_i2f_small((int32_t)(v >> 24)) * s);
     }
     case DXB_FMT_B8G8R8A8_UNORM:
     case DXB_FMT_B8G8R8A8_UNORM_SRGB:
     {
         const uint32_t v = ((const uint32_t*)row)[i];
         const float s = 1.0f / 255.0f;
-        return dxb_make_px((float)((v >> 16) & 0xFF) * s, (float)((v >> 8) & 0xFF) * s, (float)(v & 0xFF) * s, (float)(v >> 24) * s);
+        return dxb_make_px(dxb_i2f_small((int32_t)((v >> 16) & 0xFF)) * s, dxb_i2f_small((int32_t)((v >> 8) & 0xFF)) * s, dxb_i2f_small((int32_t)(v & 0xFF)) * s, dxb_i2f_small((int32_t)(v >> 24)) * s);
     }
     case DXB_FMT_B8G8R8X8_UNORM:
     case DXB_FMT_B8G8R8X8_UNORM_SRGB:
     {
         const uint32_t v = ((const uint32_t*)row)[i];
         const float s = 1.0f / 255.0f;
-        return dxb_make_px((float)((v >> 16) & 0xFF) * s, (float)((v >> 8) & 0xFF) * s, (float)(v & 0xFF) * s, 1.0f);
+        return dxb_make_px(dxb_i2f_small((int32_t)((v >> 16) & 0xFF)) * s, dxb_i2f_small((int32_t)((v >> 8) & 0xFF)) * s, dxb_i2f_small((int32_t)(v & 0xFF)) * s, 1.0f);
     }
     case DXB_FMT_R8G8B8A8_SNORM:
     {
@@ -108,7 +108,7 @@ DXB_DEV dxb_px dxb_load_pixel(uint32_t fmt, const uint8_t* row, size_t i)
     {
         const uint16_t* p = (const uint16_t*)row + i * 2;
         const float s = 1.0f / 65535.0f;
-        return dxb_make_px((float)p[0] * s, (float)p[1] * s, 0.0f, 1.0f);
+        return dxb_make_px(dxb_i2f_small((int32_t)p[0]) * s, dxb_i2f_small((int32_t)p[1]) * s, 0.0f, 1.0f);
     }
     case DXB_FMT_R16G16_SNORM:
     {
@@ -122,7 +122,7 @@ DXB_DEV dxb_px dxb_load_pixel(uint32_t fmt, const uint8_t* row, size_t i)
     {
         const uint8_t* p = row + i * 2;
         const float s = 1.0f / 255.0f;
-        return dxb_make_px((float)p[0] * s, (float)p[1] * s, 0.0f, 1.0f);
+        return dxb_make_px(dxb_i2f_small((int32_t)p[0]) * s, dxb_i2f_small((int32_t)p[1]) * s, 0.0f, 1.0f);
     }
     case DXB_FMT_R8G8_SNORM:
     {
@@ -133,15 +133,15 @@ DXB_DEV dxb_px dxb_load_pixel(uint32_t fmt, const uint8_t* row, size_t i)
     case DXB_FMT_R16_FLOAT:
         return dxb_make_px(dxb_half_to_float(((const uint16_t*)row)[i]), 0.0f, 0.0f, 1.0f);
     case DXB_FMT_R16_UNORM:      // true division: DirectXTexConvert.cpp:1062
-        return dxb_make_px(dxb_div_small((float)((const uint16_t*)row)[i], 65535.0f), 0.0f, 0.0f, 1.0f);
+        return dxb_make_px(dxb_div_small(dxb_i2f_small((int32_t)((const uint16_t*)row)[i]), 65535.0f), 0.0f, 0.0f, 1.0f);
     case DXB_FMT_R16_SNORM:      // :1088 (no clamp of -32768)
-        return dxb_make_px(dxb_div_small((float)((const int16_t*)row)[i], 32767.0f), 0.0f, 0.0f, 1.0f);
+        return dxb_make_px(dxb_div_small(dxb_i2f_small((int32_t)((const int16_t*)row)[i]), 32767.0f), 0.0f, 0.0f, 1.0f);
     case DXB_FMT_R8_UNORM:       // :1113
-        return dxb_make_px(dxb_div_small((float)row[i], 255.0f), 0.0f, 0.0f, 1.0f);
+        return dxb_make_px(dxb_div_small(dxb_i2f_small((int32_t)row[i]), 255.0f), 0.0f, 0.0f, 1.0f);
     case DXB_FMT_R8_SNORM:       // :1139
-        return dxb_make_px(dxb_div_small((float)((const int8_t*)row)[i], 127.0f), 0.0f, 0.0f, 1.0f);
+        return dxb_make_px(dxb_div_small(dxb_i2f_small((int32_t)((const int8_t*)row)[i]), 127.0f), 0.0f, 0.0f, 1.0f);
     case DXB_FMT_A8_UNORM:       // :1165
-        return dxb_make_px(0.0f, 0.0f, 0.0f, dxb_div_small((float)row[i], 255.0f));
+        return dxb_make_px(0.0f, 0.0f, 0.0f, dxb_div_small(dxb_i2f_small((int32_t)row[i]), 255.0f));
     default:
         return dxb_make_px(0.0f, 0.0f, 0.0f, 1.0f);
     }
@@ -302,14 +302,14 @@ DXB_DEV dxb_px dxb_convert_pixel(dxb_px v, uint32_t inF, uint32_t outF, uint32_t
 DXB_DEV uint32_t dxb_unorm8_trunc(float v)       // +0.5/255 bias, saturate, *255, truncate
 {
     const float b = v + (0.5f / 255.0f);
-    return (uint32_t)dxb_f2i(dxb_clamp(b, 0.0f, 1.0f) * 255.0f);
+    return dxb_f2u_trunc_small(dxb_clamp(b, 0.0f, 1.0f) * 255.0f);
 }
 DXB_DEV uint32_t dxb_unorm8_scalar(float v)      // scalar R8/A8 path: std::max(std::min(v,1),0)
 {
     float b = v + (0.5f / 255.0f);
     b = (1.0f < b) ? 1.0f : b;
     b = (b < 0.0f) ? 0.0f : b;
-    return (uint32_t)dxb_f2i(b * 255.0f);
+    return dxb_f2u_trunc_small(fmaxf(b, 0.0f) * 255.0f);      // fmaxf also maps NaN to 0 like the cast did
 }
 DXB_DEV float dxb_stdclamp(float v, float lo, float hi)   // std::max(std::min(v, hi), lo)
 {
@@ -341,15 +341,15 @@ DXB_DEV void dxb_store_pixel(uint32_t fmt, uint8_t* row, size_t i, dxb_px v)
     case DXB_FMT_R16G16B16A16_UNORM:
     {
         uint16_t* p = (uint16_t*)row + i * 4;
-        p[0] = (uint16_t)dxb_f2i_rn(dxb_clamp(v.x, 0.0f, 1.0f) * 65535.0f); p[1] = (uint16_t)dxb_f2i_rn(dxb_clamp(v.y, 0.0f, 1.0f) * 65535.0f);
-        p[2] = (uint16_t)dxb_f2i_rn(dxb_clamp(v.z, 0.0f, 1.0f) * 65535.0f); p[3] = (uint16_t)dxb_f2i_rn(dxb_clamp(v.w, 0.0f, 1.0f) * 65535.0f);
+        p[0] = (uint16_t)dxb_f2i_rn_small(dxb_clamp(v.x, 0.0f, 1.0f) * 65535.0f); p[1] = (uint16_t)dxb_f2i_rn_small(dxb_clamp(v.y, 0.0f, 1.0f) * 65535.0f);
+        p[2] = (uint16_t)dxb_f2i_rn_small(dxb_clamp(v.z, 0.0f, 1.0f) * 65535.0f); p[3] = (uint16_t)dxb_f2i_rn_small(dxb_clamp(v.w, 0.0f, 1.0f) * 65535.0f);
         return;
     }
     case DXB_FMT_R16G16B16A16_SNORM:
     {
         int16_t* p = (int16_t*)row + i * 4;
-        p[0] = (int16_t)dxb_f2i_rn(dxb_clamp(v.x, -1.0f, 1.0f) * 32767.0f); p[1] = (int16_t)dxb_f2i_rn(dxb_clamp(v.y, -1.0f, 1.0f) * 32767.0f);
-        p[2] = (int16_t)dxb_f2i_rn(dxb_clamp(v.z, -1.0f, 1.0f) * 32767.0f); p[3] = (int16_t)dxb_f2i_rn(dxb_clamp(v.w, -1.0f, 1.0f) * 32767.0f);
+        p[0] = (int16_t)dxb_f2i_rn_small(dxb_clamp(v.x, -1.0f, 1.0f) * 32767.0f); p[1] = (int16_t)dxb_f2i_rn_small(dxb_clamp(v.y, -1.0f, 1.0f) * 32767.0f);
+        p[2] = (int16_t)dxb_f2i_rn_small(dxb_clamp(v.z, -1.0f, 1.0f) * 32767.0f); p[3] = (int16_t)dxb_f2i_rn_small(dxb_clamp(v.w, -1.0f, 1.0f) * 32767.0f);
         return;
     }
     case DXB_FMT_R32G32_FLOAT:
@@ -358,8 +358,8 @@ DXB_DEV void dxb_store_pixel(uint32_t fmt, uint8_t* row, size_t i, dxb_px v)
     }
     case DXB_FMT_R10G10B10A2_UNORM:
     {
-        const uint32_t x = (uint32_t)dxb_f2i(dxb_clamp(v.x, 0.0f, 1.0f) * 1023.0f), y = (uint32_t)dxb_f2i(dxb_clamp(v.y, 0.0f, 1.0f) * 1023.0f);
-        const uint32_t z = (uint32_t)dxb_f2i(dxb_clamp(v.z, 0.0f, 1.0f) * 1023.0f), w = (uint32_t)dxb_f2i(dxb_clamp(v.w, 0.0f, 1.0f) * 3.0f);
+        const uint32_t x = dxb_f2u_trunc_small(dxb_clamp(v.x, 0.0f, 1.0f) * 1023.0f), y = dxb_f2u_trunc_small(dxb_clamp(v.y, 0.0f, 1.0f) * 1023.0f);
+        const uint32_t z = dxb_f2u_trunc_small(dxb_clamp(v.z, 0.0f, 1.0f) * 1023.0f), w = dxb_f2u_trunc_small(dxb_clamp(v.w, 0.0f, 1.0f) * 3.0f);
         ((uint32_t*)row)[i] = (w << 30) | ((z & 0x3FF) << 20) | ((y & 0x3FF) << 10) | (x & 0x3FF);
         return;
     }
@@ -378,8 +378,8 @@ DXB_DEV void dxb_store_pixel(uint32_t fmt, uint8_t* row, size_t i, dxb_px v)
     case DXB_FMT_R8G8B8A8_SNORM:
     {
         int8_t* p = (int8_t*)row + i * 4;
-        p[0] = (int8_t)dxb_f2i_rn(dxb_clamp(v.x, -1.0f, 1.0f) * 127.0f); p[1] = (int8_t)dxb_f2i_rn(dxb_clamp(v.y, -1.0f, 1.0f) * 127.0f);
-        p[2] = (int8_t)dxb_f2i_rn(dxb_clamp(v.z, -1.0f, 1.0f) * 127.0f); p[3] = (int8_t)dxb_f2i_rn(dxb_clamp(v.w, -1.0f, 1.0f) * 127.0f);
+        p[0] = (int8_t)dxb_f2i_rn_small(dxb_clamp(v.x, -1.0f, 1.0f) * 127.0f); p[1] = (int8_t)dxb_f2i_rn_small(dxb_clamp(v.y, -1.0f, 1.0f) * 127.0f);
+        p[2] = (int8_t)dxb_f2i_rn_small(dxb_clamp(v.z, -1.0f, 1.0f) * 127.0f); p[3] = (int8_t)dxb_f2i_rn_small(dxb_clamp(v.w, -1.0f, 1.0f) * 127.0f);
         return;
     }
     case DXB_FMT_R16G16_FLOAT:
@@ -391,13 +391,13 @@ DXB_DEV void dxb_store_pixel(uint32_t fmt, uint8_t* row, size_t i, dxb_px v)
     case DXB_FMT_R16G16_UNORM:
     {
         uint16_t* p = (uint16_t*)row + i * 2;
-        p[0] = (uint16_t)dxb_f2i_rn(dxb_clamp(v.x, 0.0f, 1.0f) * 65535.0f); p[1] = (uint16_t)dxb_f2i_rn(dxb_clamp(v.y, 0.0f, 1.0f) * 65535.0f);
+        p[0] = (uint16_t)dxb_f2i_rn_small(dxb_clamp(v.x, 0.0f, 1.0f) * 65535.0f); p[1] = (uint16_t)dxb_f2i_rn_small(dxb_clamp(v.y, 0.0f, 1.0f) * 65535.0f);
         return;
     }
     case DXB_FMT_R16G16_SNORM:
     {
         int16_t* p = (int16_t*)row + i * 2;
-        p[0] = (int16_t)dxb_f2i_rn(dxb_clamp(v.x, -1.0f, 1.0f) * 32767.0f); p[1] = (int16_t)dxb_f2i_rn(dxb_clamp(v.y, -1.0f, 1.0f) * 32767.0f);
+        p[0] = (int16_t)dxb_f2i_rn_small(dxb_clamp(v.x, -1.0f, 1.0f) * 32767.0f); p[1] = (int16_t)dxb_f2i_rn_small(dxb_clamp(v.y, -1.0f, 1.0f) * 32767.0f);
         return;
     }
     case DXB_FMT_R32_FLOAT:
@@ -405,13 +405,13 @@ DXB_DEV void dxb_store_pixel(uint32_t fmt, uint8_t* row, size_t i, dxb_px v)
     case DXB_FMT_R8G8_UNORM:
     {
         uint8_t* p = row + i * 2;
-        p[0] = (uint8_t)dxb_f2i_rn(dxb_clamp(v.x, 0.0f, 1.0f) * 255.0f); p[1] = (uint8_t)dxb_f2i_rn(dxb_clamp(v.y, 0.0f, 1.0f) * 255.0f);
+        p[0] = (uint8_t)dxb_f2i_rn_small(dxb_clamp(v.x, 0.0f, 1.0f) * 255.0f); p[1] = (uint8_t)dxb_f2i_rn_small(dxb_clamp(v.y, 0.0f, 1.0f) * 255.0f);
         return;
     }
     case DXB_FMT_R8G8_SNORM:
     {
         int8_t* p = (int8_t*)row + i * 2;
-        p[0] = (int8_t)dxb_f2i_rn(dxb_clamp(v.x, -1.0f, 1.0f) * 127.0f); p[1] = (int8_t)dxb_f2i_rn(dxb_clamp(v.y, -1.0f, 1.0f) * 127.0f);
+        p[0] = (int8_t)dxb_f2i_rn_small(dxb_clamp(v.x, -1.0f, 1.0f) * 127.0f); p[1] = (int8_t)dxb_f2i_rn_small(dxb_clamp(v.y, -1.0f, 1.0f) * 127.0f);
         return;
     }
     case DXB_FMT_R16_FLOAT:

@@ -41,6 +41,36 @@ DXB_DEV uint32_t dxb_f2u(float f)
 #endif
 }
 // round to nearest even (cvtps_epi32 / nearbyintf)
+// Exact int <-> float conversions of SMALL values on the full-rate FP32/INT pipes instead of the quarter-rate
+// conversion unit (I2F / F2I); the 8/10/16-bit pixel loads and stores of the HBM-bound row kernels were XU-bound.
+//   dxb_i2f_small: |n| < 2^22      (1.5*2^23 + n is exact, so is the subtraction)
+//   dxb_f2u_trunc_small: 0 <= f < 2^23, truncation: 2^23 + f rounded toward zero has floor(f) in its mantissa
+//   dxb_f2i_rn_small: |f| < 2^22, round to nearest even (the magic-number add)
+// The host build keeps the plain casts, which give the same values.
+DXB_DEV float dxb_i2f_small(int32_t n)
+{
+#if DXB_ON_DEVICE
+    return __int_as_float(0x4B400000 + n) - 12582912.0f;
+#else
+    return (float)n;
+#endif
+}
+DXB_DEV uint32_t dxb_f2u_trunc_small(float f)
+{
+#if DXB_ON_DEVICE
+    return __float_as_uint(__fadd_rz(f, 8388608.0f)) & 0x7FFFFFu;
+#else
+    return (uint32_t)(int32_t)f;
+#endif
+}
+DXB_DEV int32_t dxb_f2i_rn_small(float f)
+{
+#if DXB_ON_DEVICE
+    return __float_as_int(f + 12582912.0f) - 0x4B400000;
+#else
+    return (int32_t)nearbyintf(f);
+#endif
+}
 DXB_DEV int32_t dxb_f2i_rn(float f)
 {
 #if DXB_ON_DEVICE
