@@ -77,21 +77,21 @@ DXB_DEV dxb_px dxb_load_pixel(uint32_t fmt, const uint8_t* row, size_t i)
     {
         const uint32_t v = ((const uint32_t*)row)[i];
         const float s = 1.0f / 255.0f;
-        return dxb_make_px(dxb_i2f_small((int32_t)(v & 0xFF)) * s, dxb_i2f_small((int32_t)((v >> 8) & 0xFF)) * s, dxb_i2f_small((int32_t)((v >> 16) & 0xFF)) * s, dxb_i2f_small((int32_t)(v >> 24)) * s);
+        return dxb_make_px(dxb_byte_to_float(v, 0) * s, dxb_byte_to_float(v, 1) * s, dxb_byte_to_float(v, 2) * s, dxb_byte_to_float(v, 3) * s);
     }
     case DXB_FMT_B8G8R8A8_UNORM:
     case DXB_FMT_B8G8R8A8_UNORM_SRGB:
     {
         const uint32_t v = ((const uint32_t*)row)[i];
         const float s = 1.0f / 255.0f;
-        return dxb_make_px(dxb_i2f_small((int32_t)((v >> 16) & 0xFF)) * s, dxb_i2f_small((int32_t)((v >> 8) & 0xFF)) * s, dxb_i2f_small((int32_t)(v & 0xFF)) * s, dxb_i2f_small((int32_t)(v >> 24)) * s);
+        return dxb_make_px(dxb_byte_to_float(v, 2) * s, dxb_byte_to_float(v, 1) * s, dxb_byte_to_float(v, 0) * s, dxb_byte_to_float(v, 3) * s);
     }
     case DXB_FMT_B8G8R8X8_UNORM:
     case DXB_FMT_B8G8R8X8_UNORM_SRGB:
     {
         const uint32_t v = ((const uint32_t*)row)[i];
         const float s = 1.0f / 255.0f;
-        return dxb_make_px(dxb_i2f_small((int32_t)((v >> 16) & 0xFF)) * s, dxb_i2f_small((int32_t)((v >> 8) & 0xFF)) * s, dxb_i2f_small((int32_t)(v & 0xFF)) * s, 1.0f);
+        return dxb_make_px(dxb_byte_to_float(v, 2) * s, dxb_byte_to_float(v, 1) * s, dxb_byte_to_float(v, 0) * s, 1.0f);
     }
     case DXB_FMT_R8G8B8A8_SNORM:
     {
@@ -304,6 +304,20 @@ DXB_DEV uint32_t dxb_unorm8_trunc(float v)       // +0.5/255 bias, saturate, *25
     const float b = v + (0.5f / 255.0f);
     return dxb_f2u_trunc_small(dxb_clamp(b, 0.0f, 1.0f) * 255.0f);
 }
+// four channels stored with dxb_unorm8_trunc semantics, packed b0 | b1 << 8 | b2 << 16 | b3 << 24
+DXB_DEV uint32_t dxb_pack_unorm8x4(float b0, float b1, float b2, float b3)
+{
+#if DXB_ON_DEVICE
+    // 2^23 + x rounded toward zero keeps floor(x) (<= 255) in the low mantissa byte: three PRMTs gather the four bytes
+    const uint32_t u0 = __float_as_uint(__fadd_rz(dxb_clamp(b0 + (0.5f / 255.0f), 0.0f, 1.0f) * 255.0f, 8388608.0f));
+    const uint32_t u1 = __float_as_uint(__fadd_rz(dxb_clamp(b1 + (0.5f / 255.0f), 0.0f, 1.0f) * 255.0f, 8388608.0f));
+    const uint32_t u2 = __float_as_uint(__fadd_rz(dxb_clamp(b2 + (0.5f / 255.0f), 0.0f, 1.0f) * 255.0f, 8388608.0f));
+    const uint32_t u3 = __float_as_uint(__fadd_rz(dxb_clamp(b3 + (0.5f / 255.0f), 0.0f, 1.0f) * 255.0f, 8388608.0f));
+    return __byte_perm(__byte_perm(u0, u1, 0x0040), __byte_perm(u2, u3, 0x0040), 0x5410);
+#else
+    return dxb_unorm8_trunc(b0) | (dxb_unorm8_trunc(b1) << 8) | (dxb_unorm8_trunc(b2) << 16) | (dxb_unorm8_trunc(b3) << 24);
+#endif
+}
 DXB_DEV uint32_t dxb_unorm8_scalar(float v)      // scalar R8/A8 path: std::max(std::min(v,1),0)
 {
     float b = v + (0.5f / 255.0f);
@@ -365,15 +379,15 @@ DXB_DEV void dxb_store_pixel(uint32_t fmt, uint8_t* row, size_t i, dxb_px v)
     }
     case DXB_FMT_R8G8B8A8_UNORM:
     case DXB_FMT_R8G8B8A8_UNORM_SRGB:
-        ((uint32_t*)row)[i] = dxb_unorm8_trunc(v.x) | (dxb_unorm8_trunc(v.y) << 8) | (dxb_unorm8_trunc(v.z) << 16) | (dxb_unorm8_trunc(v.w) << 24);
+        ((uint32_t*)row)[i] = dxb_pack_unorm8x4(v.x, v.y, v.z, v.w);
         return;
     case DXB_FMT_B8G8R8A8_UNORM:
     case DXB_FMT_B8G8R8A8_UNORM_SRGB:
-        ((uint32_t*)row)[i] = dxb_unorm8_trunc(v.z) | (dxb_unorm8_trunc(v.y) << 8) | (dxb_unorm8_trunc(v.x) << 16) | (dxb_unorm8_trunc(v.w) << 24);
+        ((uint32_t*)row)[i] = dxb_pack_unorm8x4(v.z, v.y, v.x, v.w);
         return;
     case DXB_FMT_B8G8R8X8_UNORM:
     case DXB_FMT_B8G8R8X8_UNORM_SRGB:
-        ((uint32_t*)row)[i] = dxb_unorm8_trunc(v.z) | (dxb_unorm8_trunc(v.y) << 8) | (dxb_unorm8_trunc(v.x) << 16) | (dxb_unorm8_trunc(1.0f) << 24);
+        ((uint32_t*)row)[i] = dxb_pack_unorm8x4(v.z, v.y, v.x, 1.0f);
         return;
     case DXB_FMT_R8G8B8A8_SNORM:
     {

@@ -55,6 +55,15 @@ DXB_DEV float dxb_i2f_small(int32_t n)
     return (float)n;
 #endif
 }
+// byte k (0..3) of a 32-bit word as float: one PRMT drops the byte into the mantissa of 1.5*2^23
+DXB_DEV float dxb_byte_to_float(uint32_t v, uint32_t k)
+{
+#if DXB_ON_DEVICE
+    return __uint_as_float(__byte_perm(v, 0x4B400000u, 0x7650u + k)) - 12582912.0f;
+#else
+    return (float)((v >> (8u * k)) & 0xFFu);
+#endif
+}
 DXB_DEV uint32_t dxb_f2u_trunc_small(float f)
 {
 #if DXB_ON_DEVICE
