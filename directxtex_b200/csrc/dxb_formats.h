@@ -187,6 +187,13 @@ DXB_FMT_FN int dxb_is_srgb_format(uint32_t fmt)
 }
 
 // Resolve the sRGB bits exactly as ConvertScanline does (DirectXTexConvert.cpp:3121-3167).
+// conversion flags CompressBC passes for a BC1-5 target when the caller gives no sRGB flags and source/target agree
+// on sRGB-ness (DetermineEncoderSettings, DirectXTexCompress.cpp:46-68)
+DXB_FMT_FN uint32_t dxb_bc15_default_cflags(uint32_t dstFmt)
+{
+    return (dstFmt == DXB_FMT_BC4_UNORM || dstFmt == DXB_FMT_BC4_SNORM) ? (uint32_t)DXB_FILTER_RGB_COPY_RED
+         : (dstFmt == DXB_FMT_BC5_UNORM || dstFmt == DXB_FMT_BC5_SNORM) ? (uint32_t)(DXB_FILTER_RGB_COPY_RED | DXB_FILTER_RGB_COPY_GREEN) : 0u;
+}
 DXB_FMT_FN uint32_t dxb_resolve_srgb_convert(uint32_t flags, uint32_t inFmt, uint32_t outFmt)
 {
     if (dxb_is_srgb_format(inFmt)) flags |= DXB_FILTER_SRGB_IN;
