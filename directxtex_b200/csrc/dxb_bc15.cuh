@@ -127,6 +127,9 @@ DXB_DEV void dxb_optimize_rgb(dxb_rgb* pX, dxb_rgb* pY, const dxb_rgb* pts, uint
 
     const float fSteps = (float)(cSteps - 1);
 
+#if DXB_ON_DEVICE
+    #pragma unroll 1      // keeps the kernel small: straight-line code this long is instruction-fetch bound
+#endif
     for (int iter = 0; iter < 8; ++iter)
     {
         dxb_rgb pSteps[4];
@@ -447,6 +450,9 @@ DXB_DEV void dxb_optimize_alpha(float* pX, float* pY, const float* pPoints, uint
 
     const float fSteps = (float)(cSteps - 1);
 
+#if DXB_ON_DEVICE
+    #pragma unroll 1      // keeps the kernel small: straight-line code this long is instruction-fetch bound
+#endif
     for (int iter = 0; iter < 8; ++iter)
     {
         if ((fY - fX) < (1.0f / 256.0f)) break;
