@@ -35,3 +35,40 @@ DXB_DEV void dxb_gather_block(const dxb_image_desc& img, uint32_t bx, uint32_t b
     }
     for (int i = 0; i < 16; ++i) px[i] = dxb_convert_pixel(px[i], inF, outF, cflags);
 }
+
+#if DXB_ON_DEVICE
+// Same result as dxb_gather_block for a compile-time source format: a full 4x4 block whose rows are suitably aligned
+// is fetched with ONE vector load per row (4 pixels = 4..64 bytes) instead of 16 scalar pixel loads, then decoded
+// from registers by the same dxb_load_pixel code.
+template <uint32_t SF>
+__device__ __forceinline__ void dxb_gather_block_t(const dxb_image_desc& img, uint32_t bx, uint32_t by,
+                                                   uint32_t inF, uint32_t outF, uint32_t cflags, dxb_px* px)
+{
+    constexpr uint32_t B = dxb_bytes_per_pixel(SF);
+    constexpr uint32_t ROWB = 4u * B;                                     // bytes of 4 pixels
+    constexpr uint32_t V = (ROWB >= 16u) ? 16u : ROWB;                    // vector width used
+    const uint32_t x0 = bx * 4u, y0 = by * 4u;
+    const uint8_t* p0 = img.pixels + (size_t)y0 * img.rowPitch + (size_t)x0 * B;
+    const bool full = (img.width - x0 >= 4u) && (img.height - y0 >= 4u);
+    if (!(full && (((uintptr_t)p0 | img.rowPitch) & (V - 1u)) == 0u))
+    {
+        dxb_gather_block(img, bx, by, inF, outF, cflags, px);
+        return;
+    }
+    #pragma unroll
+    for (uint32_t t = 0; t < 4; ++t)
+    {
+        __align__(16) uint8_t row[ROWB];
+        const uint8_t* p = p0 + (size_t)t * img.rowPitch;
+        #pragma unroll
+        for (uint32_t k = 0; k < ROWB; k += V)
+        {
+            if (V == 16u) *reinterpret_cast<uint4*>(row + k) = __ldg(reinterpret_cast<const uint4*>(p + k));
+            else if (V == 8u) *reinterpret_cast<uint2*>(row + k) = __ldg(reinterpret_cast<const uint2*>(p + k));
+            else *reinterpret_cast<uint32_t*>(row + k) = __ldg(reinterpret_cast<const uint32_t*>(p + k));
+        }
+        #pragma unroll
+        for (uint32_t s2 = 0; s2 < 4; ++s2) px[(t << 2) | s2] = dxb_convert_pixel(dxb_load_pixel(SF, row, s2), inF, outF, cflags);
+    }
+}
+#endif

@@ -22,7 +22,8 @@ __device__ __forceinline__ void bc15_body(const dxb_job* __restrict__ jobs, cons
         const uint32_t by = local / j.nbx, bx = local - by * j.nbx;
         dxb_image_desc img; img.pixels = j.src; img.rowPitch = j.srcPitch; img.width = j.width; img.height = j.height; img.format = srcFormat;
         dxb_px px[16];
-        dxb_gather_block(img, bx, by, inF, outF, cflags, px);
+        if (GENERIC) dxb_gather_block(img, bx, by, inF, outF, cflags, px);
+        else dxb_gather_block_t<GENERIC ? 2u : SF>(img, bx, by, inF, outF, cflags, px);
         const uint32_t bs = dxb_bc_block_bytes(dstFormat);
         uint8_t* out = j.dst + (size_t)by * j.dstPitch + (size_t)bx * bs;
         __align__(16) uint8_t blk[16];
