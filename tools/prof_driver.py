@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs each hot-path kernel a few times on device-resident data so that `ncu` can capture it
-(profiles/README.md lists the exact ncu command lines).  Usage: python tools/prof_driver.py [bc7|bc6h|bc15|rows|all] [reps]"""
+(profiles/README.md lists the exact ncu command lines).  Usage: python tools/prof_driver.py [bc7|bc6h|bc15|dec|rows|all] [reps]"""
 import ctypes as C
 import os
 import sys
@@ -67,6 +67,18 @@ if what in ("bc15", "all"):
         s = capi.images([capi.Image(w, h, 28, *F.compute_pitch(28, w, h), d_in.data_ptr())])
         d = capi.images([capi.Image(w, h, fmt, *F.compute_pitch(fmt, w, h), d_out.data_ptr())])
         timed("%s 4096^2 rgba8" % nm, lambda: capi.lib.dxb200_compress_device(s, 1, fmt, 0, 0.5, 1.0, d, st), w * h)
+
+if what in ("dec", "all"):
+    w = h = 4096
+    for bc, dfmt, nm in ((98, 28, "bc7"), (71, 28, "bc1"), (80, 61, "bc4")):
+        nb = F.compute_pitch(bc, w, h)[1]
+        d_in = torch.randint(0, 256, (nb,), dtype=torch.uint8, device="cuda")
+        if bc == 98:
+            d_in.view(-1, 16)[:, 0] = 0x40       # valid mode-6 blocks
+        d_out = torch.zeros(F.compute_pitch(dfmt, w, h)[1], dtype=torch.uint8, device="cuda")
+        s = capi.images([capi.Image(w, h, bc, *F.compute_pitch(bc, w, h), d_in.data_ptr())])
+        d = capi.images([capi.Image(w, h, dfmt, *F.compute_pitch(dfmt, w, h), d_out.data_ptr())])
+        timed("decompress %s 4096^2" % nm, lambda: capi.lib.dxb200_decompress_device(s, 1, dfmt, d, st), w * h)
 
 if what in ("rows", "all"):
     w = h = 8192
