@@ -7,4 +7,12 @@ it contains no codec logic and no fallback: if the shared library is missing, im
 ``directxtex_b200.capi`` raises.
 """
 from .formats import *          # noqa: F401,F403
-from . import capi              # noqa: F401
+
+
+def __getattr__(name):
+    # `capi` loads the shared library at import time; keep it lazy so that `directxtex_b200.build` can be imported
+    # (and run) when the library does not exist yet or is stale
+    if name == "capi":
+        import importlib
+        return importlib.import_module(".capi", __name__)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))

@@ -13,6 +13,7 @@ SYMBOLS = [
     "dxb200_host_alloc", "dxb200_host_free", "dxb200_compute_pitch", "dxb200_calculate_mip_levels",
     "dxb200_compress", "dxb200_compress_device", "dxb200_decompress", "dxb200_decompress_device",
     "dxb200_convert", "dxb200_convert_device", "dxb200_generate_mipmaps", "dxb200_generate_mipmaps_device",
+    "dxb200_resize", "dxb200_resize_device",
 ]
 
 
@@ -33,6 +34,9 @@ def _load():
         raise ImportError("libdxtex_b200.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`. "
                           "There is no CPU fallback." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
+    missing = [n for n in SYMBOLS if not hasattr(lib, n)]
+    if missing:
+        raise ImportError("%s is stale (missing %s); rebuild with `python -c 'import __graft_entry__ as g; g.build()'`" % (LIB_PATH, ", ".join(missing)))
     IP = C.POINTER(Image)
     lib.dxb200_version.restype = C.c_char_p
     lib.dxb200_last_error.restype = C.c_char_p
@@ -51,9 +55,11 @@ def _load():
     lib.dxb200_convert_device.argtypes = [IP, C.c_size_t, C.c_uint32, C.c_uint32, C.c_float, IP, C.c_void_p]
     lib.dxb200_generate_mipmaps.argtypes = [IP, C.c_size_t, C.c_size_t, C.c_uint32]
     lib.dxb200_generate_mipmaps_device.argtypes = [IP, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p]
+    lib.dxb200_resize.argtypes = [IP, C.c_size_t, C.c_uint32, IP]
+    lib.dxb200_resize_device.argtypes = [IP, C.c_size_t, C.c_uint32, IP, C.c_void_p]
     for name in ("dxb200_init", "dxb200_device_count", "dxb200_compute_pitch", "dxb200_calculate_mip_levels", "dxb200_compress",
                  "dxb200_compress_device", "dxb200_decompress", "dxb200_decompress_device", "dxb200_convert",
-                 "dxb200_convert_device", "dxb200_generate_mipmaps", "dxb200_generate_mipmaps_device"):
+                 "dxb200_convert_device", "dxb200_generate_mipmaps", "dxb200_generate_mipmaps_device", "dxb200_resize", "dxb200_resize_device"):
         getattr(lib, name).restype = C.c_int32
     return lib
 
@@ -141,6 +147,20 @@ def generate_mipmaps(src, w, h, fmt, filter=0, levels=0):
     if hr != 0:
         raise DxTexError(hr, "dxb200_generate_mipmaps")
     return chain, layout
+
+
+def resize(src, w, h, fmt, width, height, filter=0):
+    """DirectX::Resize of one image; returns the width x height result as tightly packed bytes."""
+    src = np.ascontiguousarray(src).view(np.uint8).reshape(-1)
+    srow, ssl = F.compute_pitch(fmt, w, h)
+    drow, dsl = F.compute_pitch(fmt, width, height)
+    out = np.zeros(dsl, np.uint8)
+    s = images([Image(w, h, fmt, srow, ssl, _np_ptr(src))])
+    d = images([Image(width, height, fmt, drow, dsl, _np_ptr(out))])
+    hr = lib.dxb200_resize(s, 1, filter, d)
+    if hr != 0:
+        raise DxTexError(hr, "dxb200_resize")
+    return out
 
 
 def decompress(blocks, w, h, bc_fmt, dst_fmt):

@@ -382,6 +382,35 @@ int32_t plan_mips(const dxb200_image* chain, size_t items, size_t levels, uint32
     return DXB_S_OK;
 }
 
+// Resize = one filter pass from src[i] to dst[i] (PerformResizeUsingCustomFilters, DirectXTexResize.cpp:805-837)
+int32_t plan_resize(const dxb200_image* src, size_t n, uint32_t filter, const dxb200_image* dst, uint32_t* mode)
+{
+    if (!src || !dst || !n) return DXB_E_INVALIDARG;
+    const uint32_t fmt = src[0].format;
+    if (is_compressed(fmt)) return DXB_E_NOT_SUPPORTED;                         // Resize :875-879
+    if (!is_supported_pixel_format(fmt)) return DXB_E_NOT_SUPPORTED;
+    const size_t sw = src[0].width, sh = src[0].height, dw = dst[0].width, dh = dst[0].height;
+    if (!sw || !sh || !dw || !dh) return DXB_E_INVALIDARG;
+    if (sw > 0xFFFFFFFFull || sh > 0xFFFFFFFFull || dw > 0xFFFFFFFFull || dh > 0xFFFFFFFFull) return DXB_E_INVALIDARG;
+    for (size_t i = 0; i < n; ++i)
+    {
+        if (!src[i].pixels || !dst[i].pixels) return DXB_E_POINTER;
+        if (src[i].format != fmt || dst[i].format != fmt) return DXB_E_INVALIDARG;
+        if (src[i].width != sw || src[i].height != sh || dst[i].width != dw || dst[i].height != dh) return DXB_E_INVALIDARG;
+    }
+    uint32_t m = filter & DXB_FILTER_MODE_MASK;
+    if (!m) m = ((dw << 1) == sw && (dh << 1) == sh) ? DXB_FILTER_BOX : DXB_FILTER_LINEAR;      // :812-817
+    switch (m)
+    {
+    case DXB_FILTER_BOX: if ((dw << 1) != sw || (dh << 1) != sh) return DXB_E_FAIL; break;      // :318-319
+    case DXB_FILTER_POINT: case DXB_FILTER_LINEAR: case DXB_FILTER_CUBIC: case DXB_FILTER_TRIANGLE: break;
+    default: return DXB_E_NOT_SUPPORTED;
+    }
+    if ((uint64_t)dw * dh * n > 0x7FFFFFFFull) return DXB_E_INVALIDARG;
+    *mode = m;
+    return DXB_S_OK;
+}
+
 // chain[] holds DEVICE pointers; level 0 of each item is populated
 int32_t launch_mips(const dxb200_image* chain, size_t items, size_t levels, uint32_t filter, uint32_t mode, cudaStream_t stream)
 {
@@ -740,6 +769,64 @@ int32_t dxb200_generate_mipmaps(const dxb200_image* chain, size_t items, size_t 
                 hr = cuda_hr(cudaMemcpyAsync(chain[it * levels + m].pixels, dev[m].pixels, dev[m].slicePitch, cudaMemcpyDeviceToHost, st), "D2H");
         if (hr) break;
         hr = cuda_hr(cudaStreamSynchronize(st), "mips sync");
+        it = k;
+    }
+    return hr;
+}
+
+int32_t dxb200_resize_device(const dxb200_image* src, size_t nimages, uint32_t filter, const dxb200_image* dst, void* stream)
+{
+    uint32_t mode = 0;
+    int32_t hr = plan_resize(src, nimages, filter, dst, &mode);
+    if (hr != DXB_S_OK) return hr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        hr = ensure_init_locked();
+    }
+    if (hr != DXB_S_OK) return hr;
+    // a resize is a two-"level" chain per item whose second level has an arbitrary size
+    std::vector<dxb200_image> pairs(2 * nimages);
+    for (size_t i = 0; i < nimages; ++i) { pairs[2 * i] = src[i]; pairs[2 * i + 1] = dst[i]; }
+    return launch_mips(pairs.data(), nimages, 2, filter, mode, static_cast<cudaStream_t>(stream));
+}
+
+int32_t dxb200_resize(const dxb200_image* src, size_t nimages, uint32_t filter, const dxb200_image* dst)
+{
+    uint32_t mode = 0;
+    int32_t hr = plan_resize(src, nimages, filter, dst, &mode);
+    if (hr != DXB_S_OK) return hr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    hr = ensure_init_locked();
+    if (hr != DXB_S_OK) return hr;
+    const size_t CHUNK = size_t(1) << 30;
+    cudaStream_t st = g.streams[0];
+    size_t it = 0;
+    while (it < nimages && hr == DXB_S_OK)
+    {
+        size_t bytes = 0, k = it;
+        while (k < nimages)
+        {
+            const size_t b = ((src[k].slicePitch + 255) & ~size_t(255)) + ((dst[k].slicePitch + 255) & ~size_t(255));
+            if (k > it && bytes + b > CHUNK) break;
+            bytes += b; ++k;
+        }
+        hr = ensure_buffer(&g.dIn[0], &g.dInCap[0], bytes); if (hr) break;
+        std::vector<dxb200_image> pairs(2 * (k - it));
+        size_t off = 0;
+        for (size_t i = it; i < k && hr == DXB_S_OK; ++i)
+        {
+            dxb200_image& s = pairs[2 * (i - it)]; dxb200_image& d = pairs[2 * (i - it) + 1];
+            s = src[i]; d = dst[i];
+            s.pixels = static_cast<uint8_t*>(g.dIn[0]) + off; off += (s.slicePitch + 255) & ~size_t(255);
+            d.pixels = static_cast<uint8_t*>(g.dIn[0]) + off; off += (d.slicePitch + 255) & ~size_t(255);
+            hr = cuda_hr(cudaMemcpyAsync(s.pixels, src[i].pixels, s.slicePitch, cudaMemcpyHostToDevice, st), "H2D");
+        }
+        if (hr) break;
+        hr = launch_mips(pairs.data(), k - it, 2, filter, mode, st); if (hr) break;
+        for (size_t i = it; i < k && hr == DXB_S_OK; ++i)
+            hr = cuda_hr(cudaMemcpyAsync(dst[i].pixels, pairs[2 * (i - it) + 1].pixels, dst[i].slicePitch, cudaMemcpyDeviceToHost, st), "D2H");
+        if (hr) break;
+        hr = cuda_hr(cudaStreamSynchronize(st), "resize sync");
         it = k;
     }
     return hr;

@@ -362,4 +362,46 @@ HRESULT GenerateMipMaps(const Image* srcImages, size_t nimages, const TexMetadat
     return hr;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Resize (DirectXTexResize.cpp:854-935, 942-1120): 2D textures and arrays, top level only (the result has one mip level)
+HRESULT Resize(const Image& srcImage, size_t width, size_t height, TEX_FILTER_FLAGS filter, ScratchImage& image) noexcept
+{
+    if (width == 0 || height == 0) return E_INVALIDARG;
+    if (!srcImage.pixels) return E_POINTER;
+    TexMetadata m{};
+    m.width = srcImage.width; m.height = srcImage.height; m.depth = 1; m.arraySize = 1; m.mipLevels = 1;
+    m.format = srcImage.format; m.dimension = TEX_DIMENSION_TEXTURE2D;
+    return Resize(&srcImage, 1, m, width, height, filter, image);
+}
+
+HRESULT Resize(const Image* srcImages, size_t nimages, const TexMetadata& metadata, size_t width, size_t height, TEX_FILTER_FLAGS filter, ScratchImage& result) noexcept
+{
+    if (!srcImages || !nimages || width == 0 || height == 0) return E_INVALIDARG;
+    if (metadata.IsVolumemap()) return HRESULT_E_NOT_SUPPORTED;
+    if (IsCompressed(metadata.format)) return HRESULT_E_NOT_SUPPORTED;
+    if (!implemented_pixel_format(metadata.format)) return HRESULT_E_NOT_SUPPORTED;
+    try
+    {
+        TexMetadata m2 = metadata;
+        m2.width = width; m2.height = height; m2.mipLevels = 1;
+        HRESULT hr = result.Initialize(m2);
+        if (FAILED(hr)) return hr;
+        // the base image of every array item (metadata.ComputeIndex(0, item, 0) in the reference)
+        std::vector<dxb200_image> src(metadata.arraySize), dst(metadata.arraySize);
+        for (size_t item = 0; item < metadata.arraySize; ++item)
+        {
+            const size_t srcIndex = item * metadata.mipLevels;
+            if (srcIndex >= nimages) { result.Release(); return E_FAIL; }
+            const Image* d = result.GetImage(0, item, 0);
+            if (!d) { result.Release(); return E_POINTER; }
+            if (srcImages[srcIndex].format != metadata.format) { result.Release(); return E_FAIL; }
+            src[item] = to_c(srcImages[srcIndex]); dst[item] = to_c(*d);
+        }
+        hr = dxb200_resize(src.data(), src.size(), static_cast<uint32_t>(filter), dst.data());
+        if (FAILED(hr)) result.Release();
+        return hr;
+    }
+    catch (...) { return E_FAIL; }
+}
+
 } // namespace DirectX

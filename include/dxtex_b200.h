@@ -92,6 +92,15 @@ DXB200_API int32_t  dxb200_convert_device(const dxb200_image* src, size_t nimage
 DXB200_API int32_t  dxb200_generate_mipmaps(const dxb200_image* chain, size_t items, size_t levels, uint32_t filter);
 DXB200_API int32_t  dxb200_generate_mipmaps_device(const dxb200_image* chain, size_t items, size_t levels, uint32_t filter, void* stream);
 
+/* DirectX::Resize (DirectXTexResize.cpp:854-935 single image, :942-1120 arrays; custom filters ResizePointFilter /
+ * ResizeBoxFilter / ResizeLinearFilter / ResizeCubicFilter / ResizeTriangleFilter :255-798, selection :805-837).
+ *   src[i] -> dst[i], i < nimages; all sources share one size and format, all destinations share one size and the
+ *   source format.  filter = TEX_FILTER_FLAGS; mode 0 selects BOX when the target is exactly half the source in both
+ *   directions, else LINEAR (:812-817); BOX on any other ratio -> E_FAIL (:318-319); compressed formats ->
+ *   HRESULT_E_NOT_SUPPORTED (:875-879).  (the texconv step in front of Convert.) */
+DXB200_API int32_t  dxb200_resize(const dxb200_image* src, size_t nimages, uint32_t filter, const dxb200_image* dst);
+DXB200_API int32_t  dxb200_resize_device(const dxb200_image* src, size_t nimages, uint32_t filter, const dxb200_image* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,6 +112,20 @@ int32_t ref_generate_mipmaps(const uint8_t* src, size_t w, size_t h, uint32_t fm
     return hr;
 }
 
+// DirectX::Resize single image (DirectXTexResize.cpp:854-935; custom filters :255-837).  dst = width*height pixels, tightly
+// packed as the result ScratchImage lays them out.
+int32_t ref_resize(const uint8_t* src, size_t w, size_t h, uint32_t fmt, size_t srcRowPitch,
+                   size_t width, size_t height, uint32_t filter, uint8_t* dst, size_t dstBytes)
+{
+    Image img = make_image(src, w, h, fmt, srcRowPitch);
+    ScratchImage out;
+    HRESULT hr = Resize(img, width, height, static_cast<TEX_FILTER_FLAGS>(filter), out);
+    if (FAILED(hr)) return hr;
+    if (out.GetPixelsSize() > dstBytes) return E_NOT_SUFFICIENT_BUFFER;
+    memcpy(dst, out.GetPixels(), out.GetPixelsSize());
+    return hr;
+}
+
 double ref_generate_mipmaps_timed(const uint8_t* src, size_t w, size_t h, uint32_t fmt, uint32_t filter, size_t levels)
 {
     Image img = make_image(src, w, h, fmt, 0);

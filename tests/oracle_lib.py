@@ -44,6 +44,7 @@ class Ref:
         L.ref_convert_timed.restype = C.c_double
         L.ref_generate_mipmaps.argtypes = [vp, sz, sz, u32, sz, u32, sz, vp, sz, C.POINTER(sz), C.POINTER(sz)]
         L.ref_generate_mipmaps_timed.argtypes = [vp, sz, sz, u32, u32, sz]
+        L.ref_resize.argtypes = [vp, sz, sz, u32, sz, sz, sz, u32, vp, sz]
         L.ref_generate_mipmaps_timed.restype = C.c_double
         L.ref_compute_mse.argtypes = [vp, u32, vp, u32, sz, sz, C.POINTER(f32), C.POINTER(f32), u32]
         L.ref_encode_block.argtypes = [u32, vp, u32, f32, vp]
@@ -85,6 +86,13 @@ class Ref:
         out = np.zeros(total, np.uint8)
         nl, nb = C.c_size_t(), C.c_size_t()
         hr = self.L.ref_generate_mipmaps(src.ctypes.data, w, h, fmt, 0, filter, levels, out.ctypes.data, total, nl, nb)
+        return F.hr_u32(hr), out
+
+    def resize(self, src, w, h, fmt, width, height, filter=0):
+        src = np.ascontiguousarray(src)
+        n = width * height * F.BYTES_PER_PIXEL[fmt]
+        out = np.zeros(n, np.uint8)
+        hr = self.L.ref_resize(src.ctypes.data, w, h, fmt, 0, width, height, filter, out.ctypes.data, n)
         return F.hr_u32(hr), out
 
     def decompress(self, blocks, w, h, bc_fmt, dst_fmt):

@@ -98,6 +98,14 @@ def test_argument_validation_hresults():
     assert F.hr_u32(L.dxb200_generate_mipmaps(chain, 1, 5, 0)) == F.E_INVALIDARG               # more levels than the size allows
     odd = capi.images([_img(a, 6, 8, 28), capi.Image(3, 4, 28, 12, 48, out.ctypes.data)])
     assert F.hr_u32(L.dxb200_generate_mipmaps(odd, 1, 2, F.TEX_FILTER_BOX)) == F.E_FAIL        # box needs powers of two (:1005-1006)
+    # Resize argument checking (DirectXTexResize.cpp:318-319, 875-879)
+    r53 = capi.images([capi.Image(5, 3, 28, 20, 60, out.ctypes.data)])
+    assert F.hr_u32(L.dxb200_resize(s, 1, F.TEX_FILTER_BOX, r53)) == F.E_FAIL                  # box is 2:1 only
+    assert F.hr_u32(L.dxb200_resize(s, 0, 0, r53)) == F.E_INVALIDARG
+    bc = capi.images([capi.Image(8, 8, 71, 16, 32, out.ctypes.data)])
+    assert F.hr_u32(L.dxb200_resize(bc, 1, 0, bc)) == F.HRESULT_E_NOT_SUPPORTED                # compressed source
+    wrongfmt = capi.images([capi.Image(4, 4, 2, 64, 256, out.ctypes.data)])
+    assert F.hr_u32(L.dxb200_resize(s, 1, 0, wrongfmt)) == F.E_INVALIDARG                      # Resize never converts
 
 
 def test_compute_entry_points_fail_loudly_without_gpu():
@@ -111,3 +119,5 @@ def test_compute_entry_points_fail_loudly_without_gpu():
         capi.convert(a, 8, 8, 28, 2)
     with pytest.raises(capi.DxTexError):
         capi.generate_mipmaps(a, 8, 8, 28)
+    with pytest.raises(capi.DxTexError):
+        capi.resize(a, 8, 8, 28, 5, 3)

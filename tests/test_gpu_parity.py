@@ -116,6 +116,21 @@ def test_mips_vs_oracle(oracle, fl):
         assert hr == 0 and np.array_equal(got, want), (fmt, w, h, hex(fl))
 
 
+@pytest.mark.parametrize("fl", [0, F.TEX_FILTER_POINT, F.TEX_FILTER_BOX, F.TEX_FILTER_LINEAR, F.TEX_FILTER_CUBIC, F.TEX_FILTER_TRIANGLE,
+                                F.TEX_FILTER_LINEAR | F.TEX_FILTER_WRAP, F.TEX_FILTER_CUBIC | F.TEX_FILTER_MIRROR])
+def test_resize_vs_oracle(oracle, fl):
+    """SURVEY 8(f) rank 2: DirectX::Resize with the custom filters, bit-exact vs the reference (down-, up-scaling, odd sizes)."""
+    rng = np.random.default_rng(16)
+    for (fmt, w, h, nw, nh) in [(28, 64, 64, 32, 32), (28, 100, 60, 37, 91), (2, 48, 32, 96, 80), (10, 33, 17, 16, 8),
+                                (61, 128, 16, 64, 8), (87, 40, 40, 40, 13)]:
+        if (fl & 0xF00000) == F.TEX_FILTER_BOX and (nw * 2 != w or nh * 2 != h):
+            continue
+        src = oracle_lib.random_image(fmt, w, h, rng)
+        hr, want = oracle.resize(src, w, h, fmt, nw, nh, fl)
+        got = capi.resize(src, w, h, fmt, nw, nh, fl)
+        assert hr == 0 and np.array_equal(got, want), (fmt, w, h, nw, nh, hex(fl))
+
+
 def test_bc7_equals_emulator_and_quality(oracle, emul):
     """GPU BC7 == host lock-step emulator (same source, explicit fmaf, -fmad=false) bit for bit, and
     MSE <= 1.02 x the reference CPU encoder's MSE (golden anchor) on each test image."""
