@@ -194,7 +194,7 @@ int32_t launch_compress(const CompressPlan& plan, const dxb200_image* src, const
     if (hr != DXB_S_OK) return hr;
     if (plan.bc6h)
     {
-        const uint32_t need = (uint32_t)((total + DXB_BC6H_WARPS - 1) / DXB_BC6H_WARPS);
+        const uint32_t need = (uint32_t)((total + 2 * DXB_BC6H_WARPS - 1) / (2 * DXB_BC6H_WARPS));
         const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridBC6H * 4u));
         dxb_launch_bc6h(grid, stream, dj.d, jobs[0], P);
         hr = check_launch("k_compress_bc6h");

@@ -1,4 +1,4 @@
-// dxb_bc6h.cuh — BC6H (UF16 / SF16) block encoder, ONE WARP PER 4x4 BLOCK (single-source SPMD, dxb_warp.cuh).
+// dxb_bc6h.cuh — BC6H (UF16 / SF16) block encoder, ONE HALF-WARP PER 4x4 BLOCK, two blocks per warp (single-source SPMD, dxb_warp.cuh).
 //
 // Replaces D3DXEncodeBC6HU/S -> D3DX_BC6H::Encode (BC6HBC7.cpp:3624-3639, 1817-1859).  Parity contract as for BC7:
 // a valid stream for the reference decoder (D3DX_BC6H::Decode, :1658-1813) whose error — in the reference
@@ -7,8 +7,8 @@
 //
 // Pixel domain = the reference's INTColor domain: F16ToINT(half(rgb)) (:534-552): unsigned -> half bits with
 // negatives clamped to 0; signed -> sign-magnitude integer, magnitude clamped to 0x7BFF.
-//   stage 1  the 32 two-region shapes ranked by a line-fit residual (one shape per lane), 15 best kept
-//   stage 2  lanes 0..29 = 15 shapes x 2 regions, lane 30 = the one-region fit: PCA axis + least-squares refit
+//   stage 1  the 32 two-region shapes ranked by a line-fit residual (two shapes per lane), 7 best kept
+//   stage 2  lanes 0..13 = 7 shapes x 2 regions, lane 14 = the one-region fit: PCA axis + least-squares refit
 //            of continuous endpoints (3-bit / 4-bit interpolation weights)
 //   stage 3  region pairs exchange endpoints (__shfl_xor) and pick the format mode: the highest base precision
 //            whose delta fields can hold the endpoint differences (modes 3,4,5 > 1 > 6 > 7,8,9 > 2 > 10 for two
@@ -345,77 +345,107 @@ DXB_DEV void dxb_bc6h_refine_region(const dxb_px* px, uint32_t mask, const float
 }
 
 // ---------------------------------------------------------------------------------------------------
-// whole block, SPMD over the warp.  spx = 16 pixels in the INT domain (x,y,z; w unused), out = 16 bytes.
-DXB_DEV void dxb_bc6h_encode_warp(const dxb_px* spx, bool bSigned, uint8_t* out)
+// The encoder proper, SPMD over the warp: TWO blocks per warp, one per 16-lane half (as dxb_bc7_encode_pair).
+//   spx : 32 pixels in the INT domain (x,y,z; w unused): spx[16 h + i] = pixel i of the half-h block
+//   out0/out1 : 16 output bytes of the half-0 / half-1 block (nullptr = that half carries no block)
+// Per block: stage 1 ranks the 32 two-region shapes (2 per lane) and keeps 7; stage 2/3 lanes 0..13 = 7 shapes x 2
+// regions, lane 14 = the one-region fit, lane 15 idles on a copy; stage 4 lanes = pixels.
+#define DXB_BC6H_KSHAPES 7
+
+DXB_DEV void dxb_bc6h_encode_pair(const dxb_px* spx, bool bSigned, uint8_t* out0, uint8_t* out1)
 {
     const float lo = bSigned ? -31743.0f : 0.0f, hi = 31743.0f;
-    // block centre (keeps the fp32 moments well conditioned: values are up to 3e4, squares 1e9)
-    float ctr[3] = { 0, 0, 0 };
-    for (int i = 0; i < 16; ++i) { ctr[0] += spx[i].x; ctr[1] += spx[i].y; ctr[2] += spx[i].z; }
-    ctr[0] *= (1.0f / 16.0f); ctr[1] *= (1.0f / 16.0f); ctr[2] *= (1.0f / 16.0f);
 
-    // ---- stage 1: one shape per lane (BC6H uses the first 32 two-subset shapes)
-    uint32_t key[DXB_NL];
-    DXB_LANES_BEGIN
-        // centred moments of subset 1 and of the whole block
-        float n1 = 0, s[3] = { 0, 0, 0 }, m[6] = { 0, 0, 0, 0, 0, 0 }, ts[3] = { 0, 0, 0 }, tm[6] = { 0, 0, 0, 0, 0, 0 };
-        const uint32_t mask1 = dxb_part2[lane];
-        for (int i = 0; i < 16; ++i)
-        {
-            const float f = dxb_bit_as_float(mask1, i);
-            const dxb_px p = spx[i];
-            const float X = p.x - ctr[0], Y = p.y - ctr[1], Z = p.z - ctr[2];
-            const float x = X * f, y = Y * f, z = Z * f;
-            n1 += f; s[0] += x; s[1] += y; s[2] += z;
-            m[0] = dxb_fma(x, X, m[0]); m[1] = dxb_fma(x, Y, m[1]); m[2] = dxb_fma(x, Z, m[2]);
-            m[3] = dxb_fma(y, Y, m[3]); m[4] = dxb_fma(y, Z, m[4]); m[5] = dxb_fma(z, Z, m[5]);
-            ts[0] += X; ts[1] += Y; ts[2] += Z;
-            tm[0] = dxb_fma(X, X, tm[0]); tm[1] = dxb_fma(X, Y, tm[1]); tm[2] = dxb_fma(X, Z, tm[2]);
-            tm[3] = dxb_fma(Y, Y, tm[3]); tm[4] = dxb_fma(Y, Z, tm[4]); tm[5] = dxb_fma(Z, Z, tm[5]);
-        }
-        const float v1[14] = { s[0], s[1], s[2], 0.0f, m[0], m[1], m[2], 0.0f, m[3], m[4], 0.0f, m[5], 0.0f, 0.0f };
-        const float v0[14] = { ts[0] - s[0], ts[1] - s[1], ts[2] - s[2], 0.0f, tm[0] - m[0], tm[1] - m[1], tm[2] - m[2], 0.0f,
-                               tm[3] - m[3], tm[4] - m[4], 0.0f, tm[5] - m[5], 0.0f, 0.0f };
-        const uint32_t c1 = dxb_popc16(mask1);
-        (void)n1;
-        const float est = dxb_bc7_subset_estimate(16u - c1, v0, 1.0f / 49.0f) + dxb_bc7_subset_estimate(c1, v1, 1.0f / 49.0f);
-        key[L] = (dxb_float_as_uint(fmaxf(est, 0.0f)) & 0xFFFFFFE0u) | (uint32_t)lane;
-    DXB_LANES_END
-    uint32_t sel[15];
-    for (int r = 0; r < 15; ++r)
+    // ---- block centre (keeps the fp32 moments well conditioned: values are up to 3e4, squares 1e9) and stage 1
+    float cx[DXB_NL], cy[DXB_NL], cz[DXB_NL];
+    uint32_t sel[DXB_BC6H_KSHAPES][DXB_NL];
     {
-        const uint32_t win = dxb_warp_min_u32(key);
-        sel[r] = win & 31u;
+        uint32_t k0[DXB_NL], k1[DXB_NL];
         DXB_LANES_BEGIN
-            if (key[L] == win) key[L] = 0xFFFFFFFFu;
+            const dxb_px* px = spx + (lane & 16);
+            float ctr[3] = { 0, 0, 0 };
+            for (int i = 0; i < 16; ++i) { ctr[0] += px[i].x; ctr[1] += px[i].y; ctr[2] += px[i].z; }
+            ctr[0] *= (1.0f / 16.0f); ctr[1] *= (1.0f / 16.0f); ctr[2] *= (1.0f / 16.0f);
+            cx[L] = ctr[0]; cy[L] = ctr[1]; cz[L] = ctr[2];
+            // centred moments (scaled by 2^-7, exact: dxb_bc7_subset_estimate needs covariance entries below ~5e6) of
+            // subset 1 of this lane's two shapes and of the whole block
+            const uint32_t maskA = dxb_part2[lane & 15], maskB = dxb_part2[(lane & 15) + 16];
+            float sa[3] = { 0, 0, 0 }, ma[6] = { 0, 0, 0, 0, 0, 0 }, sb[3] = { 0, 0, 0 }, mb[6] = { 0, 0, 0, 0, 0, 0 };
+            float ts[3] = { 0, 0, 0 }, tm[6] = { 0, 0, 0, 0, 0, 0 };
+#if DXB_ON_DEVICE
+            #pragma unroll 4
+#endif
+            for (int i = 0; i < 16; ++i)
+            {
+                const float fa = dxb_bit_as_float(maskA, i), fb = dxb_bit_as_float(maskB, i);
+                const dxb_px p = px[i];
+                const float X = (p.x - ctr[0]) * (1.0f / 128.0f), Y = (p.y - ctr[1]) * (1.0f / 128.0f), Z = (p.z - ctr[2]) * (1.0f / 128.0f);
+                const float xx = X * X, xy = X * Y, xz = X * Z, yy = Y * Y, yz = Y * Z, zz = Z * Z;
+                ts[0] += X; ts[1] += Y; ts[2] += Z;
+                tm[0] += xx; tm[1] += xy; tm[2] += xz; tm[3] += yy; tm[4] += yz; tm[5] += zz;
+                sa[0] = dxb_fma(fa, X, sa[0]); sa[1] = dxb_fma(fa, Y, sa[1]); sa[2] = dxb_fma(fa, Z, sa[2]);
+                ma[0] = dxb_fma(fa, xx, ma[0]); ma[1] = dxb_fma(fa, xy, ma[1]); ma[2] = dxb_fma(fa, xz, ma[2]);
+                ma[3] = dxb_fma(fa, yy, ma[3]); ma[4] = dxb_fma(fa, yz, ma[4]); ma[5] = dxb_fma(fa, zz, ma[5]);
+                sb[0] = dxb_fma(fb, X, sb[0]); sb[1] = dxb_fma(fb, Y, sb[1]); sb[2] = dxb_fma(fb, Z, sb[2]);
+                mb[0] = dxb_fma(fb, xx, mb[0]); mb[1] = dxb_fma(fb, xy, mb[1]); mb[2] = dxb_fma(fb, xz, mb[2]);
+                mb[3] = dxb_fma(fb, yy, mb[3]); mb[4] = dxb_fma(fb, yz, mb[4]); mb[5] = dxb_fma(fb, zz, mb[5]);
+            }
+            uint32_t key[2];
+            for (int j = 0; j < 2; ++j)
+            {
+                const float* s = j ? sb : sa; const float* m = j ? mb : ma;
+                const uint32_t mask1 = j ? maskB : maskA;
+                const float v1[14] = { s[0], s[1], s[2], 0.0f, m[0], m[1], m[2], 0.0f, m[3], m[4], 0.0f, m[5], 0.0f, 0.0f };
+                const float v0[14] = { ts[0] - s[0], ts[1] - s[1], ts[2] - s[2], 0.0f, tm[0] - m[0], tm[1] - m[1], tm[2] - m[2], 0.0f,
+                                       tm[3] - m[3], tm[4] - m[4], 0.0f, tm[5] - m[5], 0.0f, 0.0f };
+                const uint32_t c1 = dxb_popc16(mask1);
+                const float est = dxb_bc7_subset_estimate(16u - c1, v0, 1.0f / 49.0f) + dxb_bc7_subset_estimate(c1, v1, 1.0f / 49.0f);
+                key[j] = (dxb_float_as_uint(fmaxf(est, 0.0f)) & 0xFFFFFFE0u) | ((uint32_t)(lane & 15) + 16u * (uint32_t)j);
+            }
+            k0[L] = (key[0] < key[1]) ? key[0] : key[1];
+            k1[L] = (key[0] < key[1]) ? key[1] : key[0];
         DXB_LANES_END
+        for (int r = 0; r < DXB_BC6H_KSHAPES; ++r)
+        {
+            uint32_t win[DXB_NL];
+            dxb_half_min_u32(k0, win);
+            DXB_LANES_BEGIN
+                sel[r][L] = win[L] & 31u;
+                if (k0[L] == win[L]) { k0[L] = k1[L]; k1[L] = 0xFFFFFFFFu; }
+            DXB_LANES_END
+        }
     }
 
-    // ---- stage 2: continuous fits.  lanes 0..29: (shape sel[lane>>1], region lane&1); lane 30: one region; lane 31 idles on a copy
+    // ---- stage 2: continuous fits
     float e0x[DXB_NL], e0y[DXB_NL], e0z[DXB_NL], e1x[DXB_NL], e1y[DXB_NL], e1z[DXB_NL];
     uint32_t tShape[DXB_NL], tMask[DXB_NL];
     DXB_LANES_BEGIN
-        const bool one = (lane >= 30);
-        const uint32_t shape = one ? 0u : sel[lane >> 1];
+        const int hl = lane & 15;
+        const bool one = (hl >= 2 * DXB_BC6H_KSHAPES);
+        uint32_t shape = 0;
+        for (int r = 0; r < DXB_BC6H_KSHAPES; ++r) shape = ((hl >> 1) == r) ? sel[r][L] : shape;
         const uint32_t m1 = dxb_part2[shape];
-        const uint32_t mask = one ? 0xFFFFu : ((lane & 1) ? m1 : (~m1 & 0xFFFFu));
-        const int anchor = one ? 0 : ((lane & 1) ? (int)dxb_anchor2[shape] : 0);
+        const uint32_t mask = one ? 0xFFFFu : ((hl & 1) ? m1 : (~m1 & 0xFFFFu));
+        const int anchor = one ? 0 : ((hl & 1) ? (int)dxb_anchor2[shape] : 0);
+        const float ctr[3] = { cx[L], cy[L], cz[L] };
         float E0[3], E1[3];
-        dxb_bc6h_fit(spx, mask, one ? 4u : 3u, anchor, ctr, lo, hi, E0, E1);
+        dxb_bc6h_fit(spx + (lane & 16), mask, one ? 4u : 3u, anchor, ctr, lo, hi, E0, E1);
         e0x[L] = E0[0]; e0y[L] = E0[1]; e0z[L] = E0[2]; e1x[L] = E1[0]; e1y[L] = E1[1]; e1z[L] = E1[2];
-        tShape[L] = shape; tMask[L] = mask;
+        tShape[L] = one ? 0u : shape; tMask[L] = mask;
     DXB_LANES_END
 
-    // ---- stage 3: partner exchange, mode choice, exact region error
+    // ---- stage 3: partner exchange, mode choice, refinement, region error
     float p0x[DXB_NL], p0y[DXB_NL], p0z[DXB_NL], p1x[DXB_NL], p1y[DXB_NL], p1z[DXB_NL];
     dxb_xchg_xor_f32(e0x, p0x, 1); dxb_xchg_xor_f32(e0y, p0y, 1); dxb_xchg_xor_f32(e0z, p0z, 1);
     dxb_xchg_xor_f32(e1x, p1x, 1); dxb_xchg_xor_f32(e1y, p1y, 1); dxb_xchg_xor_f32(e1z, p1z, 1);
     uint32_t rErr[DXB_NL], rMode[DXB_NL];
-    uint32_t rq[DXB_NL][12];            // quantised endpoints A0 B0 A1 B1 (two's complement ints)
+    uint32_t rq[12][DXB_NL];            // quantised endpoints A0 B0 A1 B1 (two's complement ints)
     uint32_t mine[6][DXB_NL], theirs[6][DXB_NL];      // refined endpoints of this lane's region / of the partner's
     DXB_LANES_BEGIN
-        const bool one = (lane >= 30);
-        const bool second = !one && (lane & 1);
+        const int hl = lane & 15;
+        const bool one = (hl >= 2 * DXB_BC6H_KSHAPES);
+        const bool second = !one && (hl & 1);
+        const float ctr[3] = { cx[L], cy[L], cz[L] };
         int32_t ep[4][3];
         // region 0 endpoints come from the even lane, region 1 from the odd lane
         const float mine0[3] = { e0x[L], e0y[L], e0z[L] }, mine1[3] = { e1x[L], e1y[L], e1z[L] };
@@ -434,16 +464,18 @@ DXB_DEV void dxb_bc6h_encode_warp(const dxb_px* spx, bool bSigned, uint8_t* out)
         // +-1 code refinement of this lane's own region
         int32_t qa[3], qb[3];
         for (int c = 0; c < 3; ++c) { qa[c] = second ? q[2][c] : q[0][c]; qb[c] = second ? q[3][c] : q[1][c]; }
-        if (one) dxb_bc6h_refine_region<16>(spx, 0xFFFFu, ctr, qa, qb, prec, bSigned);
-        else dxb_bc6h_refine_region<8>(spx, tMask[L], ctr, qa, qb, prec, bSigned);
+        if (one) dxb_bc6h_refine_region<16>(spx + (lane & 16), 0xFFFFu, ctr, qa, qb, prec, bSigned);
+        else dxb_bc6h_refine_region<8>(spx + (lane & 16), tMask[L], ctr, qa, qb, prec, bSigned);
         for (int c = 0; c < 3; ++c) { mine[c][L] = (uint32_t)qa[c]; mine[3 + c][L] = (uint32_t)qb[c]; }
         rMode[L] = (uint32_t)mode;
-        for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) rq[L][e * 3 + c] = (uint32_t)q[e][c];
+        for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) rq[e * 3 + c][L] = (uint32_t)q[e][c];
     DXB_LANES_END
     for (int k = 0; k < 6; ++k) dxb_xchg_xor_u32(mine[k], theirs[k], 1);
     DXB_LANES_BEGIN
-        const bool one = (lane >= 30);
-        const bool second = !one && (lane & 1);
+        const int hl = lane & 15;
+        const bool one = (hl >= 2 * DXB_BC6H_KSHAPES);
+        const bool second = !one && (hl & 1);
+        const float ctr[3] = { cx[L], cy[L], cz[L] };
         const int mode = (int)rMode[L];
         const uint32_t info = dxb_bc6h_info[mode];
         const int32_t prec = (int32_t)((info >> 8) & 31u);
@@ -463,131 +495,136 @@ DXB_DEV void dxb_bc6h_encode_warp(const dxb_px* spx, bool bSigned, uint8_t* out)
             for (int e = 1; e < (one ? 2 : 4); ++e)
                 for (int c = 0; c < 3; ++c) ok = ok && dxb_fits_signed(r[e][c] - r[0][c], db[c]);
         int32_t q[4][3];
-        for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) q[e][c] = ok ? r[e][c] : (int32_t)rq[L][e * 3 + c];
+        for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) q[e][c] = ok ? r[e][c] : (int32_t)rq[e * 3 + c][L];
         float err;
-        if (one) err = dxb_bc6h_region_error<16>(spx, 0xFFFFu, ctr, q[0], q[1], prec, bSigned);
-        else err = dxb_bc6h_region_error<8>(spx, tMask[L], ctr, second ? q[2] : q[0], second ? q[3] : q[1], prec, bSigned);
+        if (one) err = dxb_bc6h_region_error<16>(spx + (lane & 16), 0xFFFFu, ctr, q[0], q[1], prec, bSigned);
+        else err = dxb_bc6h_region_error<8>(spx + (lane & 16), tMask[L], ctr, second ? q[2] : q[0], second ? q[3] : q[1], prec, bSigned);
         // errors are sums of squared differences of 15-bit integers: scale into 27 bits for the integer key
-        rErr[L] = (lane == 31) ? 0x07FFFFFFu : (uint32_t)dxb_f2i(fminf(err * (1.0f / 1024.0f), 6.0e7f));
-        for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) rq[L][e * 3 + c] = (uint32_t)q[e][c];
+        rErr[L] = (hl == 15) ? 0x07FFFFFFu : (uint32_t)dxb_f2i(fminf(err * (1.0f / 1024.0f), 6.0e7f));
+        for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) rq[e * 3 + c][L] = (uint32_t)q[e][c];
     DXB_LANES_END
     uint32_t partner[DXB_NL];
     dxb_xchg_xor_u32(rErr, partner, 1);
-    uint32_t wkeys[DXB_NL];
+    uint32_t wkeys[DXB_NL], wkey[DXB_NL], src[DXB_NL];
     DXB_LANES_BEGIN
+        const int hl = lane & 15;
         uint32_t e = rErr[L];
-        if (lane < 30) e += partner[L];
+        if (hl < 2 * DXB_BC6H_KSHAPES) e += partner[L];
         e = (e > 0x07FFFFFFu) ? 0x07FFFFFFu : e;
-        wkeys[L] = (e << 5) | (uint32_t)lane;
-        if (lane == 31) wkeys[L] = 0xFFFFFFFFu;
+        wkeys[L] = (e << 4) | (uint32_t)hl;
+        if (hl == 15) wkeys[L] = 0xFFFFFFFFu;
     DXB_LANES_END
-    const uint32_t wkey = dxb_warp_min_u32(wkeys);
-    const int wl = (int)(wkey & 31u) & ~1;                  // even lane of the winning pair (lane 30 for one region)
-    const bool two = (wl < 30);
-    const uint32_t wMode = dxb_bcast_u32(rMode, wl);
-    const uint32_t wShape = two ? dxb_bcast_u32(tShape, wl) : 0u;
-    int32_t wq[4][3];
-    for (int e = 0; e < 4; ++e)
-        for (int c = 0; c < 3; ++c)
-        {
-            uint32_t col[DXB_NL];
-            DXB_LANES_BEGIN
-                col[L] = rq[L][e * 3 + c];
-            DXB_LANES_END
-            wq[e][c] = (int32_t)dxb_bcast_u32(col, wl);
-        }
+    dxb_half_min_u32(wkeys, wkey);
+    DXB_LANES_BEGIN
+        src[L] = (wkey[L] & 15u) & ~1u;                      // even lane of the winning pair (lane 14 for one region)
+    DXB_LANES_END
+    uint32_t wMode[DXB_NL], wShape[DXB_NL], wq[12][DXB_NL];
+    dxb_half_gather_u32(rMode, src, wMode);
+    dxb_half_gather_u32(tShape, src, wShape);
+    for (int k = 0; k < 12; ++k) dxb_half_gather_u32(rq[k], src, wq[k]);
 
-    // ---- stage 4: indices against the exact palette, header + index packing
-    const uint32_t info = dxb_bc6h_info[wMode];
-    const int32_t prec = (int32_t)((info >> 8) & 31u);
-    const bool transformed = ((info >> 6) & 1u) != 0u;
-    const uint32_t ib = two ? 3u : 4u;
-    const uint32_t part = two ? dxb_part2[wShape] : 0u;
-    const uint32_t anchor1 = two ? dxb_anchor2[wShape] : 0u;
-    int32_t ua[2][3], ub[2][3];
-    for (int r = 0; r < 2; ++r)
-        for (int c = 0; c < 3; ++c)
-        {
-            ua[r][c] = dxb_bc6h_unquantize(wq[r * 2][c], prec, bSigned);
-            ub[r][c] = dxb_bc6h_unquantize(wq[r * 2 + 1][c], prec, bSigned);
-        }
+    // ---- stage 4: indices against the exact palette (lane = pixel)
     uint32_t idx[DXB_NL];
     DXB_LANES_BEGIN
-        idx[L] = 0;
-        if (lane < 16)
+        const uint32_t hl = (uint32_t)(lane & 15);
+        const bool two = (src[L] < 2u * DXB_BC6H_KSHAPES);
+        const uint32_t info = dxb_bc6h_info[wMode[L]];
+        const int32_t prec = (int32_t)((info >> 8) & 31u);
+        const uint32_t ib = two ? 3u : 4u;
+        const uint32_t part = two ? dxb_part2[wShape[L]] : 0u;
+        const uint32_t anchor1 = two ? dxb_anchor2[wShape[L]] : 0u;
+        const int r = (int)((part >> hl) & 1u);
+        int32_t ua[3], ub[3];
+        for (int c = 0; c < 3; ++c)
         {
-            const int r = (int)((part >> lane) & 1u);
-            const dxb_px p = spx[lane];
-            const bool isAnchor = (lane == 0) || (two && (uint32_t)lane == anchor1);
-            const uint32_t nk = isAnchor ? (1u << (ib - 1u)) : (1u << ib);       // anchors only have ib-1 bits
-            float best = 3.0e38f; uint32_t bk = 0;
-            for (uint32_t k = 0; k < nk; ++k)
-            {
-                const int32_t w = (int32_t)dxb_bc7_weight(ib, k);
-                const float dx = p.x - (float)dxb_bc6h_palette(ua[r][0], ub[r][0], w, bSigned);
-                const float dy = p.y - (float)dxb_bc6h_palette(ua[r][1], ub[r][1], w, bSigned);
-                const float dz = p.z - (float)dxb_bc6h_palette(ua[r][2], ub[r][2], w, bSigned);
-                const float e = dxb_fma(dx, dx, dxb_fma(dy, dy, dz * dz));
-                if (e < best) { best = e; bk = k; }
-            }
-            idx[L] = bk;
+            ua[c] = dxb_bc6h_unquantize((int32_t)(r ? wq[6 + c][L] : wq[c][L]), prec, bSigned);
+            ub[c] = dxb_bc6h_unquantize((int32_t)(r ? wq[9 + c][L] : wq[3 + c][L]), prec, bSigned);
         }
+        const dxb_px p = spx[lane];
+        const bool isAnchor = (hl == 0) || (two && hl == anchor1);
+        const uint32_t nk = isAnchor ? (1u << (ib - 1u)) : (1u << ib);       // anchors only have ib-1 bits
+        float best = 3.0e38f; uint32_t bk = 0;
+#if DXB_ON_DEVICE
+        #pragma unroll 2
+#endif
+        for (uint32_t k = 0; k < 16u; ++k)
+        {
+            const int32_t w = (int32_t)dxb_bc7_weight(ib, k);
+            const float dx = p.x - (float)dxb_bc6h_palette(ua[0], ub[0], w, bSigned);
+            const float dy = p.y - (float)dxb_bc6h_palette(ua[1], ub[1], w, bSigned);
+            const float dz = p.z - (float)dxb_bc6h_palette(ua[2], ub[2], w, bSigned);
+            const float e = dxb_fma(dx, dx, dxb_fma(dy, dy, dz * dz));
+            if (k < nk && e < best) { best = e; bk = k; }
+        }
+        idx[L] = bk;
     DXB_LANES_END
 
-    // header fields: endpoint 0 A as is, the others as deltas in transformed modes, masked to their field widths
-    const int32_t db[3] = { (int32_t)((info >> 16) & 15u), (int32_t)((info >> 20) & 15u), (int32_t)((info >> 24) & 15u) };
-    uint32_t field[15];
-    field[0] = 0; field[1] = info & 31u; field[2] = wShape;
-    for (int c = 0; c < 3; ++c)
-    {
-        const uint32_t m0 = (prec >= 32) ? 0xFFFFFFFFu : ((1u << prec) - 1u);
-        const uint32_t md = transformed ? ((1u << db[c]) - 1u) : m0;
-        const int32_t a0 = wq[0][c];
-        field[3 + 4 * c + 0] = (uint32_t)a0 & m0;
-        field[3 + 4 * c + 1] = (uint32_t)(transformed ? wq[1][c] - a0 : wq[1][c]) & md;
-        field[3 + 4 * c + 2] = (uint32_t)(transformed ? wq[2][c] - a0 : wq[2][c]) & md;
-        field[3 + 4 * c + 3] = (uint32_t)(transformed ? wq[3][c] - a0 : wq[3][c]) & md;
-    }
-    const uint32_t hdrBits = two ? 82u : 65u;
+    // header fields: endpoint 0 A as is, the others as deltas in transformed modes, masked to their field widths;
+    // lane l deposits header bits l, l+16, l+32, ... and its pixel's index field
     uint32_t w0[DXB_NL], w1[DXB_NL], w2[DXB_NL], w3[DXB_NL];
     DXB_LANES_BEGIN
-        dxb_u128 bits; bits.lo = 0; bits.hi = 0;
-        // header: lane l deposits bits l, l+32, l+64
-        for (uint32_t b = (uint32_t)lane; b < hdrBits; b += 32u)
+        const uint32_t hl = (uint32_t)(lane & 15);
+        const bool two = (src[L] < 2u * DXB_BC6H_KSHAPES);
+        const uint32_t mode = wMode[L];
+        const uint32_t info = dxb_bc6h_info[mode];
+        const int32_t prec = (int32_t)((info >> 8) & 31u);
+        const bool transformed = ((info >> 6) & 1u) != 0u;
+        const uint32_t ib = two ? 3u : 4u;
+        const uint32_t anchor1 = two ? dxb_anchor2[wShape[L]] : 0u;
+        const int32_t db[3] = { (int32_t)((info >> 16) & 15u), (int32_t)((info >> 20) & 15u), (int32_t)((info >> 24) & 15u) };
+        uint32_t field[15];
+        field[0] = 0; field[1] = info & 31u; field[2] = wShape[L];
+        for (int c = 0; c < 3; ++c)
         {
-            const uint32_t d = dxb_bc6h_desc[wMode][b];
+            const uint32_t m0 = (prec >= 32) ? 0xFFFFFFFFu : ((1u << prec) - 1u);
+            const uint32_t md = transformed ? ((1u << db[c]) - 1u) : m0;
+            const int32_t a0 = (int32_t)wq[c][L], b0 = (int32_t)wq[3 + c][L], a1 = (int32_t)wq[6 + c][L], b1 = (int32_t)wq[9 + c][L];
+            field[3 + 4 * c + 0] = (uint32_t)a0 & m0;
+            field[3 + 4 * c + 1] = (uint32_t)(transformed ? b0 - a0 : b0) & md;
+            field[3 + 4 * c + 2] = (uint32_t)(transformed ? a1 - a0 : a1) & md;
+            field[3 + 4 * c + 3] = (uint32_t)(transformed ? b1 - a0 : b1) & md;
+        }
+        const uint32_t hdrBits = two ? 82u : 65u;
+        dxb_u128 bits; bits.lo = 0; bits.hi = 0;
+        for (uint32_t b = hl; b < hdrBits; b += 16u)
+        {
+            const uint32_t d = dxb_bc6h_desc[mode][b];
             uint32_t f = 0;
             // field[] is indexed with a lane-varying value: select chain keeps it in registers
             const uint32_t fi = d >> 4;
             for (uint32_t k = 1; k < 15; ++k) f = (fi == k) ? field[k] : f;
             dxb_put_bits(&bits, b, 1, (f >> (d & 15u)) & 1u);
         }
-        if (lane < 16)
         {
-            const uint32_t i = (uint32_t)lane;
-            const uint32_t before = (i > 0 ? 1u : 0u) + ((two && i > anchor1) ? 1u : 0u);
-            const bool isAnchor = (i == 0) || (two && i == anchor1);
-            dxb_put_bits(&bits, hdrBits + i * ib - before, isAnchor ? ib - 1u : ib, idx[L]);
+            const uint32_t before = (hl > 0 ? 1u : 0u) + ((two && hl > anchor1) ? 1u : 0u);
+            const bool isAnchor = (hl == 0) || (two && hl == anchor1);
+            dxb_put_bits(&bits, hdrBits + hl * ib - before, isAnchor ? ib - 1u : ib, idx[L]);
         }
         w0[L] = (uint32_t)bits.lo; w1[L] = (uint32_t)(bits.lo >> 32); w2[L] = (uint32_t)bits.hi; w3[L] = (uint32_t)(bits.hi >> 32);
     DXB_LANES_END
-    const uint32_t o0 = dxb_warp_or_u32(w0), o1 = dxb_warp_or_u32(w1), o2 = dxb_warp_or_u32(w2), o3 = dxb_warp_or_u32(w3);
+    uint32_t o0[DXB_NL], o1[DXB_NL], o2[DXB_NL], o3[DXB_NL];
+    dxb_half_or_u32(w0, o0); dxb_half_or_u32(w1, o1); dxb_half_or_u32(w2, o2); dxb_half_or_u32(w3, o3);
     DXB_LANES_BEGIN
-        if (lane == 0)
+        uint8_t* out = (lane & 16) ? out1 : out0;
+        if ((lane & 15) == 0 && out)
         {
             uint32_t* o = (uint32_t*)out;
-            o[0] = o0; o[1] = o1; o[2] = o2; o[3] = o3;
+            o[0] = o0[L]; o[1] = o1[L]; o[2] = o2[L]; o[3] = o3[L];
         }
     DXB_LANES_END
 }
 
 #if !DXB_ON_DEVICE
-// emulator entry: px = 16 RGBA fp32 pixels after ConvertScanline
-static inline void dxb_bc6h_encode_block_emul(const dxb_px* px, bool bSigned, uint8_t* out)
+// emulator entry: pxA / pxB = 16 RGBA fp32 pixels each after ConvertScanline; pxB / outB may be null (odd block count)
+static inline void dxb_bc6h_encode_pair_emul(const dxb_px* pxA, const dxb_px* pxB, bool bSigned, uint8_t* outA, uint8_t* outB)
 {
-    dxb_px ip[16];
+    dxb_px ip[32];
     for (int i = 0; i < 16; ++i)
-        ip[i] = dxb_make_px(dxb_bc6h_to_int(px[i].x, bSigned), dxb_bc6h_to_int(px[i].y, bSigned), dxb_bc6h_to_int(px[i].z, bSigned), 0.0f);
-    dxb_bc6h_encode_warp(ip, bSigned, out);
+    {
+        ip[i] = dxb_make_px(dxb_bc6h_to_int(pxA[i].x, bSigned), dxb_bc6h_to_int(pxA[i].y, bSigned), dxb_bc6h_to_int(pxA[i].z, bSigned), 0.0f);
+        ip[16 + i] = pxB ? dxb_make_px(dxb_bc6h_to_int(pxB[i].x, bSigned), dxb_bc6h_to_int(pxB[i].y, bSigned), dxb_bc6h_to_int(pxB[i].z, bSigned), 0.0f)
+                         : dxb_make_px(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    dxb_bc6h_encode_pair(ip, bSigned, outA, pxB ? outB : nullptr);
 }
 #endif

@@ -79,9 +79,8 @@ DXB_DEV dxb_px dxb_bc7_rotate(dxb_px p, int rot)
 // ---------------------------------------------------------------------------------------------------
 // stage 1: residual of the best line through one subset, from its moments v[14] (4 sums, 10 products).
 // est = (trace - lambda_max) + lambda_max * qf  where qf models the index quantisation along the axis.
-// lambda_max: three power-iteration steps on the covariance scaled to unit trace (so nothing needs
-// renormalising between steps: the largest eigenvalue of the scaled matrix is >= 1/4), Rayleigh quotient
-// at the end.  n = pixel count of the subset (0..16).
+// lambda_max: DXB_BC7_EST_ITERS un-normalised power-iteration steps, Rayleigh quotient at the end.
+// n = pixel count of the subset (0..16).
 DXB_TABLE float dxb_rcp16[17] = { 1.0f, 1.0f, 1.0f / 2.0f, 1.0f / 3.0f, 1.0f / 4.0f, 1.0f / 5.0f, 1.0f / 6.0f, 1.0f / 7.0f, 1.0f / 8.0f,
                                   1.0f / 9.0f, 1.0f / 10.0f, 1.0f / 11.0f, 1.0f / 12.0f, 1.0f / 13.0f, 1.0f / 14.0f, 1.0f / 15.0f, 1.0f / 16.0f };
 
@@ -89,17 +88,16 @@ DXB_DEV float dxb_bc7_subset_estimate(uint32_t n, const float* v, float qf)
 {
     const float inv = dxb_rcp16[n];
     const float* s = v; const float* m = v + 4;
-    const float a00 = dxb_fma(-s[0] * inv, s[0], m[0]), a01 = dxb_fma(-s[0] * inv, s[1], m[1]);
-    const float a02 = dxb_fma(-s[0] * inv, s[2], m[2]), a03 = dxb_fma(-s[0] * inv, s[3], m[3]);
-    const float a11 = dxb_fma(-s[1] * inv, s[1], m[4]), a12 = dxb_fma(-s[1] * inv, s[2], m[5]);
-    const float a13 = dxb_fma(-s[1] * inv, s[3], m[6]), a22 = dxb_fma(-s[2] * inv, s[2], m[7]);
-    const float a23 = dxb_fma(-s[2] * inv, s[3], m[8]), a33 = dxb_fma(-s[3] * inv, s[3], m[9]);
-    const float tr = (a00 + a11) + (a22 + a33);
+    const float c00 = dxb_fma(-s[0] * inv, s[0], m[0]), c01 = dxb_fma(-s[0] * inv, s[1], m[1]);
+    const float c02 = dxb_fma(-s[0] * inv, s[2], m[2]), c03 = dxb_fma(-s[0] * inv, s[3], m[3]);
+    const float c11 = dxb_fma(-s[1] * inv, s[1], m[4]), c12 = dxb_fma(-s[1] * inv, s[2], m[5]);
+    const float c13 = dxb_fma(-s[1] * inv, s[3], m[6]), c22 = dxb_fma(-s[2] * inv, s[2], m[7]);
+    const float c23 = dxb_fma(-s[2] * inv, s[3], m[8]), c33 = dxb_fma(-s[3] * inv, s[3], m[9]);
+    const float tr = (c00 + c11) + (c22 + c33);
     const bool flat = !(tr > 1e-3f) || (n < 2u);
-    const float sc = flat ? 0.0f : 1.0f / tr;
-    const float c00 = a00 * sc, c01 = a01 * sc, c02 = a02 * sc, c03 = a03 * sc, c11 = a11 * sc;
-    const float c12 = a12 * sc, c13 = a13 * sc, c22 = a22 * sc, c23 = a23 * sc, c33 = a33 * sc;
-    // start from the row with the largest diagonal
+    // start from the row with the largest diagonal.  Entries are at most 16 * 255^2 * 4 = 4.2e6 (and 1.6e10 for the
+    // half-float domain of BC6H), so two un-normalised steps stay inside fp32: |v| <= c^2 * 4, |w| <= c^3 * 16,
+    // v.w <= 4.5e32 (BC6H: scaled by the caller's centring, see dxb_bc6h.cuh)
     const bool b0 = (c00 >= c11 && c00 >= c22 && c00 >= c33);
     const bool b1 = !b0 && (c11 >= c22 && c11 >= c33);
     const bool b2 = !b0 && !b1 && (c22 >= c33);
@@ -118,9 +116,9 @@ DXB_DEV float dxb_bc7_subset_estimate(uint32_t n, const float* v, float qf)
     }
     const float vv = dxb_fma(v0, v0, dxb_fma(v1, v1, dxb_fma(v2, v2, v3 * v3)));
     const float vw = dxb_fma(v0, w0, dxb_fma(v1, w1, dxb_fma(v2, w2, v3 * w3)));
-    const float lam = (vv > 0.0f) ? fminf(vw / vv, 1.0f) : 0.0f;        // of the unit-trace matrix
-    // tr * ((1 - lam) + lam * qf)
-    const float e = tr * dxb_fma(lam, qf, fmaxf(1.0f - lam, 0.0f));
+    const float lam = (vv > 0.0f) ? fminf(vw / vv, tr) : 0.0f;
+    // (tr - lam) + lam * qf
+    const float e = dxb_fma(lam, qf, fmaxf(tr - lam, 0.0f));
     return flat ? 0.0f : e;
 }
 

@@ -62,6 +62,25 @@ int32_t emul_compress(const uint8_t* src, size_t w, size_t h, uint32_t srcFmt, s
         return DXB_S_OK;
     }
 #endif
+#ifdef DXB_EMUL_BC7
+    if (dstFmt == DXB_FMT_BC6H_UF16 || dstFmt == DXB_FMT_BC6H_SF16)
+    {
+        const long total = (long)nbx * (long)nby;
+        #pragma omp parallel for schedule(dynamic, 32)
+        for (long pair = 0; pair < (total + 1) / 2; ++pair)
+        {
+            dxb_px px[2][16];
+            alignas(16) uint8_t blk[2][16];
+            const long u0 = 2 * pair, u1 = u0 + 1;
+            dxb_gather_block(img, (uint32_t)(u0 % nbx), (uint32_t)(u0 / nbx), inF, outF, cflags, px[0]);
+            if (u1 < total) dxb_gather_block(img, (uint32_t)(u1 % nbx), (uint32_t)(u1 / nbx), inF, outF, cflags, px[1]);
+            dxb_bc6h_encode_pair_emul(px[0], (u1 < total) ? px[1] : nullptr, dstFmt == DXB_FMT_BC6H_SF16, blk[0], blk[1]);
+            memcpy(dst + (size_t)u0 * bs, blk[0], bs);
+            if (u1 < total) memcpy(dst + (size_t)u1 * bs, blk[1], bs);
+        }
+        return DXB_S_OK;
+    }
+#endif
     #pragma omp parallel for schedule(dynamic, 8)
     for (long by = 0; by < (long)nby; ++by)
         for (uint32_t bx = 0; bx < nbx; ++bx)
@@ -69,12 +88,7 @@ int32_t emul_compress(const uint8_t* src, size_t w, size_t h, uint32_t srcFmt, s
             dxb_px px[16];
             dxb_gather_block(img, bx, (uint32_t)by, inF, outF, cflags, px);
             alignas(16) uint8_t blk[16];
-#ifdef DXB_EMUL_BC7
-            if (dstFmt == DXB_FMT_BC6H_UF16 || dstFmt == DXB_FMT_BC6H_SF16)
-                dxb_bc6h_encode_block_emul(px, dstFmt == DXB_FMT_BC6H_SF16, blk);
-            else
-#endif
-                dxb_encode_block_bc15(dstFmt, px, bcflags, threshold, blk);
+            dxb_encode_block_bc15(dstFmt, px, bcflags, threshold, blk);
             memcpy(dst + ((size_t)by * nbx + bx) * bs, blk, bs);
         }
     return DXB_S_OK;
