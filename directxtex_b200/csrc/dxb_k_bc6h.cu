@@ -2,7 +2,7 @@
 #include "dxb_launch.h"
 #include "dxb_bc6h.cuh"
 
-__global__ void __launch_bounds__(DXB_BC6H_WARPS * 32) k_compress_bc6h(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
+__global__ void __launch_bounds__(DXB_BC6H_WARPS * 32, DXB_BC6H_MINB) k_compress_bc6h(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
 {
     __shared__ dxb_px spx[DXB_BC6H_WARPS][32];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, hl = lane & 15u;

@@ -43,7 +43,12 @@ struct dxb_mip_params
 #ifndef DXB_BC7_MINB
 #define DXB_BC7_MINB 3        // __launch_bounds__ min CTAs per SM of k_compress_bc7
 #endif
-#define DXB_BC6H_WARPS 8      // warps per CTA of k_compress_bc6h (one block per warp)
+#ifndef DXB_BC6H_WARPS
+#define DXB_BC6H_WARPS 8      // warps per CTA of k_compress_bc6h (two blocks per warp)
+#endif
+#ifndef DXB_BC6H_MINB
+#define DXB_BC6H_MINB 2
+#endif
 
 // launchers: `grid` CTAs on `stream`; jobs == nullptr -> `single` is used
 void dxb_launch_bc15(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job& single, const dxb_compress_params& P);
