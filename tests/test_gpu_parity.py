@@ -61,6 +61,20 @@ def test_compress_array_batch(oracle):
         assert hr == 0 and np.array_equal(o, want)
 
 
+def test_bc7_bc6h_array_batch_equals_single_images(emul):
+    """BC7 / BC6H encode two consecutive blocks per warp over the whole batch, so a pair can straddle two images (15
+    blocks per image here); the halves are independent, so every image must equal its single-image (emulator) result."""
+    rng = np.random.default_rng(19)
+    w, h = 20, 12
+    srcs = [rng.random((h, w, 4), dtype=np.float32) for _ in range(5)]
+    srcs[2][..., 3] = 1.0
+    for dfmt in (98, 95):
+        outs = capi.compress_array(srcs, w, h, 2, dfmt)
+        for s_, o in zip(srcs, outs):
+            he, want = emul.compress(s_, w, h, 2, dfmt)
+            assert he == 0 and np.array_equal(o, want), dfmt
+
+
 def test_convert_golden_and_random(oracle):
     for name, src, meta, exp in golden_util.cases("convert_"):
         w, h, sf, df, fl = (int(v) for v in meta)
