@@ -13,7 +13,7 @@ SYMBOLS = [
     "dxb200_host_alloc", "dxb200_host_free", "dxb200_compute_pitch", "dxb200_calculate_mip_levels",
     "dxb200_compress", "dxb200_compress_device", "dxb200_decompress", "dxb200_decompress_device",
     "dxb200_convert", "dxb200_convert_device", "dxb200_generate_mipmaps", "dxb200_generate_mipmaps_device",
-    "dxb200_resize", "dxb200_resize_device",
+    "dxb200_resize", "dxb200_resize_device", "dxb200_premultiply_alpha", "dxb200_premultiply_alpha_device",
 ]
 
 
@@ -57,9 +57,11 @@ def _load():
     lib.dxb200_generate_mipmaps_device.argtypes = [IP, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p]
     lib.dxb200_resize.argtypes = [IP, C.c_size_t, C.c_uint32, IP]
     lib.dxb200_resize_device.argtypes = [IP, C.c_size_t, C.c_uint32, IP, C.c_void_p]
+    lib.dxb200_premultiply_alpha.argtypes = [IP, C.c_size_t, C.c_uint32, IP]
+    lib.dxb200_premultiply_alpha_device.argtypes = [IP, C.c_size_t, C.c_uint32, IP, C.c_void_p]
     for name in ("dxb200_init", "dxb200_device_count", "dxb200_compute_pitch", "dxb200_calculate_mip_levels", "dxb200_compress",
                  "dxb200_compress_device", "dxb200_decompress", "dxb200_decompress_device", "dxb200_convert",
-                 "dxb200_convert_device", "dxb200_generate_mipmaps", "dxb200_generate_mipmaps_device", "dxb200_resize", "dxb200_resize_device"):
+                 "dxb200_convert_device", "dxb200_generate_mipmaps", "dxb200_generate_mipmaps_device", "dxb200_resize", "dxb200_resize_device", "dxb200_premultiply_alpha", "dxb200_premultiply_alpha_device"):
         getattr(lib, name).restype = C.c_int32
     return lib
 
@@ -160,6 +162,19 @@ def resize(src, w, h, fmt, width, height, filter=0):
     hr = lib.dxb200_resize(s, 1, filter, d)
     if hr != 0:
         raise DxTexError(hr, "dxb200_resize")
+    return out
+
+
+def premultiply_alpha(src, w, h, fmt, flags=0):
+    """DirectX::PremultiplyAlpha of one image (flags = TEX_PMALPHA_FLAGS); returns the result bytes."""
+    src = np.ascontiguousarray(src).view(np.uint8).reshape(-1)
+    row, sl = F.compute_pitch(fmt, w, h)
+    out = np.zeros(sl, np.uint8)
+    s = images([Image(w, h, fmt, row, sl, _np_ptr(src))])
+    d = images([Image(w, h, fmt, row, sl, _np_ptr(out))])
+    hr = lib.dxb200_premultiply_alpha(s, 1, flags, d)
+    if hr != 0:
+        raise DxTexError(hr, "dxb200_premultiply_alpha")
     return out
 
 

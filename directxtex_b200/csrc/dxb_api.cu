@@ -346,6 +346,53 @@ int32_t launch_convert(dxb_convert_params P, const dxb200_image* src, const dxb2
     return hr;
 }
 
+// ---- PremultiplyAlpha ---------------------------------------------------------------------------
+int32_t plan_pmalpha(const dxb200_image* src, size_t n, uint32_t flags, const dxb200_image* dst, dxb_convert_params* P)
+{
+    if (!src || !dst || !n) return DXB_E_INVALIDARG;
+    const uint32_t fmt = src[0].format;
+    if (is_compressed(fmt)) return DXB_E_NOT_SUPPORTED;                                 // :224-229
+    if (!is_supported_pixel_format(fmt)) return DXB_E_NOT_SUPPORTED;
+    if (!(dxb_convert_flags(fmt) & DXB_CONVF_A)) return DXB_E_NOT_SUPPORTED;            // !HasAlpha
+    for (size_t i = 0; i < n; ++i)
+    {
+        if (!src[i].pixels || !dst[i].pixels) return DXB_E_POINTER;
+        if (src[i].format != fmt || dst[i].format != fmt) return DXB_E_INVALIDARG;
+        if (src[i].width != dst[i].width || src[i].height != dst[i].height || !src[i].width || !src[i].height) return DXB_E_INVALIDARG;
+    }
+    memset(P, 0, sizeof(*P));
+    P->srcFormat = fmt; P->dstFormat = fmt; P->inF = P->outF = dxb_convert_flags(fmt);
+    // TEX_PMALPHA_IGNORE_SRGB = 0x1, TEX_PMALPHA_REVERSE = 0x2; the SRGB bits equal TEX_FILTER_SRGB_IN/OUT (:21-26)
+    const uint32_t lflags = (flags & 0x1u) ? 0u : dxb_resolve_srgb_linear(flags & DXB_FILTER_SRGB_MASK, fmt);
+    P->flags = (lflags & (DXB_FILTER_SRGB_IN | DXB_FILTER_SRGB_OUT)) | ((flags & 0x2u) ? 1u : 0u);
+    return DXB_S_OK;
+}
+
+int32_t launch_pmalpha(dxb_convert_params P, const dxb200_image* src, const dxb200_image* dst, size_t n, cudaStream_t stream)
+{
+    std::vector<dxb_job> jobs(n);
+    uint64_t total = 0;
+    for (size_t i = 0; i < n; ++i)
+    {
+        dxb_job& j = jobs[i];
+        j.src = src[i].pixels; j.dst = dst[i].pixels; j.srcPitch = src[i].rowPitch; j.dstPitch = dst[i].rowPitch;
+        j.width = (uint32_t)src[i].width; j.height = (uint32_t)src[i].height; j.nbx = j.nby = 0; j.pad = 0;
+        j.firstUnit = (uint32_t)total;
+        total += (uint64_t)j.width * j.height;
+        if (total > 0x7FFFFFFFull) return DXB_E_INVALIDARG;
+    }
+    P.totalUnits = (uint32_t)total; P.njobs = (uint32_t)n;
+    DeviceJobs<dxb_job> dj;
+    int32_t hr = dj.upload(jobs, stream);
+    if (hr != DXB_S_OK) return hr;
+    const uint32_t need = (uint32_t)((total + 255) / 256);
+    const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridRow * 8u));
+    dxb_launch_pmalpha(grid, stream, dj.d, jobs.data(), P);
+    hr = check_launch("k_pmalpha");
+    dj.release();
+    return hr;
+}
+
 // ---- GenerateMipMaps ----------------------------------------------------------------------------
 bool ispow2(size_t x) { return ((x != 0) && !(x & (x - 1))); }
 
@@ -772,6 +819,33 @@ int32_t dxb200_generate_mipmaps(const dxb200_image* chain, size_t items, size_t 
         it = k;
     }
     return hr;
+}
+
+int32_t dxb200_premultiply_alpha_device(const dxb200_image* src, size_t nimages, uint32_t flags, const dxb200_image* dst, void* stream)
+{
+    dxb_convert_params P;
+    int32_t hr = plan_pmalpha(src, nimages, flags, dst, &P);
+    if (hr != DXB_S_OK) return hr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        hr = ensure_init_locked();
+    }
+    if (hr != DXB_S_OK) return hr;
+    return launch_pmalpha(P, src, dst, nimages, static_cast<cudaStream_t>(stream));
+}
+
+int32_t dxb200_premultiply_alpha(const dxb200_image* src, size_t nimages, uint32_t flags, const dxb200_image* dst)
+{
+    dxb_convert_params P;
+    int32_t hr = plan_pmalpha(src, nimages, flags, dst, &P);
+    if (hr != DXB_S_OK) return hr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    hr = ensure_init_locked();
+    if (hr != DXB_S_OK) return hr;
+    BandSplit bands;
+    split_bands(src, dst, nimages, 1, 1, false, false, bands);
+    return run_staged(bands.src.data(), bands.dst.data(), bands.src.size(),
+        [&](const dxb200_image* ds, const dxb200_image* dd, size_t cnt, cudaStream_t st) { return launch_pmalpha(P, ds, dd, cnt, st); });
 }
 
 int32_t dxb200_resize_device(const dxb200_image* src, size_t nimages, uint32_t filter, const dxb200_image* dst, void* stream)

@@ -154,6 +154,84 @@ void dxb_launch_convert(unsigned grid, cudaStream_t stream, const dxb_job* jobs,
     k_convert<<<grid, 256, 0, stream>>>(jobs, hostJobs[0], P);
 }
 
+// ------------------------------------------------------------------------------------------------ premultiplied alpha
+// PremultiplyAlpha_ / PremultiplyAlphaLinear / DemultiplyAlpha / DemultiplyAlphaLinear (DirectXTexPMAlpha.cpp:30-208):
+// load (linear), rgb *= a  or  (a > 0) rgb /= a, store (linear).  P.flags = resolved TEX_FILTER_SRGB_IN/OUT bits, bit 0 = reverse.
+__device__ __forceinline__ dxb_px dxb_pmalpha_op(dxb_px v, bool reverse)
+{
+    if (!reverse) return dxb_make_px(v.x * v.w, v.y * v.w, v.z * v.w, v.w);
+    if (v.w > 0.0f) return dxb_make_px(v.x / v.w, v.y / v.w, v.z / v.w, v.w);
+    return dxb_make_px(v.w, v.w, v.w, v.w);       // alpha <= 0: the reference selects xyz from the un-divided splat of w (:139-146)
+}
+__global__ void __launch_bounds__(256) k_pmalpha(const dxb_job* __restrict__ jobs, dxb_job single, dxb_convert_params P)
+{
+    const uint32_t lflags = P.flags & (DXB_FILTER_SRGB_IN | DXB_FILTER_SRGB_OUT);
+    const bool reverse = (P.flags & 1u) != 0u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x; unit < P.totalUnits; unit += stride)
+    {
+        const dxb_job& j = dxb_find_job(jobs, P.njobs, single, unit);
+        const uint32_t local = unit - j.firstUnit;
+        const uint32_t y = local / j.width, x = local - y * j.width;
+        const dxb_px v = dxb_load_linear(P.srcFormat, j.src, j.srcPitch, x, y, lflags);
+        dxb_store_linear(P.srcFormat, j.dst, j.dstPitch, x, y, dxb_pmalpha_op(v, reverse), lflags);
+    }
+}
+// hot formats: compile-time format / direction / sRGB-ness, one 16-byte vector (16/bpp pixels) per thread,
+// grid = (ceil(chunksPerRow / 256), rows, jobs)
+template <uint32_t FMT, bool REVERSE, bool SRGB>
+__global__ void __launch_bounds__(256) k_pmalpha_vec(const dxb_job* __restrict__ jobs, dxb_job single, dxb_convert_params P)
+{
+    constexpr int B = (int)dxb_bytes_per_pixel(FMT), PPT = 16 / B;
+    constexpr uint32_t LF = SRGB ? (DXB_FILTER_SRGB_IN | DXB_FILTER_SRGB_OUT) : 0u;
+    const dxb_job& j = (jobs == nullptr) ? single : jobs[blockIdx.z];
+    const uint32_t y = blockIdx.y;
+    const uint32_t x0 = (blockIdx.x * 256u + threadIdx.x) * PPT;
+    if (x0 >= j.width) return;
+    const uint8_t* srow = j.src + (size_t)y * j.srcPitch;
+    uint8_t* drow = j.dst + (size_t)y * j.dstPitch;
+    if (x0 + PPT <= j.width)
+    {
+        __align__(16) uint8_t buf[16];
+        *reinterpret_cast<uint4*>(buf) = dxb_ld_stream<16>(srow + (size_t)x0 * B);
+        #pragma unroll
+        for (int k = 0; k < PPT; ++k)
+        {
+            dxb_px v = dxb_load_pixel(FMT, buf, k);
+            if (LF & DXB_FILTER_SRGB_IN) v = dxb_srgb_to_linear(v);
+            v = dxb_pmalpha_op(v, REVERSE);
+            if (LF & DXB_FILTER_SRGB_OUT) v = dxb_linear_to_srgb(v);
+            dxb_store_pixel(FMT, buf, k, v);
+        }
+        dxb_st_stream<16>(drow + (size_t)x0 * B, *reinterpret_cast<const uint4*>(buf));
+    }
+    else
+        for (uint32_t x = x0; x < j.width; ++x)
+            dxb_store_linear(FMT, drow, 0, x, 0, dxb_pmalpha_op(dxb_load_linear(FMT, srow, 0, x, 0, LF), REVERSE), LF);
+}
+
+void dxb_launch_pmalpha(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job* hostJobs, const dxb_convert_params& P)
+{
+    const uint32_t lf = P.flags & (DXB_FILTER_SRGB_IN | DXB_FILTER_SRGB_OUT);
+    const bool srgb = (lf == (DXB_FILTER_SRGB_IN | DXB_FILTER_SRGB_OUT)), rev = (P.flags & 1u) != 0u;
+    const uint32_t B = dxb_bytes_per_pixel(P.srcFormat);
+    if ((srgb || lf == 0) && (B == 4 || B == 8 || B == 16) && convert_vec_ok(hostJobs, P.njobs, B, B))
+    {
+        const uint32_t ppt = 16u / B;
+        const uint32_t chunksPerRow = (hostJobs[0].width + ppt - 1) / ppt;
+        const dim3 g((chunksPerRow + 255u) / 256u, hostJobs[0].height, P.njobs);
+#define DXB_X(FMT) if (P.srcFormat == FMT) { \
+            if (rev && srgb) k_pmalpha_vec<FMT, true, true><<<g, 256, 0, stream>>>(jobs, hostJobs[0], P); \
+            else if (rev) k_pmalpha_vec<FMT, true, false><<<g, 256, 0, stream>>>(jobs, hostJobs[0], P); \
+            else if (srgb) k_pmalpha_vec<FMT, false, true><<<g, 256, 0, stream>>>(jobs, hostJobs[0], P); \
+            else k_pmalpha_vec<FMT, false, false><<<g, 256, 0, stream>>>(jobs, hostJobs[0], P); \
+            return; }
+        DXB_X(28) DXB_X(29) DXB_X(87) DXB_X(91) DXB_X(10) DXB_X(2)
+#undef DXB_X
+    }
+    k_pmalpha<<<grid, 256, 0, stream>>>(jobs, hostJobs[0], P);
+}
+
 // ------------------------------------------------------------------------------------------------ tiled mips
 template <uint32_t FMT, uint32_t MODE>
 __device__ __forceinline__ dxb_px dxb_mip_eval(const dxb_mip_job& j, uint32_t x, uint32_t y, const dxb_mip_params& P, uint32_t lflags)

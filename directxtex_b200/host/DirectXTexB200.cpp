@@ -404,4 +404,59 @@ HRESULT Resize(const Image* srcImages, size_t nimages, const TexMetadata& metada
     catch (...) { return E_FAIL; }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// PremultiplyAlpha (DirectXTexPMAlpha.cpp:214-344)
+HRESULT PremultiplyAlpha(const Image& srcImage, TEX_PMALPHA_FLAGS flags, ScratchImage& image) noexcept
+{
+    if (!srcImage.pixels) return E_POINTER;
+    if (IsCompressed(srcImage.format) || !implemented_pixel_format(srcImage.format)) return HRESULT_E_NOT_SUPPORTED;
+    try
+    {
+        HRESULT hr = image.Initialize2D(srcImage.format, srcImage.width, srcImage.height, 1, 1);
+        if (FAILED(hr)) return hr;
+        const Image* r = image.GetImage(0, 0, 0);
+        if (!r) { image.Release(); return E_POINTER; }
+        const dxb200_image s = to_c(srcImage), d = to_c(*r);
+        hr = dxb200_premultiply_alpha(&s, 1, static_cast<uint32_t>(flags), &d);
+        if (FAILED(hr)) image.Release();
+        return hr;
+    }
+    catch (...) { return E_FAIL; }
+}
+
+HRESULT PremultiplyAlpha(const Image* srcImages, size_t nimages, const TexMetadata& metadata, TEX_PMALPHA_FLAGS flags, ScratchImage& result) noexcept
+{
+    if (!srcImages || !nimages) return E_INVALIDARG;
+    if (IsCompressed(metadata.format) || !implemented_pixel_format(metadata.format)) return HRESULT_E_NOT_SUPPORTED;
+    if (metadata.IsPMAlpha() != ((flags & TEX_PMALPHA_REVERSE) != 0)) return E_FAIL;                       // :297-298
+    try
+    {
+        TexMetadata m2 = metadata;
+        m2.SetAlphaMode((flags & TEX_PMALPHA_REVERSE) ? TEX_ALPHA_MODE_STRAIGHT : TEX_ALPHA_MODE_PREMULTIPLIED);
+        HRESULT hr = result.Initialize(m2);
+        if (FAILED(hr)) return hr;
+        if (nimages != result.GetImageCount()) { result.Release(); return E_FAIL; }
+        std::vector<dxb200_image> src(nimages), dst(nimages);
+        for (size_t i = 0; i < nimages; ++i)
+        {
+            const Image& s = srcImages[i]; const Image& d = result.GetImages()[i];
+            if (s.format != metadata.format) { result.Release(); return E_FAIL; }
+            if (s.width != d.width || s.height != d.height) { result.Release(); return E_FAIL; }
+            src[i] = to_c(s); dst[i] = to_c(d);
+        }
+        // mip levels have different sizes: one call per distinct size keeps every call uniform
+        size_t i = 0;
+        while (i < nimages && SUCCEEDED(hr))
+        {
+            size_t k = i + 1;
+            while (k < nimages && src[k].width == src[i].width && src[k].height == src[i].height) ++k;
+            hr = dxb200_premultiply_alpha(src.data() + i, k - i, static_cast<uint32_t>(flags), dst.data() + i);
+            i = k;
+        }
+        if (FAILED(hr)) result.Release();
+        return hr;
+    }
+    catch (...) { return E_FAIL; }
+}
+
 } // namespace DirectX

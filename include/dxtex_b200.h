@@ -101,6 +101,13 @@ DXB200_API int32_t  dxb200_generate_mipmaps_device(const dxb200_image* chain, si
 DXB200_API int32_t  dxb200_resize(const dxb200_image* src, size_t nimages, uint32_t filter, const dxb200_image* dst);
 DXB200_API int32_t  dxb200_resize_device(const dxb200_image* src, size_t nimages, uint32_t filter, const dxb200_image* dst, void* stream);
 
+/* DirectX::PremultiplyAlpha (DirectXTexPMAlpha.cpp:214-344; PremultiplyAlpha_ / PremultiplyAlphaLinear / DemultiplyAlpha /
+ * DemultiplyAlphaLinear :30-208).  src[i] -> dst[i], same size and format; flags = TEX_PMALPHA_FLAGS (DirectXTex.h:860-879):
+ * 0x1 IGNORE_SRGB, 0x2 REVERSE (premultiplied -> straight), 0x1000000 / 0x2000000 SRGB_IN / SRGB_OUT.
+ * Formats without alpha or compressed -> HRESULT_E_NOT_SUPPORTED (:224-229).  (first part.) */
+DXB200_API int32_t  dxb200_premultiply_alpha(const dxb200_image* src, size_t nimages, uint32_t flags, const dxb200_image* dst);
+DXB200_API int32_t  dxb200_premultiply_alpha_device(const dxb200_image* src, size_t nimages, uint32_t flags, const dxb200_image* dst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -126,6 +126,18 @@ int32_t ref_resize(const uint8_t* src, size_t w, size_t h, uint32_t fmt, size_t 
     return hr;
 }
 
+// DirectX::PremultiplyAlpha single image (DirectXTexPMAlpha.cpp:214-266)
+int32_t ref_premultiply_alpha(const uint8_t* src, size_t w, size_t h, uint32_t fmt, size_t srcRowPitch, uint32_t flags, uint8_t* dst, size_t dstBytes)
+{
+    Image img = make_image(src, w, h, fmt, srcRowPitch);
+    ScratchImage out;
+    HRESULT hr = PremultiplyAlpha(img, static_cast<TEX_PMALPHA_FLAGS>(flags), out);
+    if (FAILED(hr)) return hr;
+    if (out.GetPixelsSize() > dstBytes) return E_NOT_SUFFICIENT_BUFFER;
+    memcpy(dst, out.GetPixels(), out.GetPixelsSize());
+    return hr;
+}
+
 double ref_generate_mipmaps_timed(const uint8_t* src, size_t w, size_t h, uint32_t fmt, uint32_t filter, size_t levels)
 {
     Image img = make_image(src, w, h, fmt, 0);

@@ -45,6 +45,7 @@ class Ref:
         L.ref_generate_mipmaps.argtypes = [vp, sz, sz, u32, sz, u32, sz, vp, sz, C.POINTER(sz), C.POINTER(sz)]
         L.ref_generate_mipmaps_timed.argtypes = [vp, sz, sz, u32, u32, sz]
         L.ref_resize.argtypes = [vp, sz, sz, u32, sz, sz, sz, u32, vp, sz]
+        L.ref_premultiply_alpha.argtypes = [vp, sz, sz, u32, sz, u32, vp, sz]
         L.ref_generate_mipmaps_timed.restype = C.c_double
         L.ref_compute_mse.argtypes = [vp, u32, vp, u32, sz, sz, C.POINTER(f32), C.POINTER(f32), u32]
         L.ref_encode_block.argtypes = [u32, vp, u32, f32, vp]
@@ -93,6 +94,13 @@ class Ref:
         n = width * height * F.BYTES_PER_PIXEL[fmt]
         out = np.zeros(n, np.uint8)
         hr = self.L.ref_resize(src.ctypes.data, w, h, fmt, 0, width, height, filter, out.ctypes.data, n)
+        return F.hr_u32(hr), out
+
+    def premultiply_alpha(self, src, w, h, fmt, flags=0):
+        src = np.ascontiguousarray(src)
+        n = w * h * F.BYTES_PER_PIXEL[fmt]
+        out = np.zeros(n, np.uint8)
+        hr = self.L.ref_premultiply_alpha(src.ctypes.data, w, h, fmt, 0, flags, out.ctypes.data, n)
         return F.hr_u32(hr), out
 
     def decompress(self, blocks, w, h, bc_fmt, dst_fmt):

@@ -121,3 +121,5 @@ def test_compute_entry_points_fail_loudly_without_gpu():
         capi.generate_mipmaps(a, 8, 8, 28)
     with pytest.raises(capi.DxTexError):
         capi.resize(a, 8, 8, 28, 5, 3)
+    with pytest.raises(capi.DxTexError):
+        capi.premultiply_alpha(a, 8, 8, 28)

@@ -145,6 +145,25 @@ def test_resize_vs_oracle(oracle, fl):
         assert hr == 0 and np.array_equal(got, want), (fmt, w, h, nw, nh, hex(fl))
 
 
+@pytest.mark.parametrize("flags", [0, 0x1, 0x2, 0x3])
+def test_premultiply_alpha_vs_oracle(oracle, flags):
+    """SURVEY 8(f) rank 4 (first part): DirectX::PremultiplyAlpha / demultiply, bit-exact vs the reference for non-sRGB formats;
+    sRGB formats without IGNORE_SRGB go through powf and are held to +-1 code."""
+    rng = np.random.default_rng(23)
+    for (fmt, w, h) in [(28, 64, 32), (87, 37, 5), (2, 33, 9), (10, 40, 8), (11, 16, 16), (24, 24, 8), (29, 64, 16)]:
+        src = oracle_lib.random_image(fmt, w, h, rng)
+        hr, want = oracle.premultiply_alpha(src, w, h, fmt, flags)
+        got = capi.premultiply_alpha(src, w, h, fmt, flags)
+        assert hr == 0
+        if fmt == 29 and not (flags & 1):
+            assert np.abs(got.astype(np.int32) - want.astype(np.int32)).max() <= 1, (fmt, flags)
+        else:
+            assert np.array_equal(got, want), (fmt, w, h, flags)
+    with pytest.raises(capi.DxTexError) as e:
+        capi.premultiply_alpha(np.zeros((8, 8), np.uint8), 8, 8, 61, 0)            # R8 has no alpha
+    assert e.value.hr == F.HRESULT_E_NOT_SUPPORTED
+
+
 def test_bc7_equals_emulator_and_quality(oracle, emul):
     """GPU BC7 == host lock-step emulator (same source, explicit fmaf, -fmad=false) bit for bit, and
     MSE <= 1.02 x the reference CPU encoder's MSE (golden anchor) on each test image."""
