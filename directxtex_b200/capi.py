@@ -14,6 +14,7 @@ SYMBOLS = [
     "dxb200_compress", "dxb200_compress_device", "dxb200_decompress", "dxb200_decompress_device",
     "dxb200_convert", "dxb200_convert_device", "dxb200_generate_mipmaps", "dxb200_generate_mipmaps_device",
     "dxb200_resize", "dxb200_resize_device", "dxb200_premultiply_alpha", "dxb200_premultiply_alpha_device",
+    "dxb200_dds_encode_header", "dxb200_dds_save_memory", "dxb200_dds_get_metadata", "dxb200_dds_load_memory",
 ]
 
 
@@ -21,6 +22,12 @@ class Image(C.Structure):
     """dxb200_image == DirectX::Image (DirectXTex.h:437-445)."""
     _fields_ = [("width", C.c_size_t), ("height", C.c_size_t), ("format", C.c_uint32),
                 ("rowPitch", C.c_size_t), ("slicePitch", C.c_size_t), ("pixels", C.c_void_p)]
+
+
+class Metadata(C.Structure):
+    """dxb200_metadata == DirectX::TexMetadata (DirectXTex.h:187-216)."""
+    _fields_ = [("width", C.c_size_t), ("height", C.c_size_t), ("depth", C.c_size_t), ("arraySize", C.c_size_t), ("mipLevels", C.c_size_t),
+                ("miscFlags", C.c_uint32), ("miscFlags2", C.c_uint32), ("format", C.c_uint32), ("dimension", C.c_uint32)]
 
 
 class DxTexError(RuntimeError):
@@ -59,6 +66,13 @@ def _load():
     lib.dxb200_resize_device.argtypes = [IP, C.c_size_t, C.c_uint32, IP, C.c_void_p]
     lib.dxb200_premultiply_alpha.argtypes = [IP, C.c_size_t, C.c_uint32, IP]
     lib.dxb200_premultiply_alpha_device.argtypes = [IP, C.c_size_t, C.c_uint32, IP, C.c_void_p]
+    MP, SP = C.POINTER(Metadata), C.POINTER(C.c_size_t)
+    lib.dxb200_dds_encode_header.argtypes = [MP, C.c_uint32, C.c_void_p, C.c_size_t, SP]
+    lib.dxb200_dds_save_memory.argtypes = [IP, C.c_size_t, MP, C.c_uint32, C.c_void_p, C.c_size_t, SP]
+    lib.dxb200_dds_get_metadata.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, MP, SP]
+    lib.dxb200_dds_load_memory.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, IP, C.c_size_t]
+    for name in ("dxb200_dds_encode_header", "dxb200_dds_save_memory", "dxb200_dds_get_metadata", "dxb200_dds_load_memory"):
+        getattr(lib, name).restype = C.c_int32
     for name in ("dxb200_init", "dxb200_device_count", "dxb200_compute_pitch", "dxb200_calculate_mip_levels", "dxb200_compress",
                  "dxb200_compress_device", "dxb200_decompress", "dxb200_decompress_device", "dxb200_convert",
                  "dxb200_convert_device", "dxb200_generate_mipmaps", "dxb200_generate_mipmaps_device", "dxb200_resize", "dxb200_resize_device", "dxb200_premultiply_alpha", "dxb200_premultiply_alpha_device"):
@@ -176,6 +190,54 @@ def premultiply_alpha(src, w, h, fmt, flags=0):
     if hr != 0:
         raise DxTexError(hr, "dxb200_premultiply_alpha")
     return out
+
+
+def texture_layout(fmt, w, h, array_size=1, mip_levels=1):
+    """(list of (offset, w, h, rowPitch, slicePitch) item-major / mip-minor, total bytes) as ScratchImage::Initialize lays it out."""
+    out, off = [], 0
+    for _ in range(array_size):
+        lw, lh = w, h
+        for _ in range(mip_levels):
+            row, sl = F.compute_pitch(fmt, lw, lh)
+            out.append((off, lw, lh, row, sl))
+            off += sl
+            lw, lh = max(1, lw >> 1), max(1, lh >> 1)
+    return out, off
+
+
+def dds_save(pixels, fmt, w, h, array_size=1, mip_levels=1, misc_flags=0, misc_flags2=0, flags=0):
+    """SaveToDDSMemory of a 2D texture whose images are packed in `pixels` in ScratchImage order; returns the file bytes."""
+    pixels = np.ascontiguousarray(pixels).view(np.uint8).reshape(-1)
+    layout, total = texture_layout(fmt, w, h, array_size, mip_levels)
+    assert pixels.size == total
+    imgs = images([Image(lw, lh, fmt, row, sl, _np_ptr(pixels) + off) for (off, lw, lh, row, sl) in layout])
+    md = Metadata(w, h, 1, array_size, mip_levels, misc_flags, misc_flags2, fmt, 3)
+    need = C.c_size_t()
+    hr = lib.dxb200_dds_save_memory(imgs, len(layout), C.byref(md), flags, None, 0, C.byref(need))
+    if hr != 0:
+        raise DxTexError(hr, "dxb200_dds_save_memory")
+    out = np.zeros(need.value, np.uint8)
+    hr = lib.dxb200_dds_save_memory(imgs, len(layout), C.byref(md), flags, _np_ptr(out), out.size, C.byref(need))
+    if hr != 0:
+        raise DxTexError(hr, "dxb200_dds_save_memory")
+    return out
+
+
+def dds_load(data, flags=0):
+    """LoadFromDDSMemory; returns (Metadata, pixels packed in ScratchImage order)."""
+    data = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+    md = Metadata()
+    off = C.c_size_t()
+    hr = lib.dxb200_dds_get_metadata(_np_ptr(data), data.size, flags, C.byref(md), C.byref(off))
+    if hr != 0:
+        raise DxTexError(hr, "dxb200_dds_get_metadata")
+    layout, total = texture_layout(md.format, md.width, md.height, md.arraySize, md.mipLevels)
+    pixels = np.zeros(total, np.uint8)
+    imgs = images([Image(lw, lh, md.format, row, sl, _np_ptr(pixels) + o) for (o, lw, lh, row, sl) in layout])
+    hr = lib.dxb200_dds_load_memory(_np_ptr(data), data.size, flags, imgs, len(layout))
+    if hr != 0:
+        raise DxTexError(hr, "dxb200_dds_load_memory")
+    return md, pixels
 
 
 def decompress(blocks, w, h, bc_fmt, dst_fmt):

@@ -6,6 +6,7 @@
 #include "DirectXTexB200.h"
 #include "../../include/dxtex_b200.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -457,6 +458,141 @@ HRESULT PremultiplyAlpha(const Image* srcImages, size_t nimages, const TexMetada
         return hr;
     }
     catch (...) { return E_FAIL; }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// DDS container (DirectXTexDDS.cpp); the format logic lives behind the C ABI (host/dxb_dds.cpp)
+Blob& Blob::operator=(Blob&& o) noexcept
+{
+    if (this != &o) { Release(); m_buffer = o.m_buffer; m_size = o.m_size; o.m_buffer = nullptr; o.m_size = 0; }
+    return *this;
+}
+HRESULT Blob::Initialize(size_t size) noexcept
+{
+    if (!size) return E_INVALIDARG;
+    Release();
+    m_buffer = static_cast<uint8_t*>(std::malloc(size));
+    if (!m_buffer) return E_OUTOFMEMORY;
+    m_size = size;
+    return S_OK;
+}
+void Blob::Release() noexcept { std::free(m_buffer); m_buffer = nullptr; m_size = 0; }
+
+namespace {
+    dxb200_metadata md_to_c(const TexMetadata& m) noexcept
+    {
+        return { m.width, m.height, m.depth, m.arraySize, m.mipLevels, m.miscFlags, m.miscFlags2, static_cast<uint32_t>(m.format), static_cast<uint32_t>(m.dimension) };
+    }
+    TexMetadata from_c(const dxb200_metadata& m) noexcept
+    {
+        TexMetadata r{};
+        r.width = m.width; r.height = m.height; r.depth = m.depth; r.arraySize = m.arraySize; r.mipLevels = m.mipLevels;
+        r.miscFlags = m.miscFlags; r.miscFlags2 = m.miscFlags2; r.format = static_cast<DXGI_FORMAT>(m.format); r.dimension = static_cast<TEX_DIMENSION>(m.dimension);
+        return r;
+    }
+    HRESULT read_file(const char* path, std::vector<uint8_t>& data) noexcept
+    {
+        if (!path) return E_INVALIDARG;
+        FILE* f = std::fopen(path, "rb");
+        if (!f) return static_cast<HRESULT>(0x80070002);                     // HRESULT_FROM_WIN32(ERROR_FILE_NOT_FOUND)
+        std::fseek(f, 0, SEEK_END); const long n = std::ftell(f); std::fseek(f, 0, SEEK_SET);
+        HRESULT hr = S_OK;
+        try { data.resize(n > 0 ? static_cast<size_t>(n) : 0); } catch (...) { hr = E_OUTOFMEMORY; }
+        if (SUCCEEDED(hr) && std::fread(data.data(), 1, data.size(), f) != data.size()) hr = E_FAIL;
+        std::fclose(f);
+        return hr;
+    }
+}
+
+HRESULT GetMetadataFromDDSMemory(const void* pSource, size_t size, DDS_FLAGS flags, TexMetadata& metadata) noexcept
+{
+    if (!pSource || !size) return E_INVALIDARG;
+    dxb200_metadata m;
+    const HRESULT hr = dxb200_dds_get_metadata(pSource, size, static_cast<uint32_t>(flags), &m, nullptr);
+    if (SUCCEEDED(hr)) metadata = from_c(m);
+    return hr;
+}
+HRESULT GetMetadataFromDDSFile(const char* szFile, DDS_FLAGS flags, TexMetadata& metadata) noexcept
+{
+    std::vector<uint8_t> data;
+    const HRESULT hr = read_file(szFile, data);
+    return FAILED(hr) ? hr : GetMetadataFromDDSMemory(data.data(), data.size(), flags, metadata);
+}
+HRESULT LoadFromDDSMemory(const void* pSource, size_t size, DDS_FLAGS flags, TexMetadata* metadata, ScratchImage& image) noexcept
+{
+    if (!pSource || !size) return E_INVALIDARG;
+    image.Release();
+    dxb200_metadata m;
+    HRESULT hr = dxb200_dds_get_metadata(pSource, size, static_cast<uint32_t>(flags), &m, nullptr);
+    if (FAILED(hr)) return hr;
+    try
+    {
+        const TexMetadata md = from_c(m);
+        hr = image.Initialize(md);
+        if (FAILED(hr)) return hr;
+        std::vector<dxb200_image> imgs(image.GetImageCount());
+        for (size_t i = 0; i < imgs.size(); ++i) imgs[i] = to_c(image.GetImages()[i]);
+        hr = dxb200_dds_load_memory(pSource, size, static_cast<uint32_t>(flags), imgs.data(), imgs.size());
+        if (FAILED(hr)) { image.Release(); return hr; }
+        if (metadata) *metadata = md;
+        return S_OK;
+    }
+    catch (...) { image.Release(); return E_OUTOFMEMORY; }
+}
+HRESULT LoadFromDDSFile(const char* szFile, DDS_FLAGS flags, TexMetadata* metadata, ScratchImage& image) noexcept
+{
+    std::vector<uint8_t> data;
+    const HRESULT hr = read_file(szFile, data);
+    return FAILED(hr) ? hr : LoadFromDDSMemory(data.data(), data.size(), flags, metadata, image);
+}
+HRESULT SaveToDDSMemory(const Image* images, size_t nimages, const TexMetadata& metadata, DDS_FLAGS flags, Blob& blob) noexcept
+{
+    if (!images || !nimages) return E_INVALIDARG;
+    try
+    {
+        std::vector<dxb200_image> imgs(nimages);
+        for (size_t i = 0; i < nimages; ++i) imgs[i] = to_c(images[i]);
+        const dxb200_metadata m = md_to_c(metadata);
+        size_t need = 0;
+        HRESULT hr = dxb200_dds_save_memory(imgs.data(), nimages, &m, static_cast<uint32_t>(flags), nullptr, 0, &need);
+        if (FAILED(hr)) return hr;
+        blob.Release();
+        hr = blob.Initialize(need);
+        if (FAILED(hr)) return hr;
+        hr = dxb200_dds_save_memory(imgs.data(), nimages, &m, static_cast<uint32_t>(flags), blob.GetBufferPointer(), blob.GetBufferSize(), &need);
+        if (FAILED(hr)) blob.Release();
+        return hr;
+    }
+    catch (...) { return E_OUTOFMEMORY; }
+}
+HRESULT SaveToDDSMemory(const Image& image, DDS_FLAGS flags, Blob& blob) noexcept
+{
+    TexMetadata m{};
+    m.width = image.width; m.height = image.height; m.depth = 1; m.arraySize = 1; m.mipLevels = 1;
+    m.format = image.format; m.dimension = TEX_DIMENSION_TEXTURE2D;
+    return SaveToDDSMemory(&image, 1, m, flags, blob);
+}
+HRESULT SaveToDDSFile(const Image* images, size_t nimages, const TexMetadata& metadata, DDS_FLAGS flags, const char* szFile) noexcept
+{
+    if (!szFile) return E_INVALIDARG;
+    Blob blob;
+    HRESULT hr = SaveToDDSMemory(images, nimages, metadata, flags, blob);
+    if (FAILED(hr)) return hr;
+    FILE* f = std::fopen(szFile, "wb");
+    if (!f) return E_FAIL;
+    if (std::fwrite(blob.GetConstBufferPointer(), 1, blob.GetBufferSize(), f) != blob.GetBufferSize()) hr = E_FAIL;
+    std::fclose(f);
+    return hr;
+}
+HRESULT SaveToDDSFile(const Image& image, DDS_FLAGS flags, const char* szFile) noexcept
+{
+    Blob blob;
+    HRESULT hr = SaveToDDSMemory(image, flags, blob);
+    if (FAILED(hr)) return hr;
+    TexMetadata m{};
+    m.width = image.width; m.height = image.height; m.depth = 1; m.arraySize = 1; m.mipLevels = 1;
+    m.format = image.format; m.dimension = TEX_DIMENSION_TEXTURE2D;
+    return SaveToDDSFile(&image, 1, m, flags, szFile);
 }
 
 } // namespace DirectX

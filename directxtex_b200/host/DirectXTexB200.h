@@ -152,6 +152,38 @@ namespace DirectX
         uint8_t* m_memory;
     };
 
+    // ---- DDS container (DirectXTex.h:232-279 DDS_FLAGS, :425-435 Blob, :518-560 the DDS I/O functions); host-side only
+    enum DDS_FLAGS : uint32_t
+    {
+        DDS_FLAGS_NONE = 0, DDS_FLAGS_IGNORE_MIPS = 0x100,
+        DDS_FLAGS_FORCE_DX10_EXT = 0x10000, DDS_FLAGS_FORCE_DX10_EXT_MISC2 = 0x20000, DDS_FLAGS_ALLOW_LARGE_FILES = 0x1000000,
+    };
+    class DXTEXB200_API Blob
+    {
+    public:
+        Blob() noexcept : m_buffer(nullptr), m_size(0) {}
+        Blob(Blob&& o) noexcept : m_buffer(o.m_buffer), m_size(o.m_size) { o.m_buffer = nullptr; o.m_size = 0; }
+        Blob& operator=(Blob&& o) noexcept;
+        Blob(const Blob&) = delete;
+        Blob& operator=(const Blob&) = delete;
+        ~Blob() { Release(); }
+        HRESULT Initialize(size_t size) noexcept;
+        void Release() noexcept;
+        uint8_t* GetBufferPointer() const noexcept { return m_buffer; }
+        const uint8_t* GetConstBufferPointer() const noexcept { return m_buffer; }
+        size_t GetBufferSize() const noexcept { return m_size; }
+    private:
+        uint8_t* m_buffer; size_t m_size;
+    };
+    DXTEXB200_API HRESULT GetMetadataFromDDSMemory(const void* pSource, size_t size, DDS_FLAGS flags, TexMetadata& metadata) noexcept;
+    DXTEXB200_API HRESULT GetMetadataFromDDSFile(const char* szFile, DDS_FLAGS flags, TexMetadata& metadata) noexcept;
+    DXTEXB200_API HRESULT LoadFromDDSMemory(const void* pSource, size_t size, DDS_FLAGS flags, TexMetadata* metadata, ScratchImage& image) noexcept;
+    DXTEXB200_API HRESULT LoadFromDDSFile(const char* szFile, DDS_FLAGS flags, TexMetadata* metadata, ScratchImage& image) noexcept;
+    DXTEXB200_API HRESULT SaveToDDSMemory(const Image& image, DDS_FLAGS flags, Blob& blob) noexcept;
+    DXTEXB200_API HRESULT SaveToDDSMemory(const Image* images, size_t nimages, const TexMetadata& metadata, DDS_FLAGS flags, Blob& blob) noexcept;
+    DXTEXB200_API HRESULT SaveToDDSFile(const Image& image, DDS_FLAGS flags, const char* szFile) noexcept;
+    DXTEXB200_API HRESULT SaveToDDSFile(const Image* images, size_t nimages, const TexMetadata& metadata, DDS_FLAGS flags, const char* szFile) noexcept;
+
     // ---- the accelerated operations: same signatures as DirectXTex.h:818-832, 841-846, 929-944, 965-968
     DXTEXB200_API HRESULT Convert(const Image& srcImage, DXGI_FORMAT format, TEX_FILTER_FLAGS filter, float threshold, ScratchImage& image) noexcept;
     DXTEXB200_API HRESULT Convert(const Image* srcImages, size_t nimages, const TexMetadata& metadata, DXGI_FORMAT format, TEX_FILTER_FLAGS filter, float threshold, ScratchImage& result) noexcept;

@@ -108,6 +108,27 @@ DXB200_API int32_t  dxb200_resize_device(const dxb200_image* src, size_t nimages
 DXB200_API int32_t  dxb200_premultiply_alpha(const dxb200_image* src, size_t nimages, uint32_t flags, const dxb200_image* dst);
 DXB200_API int32_t  dxb200_premultiply_alpha_device(const dxb200_image* src, size_t nimages, uint32_t flags, const dxb200_image* dst, void* stream);
 
+/* ---- DDS container (host-side only, no GPU work) ------------------------------------------------
+ * dxb200_metadata is a field-for-field mirror of DirectX::TexMetadata (DirectXTex.h:187-216).
+ * EncodeDDSHeader (DirectXTexDDS.cpp:711-1043), SaveToDDSMemory (:2403-2620), GetMetadataFromDDSMemory / DecodeDDSHeader
+ * (:319-683, 1960-2003), LoadFromDDSMemory (:2008-2100).  TEXTURE2D resources (arrays, cubemaps, mip chains) in the
+ * formats this library implements; flags = DDS_FLAGS (DirectXTex.h:232-279): FORCE_DX10_EXT, FORCE_DX10_EXT_MISC2,
+ * IGNORE_MIPS, ALLOW_LARGE_FILES are honoured, conversion / legacy-expansion flags -> HRESULT_E_NOT_SUPPORTED.
+ * save/encode: dst == NULL only computes *required.  load: `images` describes the destination (item-major, mip-minor)
+ * as ScratchImage::Initialize(metadata) lays it out. */
+typedef struct dxb200_metadata
+{
+    size_t   width, height, depth, arraySize, mipLevels;
+    uint32_t miscFlags, miscFlags2;
+    uint32_t format;        /* DXGI_FORMAT */
+    uint32_t dimension;     /* TEX_DIMENSION: 3 = TEXTURE2D */
+} dxb200_metadata;
+DXB200_API int32_t  dxb200_dds_encode_header(const dxb200_metadata* metadata, uint32_t flags, void* dst, size_t maxsize, size_t* required);
+DXB200_API int32_t  dxb200_dds_save_memory(const dxb200_image* images, size_t nimages, const dxb200_metadata* metadata, uint32_t flags,
+                                           void* dst, size_t maxsize, size_t* required);
+DXB200_API int32_t  dxb200_dds_get_metadata(const void* src, size_t size, uint32_t flags, dxb200_metadata* metadata, size_t* dataOffset);
+DXB200_API int32_t  dxb200_dds_load_memory(const void* src, size_t size, uint32_t flags, const dxb200_image* images, size_t nimages);
+
 #ifdef __cplusplus
 }
 #endif

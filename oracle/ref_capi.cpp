@@ -138,6 +138,47 @@ int32_t ref_premultiply_alpha(const uint8_t* src, size_t w, size_t h, uint32_t f
     return hr;
 }
 
+// DDS container (DirectXTexDDS.cpp): a 2D texture (array / cubemap / mip chain) whose images live in `pixels` in ScratchImage
+// order.  meta = {width, height, arraySize, mipLevels, format, miscFlags, miscFlags2}.
+static HRESULT build_scratch(const uint8_t* pixels, size_t pixelBytes, const uint64_t* meta, ScratchImage& img)
+{
+    TexMetadata md = {};
+    md.width = meta[0]; md.height = meta[1]; md.depth = 1; md.arraySize = meta[2]; md.mipLevels = meta[3];
+    md.format = static_cast<DXGI_FORMAT>(meta[4]); md.miscFlags = static_cast<uint32_t>(meta[5]); md.miscFlags2 = static_cast<uint32_t>(meta[6]);
+    md.dimension = TEX_DIMENSION_TEXTURE2D;
+    HRESULT hr = img.Initialize(md);
+    if (FAILED(hr)) return hr;
+    if (img.GetPixelsSize() != pixelBytes) return E_INVALIDARG;
+    memcpy(img.GetPixels(), pixels, pixelBytes);
+    return S_OK;
+}
+int32_t ref_dds_save(const uint8_t* pixels, size_t pixelBytes, const uint64_t* meta, uint32_t flags, uint8_t* dst, size_t cap, size_t* written)
+{
+    ScratchImage img;
+    HRESULT hr = build_scratch(pixels, pixelBytes, meta, img);
+    if (FAILED(hr)) return hr;
+    Blob blob;
+    hr = SaveToDDSMemory(img.GetImages(), img.GetImageCount(), img.GetMetadata(), static_cast<DDS_FLAGS>(flags), blob);
+    if (FAILED(hr)) return hr;
+    *written = blob.GetBufferSize();
+    if (blob.GetBufferSize() > cap) return E_NOT_SUFFICIENT_BUFFER;
+    memcpy(dst, blob.GetBufferPointer(), blob.GetBufferSize());
+    return hr;
+}
+// meta receives the 7 fields above; pixels = the loaded ScratchImage memory
+int32_t ref_dds_load(const uint8_t* src, size_t size, uint32_t flags, uint64_t* meta, uint8_t* pixels, size_t cap, size_t* pixelBytes)
+{
+    TexMetadata md; ScratchImage img;
+    HRESULT hr = LoadFromDDSMemory(src, size, static_cast<DDS_FLAGS>(flags), &md, img);
+    if (FAILED(hr)) return hr;
+    meta[0] = md.width; meta[1] = md.height; meta[2] = md.arraySize; meta[3] = md.mipLevels; meta[4] = md.format;
+    meta[5] = md.miscFlags; meta[6] = md.miscFlags2;
+    *pixelBytes = img.GetPixelsSize();
+    if (img.GetPixelsSize() > cap) return E_NOT_SUFFICIENT_BUFFER;
+    memcpy(pixels, img.GetPixels(), img.GetPixelsSize());
+    return hr;
+}
+
 double ref_generate_mipmaps_timed(const uint8_t* src, size_t w, size_t h, uint32_t fmt, uint32_t filter, size_t levels)
 {
     Image img = make_image(src, w, h, fmt, 0);

@@ -65,5 +65,16 @@ int main(int argc, char** argv)
         hr = Decompress(imgs[0], DXGI_FORMAT(arg), out);
     printf("hr=0x%08X images=%zu bytes=%zu\n", unsigned(hr), out.GetImageCount(), out.GetPixelsSize());
     if (FAILED(hr)) return 1;
+    // an output path ending in .dds is written as a DDS file (texconv.cpp:3877 SaveToDDSFile) and read back as a check
+    const std::string outPath = argv[3];
+    if (outPath.size() > 4 && outPath.compare(outPath.size() - 4, 4, ".dds") == 0)
+    {
+        hr = SaveToDDSFile(out.GetImages(), out.GetImageCount(), out.GetMetadata(), DDS_FLAGS_NONE, outPath.c_str());
+        TexMetadata back{}; ScratchImage re;
+        if (SUCCEEDED(hr)) hr = LoadFromDDSFile(outPath.c_str(), DDS_FLAGS_NONE, &back, re);
+        if (SUCCEEDED(hr) && (re.GetPixelsSize() != out.GetPixelsSize() || memcmp(re.GetPixels(), out.GetPixels(), out.GetPixelsSize()) != 0)) hr = E_FAIL;
+        printf("dds hr=0x%08X\n", unsigned(hr));
+        return SUCCEEDED(hr) ? 0 : 5;
+    }
     return dump(argv[3], out.GetPixels(), out.GetPixelsSize()) ? 0 : 4;
 }

@@ -46,6 +46,8 @@ class Ref:
         L.ref_generate_mipmaps_timed.argtypes = [vp, sz, sz, u32, u32, sz]
         L.ref_resize.argtypes = [vp, sz, sz, u32, sz, sz, sz, u32, vp, sz]
         L.ref_premultiply_alpha.argtypes = [vp, sz, sz, u32, sz, u32, vp, sz]
+        L.ref_dds_save.argtypes = [vp, sz, vp, u32, vp, sz, C.POINTER(sz)]
+        L.ref_dds_load.argtypes = [vp, sz, u32, vp, vp, sz, C.POINTER(sz)]
         L.ref_generate_mipmaps_timed.restype = C.c_double
         L.ref_compute_mse.argtypes = [vp, u32, vp, u32, sz, sz, C.POINTER(f32), C.POINTER(f32), u32]
         L.ref_encode_block.argtypes = [u32, vp, u32, f32, vp]
@@ -102,6 +104,22 @@ class Ref:
         out = np.zeros(n, np.uint8)
         hr = self.L.ref_premultiply_alpha(src.ctypes.data, w, h, fmt, 0, flags, out.ctypes.data, n)
         return F.hr_u32(hr), out
+
+    def dds_save(self, pixels, fmt, w, h, array_size=1, mip_levels=1, misc_flags=0, misc_flags2=0, flags=0):
+        pixels = np.ascontiguousarray(pixels).view(np.uint8).reshape(-1)
+        meta = np.array([w, h, array_size, mip_levels, fmt, misc_flags, misc_flags2], np.uint64)
+        out = np.zeros(pixels.size + 256, np.uint8)
+        n = C.c_size_t()
+        hr = self.L.ref_dds_save(pixels.ctypes.data, pixels.size, meta.ctypes.data, flags, out.ctypes.data, out.size, n)
+        return F.hr_u32(hr), out[:n.value]
+
+    def dds_load(self, data, flags=0):
+        data = np.ascontiguousarray(data).view(np.uint8).reshape(-1)
+        meta = np.zeros(7, np.uint64)
+        out = np.zeros(data.size * 2 + 64, np.uint8)
+        n = C.c_size_t()
+        hr = self.L.ref_dds_load(data.ctypes.data, data.size, flags, meta.ctypes.data, out.ctypes.data, out.size, n)
+        return F.hr_u32(hr), [int(v) for v in meta], out[:n.value]
 
     def decompress(self, blocks, w, h, bc_fmt, dst_fmt):
         blocks = np.ascontiguousarray(blocks)

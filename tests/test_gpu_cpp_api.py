@@ -66,3 +66,22 @@ def test_cpp_convert_and_mips(exe, tmp_path, oracle):
         got = run(exe, tmp_path, "mips", src, 64, 64, 28, fl)
         hr, want = oracle.generate_mipmaps(src, 64, 64, 28, fl)
         assert hr == 0 and np.array_equal(got, want), hex(fl)
+
+
+def test_cpp_pipeline_writes_dds_files_the_reference_reads(exe, tmp_path, oracle):
+    """mips -> .dds and compress -> .dds through the C++ API (SaveToDDSFile / LoadFromDDSFile): the
+    reference's LoadFromDDSMemory must return the same metadata and the pixels the reference computes itself."""
+    rng = np.random.default_rng(8)
+    src = oracle_lib.random_image(28, 64, 32, rng)
+    fin, fout = str(tmp_path / "in.raw"), str(tmp_path / "chain.dds")
+    src.tofile(fin)
+    r = subprocess.run([exe, "mips", fin, fout, "64", "32", "28", str(F.TEX_FILTER_BOX), "0", "1"], capture_output=True, text=True)
+    assert r.returncode == 0 and "dds hr=0x00000000" in r.stdout, r.stdout + r.stderr
+    hr, meta, pixels = oracle.dds_load(np.fromfile(fout, np.uint8))
+    hr2, want = oracle.generate_mipmaps(src, 64, 32, 28, F.TEX_FILTER_BOX)
+    assert hr == 0 and hr2 == 0 and meta[:5] == [64, 32, 1, 7, 28] and np.array_equal(pixels, want)
+    fout = str(tmp_path / "bc3.dds")
+    r = subprocess.run([exe, "compress", fin, fout, "64", "32", "28", "77", "0", "1"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    hr, meta, pixels = oracle.dds_load(np.fromfile(fout, np.uint8))
+    assert hr == 0 and meta[:5] == [64, 32, 1, 1, 77] and np.array_equal(pixels, oracle.compress(src, 64, 32, 28, 77)[1])
