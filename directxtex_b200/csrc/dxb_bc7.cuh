@@ -1,24 +1,27 @@
-// dxb_bc7.cuh — BC7 block encoder, ONE WARP PER 4x4 BLOCK (single-source SPMD, see dxb_warp.cuh).
+// dxb_bc7.cuh — BC7 block encoder, ONE HALF-WARP PER 4x4 BLOCK, two blocks per warp (single-source SPMD, see dxb_warp.cuh).
 //
 // What it replaces: D3DXEncodeBC7 -> D3DX_BC7::Encode (BC6HBC7.cpp:3654-3659, 2783-2889).
 // Parity contract (north_star / SURVEY.md 8(d)): NOT bit-exact; the decoded result must be a valid BC7
 // stream for the reference decoder (D3DX_BC7::Decode, BC6HBC7.cpp:2566-2780) and its RGBA MSE against the
 // source must stay within the tolerance stated in DESIGN.md of the MSE the reference CPU encoder
 // reaches on the same input.  The reference's search (Newton fit + rank 64 shapes + refine 16 with
-// +-5 exhaustive perturbation, ~7 ms/block on one CPU core) is replaced by a search shaped for a warp:
+// +-5 exhaustive perturbation, ~7 ms/block on one CPU core) is replaced by a search shaped for the machine
+// (per block = per 16-lane half of a warp):
 //
 //   stage 0  LDR pixels exactly as the reference quantises them: uint8(clamp(c*255 + 0.01))   (:2792-2799)
-//   stage 1  all 64 two-subset shapes ranked by a closed-form line-fit residual from per-subset
-//            second moments (2 shapes per lane), candidates kept in registers, integer-key warp min
-//   stage 2  32 lane tasks evaluated concurrently, one (mode, shape, subset | rotation | p-bits) each:
-//              opaque block : 7 best shapes x 2 subsets x {mode 1, mode 3}  +  mode 6 x 4 p-bit pairs
-//              alpha block  : 8 best shapes x 2 subsets x mode 7, mode 6 x 4 p-bit pairs,
-//                             mode 5 x 4 rotations, mode 4 x 4 rotations x 2 index selectors
-//            each task: PCA axis (power iteration) -> endpoints -> quantise (+p-bit choice) ->
-//            index assignment with exact integer palette error -> least-squares endpoint refit -> repeat
-//   stage 3  subset errors combined with __shfl_xor, winner by integer-key warp min (ties: lowest lane)
-//   stage 4  16 lanes = 16 pixels: exhaustive nearest palette entry, anchor fix-up, every lane shifts
-//            its field into a 128-bit word, warp OR-reduction, one 128-bit store
+//   stage 1  the moments of every two-subset shape as ONE exact matrix product on the tensor cores
+//            (dxb_bc7_build_moments), 4 shapes per lane ranked by a closed-form line-fit residual, the 3 best
+//            kept by an integer-key half-warp min
+//   stage 2  16 lane tasks evaluated concurrently, one (mode, shape, subset | rotation | p-bits) each:
+//              opaque block : 3 best shapes x 2 subsets x {mode 1, mode 3}  +  mode 6 x 4 p-bit pairs
+//              alpha block  : 3 best shapes x 2 subsets x mode 7, mode 6 x 4 p-bit pairs,
+//                             mode 5 x 4 rotations, mode 4 x 2 index selectors
+//            each task: covariance from the moment table -> PCA axis (power iteration) -> endpoints ->
+//            float-only quantisation (+p-bit choice) -> index assignment -> least-squares endpoint refit -> repeat
+//   stage 3  subset errors combined with __shfl_xor, winner by integer-key half-warp min (ties: lowest lane)
+//   stage 4  16 lanes = 16 pixels: exhaustive nearest palette entry against the exact integer palette, anchor
+//            fix-up, every lane shifts its index fields and one endpoint field into a 128-bit word, half-warp
+//            OR-reduction, one 128-bit store per block
 // Modes tried with default flags equal the reference's (1,3,4,5,6 and 7 when alpha != 255, :2803-2821);
 // BC7_QUICK keeps only mode 6 (:2811); USE_3SUBSETS is accepted and ignored (modes 0/2 are never emitted).
 // Error metric = the reference's: sum of squared 8-bit differences over R,G,B,A (ComputeError :1559-1596).
