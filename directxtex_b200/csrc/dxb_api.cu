@@ -307,7 +307,8 @@ int32_t plan_convert(const dxb200_image* src, size_t n, uint32_t dstFormat, uint
     if (srcFormat == dstFormat) return DXB_E_INVALIDARG;
     if (is_compressed(srcFormat) || is_compressed(dstFormat)) return DXB_E_INVALIDARG;
     if (!is_supported_pixel_format(srcFormat) || !is_supported_pixel_format(dstFormat)) return DXB_E_NOT_SUPPORTED;
-    if (filter & DXB_FILTER_DITHER_MASK) return DXB_E_NOT_SUPPORTED;             // dithered stores: SURVEY 8(f) "next"
+    // ordered dithering (TEX_FILTER_DITHER) is implemented; error diffusion is serial over the whole image (:4815-4858)
+    if (filter & (DXB_FILTER_DITHER_MASK & ~DXB_FILTER_DITHER)) return DXB_E_NOT_SUPPORTED;
     for (size_t i = 0; i < n; ++i)
     {
         if (!src[i].pixels || !dst[i].pixels) return DXB_E_POINTER;
@@ -758,7 +759,9 @@ int32_t dxb200_convert(const dxb200_image* src, size_t nimages, uint32_t dstForm
     hr = ensure_init_locked();
     if (hr != DXB_S_OK) return hr;
     BandSplit bands;
-    split_bands(src, dst, nimages, 1, 1, false, false, bands);
+    // bands start on multiples of 4 rows so that the 4x4 ordered-dither matrix keeps its phase
+    const size_t rowsPerUnit = (P.flags & DXB_FILTER_DITHER) ? 4 : 1;
+    split_bands(src, dst, nimages, rowsPerUnit, rowsPerUnit, false, false, bands);
     return run_staged(bands.src.data(), bands.dst.data(), bands.src.size(),
         [&](const dxb200_image* ds, const dxb200_image* dd, size_t cnt, cudaStream_t st) { return launch_convert(P, ds, dd, cnt, st); });
 }

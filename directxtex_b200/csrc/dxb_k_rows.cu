@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(256) k_convert(const dxb_job* __restrict__ job
         const uint32_t y = local / j.width, x = local - y * j.width;
         dxb_px v = dxb_load_pixel(P.srcFormat, j.src + (size_t)y * j.srcPitch, x);
         v = dxb_convert_pixel(v, P.inF, P.outF, P.flags);
-        dxb_store_pixel(P.dstFormat, j.dst + (size_t)y * j.dstPitch, x, v);
+        if (P.flags & DXB_FILTER_DITHER) dxb_store_pixel_dither(P.dstFormat, j.dst + (size_t)y * j.dstPitch, x, y, v);     // ordered dither (:4861-4879)
+        else dxb_store_pixel(P.dstFormat, j.dst + (size_t)y * j.dstPitch, x, v);
     }
 }
 
@@ -142,7 +143,7 @@ static bool convert_vec_ok(const dxb_job* hostJobs, uint32_t njobs, uint32_t SB,
 void dxb_launch_convert(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job* hostJobs, const dxb_convert_params& P)
 {
     const uint32_t SB = dxb_bytes_per_pixel(P.srcFormat), DB = dxb_bytes_per_pixel(P.dstFormat);
-    if (convert_vec_ok(hostJobs, P.njobs, SB, DB))
+    if (!(P.flags & DXB_FILTER_DITHER) && convert_vec_ok(hostJobs, P.njobs, SB, DB))
     {
         const uint32_t ppt = 16u / (SB > DB ? SB : DB);
         const uint32_t chunksPerRow = (hostJobs[0].width + ppt - 1) / ppt;

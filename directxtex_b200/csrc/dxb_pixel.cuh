@@ -448,3 +448,108 @@ DXB_DEV void dxb_store_pixel(uint32_t fmt, uint8_t* row, size_t i, dxb_px v)
         return;
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Ordered-dither store (StoreScanlineDither with pDiffusionErrors == nullptr, DirectXTexConvert.cpp:4049-4567, macros
+// STORE_SCANLINE / STORE_SCANLINE2 / STORE_SCANLINE1 :3895-4045): clamp, scale, add the 4x4 matrix entry of (x & 3, y & 3),
+// round to nearest even, clamp to the code range, truncate to the integer type.  z = 0 for 2D images.
+// Formats without a dither case fall through to the plain store (default: :4558-4559); returns nothing either way.
+#if DXB_ON_DEVICE
+static __device__ const float dxb_dither_matrix[32] =
+#else
+static const float dxb_dither_matrix[32] =
+#endif
+{   // index = (z & 3) + (y & 3) * 8 + (x & 3)   (:3863-3870)
+    0.468750f, -0.031250f, 0.343750f, -0.156250f, 0.468750f, -0.031250f, 0.343750f, -0.156250f,
+    -0.281250f, 0.218750f, -0.406250f, 0.093750f, -0.281250f, 0.218750f, -0.406250f, 0.093750f,
+    0.281250f, -0.218750f, 0.406250f, -0.093750f, 0.281250f, -0.218750f, 0.406250f, -0.093750f,
+    -0.468750f, 0.031250f, -0.343750f, 0.156250f, -0.468750f, 0.031250f, -0.343750f, 0.156250f,
+};
+DXB_DEV float dxb_round_even(float f)
+{
+#if DXB_ON_DEVICE
+    return rintf(f);
+#else
+    return nearbyintf(f);
+#endif
+}
+// one channel: returns the integer code (as int32, two's complement for the signed formats)
+DXB_DEV int32_t dxb_dither_code(float v, float scale, bool clampzero, float d)
+{
+    // norm is true for every format implemented here
+    v = clampzero ? dxb_clamp(v, 0.0f, 1.0f) : dxb_clamp(v, -1.0f, 1.0f);
+    v = v + 0.0f;                                    // + vError (zero without error diffusion)
+    v = v * scale;
+    float t = dxb_round_even(v + d);
+    t = dxb_ssemin(scale, t);
+    t = dxb_ssemax(clampzero ? 0.0f : (-scale + 1.0f), t);
+    return dxb_f2i(t);
+}
+DXB_DEV void dxb_store_pixel_dither(uint32_t fmt, uint8_t* row, size_t i, uint32_t y, dxb_px v)
+{
+    const float d = dxb_dither_matrix[((y & 3u) << 3) + (uint32_t)(i & 3u)];
+    switch (fmt)
+    {
+    case DXB_FMT_R16G16B16A16_UNORM:
+    {
+        uint16_t* p = (uint16_t*)row + 4 * i;
+        p[0] = (uint16_t)dxb_dither_code(v.x, 65535.0f, true, d); p[1] = (uint16_t)dxb_dither_code(v.y, 65535.0f, true, d);
+        p[2] = (uint16_t)dxb_dither_code(v.z, 65535.0f, true, d); p[3] = (uint16_t)dxb_dither_code(v.w, 65535.0f, true, d);
+        return;
+    }
+    case DXB_FMT_R16G16B16A16_SNORM:
+    {
+        int16_t* p = (int16_t*)row + 4 * i;
+        p[0] = (int16_t)dxb_dither_code(v.x, 32767.0f, false, d); p[1] = (int16_t)dxb_dither_code(v.y, 32767.0f, false, d);
+        p[2] = (int16_t)dxb_dither_code(v.z, 32767.0f, false, d); p[3] = (int16_t)dxb_dither_code(v.w, 32767.0f, false, d);
+        return;
+    }
+    case DXB_FMT_R10G10B10A2_UNORM:
+    {
+        const uint32_t x = (uint32_t)dxb_dither_code(v.x, 1023.0f, true, d) & 0x3FFu, yy = (uint32_t)dxb_dither_code(v.y, 1023.0f, true, d) & 0x3FFu;
+        const uint32_t z = (uint32_t)dxb_dither_code(v.z, 1023.0f, true, d) & 0x3FFu, w = (uint32_t)dxb_dither_code(v.w, 3.0f, true, d) & 0x3u;
+        ((uint32_t*)row)[i] = x | (yy << 10) | (z << 20) | (w << 30);
+        return;
+    }
+    case DXB_FMT_R8G8B8A8_UNORM: case DXB_FMT_R8G8B8A8_UNORM_SRGB:
+        ((uint32_t*)row)[i] = ((uint32_t)dxb_dither_code(v.x, 255.0f, true, d) & 0xFFu) | (((uint32_t)dxb_dither_code(v.y, 255.0f, true, d) & 0xFFu) << 8) |
+                              (((uint32_t)dxb_dither_code(v.z, 255.0f, true, d) & 0xFFu) << 16) | (((uint32_t)dxb_dither_code(v.w, 255.0f, true, d) & 0xFFu) << 24);
+        return;
+    case DXB_FMT_B8G8R8A8_UNORM: case DXB_FMT_B8G8R8A8_UNORM_SRGB:
+        ((uint32_t*)row)[i] = ((uint32_t)dxb_dither_code(v.z, 255.0f, true, d) & 0xFFu) | (((uint32_t)dxb_dither_code(v.y, 255.0f, true, d) & 0xFFu) << 8) |
+                              (((uint32_t)dxb_dither_code(v.x, 255.0f, true, d) & 0xFFu) << 16) | (((uint32_t)dxb_dither_code(v.w, 255.0f, true, d) & 0xFFu) << 24);
+        return;
+    case DXB_FMT_B8G8R8X8_UNORM: case DXB_FMT_B8G8R8X8_UNORM_SRGB:          // the X byte is written as 0 on this path (:4446)
+        ((uint32_t*)row)[i] = ((uint32_t)dxb_dither_code(v.z, 255.0f, true, d) & 0xFFu) | (((uint32_t)dxb_dither_code(v.y, 255.0f, true, d) & 0xFFu) << 8) |
+                              (((uint32_t)dxb_dither_code(v.x, 255.0f, true, d) & 0xFFu) << 16);
+        return;
+    case DXB_FMT_R8G8B8A8_SNORM:
+        ((uint32_t*)row)[i] = ((uint32_t)dxb_dither_code(v.x, 127.0f, false, d) & 0xFFu) | (((uint32_t)dxb_dither_code(v.y, 127.0f, false, d) & 0xFFu) << 8) |
+                              (((uint32_t)dxb_dither_code(v.z, 127.0f, false, d) & 0xFFu) << 16) | (((uint32_t)dxb_dither_code(v.w, 127.0f, false, d) & 0xFFu) << 24);
+        return;
+    case DXB_FMT_R16G16_UNORM:
+    {
+        uint16_t* p = (uint16_t*)row + 2 * i;
+        p[0] = (uint16_t)dxb_dither_code(v.x, 65535.0f, true, d); p[1] = (uint16_t)dxb_dither_code(v.y, 65535.0f, true, d);
+        return;
+    }
+    case DXB_FMT_R16G16_SNORM:
+    {
+        int16_t* p = (int16_t*)row + 2 * i;
+        p[0] = (int16_t)dxb_dither_code(v.x, 32767.0f, false, d); p[1] = (int16_t)dxb_dither_code(v.y, 32767.0f, false, d);
+        return;
+    }
+    case DXB_FMT_R8G8_UNORM:
+        row[2 * i] = (uint8_t)dxb_dither_code(v.x, 255.0f, true, d); row[2 * i + 1] = (uint8_t)dxb_dither_code(v.y, 255.0f, true, d);
+        return;
+    case DXB_FMT_R8G8_SNORM:
+        row[2 * i] = (uint8_t)(int8_t)dxb_dither_code(v.x, 127.0f, false, d); row[2 * i + 1] = (uint8_t)(int8_t)dxb_dither_code(v.y, 127.0f, false, d);
+        return;
+    case DXB_FMT_R16_UNORM: ((uint16_t*)row)[i] = (uint16_t)dxb_dither_code(v.x, 65535.0f, true, d); return;
+    case DXB_FMT_R16_SNORM: ((int16_t*)row)[i] = (int16_t)dxb_dither_code(v.x, 32767.0f, false, d); return;
+    case DXB_FMT_R8_UNORM: row[i] = (uint8_t)dxb_dither_code(v.x, 255.0f, true, d); return;
+    case DXB_FMT_R8_SNORM: row[i] = (uint8_t)(int8_t)dxb_dither_code(v.x, 127.0f, false, d); return;
+    case DXB_FMT_A8_UNORM: row[i] = (uint8_t)dxb_dither_code(v.w, 255.0f, true, d); return;
+    default: dxb_store_pixel(fmt, row, i, v); return;
+    }
+}
