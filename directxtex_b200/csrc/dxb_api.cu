@@ -307,8 +307,8 @@ int32_t plan_convert(const dxb200_image* src, size_t n, uint32_t dstFormat, uint
     if (srcFormat == dstFormat) return DXB_E_INVALIDARG;
     if (is_compressed(srcFormat) || is_compressed(dstFormat)) return DXB_E_INVALIDARG;
     if (!is_supported_pixel_format(srcFormat) || !is_supported_pixel_format(dstFormat)) return DXB_E_NOT_SUPPORTED;
-    // ordered dithering (TEX_FILTER_DITHER) is implemented; error diffusion is serial over the whole image (:4815-4858)
-    if (filter & (DXB_FILTER_DITHER_MASK & ~DXB_FILTER_DITHER)) return DXB_E_NOT_SUPPORTED;
+    // TEX_FILTER_DITHER = ordered 4x4 dithering; TEX_FILTER_DITHER_DIFFUSION = Floyd-Steinberg (serial per image, :4815-4858)
+    if (filter & (DXB_FILTER_DITHER_MASK & ~(DXB_FILTER_DITHER | DXB_FILTER_DITHER_DIFFUSION))) return DXB_E_NOT_SUPPORTED;
     for (size_t i = 0; i < n; ++i)
     {
         if (!src[i].pixels || !dst[i].pixels) return DXB_E_POINTER;
@@ -339,6 +339,23 @@ int32_t launch_convert(dxb_convert_params P, const dxb200_image* src, const dxb2
     DeviceJobs<dxb_job> dj;
     int32_t hr = dj.upload(jobs, stream);
     if (hr != DXB_S_OK) return hr;
+    if (P.flags & DXB_FILTER_DITHER_DIFFUSION)
+    {
+        // two error rows of (width + 2) pixels per image
+        uint32_t maxw = 0;
+        for (const dxb_job& j : jobs) maxw = std::max(maxw, j.width);
+        const uint32_t errStride = 2u * (maxw + 2u);
+        void* dErr = nullptr;
+        hr = cuda_hr(cudaMallocAsync(&dErr, (size_t)errStride * n * sizeof(float) * 4, stream), "cudaMallocAsync(errors)");
+        if (hr == DXB_S_OK)
+        {
+            dxb_launch_convert_diffuse(stream, (n > 1) ? dj.d : nullptr, jobs.data(), P, dErr, errStride);
+            hr = check_launch("k_convert_diffuse");
+            cudaFreeAsync(dErr, stream);
+        }
+        dj.release();
+        return hr;
+    }
     const uint32_t need = (uint32_t)((total + 255) / 256);
     const uint32_t grid = std::max(1u, std::min<uint32_t>(need, (uint32_t)g.gridRow * 8u));
     dxb_launch_convert(grid, stream, dj.d, jobs.data(), P);
@@ -760,7 +777,9 @@ int32_t dxb200_convert(const dxb200_image* src, size_t nimages, uint32_t dstForm
     if (hr != DXB_S_OK) return hr;
     BandSplit bands;
     // bands start on multiples of 4 rows so that the 4x4 ordered-dither matrix keeps its phase
-    const size_t rowsPerUnit = (P.flags & DXB_FILTER_DITHER) ? 4 : 1;
+    // (error diffusion carries state from row to row: whole images only)
+    size_t rowsPerUnit = (P.flags & DXB_FILTER_DITHER) ? 4 : 1;
+    if (P.flags & DXB_FILTER_DITHER_DIFFUSION) for (size_t i = 0; i < nimages; ++i) rowsPerUnit = std::max(rowsPerUnit, src[i].height);
     split_bands(src, dst, nimages, rowsPerUnit, rowsPerUnit, false, false, bands);
     return run_staged(bands.src.data(), bands.dst.data(), bands.src.size(),
         [&](const dxb200_image* ds, const dxb200_image* dd, size_t cnt, cudaStream_t st) { return launch_convert(P, ds, dd, cnt, st); });

@@ -26,6 +26,21 @@ __global__ void __launch_bounds__(256) k_convert(const dxb_job* __restrict__ job
     }
 }
 
+// Error-diffusion dithering is serial over an image (dxb_convert_diffuse_image): one thread per image, images in parallel.
+// errors: per job 2 * (width + 2) pixels of scratch.
+__global__ void __launch_bounds__(32) k_convert_diffuse(const dxb_job* __restrict__ jobs, dxb_job single, dxb_convert_params P, dxb_px* errors, uint32_t errStride)
+{
+    if (threadIdx.x != 0) return;
+    const dxb_job& j = (jobs == nullptr) ? single : jobs[blockIdx.x];
+    dxb_px* E = errors + (size_t)blockIdx.x * errStride;
+    dxb_convert_diffuse_image(P.srcFormat, P.dstFormat, P.inF, P.outF, P.flags, j.src, j.srcPitch, j.dst, j.dstPitch, j.width, j.height,
+                              E, E + (j.width + 2u));
+}
+void dxb_launch_convert_diffuse(cudaStream_t stream, const dxb_job* jobs, const dxb_job* hostJobs, const dxb_convert_params& P, void* errors, uint32_t errStride)
+{
+    k_convert_diffuse<<<P.njobs, 32, 0, stream>>>(jobs, hostJobs[0], P, static_cast<dxb_px*>(errors), errStride);
+}
+
 __global__ void __launch_bounds__(256) k_mip_level(const dxb_mip_job* __restrict__ jobs, dxb_mip_job single, dxb_mip_params P)
 {
     const uint32_t stride = gridDim.x * blockDim.x;

@@ -473,10 +473,48 @@ DXB_DEV float dxb_round_even(float f)
     return nearbyintf(f);
 #endif
 }
-// one channel: returns the integer code (as int32, two's complement for the signed formats)
+// per-format dither parameters: code range per (stored) channel, unsigned vs signed-normalised, BGR store order
+struct dxb_dither_fmt { float sx, sy, sz, sw; bool ok, clampzero, bgr; };
+DXB_DEV dxb_dither_fmt dxb_dither_format(uint32_t fmt)
+{
+    dxb_dither_fmt f; f.ok = true; f.clampzero = true; f.bgr = false; f.sx = f.sy = f.sz = f.sw = 255.0f;
+    switch (fmt)
+    {
+    case DXB_FMT_R16G16B16A16_UNORM: case DXB_FMT_R16G16_UNORM: case DXB_FMT_R16_UNORM: f.sx = f.sy = f.sz = f.sw = 65535.0f; break;
+    case DXB_FMT_R16G16B16A16_SNORM: case DXB_FMT_R16G16_SNORM: case DXB_FMT_R16_SNORM: f.sx = f.sy = f.sz = f.sw = 32767.0f; f.clampzero = false; break;
+    case DXB_FMT_R10G10B10A2_UNORM: f.sx = f.sy = f.sz = 1023.0f; f.sw = 3.0f; break;
+    case DXB_FMT_R8G8B8A8_UNORM: case DXB_FMT_R8G8B8A8_UNORM_SRGB: case DXB_FMT_R8G8_UNORM: case DXB_FMT_R8_UNORM: case DXB_FMT_A8_UNORM: break;
+    case DXB_FMT_R8G8B8A8_SNORM: case DXB_FMT_R8G8_SNORM: case DXB_FMT_R8_SNORM: f.sx = f.sy = f.sz = f.sw = 127.0f; f.clampzero = false; break;
+    case DXB_FMT_B8G8R8A8_UNORM: case DXB_FMT_B8G8R8A8_UNORM_SRGB: case DXB_FMT_B8G8R8X8_UNORM: case DXB_FMT_B8G8R8X8_UNORM_SRGB: f.bgr = true; break;
+    default: f.ok = false; break;
+    }
+    return f;
+}
+// integer codes c (already in STORE order: for BGR formats c.x = blue) -> memory
+DXB_DEV void dxb_store_codes(uint32_t fmt, uint8_t* row, size_t i, int32_t cx, int32_t cy, int32_t cz, int32_t cw)
+{
+    switch (fmt)
+    {
+    case DXB_FMT_R16G16B16A16_UNORM: case DXB_FMT_R16G16B16A16_SNORM:
+    { uint16_t* p = (uint16_t*)row + 4 * i; p[0] = (uint16_t)cx; p[1] = (uint16_t)cy; p[2] = (uint16_t)cz; p[3] = (uint16_t)cw; return; }
+    case DXB_FMT_R10G10B10A2_UNORM:
+        ((uint32_t*)row)[i] = ((uint32_t)cx & 0x3FFu) | (((uint32_t)cy & 0x3FFu) << 10) | (((uint32_t)cz & 0x3FFu) << 20) | (((uint32_t)cw & 0x3u) << 30); return;
+    case DXB_FMT_R8G8B8A8_UNORM: case DXB_FMT_R8G8B8A8_UNORM_SRGB: case DXB_FMT_R8G8B8A8_SNORM:
+    case DXB_FMT_B8G8R8A8_UNORM: case DXB_FMT_B8G8R8A8_UNORM_SRGB:
+        ((uint32_t*)row)[i] = ((uint32_t)cx & 0xFFu) | (((uint32_t)cy & 0xFFu) << 8) | (((uint32_t)cz & 0xFFu) << 16) | (((uint32_t)cw & 0xFFu) << 24); return;
+    case DXB_FMT_B8G8R8X8_UNORM: case DXB_FMT_B8G8R8X8_UNORM_SRGB:          // the X byte is written as 0 on the dither paths (:4446)
+        ((uint32_t*)row)[i] = ((uint32_t)cx & 0xFFu) | (((uint32_t)cy & 0xFFu) << 8) | (((uint32_t)cz & 0xFFu) << 16); return;
+    case DXB_FMT_R16G16_UNORM: case DXB_FMT_R16G16_SNORM: { uint16_t* p = (uint16_t*)row + 2 * i; p[0] = (uint16_t)cx; p[1] = (uint16_t)cy; return; }
+    case DXB_FMT_R8G8_UNORM: case DXB_FMT_R8G8_SNORM: row[2 * i] = (uint8_t)cx; row[2 * i + 1] = (uint8_t)cy; return;
+    case DXB_FMT_R16_UNORM: case DXB_FMT_R16_SNORM: ((uint16_t*)row)[i] = (uint16_t)cx; return;
+    case DXB_FMT_R8_UNORM: case DXB_FMT_R8_SNORM: row[i] = (uint8_t)cx; return;
+    case DXB_FMT_A8_UNORM: row[i] = (uint8_t)cw; return;
+    default: return;
+    }
+}
+// one channel of the ordered path: returns the integer code (two's complement for the signed formats)
 DXB_DEV int32_t dxb_dither_code(float v, float scale, bool clampzero, float d)
 {
-    // norm is true for every format implemented here
     v = clampzero ? dxb_clamp(v, 0.0f, 1.0f) : dxb_clamp(v, -1.0f, 1.0f);
     v = v + 0.0f;                                    // + vError (zero without error diffusion)
     v = v * scale;
@@ -487,69 +525,67 @@ DXB_DEV int32_t dxb_dither_code(float v, float scale, bool clampzero, float d)
 }
 DXB_DEV void dxb_store_pixel_dither(uint32_t fmt, uint8_t* row, size_t i, uint32_t y, dxb_px v)
 {
+    const dxb_dither_fmt f = dxb_dither_format(fmt);
+    if (!f.ok) { dxb_store_pixel(fmt, row, i, v); return; }
     const float d = dxb_dither_matrix[((y & 3u) << 3) + (uint32_t)(i & 3u)];
-    switch (fmt)
+    if (f.bgr) { const float t = v.x; v.x = v.z; v.z = t; }
+    dxb_store_codes(fmt, row, i, dxb_dither_code(v.x, f.sx, f.clampzero, d), dxb_dither_code(v.y, f.sy, f.clampzero, d),
+                    dxb_dither_code(v.z, f.sz, f.clampzero, d), dxb_dither_code(v.w, f.sw, f.clampzero, d));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Error-diffusion (Floyd-Steinberg) store of one whole image (StoreScanlineDither with pDiffusionErrors, driven by the row
+// loop of ConvertCustom :4815-4858).  Inherently serial: the quantisation error of a pixel goes to its successor in a
+// serpentine scan and to three pixels of the next row, so ONE thread walks the image; the four channels are independent
+// dependency chains.  E0 / E1 = two error rows of (width + 2) pixels (this row's incoming / the next row's outgoing errors).
+// Reference quirks kept: the incoming errors (held in store order) are added to the source before the BGR swizzle.
+DXB_DEV float dxb_dd1(float& carry, float s, float scale, bool clampzero, float& e3, float& e5, float& e1)
+{
+    float v = clampzero ? dxb_clamp(s, 0.0f, 1.0f) : dxb_clamp(s, -1.0f, 1.0f);
+    v = v + carry;
+    v = v * scale;
+    float t = dxb_round_even(v);
+    float err = v - t;
+    err = err / scale;
+    e3 = (3.0f / 16.0f) * err; e5 = (5.0f / 16.0f) * err; e1 = (1.0f / 16.0f) * err;
+    carry = err * (7.0f / 16.0f);
+    t = dxb_ssemin(scale, t);
+    t = dxb_ssemax(clampzero ? 0.0f : (-scale + 1.0f), t);
+    return t;
+}
+DXB_DEV void dxb_convert_diffuse_image(uint32_t srcFmt, uint32_t dstFmt, uint32_t inF, uint32_t outF, uint32_t flags,
+                                       const uint8_t* src, size_t srcPitch, uint8_t* dst, size_t dstPitch, uint32_t width, uint32_t height,
+                                       dxb_px* E0, dxb_px* E1)
+{
+    const dxb_dither_fmt f = dxb_dither_format(dstFmt);
+    for (uint32_t i = 0; i < width + 2u; ++i) { E0[i] = dxb_make_px(0.0f, 0.0f, 0.0f, 0.0f); E1[i] = dxb_make_px(0.0f, 0.0f, 0.0f, 0.0f); }
+    for (uint32_t y = 0; y < height; ++y)
     {
-    case DXB_FMT_R16G16B16A16_UNORM:
-    {
-        uint16_t* p = (uint16_t*)row + 4 * i;
-        p[0] = (uint16_t)dxb_dither_code(v.x, 65535.0f, true, d); p[1] = (uint16_t)dxb_dither_code(v.y, 65535.0f, true, d);
-        p[2] = (uint16_t)dxb_dither_code(v.z, 65535.0f, true, d); p[3] = (uint16_t)dxb_dither_code(v.w, 65535.0f, true, d);
-        return;
-    }
-    case DXB_FMT_R16G16B16A16_SNORM:
-    {
-        int16_t* p = (int16_t*)row + 4 * i;
-        p[0] = (int16_t)dxb_dither_code(v.x, 32767.0f, false, d); p[1] = (int16_t)dxb_dither_code(v.y, 32767.0f, false, d);
-        p[2] = (int16_t)dxb_dither_code(v.z, 32767.0f, false, d); p[3] = (int16_t)dxb_dither_code(v.w, 32767.0f, false, d);
-        return;
-    }
-    case DXB_FMT_R10G10B10A2_UNORM:
-    {
-        const uint32_t x = (uint32_t)dxb_dither_code(v.x, 1023.0f, true, d) & 0x3FFu, yy = (uint32_t)dxb_dither_code(v.y, 1023.0f, true, d) & 0x3FFu;
-        const uint32_t z = (uint32_t)dxb_dither_code(v.z, 1023.0f, true, d) & 0x3FFu, w = (uint32_t)dxb_dither_code(v.w, 3.0f, true, d) & 0x3u;
-        ((uint32_t*)row)[i] = x | (yy << 10) | (z << 20) | (w << 30);
-        return;
-    }
-    case DXB_FMT_R8G8B8A8_UNORM: case DXB_FMT_R8G8B8A8_UNORM_SRGB:
-        ((uint32_t*)row)[i] = ((uint32_t)dxb_dither_code(v.x, 255.0f, true, d) & 0xFFu) | (((uint32_t)dxb_dither_code(v.y, 255.0f, true, d) & 0xFFu) << 8) |
-                              (((uint32_t)dxb_dither_code(v.z, 255.0f, true, d) & 0xFFu) << 16) | (((uint32_t)dxb_dither_code(v.w, 255.0f, true, d) & 0xFFu) << 24);
-        return;
-    case DXB_FMT_B8G8R8A8_UNORM: case DXB_FMT_B8G8R8A8_UNORM_SRGB:
-        ((uint32_t*)row)[i] = ((uint32_t)dxb_dither_code(v.z, 255.0f, true, d) & 0xFFu) | (((uint32_t)dxb_dither_code(v.y, 255.0f, true, d) & 0xFFu) << 8) |
-                              (((uint32_t)dxb_dither_code(v.x, 255.0f, true, d) & 0xFFu) << 16) | (((uint32_t)dxb_dither_code(v.w, 255.0f, true, d) & 0xFFu) << 24);
-        return;
-    case DXB_FMT_B8G8R8X8_UNORM: case DXB_FMT_B8G8R8X8_UNORM_SRGB:          // the X byte is written as 0 on this path (:4446)
-        ((uint32_t*)row)[i] = ((uint32_t)dxb_dither_code(v.z, 255.0f, true, d) & 0xFFu) | (((uint32_t)dxb_dither_code(v.y, 255.0f, true, d) & 0xFFu) << 8) |
-                              (((uint32_t)dxb_dither_code(v.x, 255.0f, true, d) & 0xFFu) << 16);
-        return;
-    case DXB_FMT_R8G8B8A8_SNORM:
-        ((uint32_t*)row)[i] = ((uint32_t)dxb_dither_code(v.x, 127.0f, false, d) & 0xFFu) | (((uint32_t)dxb_dither_code(v.y, 127.0f, false, d) & 0xFFu) << 8) |
-                              (((uint32_t)dxb_dither_code(v.z, 127.0f, false, d) & 0xFFu) << 16) | (((uint32_t)dxb_dither_code(v.w, 127.0f, false, d) & 0xFFu) << 24);
-        return;
-    case DXB_FMT_R16G16_UNORM:
-    {
-        uint16_t* p = (uint16_t*)row + 2 * i;
-        p[0] = (uint16_t)dxb_dither_code(v.x, 65535.0f, true, d); p[1] = (uint16_t)dxb_dither_code(v.y, 65535.0f, true, d);
-        return;
-    }
-    case DXB_FMT_R16G16_SNORM:
-    {
-        int16_t* p = (int16_t*)row + 2 * i;
-        p[0] = (int16_t)dxb_dither_code(v.x, 32767.0f, false, d); p[1] = (int16_t)dxb_dither_code(v.y, 32767.0f, false, d);
-        return;
-    }
-    case DXB_FMT_R8G8_UNORM:
-        row[2 * i] = (uint8_t)dxb_dither_code(v.x, 255.0f, true, d); row[2 * i + 1] = (uint8_t)dxb_dither_code(v.y, 255.0f, true, d);
-        return;
-    case DXB_FMT_R8G8_SNORM:
-        row[2 * i] = (uint8_t)(int8_t)dxb_dither_code(v.x, 127.0f, false, d); row[2 * i + 1] = (uint8_t)(int8_t)dxb_dither_code(v.y, 127.0f, false, d);
-        return;
-    case DXB_FMT_R16_UNORM: ((uint16_t*)row)[i] = (uint16_t)dxb_dither_code(v.x, 65535.0f, true, d); return;
-    case DXB_FMT_R16_SNORM: ((int16_t*)row)[i] = (int16_t)dxb_dither_code(v.x, 32767.0f, false, d); return;
-    case DXB_FMT_R8_UNORM: row[i] = (uint8_t)dxb_dither_code(v.x, 255.0f, true, d); return;
-    case DXB_FMT_R8_SNORM: row[i] = (uint8_t)(int8_t)dxb_dither_code(v.x, 127.0f, false, d); return;
-    case DXB_FMT_A8_UNORM: row[i] = (uint8_t)dxb_dither_code(v.w, 255.0f, true, d); return;
-    default: dxb_store_pixel(fmt, row, i, v); return;
+        dxb_px* Ein = (y & 1u) ? E1 : E0;            // errors handed down by the previous row
+        dxb_px* Eout = (y & 1u) ? E0 : E1;           // errors for the next row (zero on entry)
+        const uint8_t* srow = src + (size_t)y * srcPitch;
+        uint8_t* drow = dst + (size_t)y * dstPitch;
+        dxb_px carry = dxb_make_px(0.0f, 0.0f, 0.0f, 0.0f);
+        const int delta = (y & 1u) ? -2 : 0;
+        for (uint32_t k = 0; k < width; ++k)
+        {
+            const uint32_t index = (y & 1u) ? (width - 1u - k) : k;
+            dxb_px v = dxb_convert_pixel(dxb_load_pixel(srcFmt, srow, index), inF, outF, flags);
+            if (!f.ok) { dxb_store_pixel(dstFmt, drow, index, v); continue; }      // formats without a dither case: plain store (:4558)
+            const dxb_px e = Ein[index + 1u];
+            v = dxb_make_px(v.x + e.x, v.y + e.y, v.z + e.z, v.w + e.w);
+            if (f.bgr) { const float t = v.x; v.x = v.z; v.z = t; }
+            dxb_px a, b, c;                                 // 3/16, 5/16, 1/16 shares
+            const float tx = dxb_dd1(carry.x, v.x, f.sx, f.clampzero, a.x, b.x, c.x);
+            const float ty = dxb_dd1(carry.y, v.y, f.sy, f.clampzero, a.y, b.y, c.y);
+            const float tz = dxb_dd1(carry.z, v.z, f.sz, f.clampzero, a.z, b.z, c.z);
+            const float tw = dxb_dd1(carry.w, v.w, f.sw, f.clampzero, a.w, b.w, c.w);
+            dxb_px* p3 = Eout + ((int)index - delta); dxb_px* p5 = Eout + (index + 1u); dxb_px* p1 = Eout + ((int)index + 2 + delta);
+            *p3 = dxb_make_px(a.x + p3->x, a.y + p3->y, a.z + p3->z, a.w + p3->w);
+            *p5 = dxb_make_px(b.x + p5->x, b.y + p5->y, b.z + p5->z, b.w + p5->w);
+            *p1 = dxb_make_px(c.x + p1->x, c.y + p1->y, c.z + p1->z, c.w + p1->w);
+            dxb_store_codes(dstFmt, drow, index, dxb_f2i(tx), dxb_f2i(ty), dxb_f2i(tz), dxb_f2i(tw));
+        }
+        for (uint32_t i = 0; i < width + 2u; ++i) Ein[i] = dxb_make_px(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }

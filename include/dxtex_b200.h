@@ -80,7 +80,7 @@ DXB200_API int32_t  dxb200_decompress_device(const dxb200_image* src, size_t nim
 
 /* DirectX::Convert / ConvertEx (DirectXTexConvert.cpp:5091-5404; ConvertCustom no-dither path :4888-4908).
  *   filter = TEX_FILTER_FLAGS; TEX_FILTER_DITHER = ordered dithering (StoreScanlineDither :4049-4567 without diffusion errors);
- *   TEX_FILTER_DITHER_DIFFUSION -> HRESULT_E_NOT_SUPPORTED */
+ *   TEX_FILTER_DITHER_DIFFUSION = Floyd-Steinberg error diffusion (serial per image; ConvertCustom :4815-4858) */
 DXB200_API int32_t  dxb200_convert(const dxb200_image* src, size_t nimages, uint32_t dstFormat,
                         uint32_t filter, float threshold, const dxb200_image* dst);
 DXB200_API int32_t  dxb200_convert_device(const dxb200_image* src, size_t nimages, uint32_t dstFormat,

@@ -103,6 +103,12 @@ int32_t emul_convert(const uint8_t* src, size_t w, size_t h, uint32_t srcFmt, si
     if (srcPitch == 0) srcPitch = w * dxb_bytes_per_pixel(srcFmt);
     if (dstPitch == 0) dstPitch = w * dxb_bytes_per_pixel(dstFmt);
     const uint32_t flags = dxb_resolve_srgb_convert(filter, srcFmt, dstFmt);
+    if (flags & DXB_FILTER_DITHER_DIFFUSION)
+    {
+        std::vector<dxb_px> E(2 * (w + 2));
+        dxb_convert_diffuse_image(srcFmt, dstFmt, inF, outF, flags, src, srcPitch, dst, dstPitch, (uint32_t)w, (uint32_t)h, E.data(), E.data() + w + 2);
+        return DXB_S_OK;
+    }
     for (size_t y = 0; y < h; ++y)
         for (size_t x = 0; x < w; ++x)
         {

@@ -92,7 +92,7 @@ def test_argument_validation_hresults():
     assert F.hr_u32(L.dxb200_convert(s, 1, 71, 0, 0.5, d)) == F.E_INVALIDARG                   # BC destination
     o2 = np.zeros(8 * 8 * 16, np.uint8)
     d2 = capi.images([capi.Image(8, 8, 2, 128, 1024, o2.ctypes.data)])
-    assert F.hr_u32(L.dxb200_convert(s, 1, 2, F.TEX_FILTER_DITHER_DIFFUSION, 0.5, d2)) == F.HRESULT_E_NOT_SUPPORTED   # error diffusion is serial
+    assert F.hr_u32(L.dxb200_convert(s, 1, 2, 0x40000, 0.5, d2)) == F.HRESULT_E_NOT_SUPPORTED                # unknown dither mode bit
     chain = capi.images([_img(a, 8, 8, 28), capi.Image(4, 4, 28, 16, 64, out.ctypes.data)])
     assert F.hr_u32(L.dxb200_generate_mipmaps(chain, 1, 1, 0)) == F.E_INVALIDARG
     assert F.hr_u32(L.dxb200_generate_mipmaps(chain, 1, 5, 0)) == F.E_INVALIDARG               # more levels than the size allows

@@ -210,14 +210,15 @@ def test_emulator_decompress_bit_exact(oracle, emul):
                     assert hr == 0 and he == 0 and np.array_equal(got, want), (bc, df, w, h)
 
 
-def test_emulator_ordered_dither_matches_reference(oracle, emul):
-    """The ordered-dither store of dxb_pixel.cuh (compiled for the host by tests/emul) against the reference's StoreScanlineDither."""
+def test_emulator_dither_matches_reference(oracle, emul):
+    """The ordered-dither and error-diffusion stores of dxb_pixel.cuh (compiled for the host by tests/emul) against the reference's StoreScanlineDither."""
     rng = np.random.default_rng(41)
     for sf in (2, 28):
         for df in (11, 13, 24, 28, 31, 35, 49, 51, 56, 58, 61, 63, 65, 87, 88):
             if sf == df:
                 continue
             src = oracle_lib.random_image(sf, 21, 6, rng)
-            hr, want = oracle.convert(src, 21, 6, sf, df, F.TEX_FILTER_DITHER)
-            he, got = emul.convert(src, 21, 6, sf, df, F.TEX_FILTER_DITHER)
-            assert hr == 0 and he == 0 and np.array_equal(got, want), (sf, df)
+            for fl in (F.TEX_FILTER_DITHER, F.TEX_FILTER_DITHER_DIFFUSION):
+                hr, want = oracle.convert(src, 21, 6, sf, df, fl)
+                he, got = emul.convert(src, 21, 6, sf, df, fl)
+                assert hr == 0 and he == 0 and np.array_equal(got, want), (sf, df, hex(fl))

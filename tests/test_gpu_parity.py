@@ -106,6 +106,19 @@ def test_convert_ordered_dither(oracle):
     assert hr == 0 and np.array_equal(got, want)
 
 
+def test_convert_error_diffusion_dither(oracle):
+    """TEX_FILTER_DITHER_DIFFUSION (Floyd-Steinberg, serpentine): serial over an image, one GPU thread per image; bit-exact,
+    including the reference's behaviour of adding store-order errors to the un-swizzled source for BGR formats."""
+    rng = np.random.default_rng(37)
+    for fl in (F.TEX_FILTER_DITHER_DIFFUSION, F.TEX_FILTER_DITHER | F.TEX_FILTER_DITHER_DIFFUSION):
+        for sf, df in [(2, 28), (2, 87), (2, 88), (10, 24), (2, 11), (2, 13), (28, 61), (2, 31), (2, 49), (2, 65), (28, 10)]:
+            for (w, h) in [(37, 9), (1, 5), (64, 64)]:
+                src = oracle_lib.random_image(sf, w, h, rng)
+                hr, want = oracle.convert(src, w, h, sf, df, fl)
+                got = capi.convert(src, w, h, sf, df, fl)
+                assert hr == 0 and np.array_equal(got, want), (sf, df, w, h, hex(fl))
+
+
 def test_convert_exhaustive_small_domains(oracle):
     """every value of the 8/16-bit scalar formats (they use a 3-op exact division instead of an IEEE divide)"""
     for sf, dtype, n in ((61, np.uint8, 256), (63, np.int8, 256), (65, np.uint8, 256), (56, np.uint16, 65536), (58, np.int16, 65536)):
