@@ -14,6 +14,7 @@ SYMBOLS = [
     "dxb200_compress", "dxb200_compress_device", "dxb200_decompress", "dxb200_decompress_device",
     "dxb200_convert", "dxb200_convert_device", "dxb200_generate_mipmaps", "dxb200_generate_mipmaps_device",
     "dxb200_resize", "dxb200_resize_device", "dxb200_premultiply_alpha", "dxb200_premultiply_alpha_device",
+    "dxb200_scale_mipmaps_alpha_for_coverage", "dxb200_scale_mipmaps_alpha_for_coverage_device",
     "dxb200_dds_encode_header", "dxb200_dds_save_memory", "dxb200_dds_get_metadata", "dxb200_dds_load_memory",
 ]
 
@@ -66,6 +67,10 @@ def _load():
     lib.dxb200_resize_device.argtypes = [IP, C.c_size_t, C.c_uint32, IP, C.c_void_p]
     lib.dxb200_premultiply_alpha.argtypes = [IP, C.c_size_t, C.c_uint32, IP]
     lib.dxb200_premultiply_alpha_device.argtypes = [IP, C.c_size_t, C.c_uint32, IP, C.c_void_p]
+    lib.dxb200_scale_mipmaps_alpha_for_coverage.argtypes = [IP, C.c_size_t, C.c_float, IP]
+    lib.dxb200_scale_mipmaps_alpha_for_coverage_device.argtypes = [IP, C.c_size_t, C.c_float, IP, C.c_void_p]
+    lib.dxb200_scale_mipmaps_alpha_for_coverage.restype = C.c_int32
+    lib.dxb200_scale_mipmaps_alpha_for_coverage_device.restype = C.c_int32
     MP, SP = C.POINTER(Metadata), C.POINTER(C.c_size_t)
     lib.dxb200_dds_encode_header.argtypes = [MP, C.c_uint32, C.c_void_p, C.c_size_t, SP]
     lib.dxb200_dds_save_memory.argtypes = [IP, C.c_size_t, MP, C.c_uint32, C.c_void_p, C.c_size_t, SP]
@@ -238,6 +243,19 @@ def dds_load(data, flags=0):
     if hr != 0:
         raise DxTexError(hr, "dxb200_dds_load_memory")
     return md, pixels
+
+
+def scale_mipmaps_alpha_for_coverage(chain, w, h, fmt, alpha_ref):
+    """DirectX::ScaleMipMapsAlphaForCoverage on one mip chain (bytes in ScratchImage layout); returns the new chain."""
+    chain = np.ascontiguousarray(chain).view(np.uint8).reshape(-1)
+    layout, total = F.mip_chain_layout(fmt, w, h, 0)
+    out = np.zeros(total, np.uint8)
+    s = images([Image(lw, lh, fmt, row, sl, _np_ptr(chain) + off) for (off, lw, lh, row, sl) in layout])
+    d = images([Image(lw, lh, fmt, row, sl, _np_ptr(out) + off) for (off, lw, lh, row, sl) in layout])
+    hr = lib.dxb200_scale_mipmaps_alpha_for_coverage(s, len(layout), alpha_ref, d)
+    if hr != 0:
+        raise DxTexError(hr, "dxb200_scale_mipmaps_alpha_for_coverage")
+    return out
 
 
 def decompress(blocks, w, h, bc_fmt, dst_fmt):

@@ -870,6 +870,122 @@ int32_t dxb200_premultiply_alpha(const dxb200_image* src, size_t nimages, uint32
         [&](const dxb200_image* ds, const dxb200_image* dd, size_t cnt, cudaStream_t st) { return launch_pmalpha(P, ds, dd, cnt, st); });
 }
 
+// ---- ScaleMipMapsAlphaForCoverage ----------------------------------------------------------------
+static int32_t plan_alpha_coverage(const dxb200_image* src, size_t n, const dxb200_image* dst)
+{
+    if (!src || !dst || !n) return DXB_E_INVALIDARG;
+    const uint32_t fmt = src[0].format;
+    if (is_compressed(fmt)) return DXB_E_NOT_SUPPORTED;                         // :3495-3497
+    if (!is_supported_pixel_format(fmt)) return DXB_E_NOT_SUPPORTED;
+    for (size_t i = 0; i < n; ++i)
+    {
+        if (!src[i].pixels || !dst[i].pixels) return DXB_E_POINTER;
+        if (src[i].format != fmt || dst[i].format != fmt) return DXB_E_INVALIDARG;
+        if (src[i].width != dst[i].width || src[i].height != dst[i].height || !src[i].width || !src[i].height) return DXB_E_INVALIDARG;
+        if ((uint64_t)src[i].width * src[i].height > 0x7FFFFFFFull) return DXB_E_INVALIDARG;
+    }
+    return DXB_S_OK;
+}
+
+// device pointers; count = device scratch (8 bytes).  Mirrors CalculateAlphaCoverage / EstimateAlphaScaleForCoverage.
+static int32_t alpha_coverage_device(const dxb200_image& img, float ref, float scale, unsigned long long* dCount, cudaStream_t st, float* coverage)
+{
+    *coverage = 0.0f;
+    if (img.width < 2 || img.height < 2) return DXB_S_OK;                      // no 2x2 cell: the reference's loops do not run
+    dxb_job j; memset(&j, 0, sizeof(j));
+    j.src = img.pixels; j.srcPitch = img.rowPitch; j.width = (uint32_t)img.width; j.height = (uint32_t)img.height;
+    DXB_CUDA(cudaMemsetAsync(dCount, 0, sizeof(unsigned long long), st));
+    const uint64_t cells = (uint64_t)(img.width - 1) * (img.height - 1);
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((cells + 255) / 256, (uint64_t)g.gridRow * 8u));
+    dxb_launch_alpha_coverage(grid, st, j, img.format, scale, ref, dCount);
+    int32_t hr = check_launch("k_alpha_coverage");
+    if (hr != DXB_S_OK) return hr;
+    unsigned long long hCount = 0;
+    DXB_CUDA(cudaMemcpyAsync(&hCount, dCount, sizeof(hCount), cudaMemcpyDeviceToHost, st));
+    DXB_CUDA(cudaStreamSynchronize(st));
+    const float cscale = static_cast<float>((img.width - 1) * (img.height - 1) * 8 * 8);          // :300-304
+    if (cscale > 0.0f) *coverage = static_cast<float>(hCount) / cscale;
+    return DXB_S_OK;
+}
+
+static int32_t scale_alpha_for_coverage_device(const dxb200_image* src, size_t n, float ref, const dxb200_image* dst, cudaStream_t st)
+{
+    unsigned long long* dCount = nullptr;
+    DXB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dCount), sizeof(unsigned long long), st));
+    float target = 0.0f;
+    int32_t hr = alpha_coverage_device(src[0], ref, 1.0f, dCount, st, &target);
+    // base level: plain copy (:3511-3530)
+    if (hr == DXB_S_OK)
+        hr = cuda_hr(cudaMemcpy2DAsync(dst[0].pixels, dst[0].rowPitch, src[0].pixels, src[0].rowPitch, std::min(src[0].rowPitch, dst[0].rowPitch),
+                                       src[0].slicePitch / std::max<size_t>(src[0].rowPitch, 1), cudaMemcpyDeviceToDevice, st), "copy base level");
+    for (size_t l = 1; l < n && hr == DXB_S_OK; ++l)
+    {
+        // EstimateAlphaScaleForCoverage (:310-355): bisection on [0, 4], at most 10 coverage evaluations
+        float lo = 0.0f, hi = 4.0f, scale = 1.0f;
+        for (int it = 0; it < 10 && hr == DXB_S_OK; ++it)
+        {
+            float cov = 0.0f;
+            hr = alpha_coverage_device(src[l], ref, scale, dCount, st, &cov);
+            if (hr != DXB_S_OK) break;
+            if (cov < target) lo = scale;
+            else if (cov > target) hi = scale;
+            else break;
+            scale = (lo + hi) * 0.5f;
+        }
+        if (hr != DXB_S_OK) break;
+        dxb_job j; memset(&j, 0, sizeof(j));
+        j.src = src[l].pixels; j.dst = dst[l].pixels; j.srcPitch = src[l].rowPitch; j.dstPitch = dst[l].rowPitch;
+        j.width = (uint32_t)src[l].width; j.height = (uint32_t)src[l].height;
+        const uint64_t px = (uint64_t)j.width * j.height;
+        const uint32_t grid = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>((px + 255) / 256, (uint64_t)g.gridRow * 8u));
+        dxb_launch_scale_alpha(grid, st, j, src[l].format, scale);
+        hr = check_launch("k_scale_alpha");
+    }
+    cudaFreeAsync(dCount, st);
+    return hr;
+}
+
+int32_t dxb200_scale_mipmaps_alpha_for_coverage_device(const dxb200_image* src, size_t nlevels, float alphaReference, const dxb200_image* dst, void* stream)
+{
+    int32_t hr = plan_alpha_coverage(src, nlevels, dst);
+    if (hr != DXB_S_OK) return hr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        hr = ensure_init_locked();
+    }
+    if (hr != DXB_S_OK) return hr;
+    return scale_alpha_for_coverage_device(src, nlevels, alphaReference, dst, static_cast<cudaStream_t>(stream));
+}
+
+int32_t dxb200_scale_mipmaps_alpha_for_coverage(const dxb200_image* src, size_t nlevels, float alphaReference, const dxb200_image* dst)
+{
+    int32_t hr = plan_alpha_coverage(src, nlevels, dst);
+    if (hr != DXB_S_OK) return hr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    hr = ensure_init_locked();
+    if (hr != DXB_S_OK) return hr;
+    cudaStream_t st = g.streams[0];
+    size_t bytes = 0;
+    for (size_t l = 0; l < nlevels; ++l) bytes += 2 * ((src[l].slicePitch + 255) & ~size_t(255));
+    hr = ensure_buffer(&g.dIn[0], &g.dInCap[0], bytes);
+    if (hr != DXB_S_OK) return hr;
+    std::vector<dxb200_image> ds(src, src + nlevels), dd(dst, dst + nlevels);
+    size_t off = 0;
+    for (size_t l = 0; l < nlevels && hr == DXB_S_OK; ++l)
+    {
+        ds[l].pixels = static_cast<uint8_t*>(g.dIn[0]) + off; off += (src[l].slicePitch + 255) & ~size_t(255);
+        dd[l].pixels = static_cast<uint8_t*>(g.dIn[0]) + off; off += (src[l].slicePitch + 255) & ~size_t(255);
+        dd[l].rowPitch = src[l].rowPitch; dd[l].slicePitch = src[l].slicePitch;          // device copy uses the source layout
+        hr = cuda_hr(cudaMemcpyAsync(ds[l].pixels, src[l].pixels, src[l].slicePitch, cudaMemcpyHostToDevice, st), "H2D");
+    }
+    if (hr == DXB_S_OK) hr = scale_alpha_for_coverage_device(ds.data(), nlevels, alphaReference, dd.data(), st);
+    for (size_t l = 0; l < nlevels && hr == DXB_S_OK; ++l)
+        hr = cuda_hr(cudaMemcpy2DAsync(dst[l].pixels, dst[l].rowPitch, dd[l].pixels, dd[l].rowPitch, std::min(dst[l].rowPitch, dd[l].rowPitch),
+                                       src[l].slicePitch / std::max<size_t>(src[l].rowPitch, 1), cudaMemcpyDeviceToHost, st), "D2H");
+    if (hr == DXB_S_OK) hr = cuda_hr(cudaStreamSynchronize(st), "alpha coverage sync");
+    return hr;
+}
+
 int32_t dxb200_resize_device(const dxb200_image* src, size_t nimages, uint32_t filter, const dxb200_image* dst, void* stream)
 {
     uint32_t mode = 0;

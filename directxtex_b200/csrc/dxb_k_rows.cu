@@ -248,6 +248,42 @@ void dxb_launch_pmalpha(unsigned grid, cudaStream_t stream, const dxb_job* jobs,
     k_pmalpha<<<grid, 256, 0, stream>>>(jobs, hostJobs[0], P);
 }
 
+// ------------------------------------------------------------------------------------------------ alpha coverage
+// k_alpha_coverage: one thread per 2x2 cell of one image, integer count accumulated with one atomicAdd per warp.
+__global__ void __launch_bounds__(256) k_alpha_coverage(dxb_job j, uint32_t fmt, float scale, float ref, unsigned long long* count)
+{
+    const uint32_t cw = j.width - 1u, ch = j.height - 1u;
+    const uint32_t cells = cw * ch;
+    uint32_t local = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t y = i / cw, x = i - y * cw;
+        const uint8_t* r0 = j.src + (size_t)y * j.srcPitch;
+        const uint8_t* r1 = r0 + j.srcPitch;
+        local += dxb_alpha_coverage_cell(dxb_load_pixel(fmt, r0, x).w, dxb_load_pixel(fmt, r1, x).w,
+                                         dxb_load_pixel(fmt, r0, x + 1u).w, dxb_load_pixel(fmt, r1, x + 1u).w, scale, ref);
+    }
+    local = __reduce_add_sync(0xffffffffu, local);
+    if ((threadIdx.x & 31u) == 0 && local) atomicAdd(count, (unsigned long long)local);
+}
+__global__ void __launch_bounds__(256) k_scale_alpha(dxb_job j, uint32_t fmt, float scale)
+{
+    const uint32_t n = j.width * j.height;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint32_t y = i / j.width, x = i - y * j.width;
+        dxb_scale_alpha_pixel(fmt, j.src + (size_t)y * j.srcPitch, j.dst + (size_t)y * j.dstPitch, x, scale);
+    }
+}
+void dxb_launch_alpha_coverage(unsigned grid, cudaStream_t stream, const dxb_job& j, uint32_t fmt, float scale, float ref, unsigned long long* count)
+{
+    k_alpha_coverage<<<grid, 256, 0, stream>>>(j, fmt, scale, ref, count);
+}
+void dxb_launch_scale_alpha(unsigned grid, cudaStream_t stream, const dxb_job& j, uint32_t fmt, float scale)
+{
+    k_scale_alpha<<<grid, 256, 0, stream>>>(j, fmt, scale);
+}
+
 // ------------------------------------------------------------------------------------------------ tiled mips
 template <uint32_t FMT, uint32_t MODE>
 __device__ __forceinline__ dxb_px dxb_mip_eval(const dxb_mip_job& j, uint32_t x, uint32_t y, const dxb_mip_params& P, uint32_t lflags)

@@ -188,3 +188,38 @@ DXB_DEV dxb_px dxb_mip_triangle(uint32_t fmt, const dxb_mip_job& j, uint32_t x, 
     if (fmt == DXB_FMT_R10G10B10A2_UNORM) acc.w = acc.w + 0.1f;      // Bias {0,0,0,0.1} (:1560-1575)
     return acc;
 }
+
+// ---------------------------------------------------------------------------------------------
+// ScaleMipMapsAlphaForCoverage helpers (DirectXTexMipmaps.cpp:143-356).
+// Coverage of one 2x2 cell (CalculateAlphaCoverage :213-308): the four alphas, scaled and saturated, go through the 8x8
+// bilinear sub-sample weights IN SEQUENCE: the reference overwrites its vector with the splatted weighted sum, so every
+// sub-sample after the first re-weights the previous result (kept: it defines the counts).  VectorSum = XMVectorSum
+// (DIRECTX_MATH_VERSION >= 310, :127-128) = (x + y) + (z + w) in the oracle's DirectXMath shim (M).
+// a00 = (x, y), a01 = (x, y+1), a10 = (x+1, y), a11 = (x+1, y+1).  Returns how many of the 64 sub-samples exceed `ref`.
+DXB_DEV uint32_t dxb_alpha_coverage_cell(float a00, float a01, float a10, float a11, float scale, float ref)
+{
+    float v0 = dxb_clamp(a00 * scale, 0.0f, 1.0f), v1 = dxb_clamp(a01 * scale, 0.0f, 1.0f);
+    float v2 = dxb_clamp(a10 * scale, 0.0f, 1.0f), v3 = dxb_clamp(a11 * scale, 0.0f, 1.0f);
+    uint32_t count = 0;
+    for (int sy = 0; sy < 8; ++sy)
+    {
+        const float fy = ((float)sy + 0.5f) / 8.0f, ify = 1.0f - fy;
+        for (int sx = 0; sx < 8; ++sx)
+        {
+            const float fx = ((float)sx + 0.5f) / 8.0f, ifx = 1.0f - fx;
+            const float p0 = v0 * (ifx * ify), p1 = v1 * (ifx * fy), p2 = v2 * (fx * ify), p3 = v3 * (fx * fy);
+            const float a = p0 + p1, b = p2 + p3;
+            const float sum = a + b;
+            v0 = v1 = v2 = v3 = sum;
+            if (sum > ref) ++count;
+        }
+    }
+    return count;
+}
+// ScaleAlpha (:143-193): plain Load / Store, alpha * scale
+DXB_DEV void dxb_scale_alpha_pixel(uint32_t fmt, const uint8_t* srow, uint8_t* drow, uint32_t x, float scale)
+{
+    dxb_px v = dxb_load_pixel(fmt, srow, x);
+    v.w = v.w * scale;
+    dxb_store_pixel(fmt, drow, x, v);
+}

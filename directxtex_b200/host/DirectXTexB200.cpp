@@ -461,6 +461,29 @@ HRESULT PremultiplyAlpha(const Image* srcImages, size_t nimages, const TexMetada
 }
 
 // ---------------------------------------------------------------------------------------------------
+// ScaleMipMapsAlphaForCoverage (DirectXTexMipmaps.cpp:3483-3552): srcImages = the mip levels of one item, mipChain = an
+// initialised chain of the same shape whose item `item` receives the result
+HRESULT ScaleMipMapsAlphaForCoverage(const Image* srcImages, size_t nimages, const TexMetadata& metadata, size_t item, float alphaReference, ScratchImage& mipChain) noexcept
+{
+    if (!srcImages || !nimages || nimages > metadata.mipLevels || !mipChain.GetImages()) return E_INVALIDARG;
+    if (metadata.IsVolumemap() || IsCompressed(metadata.format) || !implemented_pixel_format(metadata.format)) return HRESULT_E_NOT_SUPPORTED;
+    if (srcImages[0].format != metadata.format || srcImages[0].width != metadata.width || srcImages[0].height != metadata.height) return E_FAIL;
+    if (nimages < metadata.mipLevels) return E_FAIL;                                             // :3535-3536 (level >= nimages)
+    try
+    {
+        std::vector<dxb200_image> src(metadata.mipLevels), dst(metadata.mipLevels);
+        for (size_t level = 0; level < metadata.mipLevels; ++level)
+        {
+            const Image* d = mipChain.GetImage(level, item, 0);
+            if (!d || !d->pixels) return E_POINTER;
+            src[level] = to_c(srcImages[level]); dst[level] = to_c(*d);
+        }
+        return dxb200_scale_mipmaps_alpha_for_coverage(src.data(), src.size(), alphaReference, dst.data());
+    }
+    catch (...) { return E_OUTOFMEMORY; }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // DDS container (DirectXTexDDS.cpp); the format logic lives behind the C ABI (host/dxb_dds.cpp)
 Blob& Blob::operator=(Blob&& o) noexcept
 {

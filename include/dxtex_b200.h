@@ -109,6 +109,15 @@ DXB200_API int32_t  dxb200_resize_device(const dxb200_image* src, size_t nimages
 DXB200_API int32_t  dxb200_premultiply_alpha(const dxb200_image* src, size_t nimages, uint32_t flags, const dxb200_image* dst);
 DXB200_API int32_t  dxb200_premultiply_alpha_device(const dxb200_image* src, size_t nimages, uint32_t flags, const dxb200_image* dst, void* stream);
 
+/* DirectX::ScaleMipMapsAlphaForCoverage (DirectXTexMipmaps.cpp:3483-3552; CalculateAlphaCoverage :213-308,
+ * EstimateAlphaScaleForCoverage :310-355, ScaleAlpha :143-193) for ONE array item: src[0..nlevels) = its mip levels as
+ * GenerateMipMaps produced them, dst[0..nlevels) = the same levels of the result.  Level 0 is copied; every other level's
+ * alpha is scaled so that its alpha-test coverage at `alphaReference` matches level 0's (10-step bisection).
+ *   The _device variant synchronises `stream` internally (the bisection reads counts back). */
+DXB200_API int32_t  dxb200_scale_mipmaps_alpha_for_coverage(const dxb200_image* src, size_t nlevels, float alphaReference, const dxb200_image* dst);
+DXB200_API int32_t  dxb200_scale_mipmaps_alpha_for_coverage_device(const dxb200_image* src, size_t nlevels, float alphaReference,
+                                                                   const dxb200_image* dst, void* stream);
+
 /* ---- DDS container (host-side only, no GPU work) ------------------------------------------------
  * dxb200_metadata is a field-for-field mirror of DirectX::TexMetadata (DirectXTex.h:187-216).
  * EncodeDDSHeader (DirectXTexDDS.cpp:711-1043), SaveToDDSMemory (:2403-2620), GetMetadataFromDDSMemory / DecodeDDSHeader

@@ -179,6 +179,26 @@ int32_t ref_dds_load(const uint8_t* src, size_t size, uint32_t flags, uint64_t* 
     return hr;
 }
 
+// GenerateMipMaps then ScaleMipMapsAlphaForCoverage (DirectXTexMipmaps.cpp:3483-3552) on one image, as texconv does
+// (Texconv/texconv.cpp:3457-3480).  dst receives the whole chain in ScratchImage layout.
+int32_t ref_mips_alpha_coverage(const uint8_t* src, size_t w, size_t h, uint32_t fmt, uint32_t filter, float alphaRef,
+                                uint8_t* dst, size_t dstBytes, uint8_t* plainChain)
+{
+    Image img = make_image(src, w, h, fmt, 0);
+    ScratchImage mips;
+    HRESULT hr = GenerateMipMaps(img, static_cast<TEX_FILTER_FLAGS>(filter), 0, mips, false);
+    if (FAILED(hr)) return hr;
+    if (plainChain) memcpy(plainChain, mips.GetPixels(), mips.GetPixelsSize());
+    ScratchImage out;
+    hr = out.Initialize(mips.GetMetadata());
+    if (FAILED(hr)) return hr;
+    hr = ScaleMipMapsAlphaForCoverage(mips.GetImages(), mips.GetMetadata().mipLevels, mips.GetMetadata(), 0, alphaRef, out);
+    if (FAILED(hr)) return hr;
+    if (out.GetPixelsSize() > dstBytes) return E_NOT_SUFFICIENT_BUFFER;
+    memcpy(dst, out.GetPixels(), out.GetPixelsSize());
+    return hr;
+}
+
 double ref_generate_mipmaps_timed(const uint8_t* src, size_t w, size_t h, uint32_t fmt, uint32_t filter, size_t levels)
 {
     Image img = make_image(src, w, h, fmt, 0);

@@ -126,6 +126,10 @@ int32_t emul_convert(const uint8_t* src, size_t w, size_t h, uint32_t srcFmt, si
 #include "dxb_mips.cuh"
 #include "dxb_host_tri.h"
 
+// ScaleMipMapsAlphaForCoverage for one chain held in `src` (ScratchImage layout); result chain in `dst`
+extern "C" int32_t emul_scale_mips_alpha(const uint8_t* src, uint8_t* dst, const size_t* offsets, const size_t* widths, const size_t* heights,
+                                         const size_t* pitches, size_t levels, uint32_t fmt, float ref);
+
 extern "C" int32_t emul_generate_mipmaps(uint8_t* chainBase, const size_t* offsets, const size_t* widths, const size_t* heights,
                                          const size_t* pitches, size_t levels, uint32_t fmt, uint32_t filter)
 {
@@ -195,5 +199,43 @@ extern "C" int32_t emul_decompress(const uint8_t* blocks, size_t w, size_t h, ui
                 for (size_t s2 = 0; s2 < 4 && bx * 4 + s2 < w; ++s2)
                     dxb_store_pixel(dstFmt, dst + (by * 4 + t) * dpitch, bx * 4 + s2, dxb_convert_pixel(px[(t << 2) | s2], inF, outF, cflags));
         }
+    return DXB_S_OK;
+}
+
+static float emul_alpha_coverage(const uint8_t* img, size_t w, size_t h, size_t pitch, uint32_t fmt, float ref, float scale)
+{
+    if (w < 2 || h < 2) return 0.0f;
+    unsigned long long count = 0;
+    for (size_t y = 0; y + 1 < h; ++y)
+        for (size_t x = 0; x + 1 < w; ++x)
+        {
+            const uint8_t* r0 = img + y * pitch; const uint8_t* r1 = r0 + pitch;
+            count += dxb_alpha_coverage_cell(dxb_load_pixel(fmt, r0, x).w, dxb_load_pixel(fmt, r1, x).w,
+                                             dxb_load_pixel(fmt, r0, x + 1).w, dxb_load_pixel(fmt, r1, x + 1).w, scale, ref);
+        }
+    const float cscale = static_cast<float>((w - 1) * (h - 1) * 8 * 8);
+    return cscale > 0.0f ? static_cast<float>(count) / cscale : 0.0f;
+}
+int32_t emul_scale_mips_alpha(const uint8_t* src, uint8_t* dst, const size_t* offsets, const size_t* widths, const size_t* heights,
+                              const size_t* pitches, size_t levels, uint32_t fmt, float ref)
+{
+    if (!dxb_bytes_per_pixel(fmt)) return DXB_E_NOT_SUPPORTED;
+    const float target = emul_alpha_coverage(src + offsets[0], widths[0], heights[0], pitches[0], fmt, ref, 1.0f);
+    memcpy(dst + offsets[0], src + offsets[0], pitches[0] * heights[0]);
+    for (size_t l = 1; l < levels; ++l)
+    {
+        float lo = 0.0f, hi = 4.0f, scale = 1.0f;
+        for (int it = 0; it < 10; ++it)
+        {
+            const float cov = emul_alpha_coverage(src + offsets[l], widths[l], heights[l], pitches[l], fmt, ref, scale);
+            if (cov < target) lo = scale;
+            else if (cov > target) hi = scale;
+            else break;
+            scale = (lo + hi) * 0.5f;
+        }
+        for (size_t y = 0; y < heights[l]; ++y)
+            for (size_t x = 0; x < widths[l]; ++x)
+                dxb_scale_alpha_pixel(fmt, src + offsets[l] + y * pitches[l], dst + offsets[l] + y * pitches[l], (uint32_t)x, scale);
+    }
     return DXB_S_OK;
 }

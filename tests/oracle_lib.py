@@ -46,6 +46,7 @@ class Ref:
         L.ref_generate_mipmaps_timed.argtypes = [vp, sz, sz, u32, u32, sz]
         L.ref_resize.argtypes = [vp, sz, sz, u32, sz, sz, sz, u32, vp, sz]
         L.ref_premultiply_alpha.argtypes = [vp, sz, sz, u32, sz, u32, vp, sz]
+        L.ref_mips_alpha_coverage.argtypes = [vp, sz, sz, u32, u32, C.c_float, vp, sz, vp]
         L.ref_dds_save.argtypes = [vp, sz, vp, u32, vp, sz, C.POINTER(sz)]
         L.ref_dds_load.argtypes = [vp, sz, u32, vp, vp, sz, C.POINTER(sz)]
         L.ref_generate_mipmaps_timed.restype = C.c_double
@@ -105,6 +106,14 @@ class Ref:
         hr = self.L.ref_premultiply_alpha(src.ctypes.data, w, h, fmt, 0, flags, out.ctypes.data, n)
         return F.hr_u32(hr), out
 
+    def mips_alpha_coverage(self, src, w, h, fmt, alpha_ref, filter=0):
+        """(hr, plain GenerateMipMaps chain, chain after ScaleMipMapsAlphaForCoverage)"""
+        src = np.ascontiguousarray(src)
+        _, total = F.mip_chain_layout(fmt, w, h, 0)
+        out, plain = np.zeros(total, np.uint8), np.zeros(total, np.uint8)
+        hr = self.L.ref_mips_alpha_coverage(src.ctypes.data, w, h, fmt, filter, alpha_ref, out.ctypes.data, total, plain.ctypes.data)
+        return F.hr_u32(hr), plain, out
+
     def dds_save(self, pixels, fmt, w, h, array_size=1, mip_levels=1, misc_flags=0, misc_flags2=0, flags=0):
         pixels = np.ascontiguousarray(pixels).view(np.uint8).reshape(-1)
         meta = np.array([w, h, array_size, mip_levels, fmt, misc_flags, misc_flags2], np.uint64)
@@ -152,6 +161,7 @@ class Emul:
         L.emul_compress.argtypes = [vp, sz, sz, u32, sz, u32, u32, f32, vp]
         L.emul_convert.argtypes = [vp, sz, sz, u32, sz, u32, sz, u32, vp]
         L.emul_generate_mipmaps.argtypes = [vp] + [C.POINTER(sz)] * 4 + [sz, u32, u32]
+        L.emul_scale_mips_alpha.argtypes = [vp, vp] + [C.POINTER(sz)] * 4 + [sz, u32, C.c_float]
         L.emul_decompress.argtypes = [vp, sz, sz, u32, u32, vp]
 
     def compress(self, src, w, h, src_fmt, dst_fmt, flags=0, threshold=0.5):
@@ -182,6 +192,15 @@ class Emul:
         off, ws, hs, ps = A(*[l[0] for l in layout]), A(*[l[1] for l in layout]), A(*[l[2] for l in layout]), A(*[l[3] for l in layout])
         hr = self.L.emul_generate_mipmaps(chain.ctypes.data, off, ws, hs, ps, len(layout), fmt, filter)
         return F.hr_u32(hr), chain
+
+    def scale_mips_alpha(self, chain, w, h, fmt, alpha_ref):
+        layout, total = F.mip_chain_layout(fmt, w, h, 0)
+        chain = np.ascontiguousarray(chain).view(np.uint8).reshape(-1)
+        out = np.zeros(total, np.uint8)
+        A = C.c_size_t * len(layout)
+        off, ws, hs, ps = A(*[l[0] for l in layout]), A(*[l[1] for l in layout]), A(*[l[2] for l in layout]), A(*[l[3] for l in layout])
+        hr = self.L.emul_scale_mips_alpha(chain.ctypes.data, out.ctypes.data, off, ws, hs, ps, len(layout), fmt, alpha_ref)
+        return F.hr_u32(hr), out
 
 
 def load_ref():

@@ -222,3 +222,27 @@ def test_emulator_dither_matches_reference(oracle, emul):
                 hr, want = oracle.convert(src, 21, 6, sf, df, fl)
                 he, got = emul.convert(src, 21, 6, sf, df, fl)
                 assert hr == 0 and he == 0 and np.array_equal(got, want), (sf, df, hex(fl))
+
+
+def _alpha_test_image(fmt, w, h, rng):
+    yy, xx = np.mgrid[0:h, 0:w]
+    a = np.clip(0.5 + 0.4 * np.sin(xx * 0.4) * np.cos(yy * 0.3) + rng.normal(0, 0.12, (h, w)), 0, 1)
+    if fmt in (28, 29, 87):
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        img[..., 3] = (a * 255).astype(np.uint8)
+        return img
+    img = rng.random((h, w, 4), dtype=np.float32)
+    img[..., 3] = a
+    return img.astype(np.float16) if fmt == 10 else img
+
+
+def test_emulator_alpha_coverage_matches_reference(oracle, emul):
+    """ScaleMipMapsAlphaForCoverage: coverage counting (with the reference's sequential sub-sample quirk), the 10-step bisection
+    and ScaleAlpha, compiled for the host from the device sources, against the reference."""
+    rng = np.random.default_rng(43)
+    for fmt, w, h in [(28, 64, 64), (28, 48, 20), (2, 32, 32), (87, 16, 64), (10, 33, 17)]:
+        img = _alpha_test_image(fmt, w, h, rng)
+        for ref in (0.5, 0.25):
+            hr, plain, want = oracle.mips_alpha_coverage(img, w, h, fmt, ref)
+            he, got = emul.scale_mips_alpha(plain, w, h, fmt, ref)
+            assert hr == 0 and he == 0 and np.array_equal(got, want) and not np.array_equal(want, plain), (fmt, w, h, ref)

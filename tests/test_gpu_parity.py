@@ -195,6 +195,29 @@ def test_premultiply_alpha_vs_oracle(oracle, flags):
     assert e.value.hr == F.HRESULT_E_NOT_SUPPORTED
 
 
+def _alpha_test_image(fmt, w, h, rng):
+    yy, xx = np.mgrid[0:h, 0:w]
+    a = np.clip(0.5 + 0.4 * np.sin(xx * 0.4) * np.cos(yy * 0.3) + rng.normal(0, 0.12, (h, w)), 0, 1)
+    if fmt in (28, 29, 87):
+        img = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        img[..., 3] = (a * 255).astype(np.uint8)
+        return img
+    img = rng.random((h, w, 4), dtype=np.float32)
+    img[..., 3] = a
+    return img.astype(np.float16) if fmt == 10 else img
+
+
+def test_scale_mipmaps_alpha_for_coverage(oracle):
+    """GenerateMipMaps -> ScaleMipMapsAlphaForCoverage (texconv -keepcoverage), bit-exact vs the reference."""
+    rng = np.random.default_rng(47)
+    for fmt, w, h in [(28, 128, 128), (28, 48, 20), (2, 32, 32), (87, 16, 64), (10, 33, 17), (29, 64, 64)]:
+        img = _alpha_test_image(fmt, w, h, rng)
+        for ref in (0.5, 0.25):
+            hr, plain, want = oracle.mips_alpha_coverage(img, w, h, fmt, ref)
+            got = capi.scale_mipmaps_alpha_for_coverage(plain, w, h, fmt, ref)
+            assert hr == 0 and np.array_equal(got, want), (fmt, w, h, ref)
+
+
 def test_bc7_equals_emulator_and_quality(oracle, emul):
     """GPU BC7 == host lock-step emulator (same source, explicit fmaf, -fmad=false) bit for bit, and
     MSE <= 1.02 x the reference CPU encoder's MSE (golden anchor) on each test image."""
