@@ -249,10 +249,10 @@ def main():
                     "ms_per_step": float(te[0]), "api": "dxb200_compress (host pointers, pinned)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                         "traffic": 285322496, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_k_compress_bc7.txt",
+                         "traffic": 283828992, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_k_compress_bc7.txt",
                          "peak_source": pk_kind, "kernel": "k_compress_bc7", "kernel_ms": kern_ms,
                          "algorithmic_bytes": ALGO_BYTES,
-                         "note": "BC7 mode/partition search is issue-bound, not HBM-bound (SURVEY 8(d)): 76% of issue slots used, 3.0k warp-instructions per block, DRAM traffic = algorithmic bytes (profiles/r01_ncu_k_compress_bc7.txt)"},
+                         "note": "BC7 mode/partition search is issue-bound, not HBM-bound (SURVEY 8(d)): 76% of issue slots used, 2.6k warp-instructions per block, DRAM traffic = algorithmic bytes (profiles/r01_ncu_k_compress_bc7.txt)"},
             "cpu_baseline": {"value": cpu_rate, "unit": "Mtexels/s", "cores": cores, "kind": "reference",
                              "sample": "centre %dx%d crop of the same image, reference Compress(BC7_UNORM, DEFAULT|PARALLEL), %.2f s" % (side, side, cpu_sec)},
         }
