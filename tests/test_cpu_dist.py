@@ -2,7 +2,6 @@
 import os
 import socket
 
-import numpy as np
 import pytest
 
 from directxtex_b200 import dist as D
