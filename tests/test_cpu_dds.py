@@ -60,3 +60,23 @@ def test_dds_ignore_mips_and_errors(oracle):
     with pytest.raises(capi.DxTexError) as e:
         capi.dds_load(data[:-8])                           # truncated pixel data
     assert e.value.hr == 0x80070026 and oracle.dds_load(data[:-8])[0] == 0x80070026
+
+
+def test_cpp_dds_mirror_round_trip(tmp_path, oracle):
+    """SaveToDDSMemory / LoadFromDDSMemory / SaveToDDSFile / LoadFromDDSFile / Blob of the C++ mirror, from a C++ caller
+    (no GPU involved); the file it writes is then read by the reference."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "directxtex_b200", "_lib")
+    exe = str(tmp_path / "dds_roundtrip")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([cxx, "-std=c++17", "-O1", "-I", os.path.join(root, "directxtex_b200", "host"),
+                    os.path.join(root, "tests", "cpp", "dds_roundtrip.cpp"), "-L", libdir, "-ldxtex_b200",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    out = str(tmp_path / "pm.dds")
+    r = subprocess.run([exe, out], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+    hr, meta, pixels = oracle.dds_load(np.fromfile(out, np.uint8))
+    assert hr == 0 and meta[:5] == [16, 8, 1, 1, 77] and (meta[6] & 7) == 2          # BC3, premultiplied (DXT4)
+    assert np.array_equal(pixels, (np.arange(pixels.size, dtype=np.uint32) * 13).astype(np.uint8))
