@@ -156,7 +156,8 @@ namespace DirectX
     enum DDS_FLAGS : uint32_t
     {
         DDS_FLAGS_NONE = 0, DDS_FLAGS_IGNORE_MIPS = 0x100,
-        DDS_FLAGS_FORCE_DX10_EXT = 0x10000, DDS_FLAGS_FORCE_DX10_EXT_MISC2 = 0x20000, DDS_FLAGS_ALLOW_LARGE_FILES = 0x1000000,
+        DDS_FLAGS_FORCE_DX10_EXT = 0x10000, DDS_FLAGS_FORCE_DX10_EXT_MISC2 = 0x20000, DDS_FLAGS_FORCE_DX9_LEGACY = 0x40000,
+        DDS_FLAGS_FORCE_DXT5_RXGB = 0x80000, DDS_FLAGS_ALLOW_LARGE_FILES = 0x1000000,
     };
     class DXTEXB200_API Blob
     {

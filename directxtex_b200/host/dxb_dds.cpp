@@ -43,7 +43,10 @@ constexpr uint32_t CAPS_TEXTURE = 0x1000, CAPS_MIPMAP = 0x400008, CAPS_CUBEMAP =
 constexpr uint32_t CAPS2_CUBEMAP = 0x200, CAPS2_ALLFACES = 0xFE00;
 // DDS_FLAGS (DirectXTex.h:232-279) that this implementation understands
 constexpr uint32_t DF_FORCE_DX10 = 0x10000, DF_FORCE_DX10_MISC2 = 0x20000, DF_ALLOW_LARGE = 0x1000000, DF_IGNORE_MIPS = 0x100;
-constexpr uint32_t DF_UNSUPPORTED = 0x1 | 0x2 | 0x4 | 0x8 | 0x10 | 0x20 | 0x40 | 0x80 | 0x40000 | 0x80000 | 0x100000;
+constexpr uint32_t DF_FORCE_DX9 = 0x40000, DF_FORCE_RXGB = 0x80000;
+// load-side conversion flags (LEGACY_DWORD, NO_LEGACY_EXPANSION, NO_R10B10G10A2_FIXUP, FORCE_RGB, NO_16BPP, EXPAND_LUMINANCE,
+// BAD_DXTN_TAILS, PERMISSIVE) and FORCE_24BPP_RGB are outside this implementation
+constexpr uint32_t DF_UNSUPPORTED = 0x1 | 0x2 | 0x4 | 0x8 | 0x10 | 0x20 | 0x40 | 0x80 | 0x100000;
 constexpr uint32_t MISC_TEXTURECUBE = 0x4;
 
 // one row per legacy encoding the reference emits for a format this library implements (EncodeDDSHeader :746-790);
@@ -97,12 +100,44 @@ int32_t dxb200_dds_encode_header(const dxb200_metadata* md, uint32_t flags, void
     if (md->dimension != 3 /* TEX_DIMENSION_TEXTURE2D */ || md->depth != 1) return DXB_E_NOT_SUPPORTED;
     const bool cube = (md->miscFlags & MISC_TEXTURECUBE) != 0;
     // arrays other than a single cubemap need the DX10 extension (:728-738)
-    if (md->arraySize > 1 && !(md->arraySize == 6 && cube)) flags |= DF_FORCE_DX10;
+    if (md->arraySize > 1 && !(md->arraySize == 6 && cube))
+    {
+        if (flags & DF_FORCE_DX9) return (int32_t)0x80070052;
+        flags |= DF_FORCE_DX10;
+    }
     if (flags & DF_FORCE_DX10_MISC2) flags |= DF_FORCE_DX10;
+    if ((flags & DF_FORCE_DX9) && (flags & DF_FORCE_DX10)) return (int32_t)0x80070052;      // HRESULT_E_CANNOT_MAKE (:733-734)
     const Legacy* leg = nullptr;
+    PixelFormat legpf{};
     if (!(flags & DF_FORCE_DX10))
+    {
+        // DDS_FLAGS_FORCE_DX9_LEGACY writes the sRGB formats with their UNORM twins' legacy encodings and BC4U / BC5U as
+        // ATI1 / ATI2 (:855-911); without a legacy encoding it fails with HRESULT_E_CANNOT_MAKE (:918-919)
+        uint32_t f = md->format;
+        if (flags & DF_FORCE_DX9)
+        {
+            if (f == DXB_FMT_R8G8B8A8_UNORM_SRGB) f = DXB_FMT_R8G8B8A8_UNORM;
+            else if (f == DXB_FMT_B8G8R8A8_UNORM_SRGB) f = DXB_FMT_B8G8R8A8_UNORM;
+            else if (f == DXB_FMT_B8G8R8X8_UNORM_SRGB) f = DXB_FMT_B8G8R8X8_UNORM;
+            else if (f == DXB_FMT_BC1_UNORM_SRGB) f = DXB_FMT_BC1_UNORM;
+            else if (f == DXB_FMT_BC2_UNORM_SRGB) f = DXB_FMT_BC2_UNORM;
+            else if (f == DXB_FMT_BC3_UNORM_SRGB) f = DXB_FMT_BC3_UNORM;
+        }
         for (const Legacy& e : kLegacy)
-            if (e.format == md->format && !e.decodeOnly && (!e.pm || is_pm(*md))) { leg = &e; break; }
+            if (e.format == f && !e.decodeOnly && (!e.pm || is_pm(*md))) { leg = &e; break; }
+        if (leg)
+        {
+            legpf = leg->pf;
+            if ((flags & DF_FORCE_DX9) && md->format == DXB_FMT_BC4_UNORM) legpf.fourCC = fourcc('A', 'T', 'I', '1');
+            if ((flags & DF_FORCE_DX9) && md->format == DXB_FMT_BC5_UNORM) legpf.fourCC = fourcc('A', 'T', 'I', '2');
+            if ((flags & DF_FORCE_RXGB) && f == DXB_FMT_BC3_UNORM) legpf.fourCC = fourcc('R', 'X', 'G', 'B');      // :781-784
+        }
+        else if (flags & DF_FORCE_DX9)
+        {
+            if (md->format == DXB_FMT_R10G10B10A2_UNORM) return DXB_E_NOT_SUPPORTED;        // the D3DX-compatible mask variant is not implemented
+            return (int32_t)0x80070052;
+        }
+    }
     *required = leg ? kMinHeader : kDX10Header;
     if (!dst) return DXB_S_OK;
     if (maxsize < *required) return (int32_t)0x8007007A;                   // E_NOT_SUFFICIENT_BUFFER
@@ -124,7 +159,7 @@ int32_t dxb200_dds_encode_header(const dxb200_metadata* md, uint32_t flags, void
     if (row > 0xFFFFFFFFull || slice > 0xFFFFFFFFull) return DXB_E_FAIL;
     if (dxb_bc_block_bytes(md->format)) { h.flags |= HF_LINEARSIZE; h.pitchOrLinearSize = (uint32_t)slice; }
     else { h.flags |= HF_PITCH; h.pitchOrLinearSize = (uint32_t)row; }
-    if (leg) h.ddspf = leg->pf;
+    if (leg) h.ddspf = legpf;
     else
     {
         h.ddspf = FCC(fourcc('D', 'X', '1', '0'));

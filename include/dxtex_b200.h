@@ -123,7 +123,8 @@ DXB200_API int32_t  dxb200_scale_mipmaps_alpha_for_coverage_device(const dxb200_
  * EncodeDDSHeader (DirectXTexDDS.cpp:711-1043), SaveToDDSMemory (:2403-2620), GetMetadataFromDDSMemory / DecodeDDSHeader
  * (:319-683, 1960-2003), LoadFromDDSMemory (:2008-2100).  TEXTURE2D resources (arrays, cubemaps, mip chains) in the
  * formats this library implements; flags = DDS_FLAGS (DirectXTex.h:232-279): FORCE_DX10_EXT, FORCE_DX10_EXT_MISC2,
- * IGNORE_MIPS, ALLOW_LARGE_FILES are honoured, conversion / legacy-expansion flags -> HRESULT_E_NOT_SUPPORTED.
+ * FORCE_DX9_LEGACY, FORCE_DXT5_RXGB, IGNORE_MIPS, ALLOW_LARGE_FILES are honoured (HRESULT_E_CANNOT_MAKE as in the
+ * reference when a format has no legacy encoding); load-side conversion / legacy-expansion flags -> HRESULT_E_NOT_SUPPORTED.
  * save/encode: dst == NULL only computes *required.  load: `images` describes the destination (item-major, mip-minor)
  * as ScratchImage::Initialize(metadata) lays it out. */
 typedef struct dxb200_metadata

@@ -43,6 +43,35 @@ def test_dds_save_matches_reference_and_round_trips(oracle, case):
     assert np.array_equal(back, rback) and np.array_equal(back, px)
 
 
+DX9, RXGB = 0x40000, 0x80000
+
+
+@pytest.mark.parametrize("case", [(29, 8, 8, 1, 1, 0, 0, DX9), (91, 8, 8, 1, 2, 0, 0, DX9), (93, 8, 8, 1, 1, 0, 0, DX9), (72, 8, 8, 1, 1, 0, 0, DX9),
+                                  (75, 8, 8, 1, 1, 0, 2, DX9), (78, 8, 8, 1, 1, 0, 0, DX9), (80, 8, 8, 1, 1, 0, 0, DX9), (83, 8, 8, 1, 1, 0, 0, DX9),
+                                  (28, 8, 8, 1, 1, 0, 0, DX9), (77, 8, 8, 1, 1, 0, 0, RXGB), (28, 8, 8, 6, 1, CUBE, 0, DX9)])
+def test_dds_legacy_flags_match_reference(oracle, case):
+    fmt, w, h, n, m, misc, misc2, flags = case
+    px = _pixels(fmt, w, h, n, m, 5)
+    hr, want = oracle.dds_save(px, fmt, w, h, n, m, misc, misc2, flags)
+    assert hr == 0, hex(hr)
+    got = capi.dds_save(px, fmt, w, h, n, m, misc, misc2, flags)
+    assert np.array_equal(got, want), case
+    if flags != RXGB:                                   # the reference itself cannot read its RXGB files back as BC3
+        md, back = capi.dds_load(want)
+        hr, rmeta, rback = oracle.dds_load(want)
+        assert hr == 0 and [md.width, md.height, md.arraySize, md.mipLevels, md.format, md.miscFlags, md.miscFlags2] == rmeta
+        assert np.array_equal(back, rback)
+
+
+def test_dds_legacy_flag_failures_match_reference(oracle):
+    for fmt, n, misc, flags in [(98, 1, 0, DX9), (95, 1, 0, DX9), (28, 3, 0, DX9), (28, 1, 0, DX9 | DX10)]:
+        px = _pixels(fmt, 8, 8, n, 1, 2)
+        hr = oracle.dds_save(px, fmt, 8, 8, n, 1, misc, 0, flags)[0]
+        with pytest.raises(capi.DxTexError) as e:
+            capi.dds_save(px, fmt, 8, 8, n, 1, misc, 0, flags)
+        assert e.value.hr == hr == 0x80070052, (fmt, n, hex(flags), hex(hr))      # HRESULT_E_CANNOT_MAKE
+
+
 def test_dds_ignore_mips_and_errors(oracle):
     px = _pixels(28, 16, 16, 1, 5, 3)
     data = capi.dds_save(px, 28, 16, 16, 1, 5)
