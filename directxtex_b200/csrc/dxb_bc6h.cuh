@@ -194,17 +194,18 @@ DXB_DEV int dxb_bc6h_pick_mode(const int32_t ep[4][3], bool two, bool bSigned, i
 {
     // candidates in decreasing base precision; the last of each list has no delta restriction (always fits)
     const int order2[10] = { 2, 3, 4, 0, 5, 6, 7, 8, 1, 9 };
-    const int order1[3] = { 12, 11, 10 };
-    const int ncand = two ? 10 : 3;
+    const int order1[4] = { 13, 12, 11, 10 };          // mode 14 (16-bit endpoints, 4-bit deltas) reproduces near-flat blocks exactly
+    const int ncand = two ? 10 : 4;
     const int nep = two ? 4 : 2;
     int chosen = two ? 9 : 10;
-    int32_t q12[4][3]; bool neg[4][3];
+    int32_t q12[4][3], amag[4][3]; bool neg[4][3];
     for (int e = 0; e < 4; ++e)
         for (int c = 0; c < 3; ++c)
         {
             const int32_t v = ep[e][c];
             neg[e][c] = bSigned && (v < 0);
             const int32_t a = neg[e][c] ? -v : v;
+            amag[e][c] = a;
             q12[e][c] = bSigned ? ((a << 11) / (0x7BFF + 1)) : ((a << 12) / (0x7BFF + 1));
         }
     for (int ci = 0; ci < ncand; ++ci)
@@ -222,7 +223,15 @@ DXB_DEV int dxb_bc6h_pick_mode(const int32_t ep[4][3], bool two, bool bSigned, i
         for (int e = 0; e < nep; ++e)
             for (int c = 0; c < 3; ++c)
             {
-                const int32_t mag = q12[e][c] >> (12 - prec);
+                // prec >= 15 (unsigned) / 16 (signed): the decoder passes the code through Unquantize and scales it by 31/64
+                // (31/32 signed) in FinishUnquantize (:1893-1940); the smallest code that decodes to exactly `a` is
+                // ceil(a * 64 / 31) (ceil(a * 32 / 31)).  (The reference's own Quantize returns `a` here, :1872, 1885, which
+                // decodes to half the value, so its encoder never benefits from mode 14.)
+                const bool full = prec >= (bSigned ? 16 : 15);
+                const int32_t a = amag[e][c];
+                const int32_t wide = bSigned ? ((a * 32 + 30) / 31) : ((a * 64 + 30) / 31);
+                const int32_t mag = full ? ((wide > (bSigned ? 0x7FFF : 0xFFFF)) ? (bSigned ? 0x7FFF : 0xFFFF) : wide)
+                                         : (q12[e][c] >> (full ? 0 : (12 - prec)));
                 t[e][c] = neg[e][c] ? -mag : mag;
             }
         // a region whose two endpoints quantise to the same code wastes its interpolation levels: open the pair by one
@@ -438,7 +447,8 @@ DXB_DEV void dxb_bc6h_encode_pair(const dxb_px* spx, bool bSigned, uint8_t* out0
     float p0x[DXB_NL], p0y[DXB_NL], p0z[DXB_NL], p1x[DXB_NL], p1y[DXB_NL], p1z[DXB_NL];
     dxb_xchg_xor_f32(e0x, p0x, 1); dxb_xchg_xor_f32(e0y, p0y, 1); dxb_xchg_xor_f32(e0z, p0z, 1);
     dxb_xchg_xor_f32(e1x, p1x, 1); dxb_xchg_xor_f32(e1y, p1y, 1); dxb_xchg_xor_f32(e1z, p1z, 1);
-    uint32_t rErr[DXB_NL], rMode[DXB_NL];
+    uint32_t rMode[DXB_NL];
+    float rErrF[DXB_NL];
     uint32_t rq[12][DXB_NL];            // quantised endpoints A0 B0 A1 B1 (two's complement ints)
     uint32_t mine[6][DXB_NL], theirs[6][DXB_NL];      // refined endpoints of this lane's region / of the partner's
     DXB_LANES_BEGIN
@@ -499,19 +509,20 @@ DXB_DEV void dxb_bc6h_encode_pair(const dxb_px* spx, bool bSigned, uint8_t* out0
         float err;
         if (one) err = dxb_bc6h_region_error<16>(spx + (lane & 16), 0xFFFFu, ctr, q[0], q[1], prec, bSigned);
         else err = dxb_bc6h_region_error<8>(spx + (lane & 16), tMask[L], ctr, second ? q[2] : q[0], second ? q[3] : q[1], prec, bSigned);
-        // errors are sums of squared differences of 15-bit integers: scale into 27 bits for the integer key
-        rErr[L] = (hl == 15) ? 0x07FFFFFFu : (uint32_t)dxb_f2i(fminf(err * (1.0f / 1024.0f), 6.0e7f));
+        rErrF[L] = (hl == 15) ? 3.0e38f : fminf(fmaxf(err, 0.0f), 3.0e37f);
         for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) rq[e * 3 + c][L] = (uint32_t)q[e][c];
     DXB_LANES_END
-    uint32_t partner[DXB_NL];
-    dxb_xchg_xor_u32(rErr, partner, 1);
+    // winner key: the bit pattern of a non-negative float orders like the float itself, so the top 27 bits of the summed
+    // error keep a relative resolution of 2^-18 over the whole range (a fixed-point key rounded all small errors to zero and
+    // let a coarse two-region candidate beat an exact one-region one on flat blocks)
+    float partnerF[DXB_NL];
+    dxb_xchg_xor_f32(rErrF, partnerF, 1);
     uint32_t wkeys[DXB_NL], wkey[DXB_NL], src[DXB_NL];
     DXB_LANES_BEGIN
         const int hl = lane & 15;
-        uint32_t e = rErr[L];
-        if (hl < 2 * DXB_BC6H_KSHAPES) e += partner[L];
-        e = (e > 0x07FFFFFFu) ? 0x07FFFFFFu : e;
-        wkeys[L] = (e << 4) | (uint32_t)hl;
+        float e = rErrF[L];
+        if (hl < 2 * DXB_BC6H_KSHAPES) e = e + partnerF[L];
+        wkeys[L] = ((dxb_float_as_uint(e) >> 5) << 4) | (uint32_t)hl;
         if (hl == 15) wkeys[L] = 0xFFFFFFFFu;
     DXB_LANES_END
     dxb_half_min_u32(wkeys, wkey);

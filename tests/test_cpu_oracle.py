@@ -246,3 +246,32 @@ def test_emulator_alpha_coverage_matches_reference(oracle, emul):
             hr, plain, want = oracle.mips_alpha_coverage(img, w, h, fmt, ref)
             he, got = emul.scale_mips_alpha(plain, w, h, fmt, ref)
             assert hr == 0 and he == 0 and np.array_equal(got, want) and not np.array_equal(want, plain), (fmt, w, h, ref)
+
+
+def test_emulator_bc6h_flat_and_two_colour_blocks(oracle, emul):
+    """Flat and two-colour HDR blocks: the reference reproduces flat blocks exactly; the warp encoder must stay within a
+    fraction of a half-float code of that (mode 14 with 16-bit endpoints) and within 2 % + 1 on two-colour blocks."""
+    rng = np.random.default_rng(61)
+    blocks = []
+    for k in range(96):
+        c0 = np.exp2(rng.uniform(-6, 6, 3))
+        if k < 48:
+            b = np.tile(c0, (4, 4, 1))
+        else:
+            b = np.where(rng.integers(0, 2, (4, 4, 1)), c0, np.exp2(rng.uniform(-6, 6, 3)))
+        blocks.append(np.concatenate([b, np.ones((4, 4, 1))], -1).astype(np.float32))
+    img = np.ascontiguousarray(np.concatenate(blocks, axis=1))
+    h, w = 4, 4 * len(blocks)
+    for fmt in (95, 96):
+        he, eb = emul.compress(img, w, h, 2, fmt)
+        hr, rb = oracle.compress(img, w, h, 2, fmt)
+        assert he == 0 and hr == 0
+        src = oracle_lib.bc6h_to_int(img[..., :3], fmt == 96)
+        err = []
+        for bl in (eb, rb):
+            d = oracle_lib.bc6h_to_int(oracle.decode_blocks(fmt, bl, w, h).reshape(h, w, 4)[..., :3], fmt == 96)
+            e = (d.astype(np.float64) - src) ** 2
+            err.append(e.reshape(4, len(blocks), 4, 3).transpose(1, 0, 2, 3).reshape(len(blocks), -1).mean(1))
+        ours, ref = err
+        assert ours[:48].mean() <= ref[:48].mean() + 1.0, (fmt, ours[:48].mean(), ref[:48].mean())
+        assert ours[48:].mean() <= ref[48:].mean() * 1.02 + 1.0, (fmt, ours[48:].mean(), ref[48:].mean())
