@@ -46,6 +46,9 @@ static constexpr int dxb_bc7_pixunroll = DXB_BC7_PIXUNROLL;
 
 struct dxb_bc7_res { float err; uint32_t q0, q1, pbits; };
 
+#define DXB_MAGIC 12582912.0f                      // 1.5 * 2^23: (x + MAGIC) - MAGIC == round-to-nearest-even(x), |x| < 2^22
+DXB_DEV float dxb_rne(float x) { const float t = x + DXB_MAGIC; return t - DXB_MAGIC; }
+
 // interpolation weight of index k at `ib` index bits: {0,21,43,64} {0,9,..,64} {0,4,..,64}  (BC6HBC7.cpp:327-329)
 DXB_DEV uint32_t dxb_bc7_weight(uint32_t ib, uint32_t k)
 {
@@ -140,6 +143,7 @@ DXB_DEV float dxb_bc7_subset_estimate(uint32_t n, const float* v, float qf)
 struct dxb_bc7_scratch
 {
     dxb_px   px[32];                          // LDR pixels (floats 0..255) of the warp's two blocks: half h -> px[16h ..]
+    uint32_t pq[32];                          // the same pixels packed as bytes R | G << 8 | B << 16 | A << 24
     float    mt[2][DXB_BC7_MT_FLOATS];        // moment tables: row = shape, 16-float rows, 16-byte chunks XOR-swizzled
     // (device: the bf16 feature matrix F^T, uint16_t[2][24][16], lives in the first 1536 bytes of mt until the
     //  MMA B fragments have been read into registers)
@@ -173,12 +177,18 @@ DXB_DEV uint16_t dxb_bc7_bf16_of_byte(uint32_t n)          // bf16 bits of the i
 #endif
 
 // Fills S->mt[0..1] from S->px (both blocks of the warp).  Collective over the warp.
+DXB_DEV uint32_t dxb_bc7_pack_px(const dxb_px p)
+{
+    return (uint32_t)dxb_f2i(p.x) | ((uint32_t)dxb_f2i(p.y) << 8) | ((uint32_t)dxb_f2i(p.z) << 16) | ((uint32_t)dxb_f2i(p.w) << 24);
+}
+
 DXB_DEV void dxb_bc7_build_moments(dxb_bc7_scratch* S)
 {
 #if DXB_ON_DEVICE
     const uint32_t lane = threadIdx.x & 31u, h = lane >> 4, hl = lane & 15u;
     {
         const dxb_px p = S->px[lane];
+        S->pq[lane] = dxb_bc7_pack_px(p);
         uint16_t* F = (uint16_t*)S->mt + (h * 24 * 16 + hl);   // feature n of this pixel = F[16 * n]
         F[0] = (uint16_t)(__float_as_uint(p.x) >> 16); F[16] = (uint16_t)(__float_as_uint(p.y) >> 16);
         F[32] = (uint16_t)(__float_as_uint(p.z) >> 16); F[48] = (uint16_t)(__float_as_uint(p.w) >> 16);
@@ -234,6 +244,7 @@ DXB_DEV void dxb_bc7_build_moments(dxb_bc7_scratch* S)
     }
     __syncwarp();
 #else
+    for (int i = 0; i < 32; ++i) S->pq[i] = dxb_bc7_pack_px(S->px[i]);
     for (int hb = 0; hb < 2; ++hb)
         for (int row = 0; row < DXB_BC7_MT_ROWS; ++row)
         {
@@ -295,11 +306,163 @@ DXB_DEV float dxb_bc7_shape_estimate(const float* mt, uint32_t shape, float qf, 
     return dxb_bc7_subset_estimate(16u - n1, v0, qf) + dxb_bc7_subset_estimate(n1, v1, qf);
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// stage 1 shape estimate "h1": what the block would cost with this two-subset shape when every subset is coded as
+// nl + 1 evenly spaced points between the extreme projections on its principal axis (the un-quantised endpoints a
+// task of stage 2 starts from).  It follows the reference's ranking pass (RoughMSE of every shape, BC6HBC7.cpp:3045-3110)
+// in spirit: shapes are ranked by an actual index-quantisation error, not by a model of it -- the closed-form
+// line-fit residual (dxb_bc7_subset_estimate) ranks collinear content (text, two-colour edges with blends) badly,
+// because there every shape has residual zero and only the position of the points along the line matters.
+// Exact-integer formulation (device == host emulator bit for bit, whatever the evaluation order of the dot products):
+// the axis is quantised to 8-bit integers, pixels are bytes, so a projection is one u8 x s8 dot product (dp4a).
+DXB_DEV int32_t dxb_dp4a_u8s8(uint32_t pix, uint32_t axis)
+{
+#if DXB_ON_DEVICE
+    int32_t d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(axis), "r"(0));
+    return d;
+#else
+    int32_t d = 0;
+    for (int c = 0; c < 4; ++c) d += (int32_t)((pix >> (8 * c)) & 0xFFu) * (int32_t)(int8_t)((axis >> (8 * c)) & 0xFFu);
+    return d;
+#endif
+}
+
+struct dxb_bc7_axis { uint32_t packed; float resid, inv_aa; };   // s8x4 axis, off-axis residual tr - a'Ca/|a|^2, 1/|a|^2
+
+// principal axis of one subset from its moments v[14] (n pixels): DXB_BC7_EST_ITERS un-normalised power-iteration steps
+// from the covariance row with the largest diagonal, then quantised to integers of magnitude <= 127
+DXB_DEV dxb_bc7_axis dxb_bc7_subset_axis(uint32_t n, const float* v, bool opaque)
+{
+    const float inv = dxb_rcp16[n];
+    const float c00 = dxb_fma(-v[0] * inv, v[0], v[4]), c01 = dxb_fma(-v[0] * inv, v[1], v[5]), c02 = dxb_fma(-v[0] * inv, v[2], v[6]);
+    const float c11 = dxb_fma(-v[1] * inv, v[1], v[8]), c12 = dxb_fma(-v[1] * inv, v[2], v[9]), c22 = dxb_fma(-v[2] * inv, v[2], v[11]);
+    float c03 = 0.0f, c13 = 0.0f, c23 = 0.0f, c33 = 0.0f;
+    if (!opaque)
+    {
+        c03 = dxb_fma(-v[0] * inv, v[3], v[7]); c13 = dxb_fma(-v[1] * inv, v[3], v[10]);
+        c23 = dxb_fma(-v[2] * inv, v[3], v[12]); c33 = dxb_fma(-v[3] * inv, v[3], v[13]);
+    }
+    const float tr = (c00 + c11) + (c22 + c33);
+    const bool flat = !(tr > 1e-3f) || (n < 2u);
+    const bool b0 = (c00 >= c11 && c00 >= c22 && c00 >= c33);
+    const bool b1 = !b0 && (c11 >= c22 && c11 >= c33);
+    const bool b2 = !b0 && !b1 && (c22 >= c33);
+    float v0 = b0 ? c00 : (b1 ? c01 : (b2 ? c02 : c03));
+    float v1 = b0 ? c01 : (b1 ? c11 : (b2 ? c12 : c13));
+    float v2 = b0 ? c02 : (b1 ? c12 : (b2 ? c22 : c23));
+    float v3 = b0 ? c03 : (b1 ? c13 : (b2 ? c23 : c33));
+    for (int it = 0; it < DXB_BC7_EST_ITERS; ++it)
+    {
+        const float w0 = dxb_fma(c00, v0, dxb_fma(c01, v1, dxb_fma(c02, v2, c03 * v3)));
+        const float w1 = dxb_fma(c01, v0, dxb_fma(c11, v1, dxb_fma(c12, v2, c13 * v3)));
+        const float w2 = dxb_fma(c02, v0, dxb_fma(c12, v1, dxb_fma(c22, v2, c23 * v3)));
+        const float w3 = opaque ? 0.0f : dxb_fma(c03, v0, dxb_fma(c13, v1, dxb_fma(c23, v2, c33 * v3)));
+        v0 = w0; v1 = w1; v2 = w2; v3 = w3;
+    }
+    const float mx = fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3)));
+    const float sc = (!flat && mx > 0.0f) ? 127.0f / mx : 0.0f;
+    const float a0 = dxb_rne(v0 * sc), a1 = dxb_rne(v1 * sc), a2 = dxb_rne(v2 * sc), a3 = dxb_rne(v3 * sc);
+    dxb_bc7_axis A;
+    A.packed = ((uint32_t)dxb_f2i(a0) & 0xFFu) | (((uint32_t)dxb_f2i(a1) & 0xFFu) << 8) | (((uint32_t)dxb_f2i(a2) & 0xFFu) << 16) | (((uint32_t)dxb_f2i(a3) & 0xFFu) << 24);
+    const float aa = dxb_fma(a0, a0, dxb_fma(a1, a1, dxb_fma(a2, a2, a3 * a3)));
+    // a' C a
+    const float q0 = dxb_fma(c00, a0, dxb_fma(c01, a1, dxb_fma(c02, a2, c03 * a3)));
+    const float q1 = dxb_fma(c01, a0, dxb_fma(c11, a1, dxb_fma(c12, a2, c13 * a3)));
+    const float q2 = dxb_fma(c02, a0, dxb_fma(c12, a1, dxb_fma(c22, a2, c23 * a3)));
+    const float q3 = dxb_fma(c03, a0, dxb_fma(c13, a1, dxb_fma(c23, a2, c33 * a3)));
+    const float aCa = dxb_fma(a0, q0, dxb_fma(a1, q1, dxb_fma(a2, q2, a3 * q3)));
+    A.inv_aa = (aa > 0.0f) ? 1.0f / aa : 0.0f;
+    A.resid = flat ? 0.0f : fmaxf(dxb_fma(-aCa, A.inv_aa, tr), 0.0f);
+    return A;
+}
+
+#define DXB_BC7_H1_OFF (1 << 20)          // separates the two subsets' projections (|t| <= 4 * 255 * 127 < 2^17)
+
+// pq = the block's 16 LDR pixels packed as bytes (R | G << 8 | B << 16 | A << 24); nl = 2^indexbits - 1 as float
+DXB_DEV float dxb_bc7_shape_h1(const uint32_t* pq, const float* mt, uint32_t shape, float nl, const float* tot, bool opaque)
+{
+    float v1[14], v0[14];
+    dxb_bc7_mt_load(mt, (int)shape, v1);
+    for (int k = 0; k < 14; ++k) v0[k] = tot[k] - v1[k];
+    const uint32_t mask = dxb_part2[shape];
+    const uint32_t n1 = dxb_popc16(mask);
+    const dxb_bc7_axis A0 = dxb_bc7_subset_axis(16u - n1, v0, opaque), A1 = dxb_bc7_subset_axis(n1, v1, opaque);
+    int32_t T[16];
+    int32_t mnv = 0x7fffffff, mxv = -0x7fffffff, mny = 0x7fffffff, mxy = -0x7fffffff;
+#if DXB_ON_DEVICE
+    #pragma unroll
+#endif
+    for (int p = 0; p < 16; ++p)
+    {
+        const bool m = ((mask >> p) & 1u) != 0u;
+        const int32_t t = dxb_dp4a_u8s8(pq[p], m ? A1.packed : A0.packed);
+        T[p] = t;
+        const int32_t off = m ? DXB_BC7_H1_OFF : 0;
+        const int32_t v = t + off, y = t - off;
+        mnv = (v < mnv) ? v : mnv; mxv = (v > mxv) ? v : mxv;
+        mny = (y < mny) ? y : mny; mxy = (y > mxy) ? y : mxy;
+    }
+    // subset 0 = the small keys of v and the large keys of y; both subsets of a valid shape are non-empty
+    const int32_t tmin0 = mnv, tmax1 = mxv - DXB_BC7_H1_OFF, tmax0 = mxy, tmin1 = mny + DXB_BC7_H1_OFF;
+    const float r0 = (float)(tmax0 - tmin0), r1 = (float)(tmax1 - tmin1);
+    const float i0 = (r0 > 0.0f) ? 1.0f / r0 : 0.0f, i1 = (r1 > 0.0f) ? 1.0f / r1 : 0.0f;
+    // opaque blocks: the better of 3-bit indices (mode 1) and 2-bit indices (mode 3); alpha blocks: 2-bit (mode 7).
+    // e?a = error in units of (range / nl)^2 at nl, e?b at 3 levels
+    float e0a = 0.0f, e1a = 0.0f, e0b = 0.0f, e1b = 0.0f;
+#if DXB_ON_DEVICE
+    #pragma unroll
+#endif
+    for (int p = 0; p < 16; ++p)
+    {
+        const bool m = ((mask >> p) & 1u) != 0u;
+        const float x = (float)(T[p] - (m ? tmin1 : tmin0)) * (m ? i1 : i0);       // position in [0, 1]
+        const float ua = x * nl, ub = x * 3.0f;
+        const float da = ua - dxb_rne(ua), db = ub - dxb_rne(ub);
+        const float dda = da * da, ddb = db * db;
+        e0a += m ? 0.0f : dda; e1a += m ? dda : 0.0f;
+        e0b += m ? 0.0f : ddb; e1b += m ? ddb : 0.0f;
+    }
+    // index-quantisation error in pixel units: e * (range / nl)^2 / |a|^2
+    const float w0 = (r0 * r0) * A0.inv_aa, w1 = (r1 * r1) * A1.inv_aa;
+    const float inl2 = 1.0f / (nl * nl);
+    const float qa = dxb_fma(e0a, w0, e1a * w1) * inl2, qb = dxb_fma(e0b, w0, e1b * w1) * (1.0f / 9.0f);
+    return (A0.resid + A1.resid) + fminf(qa, qb);
+}
+
+
+// rotation heuristic for modes 4/5: cost of coding channel c as the separate scalar and the remaining channels as the
+// vector, from the block totals (moments row 64): line-fit residual of the rest + index-quantisation models.
+// Returns est[4] for scalar channel c = 0..3 (c = 3: alpha, rotation 0).
+DXB_DEV float dxb_bc7_rotation_estimate1(float c00, float c01, float c02, float c11, float c12, float c22, float css, float qfv, float qfs)
+{
+    // remaining channels: largest eigenvalue by 2 power-iteration steps from the largest-diagonal row + Rayleigh quotient
+    const float tr = (c00 + c11) + c22;
+    const bool b0 = (c00 >= c11 && c00 >= c22), b1 = !b0 && (c11 >= c22);
+    float v0 = b0 ? c00 : (b1 ? c01 : c02), v1 = b0 ? c01 : (b1 ? c11 : c12), v2 = b0 ? c02 : (b1 ? c12 : c22);
+    float w0 = dxb_fma(c00, v0, dxb_fma(c01, v1, c02 * v2)), w1 = dxb_fma(c01, v0, dxb_fma(c11, v1, c12 * v2)), w2 = dxb_fma(c02, v0, dxb_fma(c12, v1, c22 * v2));
+    v0 = w0; v1 = w1; v2 = w2;
+    w0 = dxb_fma(c00, v0, dxb_fma(c01, v1, c02 * v2)); w1 = dxb_fma(c01, v0, dxb_fma(c11, v1, c12 * v2)); w2 = dxb_fma(c02, v0, dxb_fma(c12, v1, c22 * v2));
+    const float vv = dxb_fma(v0, v0, dxb_fma(v1, v1, v2 * v2)), vw = dxb_fma(v0, w0, dxb_fma(v1, w1, v2 * w2));
+    const float lam = (vv > 0.0f) ? fminf(vw / vv, tr) : 0.0f;
+    return dxb_fma(lam, qfv, fmaxf(tr - lam, 0.0f)) + css * qfs;
+}
+DXB_DEV void dxb_bc7_rotation_estimates(const float* tot, bool opaque, float qfv, float qfs, float* est)
+{
+    const float inv = 1.0f / 16.0f, z = opaque ? 0.0f : 1.0f;
+    const float c00 = dxb_fma(-tot[0] * inv, tot[0], tot[4]), c01 = dxb_fma(-tot[0] * inv, tot[1], tot[5]), c02 = dxb_fma(-tot[0] * inv, tot[2], tot[6]);
+    const float c11 = dxb_fma(-tot[1] * inv, tot[1], tot[8]), c12 = dxb_fma(-tot[1] * inv, tot[2], tot[9]), c22 = dxb_fma(-tot[2] * inv, tot[2], tot[11]);
+    const float c03 = z * dxb_fma(-tot[0] * inv, tot[3], tot[7]), c13 = z * dxb_fma(-tot[1] * inv, tot[3], tot[10]);
+    const float c23 = z * dxb_fma(-tot[2] * inv, tot[3], tot[12]), c33 = z * dxb_fma(-tot[3] * inv, tot[3], tot[13]);
+    est[0] = dxb_bc7_rotation_estimate1(c11, c12, c13, c22, c23, c33, c00, qfv, qfs);     // scalar = R, vector = G B A
+    est[1] = dxb_bc7_rotation_estimate1(c00, c02, c03, c22, c23, c33, c11, qfv, qfs);     // scalar = G
+    est[2] = dxb_bc7_rotation_estimate1(c00, c01, c03, c11, c13, c33, c22, qfv, qfs);     // scalar = B
+    est[3] = dxb_bc7_rotation_estimate1(c00, c01, c02, c11, c12, c22, c33, qfv, qfs);     // scalar = A (rotation 0)
+}
+
 // ---------------------------------------------------------------------------------------------------
 // branch-free helpers (every lane of the warp runs the same instruction stream whatever its mode)
-#define DXB_MAGIC 12582912.0f                      // 1.5 * 2^23: (x + MAGIC) - MAGIC == round-to-nearest-even(x), |x| < 2^22
-
-DXB_DEV float dxb_rne(float x) { const float t = x + DXB_MAGIC; return t - DXB_MAGIC; }
 DXB_DEV float dxb_bit_as_float(uint32_t mask, int i)       // (mask >> i) & 1 as 0.0f / 1.0f without an I2F
 {
     return dxb_uint_as_float((0u - ((mask >> i) & 1u)) & 0x3F800000u);
@@ -357,27 +520,23 @@ DXB_DEV dxb_bc7_modecfg dxb_bc7_cfg(int mode)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// stage 2: one lane task.  px = the block's 16 LDR pixels (floats 0..255), mt = its moment table.
-//   mode 1/3/7: subset `mask` of 2-subset shape `shape`;  mode 6: whole block, forced p-bit pair;
-//   mode 4/5 : whole block, rotation `rot`, index selector `idxMode` (mode 4)
-// Everything works on pixels in their NATURAL channel order.  A rotation only decides which channel is
-// the separately coded scalar (channel rot-1, or alpha when rot = 0); vm[c] = 1 for the channels that form
-// the endpoint vector, 0 otherwise (the scalar of modes 4/5; alpha in modes 1/3).  Masked channels have zero
-// moments, axis and endpoints, so one instruction stream serves every mode; only the scalar part of
-// modes 4/5 is a divergent section.  Idle lanes (mode < 0) run the same code on dummy parameters.
-// The result's q0/q1 bytes are in the bit stream's slot order (byte 3 = the scalar / alpha slot).
-DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t shape, uint32_t mask, int mode, int rot, int idxMode, int pforce)
-{
-    const bool idle = (mode < 0);
-    if (idle) { mode = 6; mask = 0xFFFFu; }
-    const dxb_bc7_modecfg cfg = dxb_bc7_cfg(mode);
-    const bool sep = (mode == 4 || mode == 5);
-    const uint32_t ibc = (mode == 4 && idxMode) ? 3u : cfg.ib;           // vector index bits
-    const uint32_t iba = (mode == 4) ? (idxMode ? 2u : 3u) : cfg.ib2;    // scalar index bits (modes 4/5)
-    const int sc = rot ? rot - 1 : 3;                                    // natural channel of the scalar / alpha slot
-    float vm[4];
-    for (int c = 0; c < 4; ++c) vm[c] = (c == sc && (sep || mode == 1 || mode == 3)) ? 0.0f : 1.0f;
+// stage 2: one lane task = one endpoint-pair fit: the pixels of `mask` (a subset of a two-subset shape, or the whole
+// block), the channels of `chmask` (bit c = natural channel c), endpoints of `bits` bits (+ a p-bit of type `ptype`:
+// 0 none, 1 one per endpoint, 2 one shared by both endpoints), `ib` index bits.  A mode-1/3/7 candidate is two tasks
+// (the two subsets), a mode-4/5 candidate is two tasks (the vector channels and the separately coded scalar channel,
+// each with its own index set), mode 6 is one task.  px = the block's 16 LDR pixels (floats 0..255), mt = its moment
+// table.  Channels outside chmask have zero moments, axis and endpoints, so one instruction stream serves every task.
+// Idle lanes (idle = true) run the same code on dummy parameters.  The result's q0/q1 byte c = the field of natural
+// channel c (0 for channels outside chmask).
+struct dxb_bc7_task { uint32_t shape, mask, chmask, bits, ptype, ib; bool idle; };
 
+DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc7_task& T)
+{
+    const bool idle = T.idle;
+    const uint32_t mask = T.mask, shape = T.shape;
+    const uint32_t ibc = T.ib;
+    float vm[4];
+    for (int c = 0; c < 4; ++c) vm[c] = ((T.chmask >> c) & 1u) ? 1.0f : 0.0f;
     // ---- moments of the subset from the stage-1 table (exact integers): subset 1 = row `shape`,
     // subset 0 = totals - row, whole block = totals; masked channels zeroed
     const float n = (float)dxb_popc16(mask);
@@ -449,8 +608,8 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
     }
 
     // ---- evaluation rounds (vector part).  Every vector channel has cbits bits (modes 6/7: abits == cbits).
-    const uint32_t hasP = (cfg.ptype != 0u) ? 1u : 0u;
-    const dxb_bc7_qconst qk = dxb_bc7_make_qconst(cfg.cbits, hasP);
+    const uint32_t hasP = (T.ptype != 0u) ? 1u : 0u;
+    const dxb_bc7_qconst qk = dxb_bc7_make_qconst(T.bits, hasP);
     float bestErr = 3.0e38f, bqa0 = 0.0f, bqa1 = 0.0f, bqb0 = 0.0f, bqb1 = 0.0f; uint32_t bpb = 0;
     const float nmaxc = (float)((1u << ibc) - 1u);
     const float c64c = 64.0f / nmaxc;
@@ -488,9 +647,8 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
         uint32_t p0 = (err0[1] < err0[0]) ? 1u : 0u;
         uint32_t p1 = (err1[1] < err1[0]) ? 1u : 0u;
         const uint32_t ps = ((err0[1] + err1[1]) < (err0[0] + err1[0])) ? 1u : 0u;
-        if (cfg.ptype == 2u) { p0 = ps; p1 = ps; }
-        if (pforce >= 0) { p0 = (uint32_t)pforce & 1u; p1 = (cfg.ptype == 2u) ? p0 : (((uint32_t)pforce >> 1) & 1u); }
-        if (cfg.ptype == 0u) { p0 = 0u; p1 = 0u; }
+        if (T.ptype == 2u) { p0 = ps; p1 = ps; }
+        if (T.ptype == 0u) { p0 = 0u; p1 = 0u; }
         const float qa0 = p0 ? qa[1][0] : qa[0][0], qb0 = p0 ? qb[1][0] : qb[0][0];
         const float qa1 = p1 ? qa[1][1] : qa[0][1], qb1 = p1 ? qb[1][1] : qb[0][1];
         float D0[4], D1[4];
@@ -559,76 +717,21 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, uint32_t sha
             E1[c] = live ? fminf(fmaxf(b, 0.0f), 255.0f) : E1[c];
         }
     }
-    // natural-order fields as integers: n0 / n1 byte c = field of natural channel c
-    // (x + 2^23 has x in its mantissa for 0 <= x < 2^23; colour fields have at most 7 bits, so the packed value fits)
-    uint32_t n0 = (dxb_float_as_uint(bqa0 + 8388608.0f) & 0x7FFFFFu) | ((dxb_float_as_uint(bqb0 + 8388608.0f) & 0xFFu) << 24);
-    uint32_t n1 = (dxb_float_as_uint(bqa1 + 8388608.0f) & 0x7FFFFFu) | ((dxb_float_as_uint(bqb1 + 8388608.0f) & 0xFFu) << 24);
-
-    // ---- scalar part (modes 4/5): channel `sc` with its own endpoints and indices
-    if (sep)
-    {
-        const float* pf = (const float*)px + sc;                  // scalar of pixel i = pf[4 i]
-        float amin = 3.0e38f, amax = -3.0e38f;
-        for (int i = 0; i < 16; ++i) { const float A = pf[4 * i]; amin = fminf(amin, A); amax = fmaxf(amax, A); }
-        float A0 = amin, A1 = amax;
-        float bestA = 3.0e38f, ba0 = 0.0f, ba1 = 0.0f;
-        const dxb_bc7_qconst qa = dxb_bc7_make_qconst(cfg.abits, 0u);
-        const float nmaxa = (float)((1u << iba) - 1u);
-        const float c64a = 64.0f / nmaxa;
-        bool liveA = true;
-#if DXB_ON_DEVICE
-        #pragma unroll 1
-#endif
-        for (int round = 0; round < DXB_BC7_ROUNDS; ++round)
-        {
-            float d0, d1;
-            const float f0 = dxb_bc7_quant1f(A0, qa, 0.0f, &d0);
-            const float f1 = dxb_bc7_quant1f(A1, qa, 0.0f, &d1);
-            const float da = d1 - d0;
-            const float ida = (da != 0.0f) ? nmaxa / da : 0.0f;
-            float err = 0.0f, la = 0.0f, lb = 0.0f, lc = 0.0f, ua = 0.0f, va = 0.0f;
-#if DXB_ON_DEVICE
-            #pragma unroll dxb_bc7_pixunroll
-#endif
-            for (int i = 0; i < 16; ++i)
-            {
-                const float A = pf[4 * i];
-                const float kk = dxb_rne(fminf(fmaxf((A - d0) * ida, 0.0f), nmaxa));
-                const float sk = dxb_bc7_weightf(kk, c64a);
-                const float ca = dxb_rne(dxb_fma(da, sk, d0 + (1.0f / 128.0f)));
-                const float ea = A - ca;
-                err = dxb_fma(ea, ea, err);
-                const float os = 1.0f - sk;
-                la = dxb_fma(os, os, la); lb = dxb_fma(os, sk, lb); lc = dxb_fma(sk, sk, lc);
-                ua = dxb_fma(os, A, ua); va = dxb_fma(sk, A, va);
-            }
-            const bool better = liveA && (err < bestA);
-            bestA = better ? err : bestA; ba0 = better ? f0 : ba0; ba1 = better ? f1 : ba1;
-            const float det = dxb_fma(la, lc, -(lb * lb));
-            liveA = liveA && (det > 1e-4f) && (bestA > 0.0f);
-            const float id = liveA ? 1.0f / det : 0.0f;
-            const float na = dxb_fma(lc, ua, -(lb * va)) * id, nb = dxb_fma(la, va, -(lb * ua)) * id;
-            A0 = liveA ? fminf(fmaxf(na, 0.0f), 255.0f) : A0;
-            A1 = liveA ? fminf(fmaxf(nb, 0.0f), 255.0f) : A1;
-        }
-        bestErr += bestA;
-        // scalar fields into natural byte `sc`
-        const uint32_t sh = 8u * (uint32_t)sc;
-        n0 = (n0 & ~(0xFFu << sh)) | ((dxb_float_as_uint(ba0 + 8388608.0f) & 0xFFu) << sh);
-        n1 = (n1 & ~(0xFFu << sh)) | ((dxb_float_as_uint(ba1 + 8388608.0f) & 0xFFu) << sh);
-    }
-    // natural order -> slot order: a rotation swaps bytes rot-1 and 3
-    if (rot)
-    {
-        const uint32_t sh = 8u * (uint32_t)(rot - 1);
-        const uint32_t a0 = (n0 >> sh) & 0xFFu, b0 = n0 >> 24, a1 = (n1 >> sh) & 0xFFu, b1 = n1 >> 24;
-        n0 = (n0 & ~((0xFFu << sh) | 0xFF000000u)) | (b0 << sh) | (a0 << 24);
-        n1 = (n1 & ~((0xFFu << sh) | 0xFF000000u)) | (b1 << sh) | (a1 << 24);
-    }
-
+    // natural-order fields as integers: n0 / n1 byte c = field of natural channel c (bqa = f0 + 256 f1 + 65536 f2 < 2^24: exact)
+    const uint32_t n0 = (uint32_t)dxb_f2i(bqa0) | ((uint32_t)dxb_f2i(bqb0) << 24);
+    const uint32_t n1 = (uint32_t)dxb_f2i(bqa1) | ((uint32_t)dxb_f2i(bqb1) << 24);
     dxb_bc7_res R;
     R.err = idle ? 3.0e38f : bestErr; R.q0 = n0; R.q1 = n1; R.pbits = bpb;
     return R;
+}
+
+// natural channel order -> the bit stream's slot order: a rotation swaps bytes rot-1 and 3
+DXB_DEV uint32_t dxb_bc7_rotate_fields(uint32_t n, uint32_t rot)
+{
+    if (rot == 0u) return n;
+    const uint32_t sh = 8u * (rot - 1u);
+    const uint32_t a = (n >> sh) & 0xFFu, b = n >> 24;
+    return (n & ~((0xFFu << sh) | 0xFF000000u)) | (b << sh) | (a << 24);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -680,6 +783,11 @@ DXB_DEV void dxb_put_bits(dxb_u128* b, uint32_t pos, uint32_t nbits, uint32_t va
 //   out0/out1 : 16 output bytes of the half-0 / half-1 block (nullptr = that half carries no block)
 // Everything "per block" below is a lane-private value that is uniform inside a half.
 struct dxb_bc7_win { uint32_t mode, shape, rot, idx, q0[2], q1[2], pb[2]; };
+#if !DXB_ON_DEVICE
+// test-infrastructure hook of the host emulator only (tools/bc_quality.py experiments): force the first candidate
+// shape of the half-0 / half-1 block (-1 = none)
+static thread_local int dxb_bc7_dbg_force_shape[2] = { -1, -1 };
+#endif
 
 DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* out0, uint8_t* out1)
 {
@@ -704,7 +812,12 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
             for (int j = 0; j < 4; ++j)
             {
                 const uint32_t shape = (uint32_t)(lane & 15) + 16u * (uint32_t)j;
+#ifdef DXB_BC7_EST_H0
                 const float e = quick ? 0.0f : dxb_bc7_shape_estimate(mt, shape, qf, tot, hasA[L] == 0u);
+#else
+                (void)qf;
+                const float e = quick ? 0.0f : dxb_bc7_shape_h1(S->pq + (lane & 16), mt, shape, hasA[L] ? 3.0f : 7.0f, tot, hasA[L] == 0u);
+#endif
                 const uint32_t x = (dxb_float_as_uint(e) & 0xFFFFFFC0u) | shape;
                 const uint32_t lo = (x < a) ? x : a, hi = (x < a) ? a : x;               // sorted insert
                 const uint32_t lo2 = (hi < b) ? hi : b, hi2 = (hi < b) ? b : hi;
@@ -723,61 +836,123 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
         }
     }
 
+#if !DXB_ON_DEVICE
+    DXB_LANES_BEGIN
+        if (dxb_bc7_dbg_force_shape[lane >> 4] >= 0) sel[0][L] = (uint32_t)dxb_bc7_dbg_force_shape[lane >> 4];
+    DXB_LANES_END
+#endif
     dxb_phase_sync();
-    // ---- stage 2: one task per lane
-    //   opaque block: 3 best shapes x 2 subsets x {mode 1, mode 3} (lanes 0-11), mode 6 x 4 p-bit pairs (12-15)
-    //   alpha block : 3 best shapes x 2 subsets x mode 7 (0-5), mode 6 x 4 p-bit pairs (6-9),
-    //                 mode 5 x 4 rotations (10-13), mode 4 x 2 index selectors (14-15)
-    uint32_t tMeta[DXB_NL], rErr[DXB_NL], rQ0[DXB_NL], rQ1[DXB_NL];
+    // ---- stage 2: one fit task per lane (dxb_bc7_eval); a candidate encoding = one task or the sum of two.
+    //   opaque block (the modes the reference tries, BC6HBC7.cpp:2803-2821: 1, 3, 4, 5, 6):
+    //     0-7   2 best shapes x 2 subsets x {mode 1, mode 3}          (lane = 4 shape + 2 subset + modebit, partner lane ^ 2)
+    //     8     mode 6
+    //     9-12  mode 4, rotation r*: vector 2-bit, vector 3-bit, scalar 3-bit, scalar 2-bit   (index selector 0 = 9 + 11, 1 = 10 + 12)
+    //     13-14 mode 5, rotation r*: vector, scalar
+    //   alpha block (modes 4, 5, 6, 7):
+    //     0-5   3 best shapes x 2 subsets x mode 7                     (lane = 2 shape + subset, partner lane ^ 1)
+    //     6     mode 6
+    //     7-8   mode 5, rotation r*: vector, scalar;   9-10  mode 5, second-best rotation
+    //     11-14 mode 4, rotation r*: vector 2-bit, vector 3-bit, scalar 3-bit, scalar 2-bit
+    //   r* = the rotation (scalar channel) with the smallest modelled cost (dxb_bc7_rotation_estimates); the reference
+    //   tries every rotation (:2823-2829).  Lane 15 idles.
+    uint32_t tMeta[DXB_NL], rErr[DXB_NL], rQ0[DXB_NL], rQ1[DXB_NL], partner[DXB_NL];
     DXB_LANES_BEGIN
         const int hl = lane & 15;
-        int mode = -1, rot = 0, idxMode = 0, pforce = -1;
-        uint32_t mask = 0xFFFFu, shape = 0;
+        int mode = -1, idxMode = 0, part = hl;
+        uint32_t rot = 0;
+        dxb_bc7_task T;
+        T.shape = 0; T.mask = 0xFFFFu; T.chmask = 0xFu; T.bits = 7u; T.ptype = 1u; T.ib = 4u; T.idle = false;
+        // rotation ranking from the block totals
+        uint32_t r1 = 0, r2 = 0, r4 = 0;     // mode 5 rotations (best, second), mode 4 rotation
+        {
+            float tot[14], est[4];
+            dxb_bc7_mt_load(S->mt[lane >> 4], 64, tot);
+            dxb_bc7_rotation_estimates(tot, hasA[L] == 0u, 1.0f / 9.0f, 1.0f / 49.0f, est);
+            // keys: estimate bits | rotation (channel c = 3 is rotation 0, channel c < 3 rotation c + 1); opaque blocks never rotate alpha
+            uint32_t ka = 0xFFFFFFFFu, kb = 0xFFFFFFFFu;
+#if DXB_ON_DEVICE
+            #pragma unroll
+#endif
+            for (uint32_t c = 0; c < 4; ++c)
+            {
+                const uint32_t x = (c == 3u && !hasA[L]) ? 0xFFFFFFFFu : ((dxb_float_as_uint(est[c]) & 0xFFFFFFFCu) | ((c + 1u) & 3u));
+                const uint32_t lo = (x < ka) ? x : ka, hi = (x < ka) ? ka : x;
+                ka = lo; kb = (hi < kb) ? hi : kb;
+            }
+            r1 = ka & 3u; r2 = kb & 3u;
+            // alpha blocks: alpha is nearly always the channel to separate (rotation 0); the model decides the second rotation
+            r4 = r1;
+            if (hasA[L]) { r2 = (r1 != 0u) ? r1 : r2; r1 = 0u; }
+        }
+        int kind = -1;                     // 0 two-subset, 1 mode 6, 2 mode-4 part (sub = 0..3), 3 mode-5 part (sub = 0..1)
+        int sub = 0;
         if (!hasA[L])
         {
-            if (hl < 12)
+            if (hl < 8)
             {
-                const int k = hl >> 2;
-                shape = (k == 0) ? sel[0][L] : (k == 1) ? sel[1][L] : sel[2][L];
-                const uint32_t m1 = dxb_part2[shape];
-                mask = ((hl >> 1) & 1) ? m1 : (~m1 & 0xFFFFu);
-                mode = quick ? -1 : ((hl & 1) ? 3 : 1);
+                kind = 0;
+                T.shape = (hl >> 2) ? sel[1][L] : sel[0][L];
+                const uint32_t m1 = dxb_part2[T.shape];
+                T.mask = ((hl >> 1) & 1) ? m1 : (~m1 & 0xFFFFu);
+                mode = (hl & 1) ? 3 : 1;
+                T.chmask = 0x7u; T.bits = (hl & 1) ? 7u : 6u; T.ptype = (hl & 1) ? 1u : 2u; T.ib = (hl & 1) ? 2u : 3u;
+                part = hl ^ 2;
             }
-            else { mode = 6; pforce = hl & 3; }
+            else if (hl == 8) { kind = 1; mode = 6; }
+            else if (hl < 13) { kind = 2; sub = hl - 9; rot = r4; part = (sub < 2) ? hl + 2 : hl - 2; }
+            else if (hl < 15) { kind = 3; sub = hl - 13; rot = r1; part = (sub == 0) ? 14 : 13; }
         }
         else
         {
             if (hl < 6)
             {
+                kind = 0;
                 const int k = hl >> 1;
-                shape = (k == 0) ? sel[0][L] : (k == 1) ? sel[1][L] : sel[2][L];
-                const uint32_t m1 = dxb_part2[shape];
-                mask = (hl & 1) ? m1 : (~m1 & 0xFFFFu);
-                mode = quick ? -1 : 7;
+                T.shape = (k == 0) ? sel[0][L] : (k == 1) ? sel[1][L] : sel[2][L];
+                const uint32_t m1 = dxb_part2[T.shape];
+                T.mask = (hl & 1) ? m1 : (~m1 & 0xFFFFu);
+                mode = 7;
+                T.chmask = 0xFu; T.bits = 5u; T.ptype = 1u; T.ib = 2u;
+                part = hl ^ 1;
             }
-            else if (hl < 10) { mode = 6; pforce = hl - 6; }
-            else if (hl < 14) { mode = quick ? -1 : 5; rot = hl - 10; }
-            else { mode = quick ? -1 : 4; idxMode = hl & 1; }
+            else if (hl == 6) { kind = 1; mode = 6; }
+            else if (hl < 11) { kind = 3; sub = (hl - 7) & 1; rot = (hl < 9) ? r1 : r2; part = sub ? hl - 1 : hl + 1; }
+            else if (hl < 15) { kind = 2; sub = hl - 11; rot = r4; part = (sub < 2) ? hl + 2 : hl - 2; }
         }
-        const dxb_bc7_res res = dxb_bc7_eval(S->px + (lane & 16), S->mt[lane >> 4], shape, mask, mode, rot, idxMode, pforce);
+        if (kind == 2 || kind == 3)
+        {
+            const uint32_t sc = rot ? rot - 1u : 3u;                      // natural channel of the separately coded scalar
+            const bool scalar = (kind == 2) ? (sub >= 2) : (sub == 1);
+            T.chmask = scalar ? (1u << sc) : (0xFu & ~(1u << sc));
+            T.ptype = 0u;
+            if (kind == 2)
+            {
+                mode = 4; idxMode = sub & 1;                               // candidates: vector 2-bit + scalar 3-bit (selector 0), vector 3-bit + scalar 2-bit (1)
+                T.bits = scalar ? 6u : 5u;
+                T.ib = (sub == 0 || sub == 3) ? 2u : 3u;
+                idxMode = (sub == 1 || sub == 3) ? 1 : 0;
+            }
+            else { mode = 5; T.bits = scalar ? 8u : 7u; T.ib = 2u; }
+        }
+        if (kind < 0 || (quick && mode != 6)) { T.idle = true; mode = -1; part = hl; }
+        const dxb_bc7_res res = dxb_bc7_eval(S->px + (lane & 16), S->mt[lane >> 4], T);
         // meta word: mode(3) | shape(6) << 3 | rot(2) << 9 | idx(1) << 11 | pbits(2) << 12
-        tMeta[L] = ((uint32_t)mode & 7u) | (shape << 3) | ((uint32_t)rot << 9) | ((uint32_t)idxMode << 11) | (res.pbits << 12);
+        tMeta[L] = ((uint32_t)mode & 7u) | (T.shape << 3) | (rot << 9) | ((uint32_t)idxMode << 11) | (res.pbits << 12);
         rErr[L] = (mode < 0) ? 0x03FFFFFFu : (uint32_t)dxb_f2i(fminf(res.err, 6.0e7f));
-        rQ0[L] = res.q0; rQ1[L] = res.q1;
+        rQ0[L] = res.q0; rQ1[L] = res.q1; partner[L] = (uint32_t)part;
     DXB_LANES_END
 
     dxb_phase_sync();
-    // ---- stage 3: combine subset errors, pick the winner of each half
+    // ---- stage 3: candidate error = the task's error + its partner's; winner of each half by integer key (ties: lowest lane,
+    // which is the subset-0 / vector lane of its pair)
     dxb_bc7_win W[DXB_NL];
     {
-        uint32_t part1[DXB_NL], part2v[DXB_NL], key[DXB_NL], wkey[DXB_NL], src[DXB_NL], src1[DXB_NL], wm[DXB_NL];
+        uint32_t pe[DXB_NL], key[DXB_NL], wkey[DXB_NL], src[DXB_NL], src1[DXB_NL], wm[DXB_NL];
         uint32_t g0[DXB_NL], g1[DXB_NL], g2[DXB_NL], h0[DXB_NL], h1[DXB_NL], h2[DXB_NL];
-        dxb_xchg_xor_u32(rErr, part1, 1);
-        dxb_xchg_xor_u32(rErr, part2v, 2);
+        dxb_half_gather_u32(rErr, partner, pe);
         DXB_LANES_BEGIN
             uint32_t e = rErr[L];
-            const uint32_t md = tMeta[L] & 7u;
-            if (md == 1u || md == 3u || md == 7u) e += hasA[L] ? part1[L] : part2v[L];
+            if (partner[L] != (uint32_t)(lane & 15)) e += pe[L];
             e = (e > 0x03FFFFFFu) ? 0x03FFFFFFu : e;
             key[L] = (e << 5) | (uint32_t)(lane & 15);
         DXB_LANES_END
@@ -785,20 +960,18 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
         DXB_LANES_BEGIN
             src[L] = wkey[L] & 15u;
         DXB_LANES_END
+        dxb_half_gather_u32(partner, src, src1);
         dxb_half_gather_u32(tMeta, src, wm);
-        DXB_LANES_BEGIN
-            const uint32_t md = wm[L] & 7u;
-            const bool two = (md == 1u || md == 3u || md == 7u);
-            const uint32_t subBit = hasA[L] ? 1u : 2u;
-            src1[L] = two ? (src[L] | subBit) : src[L];
-            src[L] = two ? (src[L] & ~subBit) : src[L];
-        DXB_LANES_END
         dxb_half_gather_u32(rQ0, src, g0); dxb_half_gather_u32(rQ1, src, g1); dxb_half_gather_u32(tMeta, src, g2);
         dxb_half_gather_u32(rQ0, src1, h0); dxb_half_gather_u32(rQ1, src1, h1); dxb_half_gather_u32(tMeta, src1, h2);
         DXB_LANES_BEGIN
             W[L].mode = wm[L] & 7u; W[L].shape = (wm[L] >> 3) & 63u; W[L].rot = (wm[L] >> 9) & 3u; W[L].idx = (wm[L] >> 11) & 1u;
-            W[L].q0[0] = g0[L]; W[L].q1[0] = g1[L]; W[L].pb[0] = (g2[L] >> 12) & 3u;
-            W[L].q0[1] = h0[L]; W[L].q1[1] = h1[L]; W[L].pb[1] = (h2[L] >> 12) & 3u;
+            const bool sepA = (W[L].mode == 4u || W[L].mode == 5u);
+            // modes 4/5: vector fields | scalar field (disjoint bytes, natural order) -> slot order
+            const uint32_t a0 = sepA ? dxb_bc7_rotate_fields(g0[L] | h0[L], W[L].rot) : g0[L];
+            const uint32_t a1 = sepA ? dxb_bc7_rotate_fields(g1[L] | h1[L], W[L].rot) : g1[L];
+            W[L].q0[0] = a0; W[L].q1[0] = a1; W[L].pb[0] = (g2[L] >> 12) & 3u;
+            W[L].q0[1] = sepA ? a0 : h0[L]; W[L].q1[1] = sepA ? a1 : h1[L]; W[L].pb[1] = (h2[L] >> 12) & 3u;
         DXB_LANES_END
     }
 

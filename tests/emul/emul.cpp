@@ -27,6 +27,12 @@
 
 extern "C" {
 
+#ifdef DXB_EMUL_BC7
+// experiment hook (tools/bc_quality.py): per-block forced first candidate shape for BC7, nullptr = off
+static const int8_t* g_force_shapes = nullptr;
+void emul_bc7_force_shapes(const int8_t* shapes) { g_force_shapes = shapes; }
+#endif
+
 int32_t emul_compress(const uint8_t* src, size_t w, size_t h, uint32_t srcFmt, size_t rowPitch,
                       uint32_t dstFmt, uint32_t flags, float threshold, uint8_t* dst)
 {
@@ -55,6 +61,8 @@ int32_t emul_compress(const uint8_t* src, size_t w, size_t h, uint32_t srcFmt, s
             const long u0 = 2 * pair, u1 = u0 + 1;
             dxb_gather_block(img, (uint32_t)(u0 % nbx), (uint32_t)(u0 / nbx), inF, outF, cflags, px[0]);
             if (u1 < total) dxb_gather_block(img, (uint32_t)(u1 % nbx), (uint32_t)(u1 / nbx), inF, outF, cflags, px[1]);
+            dxb_bc7_dbg_force_shape[0] = g_force_shapes ? g_force_shapes[u0] : -1;
+            dxb_bc7_dbg_force_shape[1] = (g_force_shapes && u1 < total) ? g_force_shapes[u1] : -1;
             dxb_bc7_encode_pair_emul(px[0], (u1 < total) ? px[1] : nullptr, bcflags, blk[0], blk[1]);
             memcpy(dst + (size_t)u0 * bs, blk[0], bs);
             if (u1 < total) memcpy(dst + (size_t)u1 * bs, blk[1], bs);
@@ -239,3 +247,16 @@ int32_t emul_scale_mips_alpha(const uint8_t* src, uint8_t* dst, const size_t* of
     }
     return DXB_S_OK;
 }
+
+#ifdef DXB_EMUL_BC7
+// experiment hook: stage-1 estimates of every two-subset shape for one block (ldr = 16 RGBA pixels as floats 0..255)
+extern "C" void emul_bc7_shape_estimates(const float* ldr, float nl, int opaque, float* out64)
+{
+    static thread_local dxb_bc7_scratch S;
+    for (int i = 0; i < 16; ++i) { S.px[i] = dxb_make_px(ldr[4 * i], ldr[4 * i + 1], ldr[4 * i + 2], ldr[4 * i + 3]); S.px[16 + i] = S.px[i]; }
+    dxb_bc7_build_moments(&S);
+    float tot[14];
+    dxb_bc7_mt_load(S.mt[0], 64, tot);
+    for (uint32_t s = 0; s < 64; ++s) out64[s] = dxb_bc7_shape_h1(S.pq, S.mt[0], s, nl, tot, opaque != 0);
+}
+#endif
