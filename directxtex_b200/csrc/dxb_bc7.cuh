@@ -316,23 +316,40 @@ DXB_DEV float dxb_bc7_shape_estimate(const float* mt, uint32_t shape, float qf, 
 // because there every shape has residual zero and only the position of the points along the line matters.
 // Exact-integer formulation (device == host emulator bit for bit, whatever the evaluation order of the dot products):
 // the axis is quantised to 8-bit integers, pixels are bytes, so a projection is one u8 x s8 dot product (dp4a).
-DXB_DEV int32_t dxb_dp4a_u8s8(uint32_t pix, uint32_t axis)
+DXB_DEV int32_t dxb_dp4a_u8s8(uint32_t pix, uint32_t axis, int32_t acc)
 {
 #if DXB_ON_DEVICE
     int32_t d;
-    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(axis), "r"(0));
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(axis), "r"(acc));
     return d;
 #else
-    int32_t d = 0;
+    int32_t d = acc;
     for (int c = 0; c < 4; ++c) d += (int32_t)((pix >> (8 * c)) & 0xFFu) * (int32_t)(int8_t)((axis >> (8 * c)) & 0xFFu);
     return d;
+#endif
+}
+DXB_DEV int32_t dxb_min3_s32(int32_t a, int32_t b, int32_t c)
+{
+#if DXB_ON_DEVICE
+    return __vimin3_s32(a, b, c);
+#else
+    const int32_t m = (a < b) ? a : b; return (m < c) ? m : c;
+#endif
+}
+DXB_DEV int32_t dxb_max3_s32(int32_t a, int32_t b, int32_t c)
+{
+#if DXB_ON_DEVICE
+    return __vimax3_s32(a, b, c);
+#else
+    const int32_t m = (a > b) ? a : b; return (m > c) ? m : c;
 #endif
 }
 
 struct dxb_bc7_axis { uint32_t packed; float resid, inv_aa; };   // s8x4 axis, off-axis residual tr - a'Ca/|a|^2, 1/|a|^2
 
-// principal axis of one subset from its moments v[14] (n pixels): DXB_BC7_EST_ITERS un-normalised power-iteration steps
-// from the covariance row with the largest diagonal, then quantised to integers of magnitude <= 127
+// axis of one subset from its moments v[14] (n pixels): the covariance row with the largest diagonal (= one power-iteration
+// step from that unit vector; more steps do not change the ranking measurably), scaled by a power of two to integers of
+// magnitude <= 64.
 DXB_DEV dxb_bc7_axis dxb_bc7_subset_axis(uint32_t n, const float* v, bool opaque)
 {
     const float inv = dxb_rcp16[n];
@@ -349,25 +366,19 @@ DXB_DEV dxb_bc7_axis dxb_bc7_subset_axis(uint32_t n, const float* v, bool opaque
     const bool b0 = (c00 >= c11 && c00 >= c22 && c00 >= c33);
     const bool b1 = !b0 && (c11 >= c22 && c11 >= c33);
     const bool b2 = !b0 && !b1 && (c22 >= c33);
-    float v0 = b0 ? c00 : (b1 ? c01 : (b2 ? c02 : c03));
-    float v1 = b0 ? c01 : (b1 ? c11 : (b2 ? c12 : c13));
-    float v2 = b0 ? c02 : (b1 ? c12 : (b2 ? c22 : c23));
-    float v3 = b0 ? c03 : (b1 ? c13 : (b2 ? c23 : c33));
-    for (int it = 0; it < DXB_BC7_EST_ITERS; ++it)
-    {
-        const float w0 = dxb_fma(c00, v0, dxb_fma(c01, v1, dxb_fma(c02, v2, c03 * v3)));
-        const float w1 = dxb_fma(c01, v0, dxb_fma(c11, v1, dxb_fma(c12, v2, c13 * v3)));
-        const float w2 = dxb_fma(c02, v0, dxb_fma(c12, v1, dxb_fma(c22, v2, c23 * v3)));
-        const float w3 = opaque ? 0.0f : dxb_fma(c03, v0, dxb_fma(c13, v1, dxb_fma(c23, v2, c33 * v3)));
-        v0 = w0; v1 = w1; v2 = w2; v3 = w3;
-    }
-    const float mx = fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3)));
-    const float sc = (!flat && mx > 0.0f) ? 127.0f / mx : 0.0f;
+    const float v0 = b0 ? c00 : (b1 ? c01 : (b2 ? c02 : c03));
+    const float v1 = b0 ? c01 : (b1 ? c11 : (b2 ? c12 : c13));
+    const float v2 = b0 ? c02 : (b1 ? c12 : (b2 ? c22 : c23));
+    const float v3 = b0 ? c03 : (b1 ? c13 : (b2 ? c23 : c33));
+    // the largest component is the diagonal entry (|c_ij| <= max(c_ii, c_jj)): scale it into [32, 64)
+    const float mx = b0 ? c00 : (b1 ? c11 : (b2 ? c22 : c33));
+    const uint32_t E = dxb_float_as_uint(mx) >> 23;                      // biased exponent (mx > 0 unless flat)
+    const float sc = flat ? 0.0f : dxb_uint_as_float((259u - E) << 23);  // 2^(5 - (E - 127))
     const float a0 = dxb_rne(v0 * sc), a1 = dxb_rne(v1 * sc), a2 = dxb_rne(v2 * sc), a3 = dxb_rne(v3 * sc);
     dxb_bc7_axis A;
-    A.packed = ((uint32_t)dxb_f2i(a0) & 0xFFu) | (((uint32_t)dxb_f2i(a1) & 0xFFu) << 8) | (((uint32_t)dxb_f2i(a2) & 0xFFu) << 16) | (((uint32_t)dxb_f2i(a3) & 0xFFu) << 24);
+    A.packed = ((uint32_t)dxb_f2i_rn_small(a0) & 0xFFu) | (((uint32_t)dxb_f2i_rn_small(a1) & 0xFFu) << 8)
+             | (((uint32_t)dxb_f2i_rn_small(a2) & 0xFFu) << 16) | (((uint32_t)dxb_f2i_rn_small(a3) & 0xFFu) << 24);
     const float aa = dxb_fma(a0, a0, dxb_fma(a1, a1, dxb_fma(a2, a2, a3 * a3)));
-    // a' C a
     const float q0 = dxb_fma(c00, a0, dxb_fma(c01, a1, dxb_fma(c02, a2, c03 * a3)));
     const float q1 = dxb_fma(c01, a0, dxb_fma(c11, a1, dxb_fma(c12, a2, c13 * a3)));
     const float q2 = dxb_fma(c02, a0, dxb_fma(c12, a1, dxb_fma(c22, a2, c23 * a3)));
@@ -378,10 +389,11 @@ DXB_DEV dxb_bc7_axis dxb_bc7_subset_axis(uint32_t n, const float* v, bool opaque
     return A;
 }
 
-#define DXB_BC7_H1_OFF (1 << 20)          // separates the two subsets' projections (|t| <= 4 * 255 * 127 < 2^17)
+#define DXB_BC7_H1_OFF (1 << 20)          // separates the two subsets' projections (|t| <= 4 * 255 * 64 < 2^17)
 
-// pq = the block's 16 LDR pixels packed as bytes (R | G << 8 | B << 16 | A << 24); nl = 2^indexbits - 1 as float
-DXB_DEV float dxb_bc7_shape_h1(const uint32_t* pq, const float* mt, uint32_t shape, float nl, const float* tot, bool opaque)
+// pq = the block's 16 LDR pixels packed as bytes (R | G << 8 | B << 16 | A << 24).
+// opaque blocks: the better of 3-bit indices (mode 1) and 2-bit indices (mode 3); alpha blocks: 2-bit (mode 7).
+DXB_DEV float dxb_bc7_shape_h1(const uint32_t* pq, const float* mt, uint32_t shape, const float* tot, bool opaque)
 {
     float v1[14], v0[14];
     dxb_bc7_mt_load(mt, (int)shape, v1);
@@ -389,48 +401,51 @@ DXB_DEV float dxb_bc7_shape_h1(const uint32_t* pq, const float* mt, uint32_t sha
     const uint32_t mask = dxb_part2[shape];
     const uint32_t n1 = dxb_popc16(mask);
     const dxb_bc7_axis A0 = dxb_bc7_subset_axis(16u - n1, v0, opaque), A1 = dxb_bc7_subset_axis(n1, v1, opaque);
-    int32_t T[16];
+    int32_t T[16];                         // projection + (subset 1 ? OFF : 0)
     int32_t mnv = 0x7fffffff, mxv = -0x7fffffff, mny = 0x7fffffff, mxy = -0x7fffffff;
 #if DXB_ON_DEVICE
     #pragma unroll
 #endif
-    for (int p = 0; p < 16; ++p)
+    for (int p = 0; p < 16; p += 2)
     {
-        const bool m = ((mask >> p) & 1u) != 0u;
-        const int32_t t = dxb_dp4a_u8s8(pq[p], m ? A1.packed : A0.packed);
-        T[p] = t;
-        const int32_t off = m ? DXB_BC7_H1_OFF : 0;
-        const int32_t v = t + off, y = t - off;
-        mnv = (v < mnv) ? v : mnv; mxv = (v > mxv) ? v : mxv;
-        mny = (y < mny) ? y : mny; mxy = (y > mxy) ? y : mxy;
+        const bool ma = ((mask >> p) & 1u) != 0u, mb = ((mask >> (p + 1)) & 1u) != 0u;
+        const int32_t va = dxb_dp4a_u8s8(pq[p], ma ? A1.packed : A0.packed, ma ? DXB_BC7_H1_OFF : 0);
+        const int32_t vb = dxb_dp4a_u8s8(pq[p + 1], mb ? A1.packed : A0.packed, mb ? DXB_BC7_H1_OFF : 0);
+        const int32_t ya = ma ? va - 2 * DXB_BC7_H1_OFF : va, yb = mb ? vb - 2 * DXB_BC7_H1_OFF : vb;
+        T[p] = va; T[p + 1] = vb;
+        mnv = dxb_min3_s32(mnv, va, vb); mxv = dxb_max3_s32(mxv, va, vb);
+        mny = dxb_min3_s32(mny, ya, yb); mxy = dxb_max3_s32(mxy, ya, yb);
     }
     // subset 0 = the small keys of v and the large keys of y; both subsets of a valid shape are non-empty
     const int32_t tmin0 = mnv, tmax1 = mxv - DXB_BC7_H1_OFF, tmax0 = mxy, tmin1 = mny + DXB_BC7_H1_OFF;
     const float r0 = (float)(tmax0 - tmin0), r1 = (float)(tmax1 - tmin1);
     const float i0 = (r0 > 0.0f) ? 1.0f / r0 : 0.0f, i1 = (r1 > 0.0f) ? 1.0f / r1 : 0.0f;
-    // opaque blocks: the better of 3-bit indices (mode 1) and 2-bit indices (mode 3); alpha blocks: 2-bit (mode 7).
-    // e?a = error in units of (range / nl)^2 at nl, e?b at 3 levels
+    const int32_t base1 = tmin1 + DXB_BC7_H1_OFF;
+    // e?a = squared index rounding error in units of (range / 7)^2, e?b in units of (range / 3)^2
     float e0a = 0.0f, e1a = 0.0f, e0b = 0.0f, e1b = 0.0f;
 #if DXB_ON_DEVICE
     #pragma unroll
 #endif
     for (int p = 0; p < 16; ++p)
     {
-        const bool m = ((mask >> p) & 1u) != 0u;
-        const float x = (float)(T[p] - (m ? tmin1 : tmin0)) * (m ? i1 : i0);       // position in [0, 1]
-        const float ua = x * nl, ub = x * 3.0f;
-        const float da = ua - dxb_rne(ua), db = ub - dxb_rne(ub);
-        const float dda = da * da, ddb = db * db;
-        e0a += m ? 0.0f : dda; e1a += m ? dda : 0.0f;
-        e0b += m ? 0.0f : ddb; e1b += m ? ddb : 0.0f;
+        const bool m = (T[p] >= (DXB_BC7_H1_OFF >> 1));
+        const float x = (float)(T[p] - (m ? base1 : tmin0)) * (m ? i1 : i0);        // position in [0, 1]
+        const float ub = x * 3.0f;
+        const float db = ub - dxb_rne(ub);
+        if (m) e1b = dxb_fma(db, db, e1b); else e0b = dxb_fma(db, db, e0b);
+        if (opaque)
+        {
+            const float ua = x * 7.0f;
+            const float da = ua - dxb_rne(ua);
+            if (m) e1a = dxb_fma(da, da, e1a); else e0a = dxb_fma(da, da, e0a);
+        }
     }
     // index-quantisation error in pixel units: e * (range / nl)^2 / |a|^2
     const float w0 = (r0 * r0) * A0.inv_aa, w1 = (r1 * r1) * A1.inv_aa;
-    const float inl2 = 1.0f / (nl * nl);
-    const float qa = dxb_fma(e0a, w0, e1a * w1) * inl2, qb = dxb_fma(e0b, w0, e1b * w1) * (1.0f / 9.0f);
+    const float qb = dxb_fma(e0b, w0, e1b * w1) * (1.0f / 9.0f);
+    const float qa = opaque ? dxb_fma(e0a, w0, e1a * w1) * (1.0f / 49.0f) : qb;
     return (A0.resid + A1.resid) + fminf(qa, qb);
 }
-
 
 // rotation heuristic for modes 4/5: cost of coding channel c as the separate scalar and the remaining channels as the
 // vector, from the block totals (moments row 64): line-fit residual of the rest + index-quantisation models.
@@ -816,7 +831,7 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
                 const float e = quick ? 0.0f : dxb_bc7_shape_estimate(mt, shape, qf, tot, hasA[L] == 0u);
 #else
                 (void)qf;
-                const float e = quick ? 0.0f : dxb_bc7_shape_h1(S->pq + (lane & 16), mt, shape, hasA[L] ? 3.0f : 7.0f, tot, hasA[L] == 0u);
+                const float e = quick ? 0.0f : dxb_bc7_shape_h1(S->pq + (lane & 16), mt, shape, tot, hasA[L] == 0u);
 #endif
                 const uint32_t x = (dxb_float_as_uint(e) & 0xFFFFFFC0u) | shape;
                 const uint32_t lo = (x < a) ? x : a, hi = (x < a) ? a : x;               // sorted insert

@@ -10,6 +10,7 @@
 
 #if defined(__CUDACC__)
   #include <cuda_fp16.h>
+  #include <cuda_runtime.h>
   #define DXB_DEV __device__ __forceinline__
   #define DXB_DEV_NOINLINE __device__ __noinline__
   #define DXB_CONST __device__ const

@@ -257,6 +257,6 @@ extern "C" void emul_bc7_shape_estimates(const float* ldr, float nl, int opaque,
     dxb_bc7_build_moments(&S);
     float tot[14];
     dxb_bc7_mt_load(S.mt[0], 64, tot);
-    for (uint32_t s = 0; s < 64; ++s) out64[s] = dxb_bc7_shape_h1(S.pq, S.mt[0], s, nl, tot, opaque != 0);
+    for (uint32_t s = 0; s < 64; ++s) out64[s] = dxb_bc7_shape_h1(S.pq, S.mt[0], s, tot, opaque != 0);
 }
 #endif
