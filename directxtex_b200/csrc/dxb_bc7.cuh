@@ -355,12 +355,10 @@ DXB_DEV dxb_bc7_axis dxb_bc7_subset_axis(uint32_t n, const float* v, bool opaque
     const float inv = dxb_rcp16[n];
     const float c00 = dxb_fma(-v[0] * inv, v[0], v[4]), c01 = dxb_fma(-v[0] * inv, v[1], v[5]), c02 = dxb_fma(-v[0] * inv, v[2], v[6]);
     const float c11 = dxb_fma(-v[1] * inv, v[1], v[8]), c12 = dxb_fma(-v[1] * inv, v[2], v[9]), c22 = dxb_fma(-v[2] * inv, v[2], v[11]);
-    float c03 = 0.0f, c13 = 0.0f, c23 = 0.0f, c33 = 0.0f;
-    if (!opaque)
-    {
-        c03 = dxb_fma(-v[0] * inv, v[3], v[7]); c13 = dxb_fma(-v[1] * inv, v[3], v[10]);
-        c23 = dxb_fma(-v[2] * inv, v[3], v[12]); c33 = dxb_fma(-v[3] * inv, v[3], v[13]);
-    }
+    // opaque blocks: alpha is the constant 255, its covariance row is zero up to rounding: forced to zero (branch-free)
+    const float z = opaque ? 0.0f : 1.0f;
+    const float c03 = z * dxb_fma(-v[0] * inv, v[3], v[7]), c13 = z * dxb_fma(-v[1] * inv, v[3], v[10]);
+    const float c23 = z * dxb_fma(-v[2] * inv, v[3], v[12]), c33 = z * dxb_fma(-v[3] * inv, v[3], v[13]);
     const float tr = (c00 + c11) + (c22 + c33);
     const bool flat = !(tr > 1e-3f) || (n < 2u);
     const bool b0 = (c00 >= c11 && c00 >= c22 && c00 >= c33);
@@ -374,10 +372,11 @@ DXB_DEV dxb_bc7_axis dxb_bc7_subset_axis(uint32_t n, const float* v, bool opaque
     const float mx = b0 ? c00 : (b1 ? c11 : (b2 ? c22 : c33));
     const uint32_t E = dxb_float_as_uint(mx) >> 23;                      // biased exponent (mx > 0 unless flat)
     const float sc = flat ? 0.0f : dxb_uint_as_float((259u - E) << 23);  // 2^(5 - (E - 127))
-    const float a0 = dxb_rne(v0 * sc), a1 = dxb_rne(v1 * sc), a2 = dxb_rne(v2 * sc), a3 = dxb_rne(v3 * sc);
+    // round to integers with the magic constant: the sum's low mantissa byte is the two's complement byte of the integer
+    const float t0 = dxb_fma(v0, sc, DXB_MAGIC), t1 = dxb_fma(v1, sc, DXB_MAGIC), t2 = dxb_fma(v2, sc, DXB_MAGIC), t3 = dxb_fma(v3, sc, DXB_MAGIC);
+    const float a0 = t0 - DXB_MAGIC, a1 = t1 - DXB_MAGIC, a2 = t2 - DXB_MAGIC, a3 = t3 - DXB_MAGIC;
     dxb_bc7_axis A;
-    A.packed = ((uint32_t)dxb_f2i_rn_small(a0) & 0xFFu) | (((uint32_t)dxb_f2i_rn_small(a1) & 0xFFu) << 8)
-             | (((uint32_t)dxb_f2i_rn_small(a2) & 0xFFu) << 16) | (((uint32_t)dxb_f2i_rn_small(a3) & 0xFFu) << 24);
+    A.packed = (dxb_float_as_uint(t0) & 0xFFu) | ((dxb_float_as_uint(t1) & 0xFFu) << 8) | ((dxb_float_as_uint(t2) & 0xFFu) << 16) | (dxb_float_as_uint(t3) << 24);
     const float aa = dxb_fma(a0, a0, dxb_fma(a1, a1, dxb_fma(a2, a2, a3 * a3)));
     const float q0 = dxb_fma(c00, a0, dxb_fma(c01, a1, dxb_fma(c02, a2, c03 * a3)));
     const float q1 = dxb_fma(c01, a0, dxb_fma(c11, a1, dxb_fma(c12, a2, c13 * a3)));
@@ -430,15 +429,9 @@ DXB_DEV float dxb_bc7_shape_h1(const uint32_t* pq, const float* mt, uint32_t sha
     {
         const bool m = (T[p] >= (DXB_BC7_H1_OFF >> 1));
         const float x = (float)(T[p] - (m ? base1 : tmin0)) * (m ? i1 : i0);        // position in [0, 1]
-        const float ub = x * 3.0f;
-        const float db = ub - dxb_rne(ub);
-        if (m) e1b = dxb_fma(db, db, e1b); else e0b = dxb_fma(db, db, e0b);
-        if (opaque)
-        {
-            const float ua = x * 7.0f;
-            const float da = ua - dxb_rne(ua);
-            if (m) e1a = dxb_fma(da, da, e1a); else e0a = dxb_fma(da, da, e0a);
-        }
+        const float ub = x * 3.0f, ua = x * 7.0f;
+        const float db = ub - dxb_rne(ub), da = ua - dxb_rne(ua);
+        if (m) { e1b = dxb_fma(db, db, e1b); e1a = dxb_fma(da, da, e1a); } else { e0b = dxb_fma(db, db, e0b); e0a = dxb_fma(da, da, e0a); }
     }
     // index-quantisation error in pixel units: e * (range / nl)^2 / |a|^2
     const float w0 = (r0 * r0) * A0.inv_aa, w1 = (r1 * r1) * A1.inv_aa;
@@ -821,6 +814,26 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
             // index quantisation factor 1/(2^b-1)^2: 3-bit for mode 1 (opaque), 2-bit for mode 7 (alpha)
             const float qf = hasA[L] ? (1.0f / 9.0f) : (1.0f / 49.0f);
             uint32_t a = 0xFFFFFFFFu, b = 0xFFFFFFFFu, c = 0xFFFFFFFFu;
+#if defined(DXB_BC7_PRUNE)
+            // per-lane pruning: the closed-form estimate keeps DXB_BC7_PRUNE of this lane's 4 shapes for the h1 estimate
+            uint32_t pk[4];
+            for (int j = 0; j < 4; ++j)
+            {
+                const uint32_t shape = (uint32_t)(lane & 15) + 16u * (uint32_t)j;
+                const float e0 = quick ? 0.0f : dxb_bc7_shape_estimate(mt, shape, qf, tot, hasA[L] == 0u);
+                pk[j] = (dxb_float_as_uint(e0) & 0xFFFFFFC0u) | shape;
+            }
+            for (int i = 0; i < 3; ++i) for (int j = 0; j < 3 - i; ++j) if (pk[j + 1] < pk[j]) { const uint32_t t = pk[j]; pk[j] = pk[j + 1]; pk[j + 1] = t; }
+            for (int j = 0; j < DXB_BC7_PRUNE; ++j)
+            {
+                const uint32_t shape = pk[j] & 63u;
+                const float e = quick ? 0.0f : dxb_bc7_shape_h1(S->pq + (lane & 16), mt, shape, tot, hasA[L] == 0u);
+                const uint32_t x = (dxb_float_as_uint(e) & 0xFFFFFFC0u) | shape;
+                const uint32_t lo = (x < a) ? x : a, hi = (x < a) ? a : x;               // sorted insert
+                const uint32_t lo2 = (hi < b) ? hi : b, hi2 = (hi < b) ? b : hi;
+                a = lo; b = lo2; c = (hi2 < c) ? hi2 : c;
+            }
+#else
 #if DXB_ON_DEVICE
             #pragma unroll 1
 #endif
@@ -838,6 +851,7 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
                 const uint32_t lo2 = (hi < b) ? hi : b, hi2 = (hi < b) ? b : hi;
                 a = lo; b = lo2; c = (hi2 < c) ? hi2 : c;
             }
+#endif
             k0[L] = a; k1[L] = b; k2[L] = c;
         DXB_LANES_END
         for (int r = 0; r < 3; ++r)
