@@ -91,8 +91,28 @@ DXB_DEV bool dxb_fits_signed(int32_t d, int32_t n) { return d >= -(1 << (n - 1))
 // stage 2: continuous endpoint fit of one region in the INT domain (3 channels), centred on `ctr`.
 //   ib = index bits (3 two-region, 4 one-region); anchor = the region's fix-up pixel
 // outputs E0/E1 (absolute INT-domain floats), ordered so that the anchor pixel projects into the first half
-DXB_DEV void dxb_bc6h_fit(const dxb_px* px, uint32_t mask, uint32_t ib, int anchor, const float* ctr, float lo, float hi, float* E0, float* E1)
+// bnd[0..2] / bnd[3..5] = clamp range of the endpoints per channel: the format range [lo, hi], except that for the signed
+// format a channel whose values have both signs inside this region is held to the region's own [min, max].  The INT
+// domain is the half-float bit pattern, i.e. logarithmic in the value, and runs through zero between the signs: a
+// least-squares endpoint that overshoots the data by 10 % of such a span is off by a factor of ten in the decoded float.
+DXB_DEV void dxb_bc6h_fit(const dxb_px* px, uint32_t mask, uint32_t ib, int anchor, const float* ctr, float lo, float hi, bool bSigned, float* E0, float* E1, float* bnd)
 {
+    {
+        float mn[3] = { 3.0e38f, 3.0e38f, 3.0e38f }, mx[3] = { -3.0e38f, -3.0e38f, -3.0e38f };
+        for (int i = 0; i < 16; ++i)
+        {
+            const bool in = ((mask >> i) & 1u) != 0u;
+            const dxb_px p = px[i];
+            mn[0] = in ? fminf(mn[0], p.x) : mn[0]; mx[0] = in ? fmaxf(mx[0], p.x) : mx[0];
+            mn[1] = in ? fminf(mn[1], p.y) : mn[1]; mx[1] = in ? fmaxf(mx[1], p.y) : mx[1];
+            mn[2] = in ? fminf(mn[2], p.z) : mn[2]; mx[2] = in ? fmaxf(mx[2], p.z) : mx[2];
+        }
+        for (int c = 0; c < 3; ++c)
+        {
+            const bool cross = bSigned && (mn[c] < 0.0f) && (mx[c] > 0.0f);
+            bnd[c] = cross ? mn[c] : lo; bnd[3 + c] = cross ? mx[c] : hi;
+        }
+    }
     float n = 0, s0 = 0, s1 = 0, s2 = 0, m00 = 0, m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0;
     for (int i = 0; i < 16; ++i)
     {
@@ -181,7 +201,7 @@ DXB_DEV void dxb_bc6h_fit(const dxb_px* px, uint32_t mask, uint32_t ib, int anch
         const bool sw = (t * 2.0f > dd);
         for (int c = 0; c < 3; ++c)
         {
-            const float a = fminf(fmaxf(A[c] + ctr[c], lo), hi), b = fminf(fmaxf(B[c] + ctr[c], lo), hi);
+            const float a = fminf(fmaxf(A[c] + ctr[c], bnd[c]), bnd[3 + c]), b = fminf(fmaxf(B[c] + ctr[c], bnd[c]), bnd[3 + c]);
             E0[c] = sw ? b : a; E1[c] = sw ? a : b;
         }
     }
@@ -255,6 +275,13 @@ DXB_DEV int dxb_bc6h_pick_mode(const int32_t ep[4][3], bool two, bool bSigned, i
     return chosen;
 }
 
+// decoded endpoint value of code q (weight 0 / 64): FinishUnquantize(Unquantize(q)) = the magnitude scaled by 31/64 (31/32
+// signed) and truncated (:1932-1942), as float.  |unq| < 2^16, so the product is exact in fp32 and truncf reproduces the shift.
+DXB_DEV float dxb_bc6h_decoded_endpoint(int32_t q, int32_t prec, bool bSigned)
+{
+    return truncf((float)dxb_bc6h_unquantize(q, prec, bSigned) * (bSigned ? (31.0f / 32.0f) : (31.0f / 64.0f)));
+}
+
 // error of one region for quantised endpoints qa/qb at `prec` bits, used to RANK the candidate shapes: indices by
 // projection, decoded values modelled in float as in dxb_bc6h_refine_region (within 2 units of the decoder's integers;
 // the winner's indices are then chosen exhaustively against the exact palette in stage 4)
@@ -262,12 +289,11 @@ template <int NIDX>
 DXB_DEV float dxb_bc6h_region_error(const dxb_px* px, uint32_t mask, const float* ctr, const int32_t* qa, const int32_t* qb, int32_t prec, bool bSigned)
 {
     const float nmax = (float)(NIDX - 1), c64 = 64.0f / nmax;
-    const float fs = bSigned ? (31.0f / 32.0f) : (31.0f / 64.0f);
     float A[3], D[3];
     for (int c = 0; c < 3; ++c)
     {
-        A[c] = dxb_fma((float)dxb_bc6h_unquantize(qa[c], prec, bSigned), fs, -ctr[c]);
-        D[c] = dxb_fma((float)dxb_bc6h_unquantize(qb[c], prec, bSigned), fs, -ctr[c]) - A[c];
+        A[c] = dxb_bc6h_decoded_endpoint(qa[c], prec, bSigned) - ctr[c];
+        D[c] = (dxb_bc6h_decoded_endpoint(qb[c], prec, bSigned) - ctr[c]) - A[c];
     }
     const float dd = dxb_fma(D[0], D[0], dxb_fma(D[1], D[1], D[2] * D[2]));
     const float idd = (dd > 0.0f) ? nmax / dd : 0.0f;
@@ -297,18 +323,17 @@ DXB_DEV float dxb_bc6h_region_error(const dxb_px* px, uint32_t mask, const float
 // floor operations (< 2 units of 65536); the caller re-measures the result against the exact palette.
 // Everything is centred on `ctr` to keep the fp32 sums well conditioned.
 template <int NIDX>
-DXB_DEV void dxb_bc6h_refine_region(const dxb_px* px, uint32_t mask, const float* ctr, int32_t* qa, int32_t* qb, int32_t prec, bool bSigned)
+DXB_DEV void dxb_bc6h_refine_region(const dxb_px* px, uint32_t mask, const float* ctr, int32_t* qa, int32_t* qb, int32_t prec, bool bSigned, const float* bnd)
 {
     const float nmax = (float)(NIDX - 1), c64 = 64.0f / nmax;
-    const float fs = bSigned ? (31.0f / 32.0f) : (31.0f / 64.0f);
     const int32_t qlo = bSigned ? -((1 << (prec - 1)) - 1) : 0, qhi = bSigned ? ((1 << (prec - 1)) - 1) : ((1 << prec) - 1);
     for (int iter = 0; iter < 2; ++iter)
     {
         float A[3], D[3];
         for (int c = 0; c < 3; ++c)
         {
-            A[c] = dxb_fma((float)dxb_bc6h_unquantize(qa[c], prec, bSigned), fs, -ctr[c]);
-            D[c] = dxb_fma((float)dxb_bc6h_unquantize(qb[c], prec, bSigned), fs, -ctr[c]) - A[c];
+            A[c] = dxb_bc6h_decoded_endpoint(qa[c], prec, bSigned) - ctr[c];
+            D[c] = (dxb_bc6h_decoded_endpoint(qb[c], prec, bSigned) - ctr[c]) - A[c];
         }
         const float dd = dxb_fma(D[0], D[0], dxb_fma(D[1], D[1], D[2] * D[2]));
         const float idd = (dd > 0.0f) ? nmax / dd : 0.0f;
@@ -334,16 +359,19 @@ DXB_DEV void dxb_bc6h_refine_region(const dxb_px* px, uint32_t mask, const float
             float ca[3], cb[3];                                      // decoded, centred values of the 3 neighbouring codes
             for (int k = 0; k < 3; ++k)
             {
-                ca[k] = dxb_fma((float)dxb_bc6h_unquantize(qa[c] + k - 1, prec, bSigned), fs, -ctr[c]);
-                cb[k] = dxb_fma((float)dxb_bc6h_unquantize(qb[c] + k - 1, prec, bSigned), fs, -ctr[c]);
+                ca[k] = dxb_bc6h_decoded_endpoint(qa[c] + k - 1, prec, bSigned) - ctr[c];
+                cb[k] = dxb_bc6h_decoded_endpoint(qb[c] + k - 1, prec, bSigned) - ctr[c];
             }
             float bestE = 3.0e38f; int32_t ba = qa[c], bb = qb[c];
             for (int da = 0; da < 3; ++da)
                 for (int dbb = 0; dbb < 3; ++dbb)
                 {
                     const int32_t a = qa[c] + da - 1, b = qb[c] + dbb - 1;
-                    const bool ok = !(a < qlo || a > qhi || b < qlo || b > qhi);
                     const float Av = ca[da], Bv = cb[dbb];
+                    // a neighbouring code must decode inside the clamp range of its channel (dxb_bc6h_fit); the centre pair always may stay
+                    const float blo = bnd[c] - ctr[c] - 0.5f, bhi = bnd[3 + c] - ctr[c] + 0.5f;
+                    const bool inb = (da == 1 || (Av >= blo && Av <= bhi)) && (dbb == 1 || (Bv >= blo && Bv <= bhi));
+                    const bool ok = !(a < qlo || a > qhi || b < qlo || b > qhi) && inb;
                     // A (A soo + 2 B sos - 2 U) + B (B sss - 2 V)
                     const float e = dxb_fma(Av, dxb_fma(Av, soo, dxb_fma(Bv + Bv, sos, -(U[c] + U[c]))), Bv * dxb_fma(Bv, sss, -(V[c] + V[c])));
                     if (ok && e < bestE) { bestE = e; ba = a; bb = b; }
@@ -428,6 +456,7 @@ DXB_DEV void dxb_bc6h_encode_pair(const dxb_px* spx, bool bSigned, uint8_t* out0
     // ---- stage 2: continuous fits
     float e0x[DXB_NL], e0y[DXB_NL], e0z[DXB_NL], e1x[DXB_NL], e1y[DXB_NL], e1z[DXB_NL];
     uint32_t tShape[DXB_NL], tMask[DXB_NL];
+    float tBnd[6][DXB_NL];
     DXB_LANES_BEGIN
         const int hl = lane & 15;
         const bool one = (hl >= 2 * DXB_BC6H_KSHAPES);
@@ -438,7 +467,9 @@ DXB_DEV void dxb_bc6h_encode_pair(const dxb_px* spx, bool bSigned, uint8_t* out0
         const int anchor = one ? 0 : ((hl & 1) ? (int)dxb_anchor2[shape] : 0);
         const float ctr[3] = { cx[L], cy[L], cz[L] };
         float E0[3], E1[3];
-        dxb_bc6h_fit(spx + (lane & 16), mask, one ? 4u : 3u, anchor, ctr, lo, hi, E0, E1);
+        float bnd[6];
+        dxb_bc6h_fit(spx + (lane & 16), mask, one ? 4u : 3u, anchor, ctr, lo, hi, bSigned, E0, E1, bnd);
+        for (int k = 0; k < 6; ++k) tBnd[k][L] = bnd[k];
         e0x[L] = E0[0]; e0y[L] = E0[1]; e0z[L] = E0[2]; e1x[L] = E1[0]; e1y[L] = E1[1]; e1z[L] = E1[2];
         tShape[L] = one ? 0u : shape; tMask[L] = mask;
     DXB_LANES_END
@@ -474,8 +505,9 @@ DXB_DEV void dxb_bc6h_encode_pair(const dxb_px* spx, bool bSigned, uint8_t* out0
         // +-1 code refinement of this lane's own region
         int32_t qa[3], qb[3];
         for (int c = 0; c < 3; ++c) { qa[c] = second ? q[2][c] : q[0][c]; qb[c] = second ? q[3][c] : q[1][c]; }
-        if (one) dxb_bc6h_refine_region<16>(spx + (lane & 16), 0xFFFFu, ctr, qa, qb, prec, bSigned);
-        else dxb_bc6h_refine_region<8>(spx + (lane & 16), tMask[L], ctr, qa, qb, prec, bSigned);
+        const float bnd[6] = { tBnd[0][L], tBnd[1][L], tBnd[2][L], tBnd[3][L], tBnd[4][L], tBnd[5][L] };
+        if (one) dxb_bc6h_refine_region<16>(spx + (lane & 16), 0xFFFFu, ctr, qa, qb, prec, bSigned, bnd);
+        else dxb_bc6h_refine_region<8>(spx + (lane & 16), tMask[L], ctr, qa, qb, prec, bSigned, bnd);
         for (int c = 0; c < 3; ++c) { mine[c][L] = (uint32_t)qa[c]; mine[3 + c][L] = (uint32_t)qb[c]; }
         rMode[L] = (uint32_t)mode;
         for (int e = 0; e < 4; ++e) for (int c = 0; c < 3; ++c) rq[e * 3 + c][L] = (uint32_t)q[e][c];
