@@ -679,19 +679,16 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
             const float ax_ = X - D0[0], ay_ = Y - D0[1], az_ = Z - D0[2], aw_ = Wv - D0[3];
             const float pr = dxb_fma(ax_, dx, dxb_fma(ay_, dy, dxb_fma(az_, dz, aw_ * dw)));
             const float tk = pr * idd;
-            // index = nearest of the uniformly spaced positions; weight of that index (palette entries are not
-            // rounded here: this error only ranks candidates, stage 4 assigns the final indices exhaustively)
+            // index = nearest of the uniformly spaced positions (stage 4 assigns the winner's final indices exhaustively)
             const float kk = dxb_rne(fminf(fmaxf(tk, 0.0f), nmaxc));
             const float sk = dxb_bc7_weightf(kk, c64c);
-#ifndef DXB_BC7_NO_ALGERR
-            // |P - D0 - sk d|^2 = |P - D0|^2 - sk (2 (P - D0).d - sk |d|^2)
-            const float e2 = dxb_fma(-sk, dxb_fma(-sk, dd, pr + pr), dxb_fma(ax_, ax_, dxb_fma(ay_, ay_, dxb_fma(az_, az_, aw_ * aw_))));
-            err = dxb_fma(f, e2, err);
-#else
-            const float ex = X - dxb_fma(dx, sk, D0[0]), ey = Y - dxb_fma(dy, sk, D0[1]);
-            const float ez = Z - dxb_fma(dz, sk, D0[2]), ew = Wv - dxb_fma(dw, sk, D0[3]);
+            // candidate error against the decoder's palette entry (e0 (64 - w) + e1 w + 32) >> 6 = round-half-up of D0 + sk d
+            // (a multiple of 1/64, so adding 1/128 before the RNE never ties).  An unrounded model mis-ranks near-lossless
+            // candidates: the rounding noise (1/12 per value) is half of the error of a smooth 8-bit gradient.
+            const float qx = dxb_rne(dxb_fma(dx, sk, D0[0] + (1.0f / 128.0f))), qy = dxb_rne(dxb_fma(dy, sk, D0[1] + (1.0f / 128.0f)));
+            const float qz = dxb_rne(dxb_fma(dz, sk, D0[2] + (1.0f / 128.0f))), qw = dxb_rne(dxb_fma(dw, sk, D0[3] + (1.0f / 128.0f)));
+            const float ex = X - qx, ey = Y - qy, ez = Z - qz, ew = Wv - qw;
             err = dxb_fma(f, dxb_fma(ex, ex, dxb_fma(ey, ey, dxb_fma(ez, ez, ew * ew))), err);
-#endif
             if (!last)
             {
                 // refit sums: only sum f s, sum f s^2 and sum f s P are accumulated; the (1 - s) sums follow from the

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from directxtex_b200 import capi, formats as F, synth
-from tests import golden_util, oracle_lib
+from tests import golden_util, oracle_lib, tolerance
 
 pytestmark = pytest.mark.gpu
 
@@ -236,6 +236,50 @@ def test_bc7_equals_emulator_and_quality(oracle, emul):
         assert nd == 0, "%d of %d blocks differ from the emulator" % (nd, got.size // 16)
 
 
+@pytest.mark.parametrize("kind,flags", tolerance.bc7_cases())
+def test_bc7_contract_per_class_on_device(oracle, emul, kind, flags):
+    """Every content class of the tolerance corpus at 256^2: the CUDA encoder's blocks are bit-identical to the host emulator's
+    and meet the BC7 contract (tests/tolerance.py) against the reference encoder's per-block errors (committed golden)."""
+    n = tolerance.SIZE
+    img = synth.content_ldr(kind, n, n, tolerance.SEED)
+    got = capi.compress(img, n, n, 2, 98, flags)
+    he, em = emul.compress(img, n, n, 2, 98, flags)
+    assert he == 0
+    nd = int((got.reshape(-1, 16) != em.reshape(-1, 16)).any(1).sum())
+    assert nd == 0, "%s: %d of %d blocks differ from the emulator" % (kind, nd, got.size // 16)
+    tolerance.check_bc7(oracle, kind, flags, got)
+
+
+@pytest.mark.parametrize("kind,fmt", tolerance.bc6h_cases())
+def test_bc6h_contract_per_class_on_device(oracle, emul, kind, fmt):
+    """As above for BC6H_UF16 / BC6H_SF16, including the float-domain bounds (sign-crossing content)."""
+    n = tolerance.SIZE
+    img = synth.content_hdr(kind, n, n, tolerance.SEED)
+    got = capi.compress(img, n, n, 2, fmt)
+    he, em = emul.compress(img, n, n, 2, fmt)
+    assert he == 0
+    nd = int((got.reshape(-1, 16) != em.reshape(-1, 16)).any(1).sum())
+    assert nd == 0, "%s: %d blocks differ from the emulator" % (kind, nd)
+    tolerance.check_bc6h(oracle, kind, fmt, got)
+
+
+def test_full_size_c2_bc7_mse_vs_reference_on_crop(oracle):
+    """BASELINE configs[1] "bit-check vs ref BC7 MSE": the 4096^2 image is compressed on the GPU; on a 512^2 aligned crop (16384
+    blocks: the blocks of a crop are the blocks of the full image, test_full_size_c2_bc7_properties) the reference encoder runs
+    here on the host and both streams are decoded by the reference decoder: MSE_gpu <= 1.02 x MSE_ref, < 1 % of blocks worse
+    than 2 x + 16."""
+    img = synth.c2_rgba32f(4096, 4096)
+    a = capi.compress(img, 4096, 4096, 2, 98).reshape(1024, 1024, 16)
+    y0, x0, s = 1536, 512, 512
+    crop = np.ascontiguousarray(img[y0:y0 + s, x0:x0 + s])
+    gpu_blocks = np.ascontiguousarray(a[y0 // 4:(y0 + s) // 4, x0 // 4:(x0 + s) // 4]).reshape(-1)
+    hr, ref_blocks = oracle.compress(crop, s, s, 2, 98, 0)
+    assert hr == 0
+    ours, theirs = tolerance.bc7_block_sse(oracle, gpu_blocks, crop), tolerance.bc7_block_sse(oracle, ref_blocks, crop)
+    assert ours.sum() <= 1.02 * theirs.sum(), ours.sum() / theirs.sum()
+    assert float((ours > 2.0 * theirs + 16.0).mean()) < 0.01
+
+
 def test_bc7_rgba8_source_partial_blocks_and_quick(oracle, emul):
     rng = np.random.default_rng(8)
     for (w, h) in [(5, 7), (1, 1), (30, 18)]:
@@ -302,7 +346,7 @@ def test_full_size_c5_bc4_and_convert_roundtrip(oracle):
 
 
 def test_bc6h_equals_emulator_and_quality(oracle, emul):
-    """GPU BC6H == host lock-step emulator bit for bit; error (reference metric) <= 1.05 x the reference CPU encoder's."""
+    """GPU BC6H == host lock-step emulator bit for bit; error (reference metric) <= 1.02 x the reference CPU encoder's."""
     z = golden_util.load()
     for j in range(4):
         w, h, seed, fmt = (int(v) for v in z["bc6h_%d_meta" % j])
@@ -312,7 +356,7 @@ def test_bc6h_equals_emulator_and_quality(oracle, emul):
         he, em = emul.compress(img, w, h, 2, fmt)
         assert he == 0
         err = oracle_lib.bc6h_int_mse(oracle.decode_blocks(fmt, got, w, h), img, fmt == 96)
-        assert err <= float(z["bc6h_%d_referr" % j][0]) * 1.05, (kind, err)
+        assert err <= float(z["bc6h_%d_referr" % j][0]) * 1.02, (kind, err)
         nd = int((got.reshape(-1, 16) != em.reshape(-1, 16)).any(1).sum())
         assert nd == 0, "%d blocks differ from the emulator" % nd
 
