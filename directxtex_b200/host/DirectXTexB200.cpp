@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <vector>
+#include <string>
 
 namespace
 {
@@ -178,6 +179,16 @@ const Image* ScratchImage::GetImage(size_t mip, size_t item, size_t slice) const
 
 // ---------------------------------------------------------------------------------------------------
 // Compress
+namespace
+{
+    // std::function status callback -> the C ABI's (done, total, user) callback
+    int status_trampoline(size_t done, size_t total, void* user)
+    {
+        auto* f = static_cast<std::function<bool(size_t, size_t)>*>(user);
+        try { return (*f)(done, total) ? 1 : 0; } catch (...) { return 0; }
+    }
+}
+
 HRESULT Compress(const Image& src, DXGI_FORMAT format, TEX_COMPRESS_FLAGS compress, float threshold, ScratchImage& image) noexcept
 {
     CompressOptions o{ compress, threshold, TEX_ALPHA_WEIGHT_DEFAULT };
@@ -198,11 +209,12 @@ HRESULT CompressEx(const Image& src, DXGI_FORMAT format, const CompressOptions& 
     if (FAILED(hr)) return hr;
     const Image* img = image.GetImage(0, 0, 0);
     if (!img) { image.Release(); return E_POINTER; }
-    if (cb && !cb(0, img->height)) { image.Release(); return E_ABORT; }
+    // the C ABI reports (rows done, height) before every band of block rows and (height, height) at the end, and returns E_ABORT
+    // between bands when the callback says stop (DirectXTexCompress.cpp:115-121, 690-724)
     const dxb200_image s = to_c(src), d = to_c(*img);
-    hr = dxb200_compress(&s, 1, static_cast<uint32_t>(format), static_cast<uint32_t>(options.flags), options.threshold, options.alphaWeight, &d);
+    hr = dxb200_compress_ex(&s, 1, static_cast<uint32_t>(format), static_cast<uint32_t>(options.flags), options.threshold, options.alphaWeight, &d,
+                            cb ? status_trampoline : nullptr, cb ? &cb : nullptr);
     if (FAILED(hr)) { image.Release(); return hr; }
-    if (cb && !cb(img->height, img->height)) { image.Release(); return E_ABORT; }
     return S_OK;
 }
 
@@ -220,7 +232,6 @@ HRESULT CompressEx(const Image* srcImages, size_t nimages, const TexMetadata& me
     if (FAILED(hr)) return hr;
     if (nimages != cImages.GetImageCount()) { cImages.Release(); return E_FAIL; }
     const Image* dest = cImages.GetImages();
-    if (cb && !cb(0, nimages)) { cImages.Release(); return E_ABORT; }
     // images of one mip level share a size; the C ABI takes arbitrary per-image sizes in one batch
     std::vector<dxb200_image> s(nimages), d(nimages);
     for (size_t i = 0; i < nimages; ++i)
@@ -228,9 +239,9 @@ HRESULT CompressEx(const Image* srcImages, size_t nimages, const TexMetadata& me
         if (srcImages[i].width != dest[i].width || srcImages[i].height != dest[i].height) { cImages.Release(); return E_FAIL; }
         s[i] = to_c(srcImages[i]); d[i] = to_c(dest[i]);
     }
-    hr = dxb200_compress(s.data(), nimages, static_cast<uint32_t>(format), static_cast<uint32_t>(options.flags), options.threshold, options.alphaWeight, d.data());
+    hr = dxb200_compress_ex(s.data(), nimages, static_cast<uint32_t>(format), static_cast<uint32_t>(options.flags), options.threshold, options.alphaWeight, d.data(),
+                            cb ? status_trampoline : nullptr, cb ? &cb : nullptr);          // (images done, nimages), :785-837
     if (FAILED(hr)) { cImages.Release(); return hr; }
-    if (cb && !cb(nimages, nimages)) { cImages.Release(); return E_ABORT; }
     return S_OK;
 }
 
@@ -298,11 +309,10 @@ HRESULT ConvertEx(const Image& src, DXGI_FORMAT format, const ConvertOptions& op
     if (FAILED(hr)) return hr;
     const Image* rimage = image.GetImage(0, 0, 0);
     if (!rimage) { image.Release(); return E_POINTER; }
-    if (cb && !cb(0, rimage->height)) { image.Release(); return E_ABORT; }
     const dxb200_image s = to_c(src), d = to_c(*rimage);
-    hr = dxb200_convert(&s, 1, static_cast<uint32_t>(format), static_cast<uint32_t>(options.filter), options.threshold, &d);
+    hr = dxb200_convert_ex(&s, 1, static_cast<uint32_t>(format), static_cast<uint32_t>(options.filter), options.threshold, &d,
+                           cb ? status_trampoline : nullptr, cb ? &cb : nullptr);
     if (FAILED(hr)) { image.Release(); return hr; }
-    if (cb && !cb(rimage->height, rimage->height)) { image.Release(); return E_ABORT; }
     return S_OK;
 }
 
@@ -316,12 +326,11 @@ HRESULT ConvertEx(const Image* srcImages, size_t nimages, const TexMetadata& met
     HRESULT hr = result.Initialize(m2);
     if (FAILED(hr)) return hr;
     if (nimages != result.GetImageCount()) { result.Release(); return E_FAIL; }
-    if (cb && !cb(0, nimages)) { result.Release(); return E_ABORT; }
     std::vector<dxb200_image> s(nimages), d(nimages);
     for (size_t i = 0; i < nimages; ++i) { s[i] = to_c(srcImages[i]); d[i] = to_c(result.GetImages()[i]); }
-    hr = dxb200_convert(s.data(), nimages, static_cast<uint32_t>(format), static_cast<uint32_t>(options.filter), options.threshold, d.data());
+    hr = dxb200_convert_ex(s.data(), nimages, static_cast<uint32_t>(format), static_cast<uint32_t>(options.filter), options.threshold, d.data(),
+                           cb ? status_trampoline : nullptr, cb ? &cb : nullptr);
     if (FAILED(hr)) { result.Release(); return hr; }
-    if (cb && !cb(nimages, nimages)) { result.Release(); return E_ABORT; }
     return S_OK;
 }
 
@@ -616,6 +625,45 @@ HRESULT SaveToDDSFile(const Image& image, DDS_FLAGS flags, const char* szFile) n
     m.width = image.width; m.height = image.height; m.depth = 1; m.arraySize = 1; m.mipLevels = 1;
     m.format = image.format; m.dimension = TEX_DIMENSION_TEXTURE2D;
     return SaveToDDSFile(&image, 1, m, flags, szFile);
+}
+
+// ---- wchar_t paths (the reference's signatures, DirectXTex.h:588-616): converted to UTF-8 and forwarded
+namespace
+{
+    bool to_utf8(const wchar_t* w, std::string& out)
+    {
+        if (!w) return false;
+        out.clear();
+        for (; *w; ++w)
+        {
+            uint32_t c = static_cast<uint32_t>(*w);
+            if (sizeof(wchar_t) == 2 && c >= 0xD800 && c <= 0xDBFF && w[1] >= 0xDC00 && w[1] <= 0xDFFF)
+            {
+                c = 0x10000u + ((c - 0xD800u) << 10) + (static_cast<uint32_t>(w[1]) - 0xDC00u); ++w;
+            }
+            if (c < 0x80) out.push_back(static_cast<char>(c));
+            else if (c < 0x800) { out.push_back(static_cast<char>(0xC0 | (c >> 6))); out.push_back(static_cast<char>(0x80 | (c & 0x3F))); }
+            else if (c < 0x10000) { out.push_back(static_cast<char>(0xE0 | (c >> 12))); out.push_back(static_cast<char>(0x80 | ((c >> 6) & 0x3F))); out.push_back(static_cast<char>(0x80 | (c & 0x3F))); }
+            else { out.push_back(static_cast<char>(0xF0 | (c >> 18))); out.push_back(static_cast<char>(0x80 | ((c >> 12) & 0x3F))); out.push_back(static_cast<char>(0x80 | ((c >> 6) & 0x3F))); out.push_back(static_cast<char>(0x80 | (c & 0x3F))); }
+        }
+        return true;
+    }
+}
+HRESULT GetMetadataFromDDSFile(const wchar_t* szFile, DDS_FLAGS flags, TexMetadata& metadata) noexcept
+{
+    try { std::string p; return to_utf8(szFile, p) ? GetMetadataFromDDSFile(p.c_str(), flags, metadata) : E_INVALIDARG; } catch (...) { return E_OUTOFMEMORY; }
+}
+HRESULT LoadFromDDSFile(const wchar_t* szFile, DDS_FLAGS flags, TexMetadata* metadata, ScratchImage& image) noexcept
+{
+    try { std::string p; return to_utf8(szFile, p) ? LoadFromDDSFile(p.c_str(), flags, metadata, image) : E_INVALIDARG; } catch (...) { return E_OUTOFMEMORY; }
+}
+HRESULT SaveToDDSFile(const Image& image, DDS_FLAGS flags, const wchar_t* szFile) noexcept
+{
+    try { std::string p; return to_utf8(szFile, p) ? SaveToDDSFile(image, flags, p.c_str()) : E_INVALIDARG; } catch (...) { return E_OUTOFMEMORY; }
+}
+HRESULT SaveToDDSFile(const Image* images, size_t nimages, const TexMetadata& metadata, DDS_FLAGS flags, const wchar_t* szFile) noexcept
+{
+    try { std::string p; return to_utf8(szFile, p) ? SaveToDDSFile(images, nimages, metadata, flags, p.c_str()) : E_INVALIDARG; } catch (...) { return E_OUTOFMEMORY; }
 }
 
 } // namespace DirectX

@@ -184,6 +184,11 @@ namespace DirectX
     DXTEXB200_API HRESULT SaveToDDSMemory(const Image* images, size_t nimages, const TexMetadata& metadata, DDS_FLAGS flags, Blob& blob) noexcept;
     DXTEXB200_API HRESULT SaveToDDSFile(const Image& image, DDS_FLAGS flags, const char* szFile) noexcept;
     DXTEXB200_API HRESULT SaveToDDSFile(const Image* images, size_t nimages, const TexMetadata& metadata, DDS_FLAGS flags, const char* szFile) noexcept;
+    // the reference's own signatures (DirectXTex.h:588-616): wchar_t paths, converted to UTF-8
+    DXTEXB200_API HRESULT GetMetadataFromDDSFile(const wchar_t* szFile, DDS_FLAGS flags, TexMetadata& metadata) noexcept;
+    DXTEXB200_API HRESULT LoadFromDDSFile(const wchar_t* szFile, DDS_FLAGS flags, TexMetadata* metadata, ScratchImage& image) noexcept;
+    DXTEXB200_API HRESULT SaveToDDSFile(const Image& image, DDS_FLAGS flags, const wchar_t* szFile) noexcept;
+    DXTEXB200_API HRESULT SaveToDDSFile(const Image* images, size_t nimages, const TexMetadata& metadata, DDS_FLAGS flags, const wchar_t* szFile) noexcept;
 
     // ---- the accelerated operations: same signatures as DirectXTex.h:818-832, 841-846, 929-944, 965-968
     DXTEXB200_API HRESULT Convert(const Image& srcImage, DXGI_FORMAT format, TEX_FILTER_FLAGS filter, float threshold, ScratchImage& image) noexcept;

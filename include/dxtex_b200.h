@@ -19,7 +19,8 @@
  *     from dxb200_compute_pitch == ComputePitch, DirectXTexUtil.cpp:961-1183) and the call fills it.
  *   - `_device` variants take device pointers in the same struct and a CUstream/cudaStream_t
  *     (as void*, may be NULL for the default stream); they only enqueue work.
- *   - thread safety: entry points may be called concurrently from several host threads.
+ *   - thread safety: entry points may be called concurrently from several host threads; each host-pointer call takes one of a
+ *     device's two staging lanes (own streams and buffers), so two calls per device really overlap; more wait.
  */
 #ifndef DXTEX_B200_H
 #define DXTEX_B200_H
@@ -49,7 +50,14 @@ typedef struct dxb200_image
 
 /* library / device management (GPUCompressBC::Initialize, BCDirectCompute.cpp:109) */
 DXB200_API const char* dxb200_version(void);
-DXB200_API int32_t  dxb200_init(int device);                 /* bind the calling process to a CUDA device; idempotent */
+DXB200_API int32_t  dxb200_init(int device);                 /* = dxb200_init_devices(1, &device); idempotent */
+/* Multi-GPU inside the library (the reference parallelises inside the call too: CompressBC_Parallel,
+ * DirectXTexCompress.cpp:210-372).  After dxb200_init_devices(n, devs) every host-pointer entry point shards its work over
+ * the n devices: contiguous ranges of images (array calls, mip chains: a chain never spans devices) or of block-row bands
+ * (one large image), one host thread and one stream set per device, no collective.  `_device` variants always run on the
+ * device that owns the caller's pointers.  Devices can be added by further calls; idempotent per device. */
+DXB200_API int32_t  dxb200_init_devices(int ndev, const int* devices);
+DXB200_API int32_t  dxb200_initialized_devices(int* devices, int maxDevices);   /* returns how many are initialised */
 DXB200_API void     dxb200_shutdown(void);                   /* release cached device / pinned buffers */
 DXB200_API int32_t  dxb200_device_count(void);
 DXB200_API uint64_t dxb200_launch_count(void);               /* number of kernels this library has launched so far */
@@ -73,6 +81,13 @@ DXB200_API int32_t  dxb200_compress(const dxb200_image* src, size_t nimages, uin
                          uint32_t flags, float threshold, float alphaWeight, const dxb200_image* dst);
 DXB200_API int32_t  dxb200_compress_device(const dxb200_image* src, size_t nimages, uint32_t dstFormat,
                                 uint32_t flags, float threshold, float alphaWeight, const dxb200_image* dst, void* stream);
+/* CompressEx / ConvertEx status callback (DirectXTex.h:929-944; DirectXTexCompress.cpp:115-121, 356-360, 785-837): called with
+ * (done, total) before every band of work rows goes to the device -- pixel rows of a single image, images of an array --
+ * and with (total, total) at the end; returning 0 stops the call between bands with E_ABORT (0x80004004).  With several
+ * devices the callback is serialised but may come from worker threads. */
+typedef int (*dxb200_status_fn)(size_t done, size_t total, void* user);
+DXB200_API int32_t  dxb200_compress_ex(const dxb200_image* src, size_t nimages, uint32_t dstFormat, uint32_t flags, float threshold,
+                            float alphaWeight, const dxb200_image* dst, dxb200_status_fn status, void* user);
 
 /* DirectX::Decompress (DirectXTexCompress.cpp:852-979; DecompressBC :425-535) */
 DXB200_API int32_t  dxb200_decompress(const dxb200_image* src, size_t nimages, uint32_t dstFormat, const dxb200_image* dst);
@@ -85,6 +100,8 @@ DXB200_API int32_t  dxb200_convert(const dxb200_image* src, size_t nimages, uint
                         uint32_t filter, float threshold, const dxb200_image* dst);
 DXB200_API int32_t  dxb200_convert_device(const dxb200_image* src, size_t nimages, uint32_t dstFormat,
                                uint32_t filter, float threshold, const dxb200_image* dst, void* stream);
+DXB200_API int32_t  dxb200_convert_ex(const dxb200_image* src, size_t nimages, uint32_t dstFormat, uint32_t filter, float threshold,
+                           const dxb200_image* dst, dxb200_status_fn status, void* user);
 
 /* DirectX::GenerateMipMaps (DirectXTexMipmaps.cpp:2828-3247; Generate2DMips{Point,Box,Linear,Cubic,Triangle}Filter :907-1602).
  *   chain = items*levels images laid out item-major, mip-minor (TexMetadata::ComputeIndex, DirectXTexUtil.cpp:1695-1741);
@@ -92,6 +109,14 @@ DXB200_API int32_t  dxb200_convert_device(const dxb200_image* src, size_t nimage
  *   filter = TEX_FILTER_FLAGS; mode 0 selects BOX for power-of-two sizes else LINEAR (:3169-3174). */
 DXB200_API int32_t  dxb200_generate_mipmaps(const dxb200_image* chain, size_t items, size_t levels, uint32_t filter);
 DXB200_API int32_t  dxb200_generate_mipmaps_device(const dxb200_image* chain, size_t items, size_t levels, uint32_t filter, void* stream);
+
+/* GenerateMipMaps followed by Compress (what texconv does, Texconv/texconv.cpp -m / -f) as ONE call whose mip chain never leaves
+ * HBM: base[i] = level 0 of item i (host), dst[i * levels + l] = the compressed image of level l of item i (host, sized by the
+ * caller as ScratchImage::Initialize2D(dstFormat, w, h, items, levels) would).  Results are identical to
+ * dxb200_generate_mipmaps + dxb200_compress (same kernels); host<->device traffic drops from (1 + 2 x 1.33) x source bytes up/down
+ * to the source up and the blocks down.  filter as dxb200_generate_mipmaps, flags / threshold as dxb200_compress. */
+DXB200_API int32_t  dxb200_mipmaps_compress(const dxb200_image* base, size_t items, size_t levels, uint32_t filter, uint32_t dstFormat,
+                                 uint32_t flags, float threshold, float alphaWeight, const dxb200_image* dst);
 
 /* DirectX::Resize (DirectXTexResize.cpp:854-935 single image, :942-1120 arrays; custom filters ResizePointFilter /
  * ResizeBoxFilter / ResizeLinearFilter / ResizeCubicFilter / ResizeTriangleFilter :255-798, selection :805-837).

@@ -3,6 +3,7 @@
 // DirectXTexB200.h and linked to libdxtex_b200.so.  Used by tests/test_gpu_cpp_api.py.
 //   texconv_mini <op> <in.raw> <out.raw> <width> <height> <srcfmt> <dstfmt|filter> [flags] [items]
 #include "DirectXTexB200.h"
+#include "../../include/dxtex_b200.h"      // dxb200_init_devices: the one call a multi-GPU caller adds
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -42,10 +43,21 @@ int main(int argc, char** argv)
     for (size_t i = 0; i < items; ++i) imgs[i] = Image{ w, h, sf, rowPitch, slicePitch, in.data() + i * slicePitch };
     TexMetadata md{}; md.width = w; md.height = h; md.depth = 1; md.arraySize = items; md.mipLevels = 1; md.format = sf; md.dimension = TEX_DIMENSION_TEXTURE2D;
 
+    // TEXCONV_MINI_DEVICES=0,1,2,...: shard array calls / large images over these GPUs (dxb200_init_devices)
+    if (const char* env = getenv("TEXCONV_MINI_DEVICES"))
+    {
+        std::vector<int> devs;
+        for (const char* c = env; *c;) { devs.push_back(atoi(c)); while (*c && *c != ',') ++c; if (*c == ',') ++c; }
+        const HRESULT hi = dxb200_init_devices(int(devs.size()), devs.data());
+        int got[16]; const int n = dxb200_initialized_devices(got, 16);
+        printf("devices=%d\n", n);
+        if (FAILED(hi)) { printf("hr=0x%08X init_devices\n", unsigned(hi)); return 1; }
+    }
     ScratchImage out;
     HRESULT hr = E_FAIL;
-    size_t calls = 0;
-    auto cb = [&](size_t, size_t) { ++calls; return true; };
+    size_t calls = 0, last = 0; bool monotone = true;
+    const size_t abortAt = getenv("TEXCONV_MINI_ABORT_AT") ? strtoull(getenv("TEXCONV_MINI_ABORT_AT"), nullptr, 10) : 0;
+    auto cb = [&](size_t done, size_t total) { ++calls; monotone = monotone && done >= last && done <= total; last = done; return !(abortAt && calls >= abortAt); };
     if (op == "compress")
         hr = (items == 1) ? Compress(imgs[0], DXGI_FORMAT(arg), TEX_COMPRESS_FLAGS(flags), TEX_THRESHOLD_DEFAULT, out)
                           : Compress(imgs.data(), items, md, DXGI_FORMAT(arg), TEX_COMPRESS_FLAGS(flags), TEX_THRESHOLD_DEFAULT, out);
@@ -53,7 +65,8 @@ int main(int argc, char** argv)
     {
         CompressOptions o{ TEX_COMPRESS_FLAGS(flags), TEX_THRESHOLD_DEFAULT, TEX_ALPHA_WEIGHT_DEFAULT };
         hr = CompressEx(imgs[0], DXGI_FORMAT(arg), o, out, cb);
-        if (SUCCEEDED(hr) && calls != 2) hr = E_FAIL;
+        printf("callbacks=%zu last=%zu\n", calls, last);
+        if (SUCCEEDED(hr) && (calls < 2 || !monotone || last != h)) hr = E_FAIL;
     }
     else if (op == "convert")
         hr = (items == 1) ? Convert(imgs[0], DXGI_FORMAT(arg), TEX_FILTER_FLAGS(flags), TEX_THRESHOLD_DEFAULT, out)

@@ -408,3 +408,57 @@ def test_compress_decompress_round_trip_full_size():
     back = capi.decompress(blocks, 4096, 4096, 98, 28).reshape(4096, 4096, 4).astype(np.float32)
     mse = float(((back - oracle_lib.bc7_ldr(img)) ** 2).mean())
     assert oracle_lib.psnr(mse) > 30.0
+
+
+def test_mipmaps_compress_equals_two_calls_and_reference(oracle):
+    """dxb200_mipmaps_compress (the chain stays in HBM) == dxb200_generate_mipmaps + dxb200_compress == the reference, bit for bit
+    (BASELINE configs[3] shape: RGBA8 -> default-filter chain -> BC3), including a non-power-of-two size (LINEAR default)."""
+    rng = np.random.default_rng(41)
+    for (w, h, n) in [(256, 256, 5), (96, 40, 3)]:
+        srcs = [oracle_lib.random_image(28, w, h, rng) for _ in range(n)]
+        outs = capi.mipmaps_compress(srcs, w, h, 28, 77)
+        for src, got in zip(srcs, outs):
+            chain, layout = capi.generate_mipmaps(src, w, h, 28, 0)
+            hr, rchain = oracle.generate_mipmaps(src, w, h, 28, 0)
+            assert hr == 0 and np.array_equal(chain, rchain)
+            want = np.concatenate([oracle.compress(rchain[off:off + sl], lw, lh, 28, 77)[1] for (off, lw, lh, row, sl) in layout])
+            assert np.array_equal(got, want), (w, h)
+
+
+def test_concurrent_host_calls_from_threads(oracle):
+    """entry points are callable concurrently: each host-pointer call takes its own staging lane (streams + buffers)"""
+    import threading
+    rng = np.random.default_rng(43)
+    srcs = [oracle_lib.random_image(28, 512, 256, rng) for _ in range(6)]
+    res = [None] * len(srcs)
+
+    def work(i):
+        res[i] = capi.compress(srcs[i], 512, 256, 28, 77 if i % 2 else 71)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(srcs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for i, s_ in enumerate(srcs):
+        hr, want = oracle.compress(s_, 512, 256, 28, 77 if i % 2 else 71)
+        assert hr == 0 and np.array_equal(res[i], want), i
+
+
+def test_multi_device_sharding_inside_the_library(oracle):
+    """dxb200_init_devices: array calls and mip chains are sharded over the GPUs inside one process; results unchanged"""
+    n = capi.lib.dxb200_device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    capi.init_devices(list(range(n)))
+    rng = np.random.default_rng(47)
+    srcs = [oracle_lib.random_image(28, 128, 64, rng) for _ in range(2 * n + 1)]
+    outs = capi.compress_array(srcs, 128, 64, 28, 77)
+    for s_, o in zip(srcs, outs):
+        hr, want = oracle.compress(s_, 128, 64, 28, 77)
+        assert hr == 0 and np.array_equal(o, want)
+    outs = capi.mipmaps_compress(srcs, 128, 64, 28, 71)
+    for s_, o in zip(srcs, outs):
+        hr, rchain = oracle.generate_mipmaps(s_, 128, 64, 28, 0)
+        layout, _ = F.mip_chain_layout(28, 128, 64, 0)
+        want = np.concatenate([oracle.compress(rchain[off:off + sl], lw, lh, 28, 71)[1] for (off, lw, lh, row, sl) in layout])
+        assert hr == 0 and np.array_equal(o, want)
