@@ -244,7 +244,7 @@ class C3:
     small_sample = {"side": 64}
 
     def __init__(self, args, world):
-        self.B = args.batch or 8
+        self.B = args.batch or 32
         self.world = world
 
     def workload(self):
@@ -506,7 +506,7 @@ class C5:
     small_sample = {"side": 1024}
 
     def __init__(self, args, world):
-        self.B = args.batch or 4
+        self.B = args.batch or 48
         self.world = world
 
     def workload(self):

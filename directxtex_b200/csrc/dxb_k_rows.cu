@@ -382,6 +382,120 @@ __global__ void __launch_bounds__(256) k_mip_tile(const dxb_mip_job* __restrict_
     dxb_store_linear(FMT, j.dst, j.dstPitch, x, y, v, LF);
 }
 
+
+// ------------------------------------------------------------------------------------------------ separable LINEAR / CUBIC
+// One CTA (8 warps) = a 32 x 16 tile of destination pixels.  The reference filters every source row horizontally and then
+// combines 2 (LINEAR) or 4 (CUBIC) of those rows vertically (DirectXTexMipmaps.cpp:1087-1197, 1204-1388); k_mip_tile redoes the
+// horizontal pass for every destination pixel and decodes ~10 source pixels per output.  Here
+//   stage A  a warp takes one source row of the tile at a time: its lanes decode the row's pixels ONCE into the warp's
+//            shared row buffer (load + format decode + sRGB linearisation),
+//   stage B  lane x filters that row horizontally for destination column x (same operands, same operation order as
+//            dxb_mip_linear / dxb_mip_cubic) into the shared H[row][x],
+//   stage C  after one barrier every thread combines the H rows of its two destination pixels vertically and stores them.
+// Per destination pixel of a 2:1 level that is 4.4 pixel decodes, 2.1 horizontal and 1 vertical filter evaluations instead
+// of 10 / 2.5 / 1.  Source coordinates are kept UNBOUNDED inside the tile (consecutive slots of the row buffer / of H) and
+// bounded (clamp / wrap / mirror, filters.h:64-104, 123-207) only when the pixel is fetched, so every addressing mode of
+// the reference takes the same path.  Requires source extent <= 3 x destination extent (every level of a mip chain).
+#define DXB_SEP_TW 32
+#define DXB_SEP_TH 16
+#define DXB_SEP_MAXC (DXB_SEP_TW * 3 + 4)
+#define DXB_SEP_MAXR (DXB_SEP_TH * 3 + 4)
+
+// unbounded tap base and weight of destination coordinate u: LINEAR taps base, base + 1 (weights w, 1 - w);
+// CUBIC taps base - 1 .. base + 2 (fraction w)
+template <uint32_t MODE>
+__device__ __forceinline__ void dxb_sep_entry(uint32_t source, uint32_t dest, uint32_t u, int32_t* base, float* w)
+{
+    const float scale = (float)source / (float)dest;
+    const float t = ((float)u + 0.5f) * scale;
+    if (MODE == DXB_FILTER_LINEAR)
+    {
+        const float srcB = t + 0.5f;
+        const int64_t isrcB = (int64_t)srcB;
+        const float wsum = 1.0f + (float)isrcB;
+        *w = wsum - srcB; *base = (int32_t)(isrcB - 1);
+    }
+    else
+    {
+        const float srcB = t - 0.5f;
+        const int64_t isrcB = (int64_t)srcB;              // always inside [0, source - 1]: dxb_cubic_entry's bounduvw is the identity on it
+        *w = srcB - (float)isrcB; *base = (int32_t)isrcB;
+    }
+}
+template <uint32_t MODE>
+__device__ __forceinline__ uint32_t dxb_sep_bound(int32_t i, uint32_t source, bool wrap, bool mirror)
+{
+    if (MODE == DXB_FILTER_LINEAR)
+    {
+        if (i < 0) return wrap ? source - 1u : 0u;                               // CreateLinearFilter (filters.h:86-97)
+        if ((uint32_t)i >= source) return wrap ? 0u : source - 1u;
+        return (uint32_t)i;
+    }
+    return (uint32_t)dxb_bounduvw((int64_t)i, (int64_t)source - 1, wrap, mirror);
+}
+
+template <uint32_t FMT, uint32_t MODE, bool SRGB>
+__global__ void __launch_bounds__(256) k_mip_sep(const dxb_mip_job* __restrict__ jobs, dxb_mip_job single, dxb_mip_params P)
+{
+    constexpr uint32_t LF = DXB_LF(SRGB);
+    constexpr int TAPS = (MODE == DXB_FILTER_CUBIC) ? 4 : 2, LEAD = (MODE == DXB_FILTER_CUBIC) ? 1 : 0;
+    const dxb_mip_job& j = (jobs == nullptr) ? single : jobs[blockIdx.z];
+    __shared__ float4 H[DXB_SEP_MAXR][DXB_SEP_TW];
+    __shared__ float4 rowbuf[8][DXB_SEP_MAXC];
+    __shared__ int32_t colBase[DXB_SEP_TW], rowBase[DXB_SEP_TH];
+    __shared__ float colW[DXB_SEP_TW], rowW[DXB_SEP_TH];
+    const uint32_t tid = threadIdx.y * 32u + threadIdx.x, warp = threadIdx.y, lane = threadIdx.x;
+    const uint32_t ox = blockIdx.x * DXB_SEP_TW, oy = blockIdx.y * DXB_SEP_TH;
+    const uint32_t tw = min((uint32_t)DXB_SEP_TW, j.dw - ox), th = min((uint32_t)DXB_SEP_TH, j.dh - oy);
+    if (tid < DXB_SEP_TW) { int32_t b; float w; dxb_sep_entry<MODE>(j.sw, j.dw, ox + min(tid, tw - 1u), &b, &w); colBase[tid] = b; colW[tid] = w; }
+    else if (tid < DXB_SEP_TW + DXB_SEP_TH) { const uint32_t r = tid - DXB_SEP_TW; int32_t b; float w; dxb_sep_entry<MODE>(j.sh, j.dh, oy + min(r, th - 1u), &b, &w); rowBase[r] = b; rowW[r] = w; }
+    __syncthreads();
+    const bool wrapU = (P.filter & DXB_FILTER_WRAP_U) != 0, mirU = (P.filter & DXB_FILTER_MIRROR_U) != 0;
+    const bool wrapV = (P.filter & DXB_FILTER_WRAP_V) != 0, mirV = (P.filter & DXB_FILTER_MIRROR_V) != 0;
+    const int32_t c0 = colBase[0] - LEAD, ncols = colBase[tw - 1u] + (TAPS - 1 - LEAD) - c0 + 1;
+    const int32_t r0 = rowBase[0] - LEAD, nrows = rowBase[th - 1u] + (TAPS - 1 - LEAD) - r0 + 1;
+    const int32_t myc = colBase[lane] - LEAD - c0;
+    const float myw = colW[lane];
+    for (int32_t r = (int32_t)warp; r < nrows; r += 8)
+    {
+        const uint32_t sy = dxb_sep_bound<MODE>(r0 + r, j.sh, wrapV, mirV);
+        for (int32_t s = (int32_t)lane; s < ncols; s += 32)
+        {
+            const dxb_px v = dxb_load_linear(FMT, j.src, j.srcPitch, dxb_sep_bound<MODE>(c0 + s, j.sw, wrapU, mirU), sy, LF);
+            rowbuf[warp][s] = make_float4(v.x, v.y, v.z, v.w);
+        }
+        __syncwarp();
+        if (lane < tw)
+        {
+            dxb_px q[TAPS];
+            #pragma unroll
+            for (int k = 0; k < TAPS; ++k) { const float4 f = rowbuf[warp][myc + k]; q[k] = dxb_make_px(f.x, f.y, f.z, f.w); }
+            dxb_px h;
+            if (MODE == DXB_FILTER_CUBIC) h = dxb_cubic4(myw, q[0], q[1], q[2], q[3]);
+            else h = dxb_px_add(dxb_px_scale(q[0], myw), dxb_px_scale(q[1], 1.0f - myw));
+            H[r][lane] = make_float4(h.x, h.y, h.z, h.w);
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (lane >= tw) return;
+    #pragma unroll
+    for (uint32_t k = 0; k < DXB_SEP_TH / 8; ++k)
+    {
+        const uint32_t y = warp + 8u * k;
+        if (y >= th) break;
+        const int32_t rr = rowBase[y] - LEAD - r0;
+        const float wy = rowW[y];
+        dxb_px c[TAPS];
+        #pragma unroll
+        for (int t = 0; t < TAPS; ++t) { const float4 f = H[rr + t][lane]; c[t] = dxb_make_px(f.x, f.y, f.z, f.w); }
+        dxb_px v;
+        if (MODE == DXB_FILTER_CUBIC) v = dxb_cubic4(wy, c[0], c[1], c[2], c[3]);
+        else v = dxb_px_add(dxb_px_scale(c[0], wy), dxb_px_scale(c[1], 1.0f - wy));
+        dxb_store_linear(FMT, j.dst, j.dstPitch, ox + lane, oy + y, v, LF);
+    }
+}
+
 // Tail of the chain: one CTA per item computes levels [first, first+count) back to back (each level reads the
 // previous one from global memory after a block barrier), replacing `count` tiny launches by one.
 // jobs is laid out [level][item]: jobs[l * items + item].
@@ -427,6 +541,21 @@ void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs,
         (P.mode == DXB_FILTER_BOX || P.mode == DXB_FILTER_LINEAR || P.mode == DXB_FILTER_CUBIC))
     {
         const dim3 blk(32, 8, 1);
+        // LINEAR / CUBIC of a chain level (source <= 3 x destination per axis): separable shared-memory kernel
+        if ((P.mode == DXB_FILTER_LINEAR || P.mode == DXB_FILTER_CUBIC) && hostJobs[0].sw <= 3u * hostJobs[0].dw && hostJobs[0].sh <= 3u * hostJobs[0].dh)
+        {
+            const dim3 gs((hostJobs[0].dw + DXB_SEP_TW - 1) / DXB_SEP_TW, (hostJobs[0].dh + DXB_SEP_TH - 1) / DXB_SEP_TH, P.njobs);
+            if (gs.y <= 65535u)
+            {
+#define DXB_X(FMT, MODE) if (P.format == FMT && P.mode == MODE) { \
+                    if (srgb) k_mip_sep<FMT, MODE, true><<<gs, blk, 0, stream>>>(jobs, hostJobs[0], P); \
+                    else k_mip_sep<FMT, MODE, false><<<gs, blk, 0, stream>>>(jobs, hostJobs[0], P); \
+                    return; }
+                DXB_MIP_FORMATS(DXB_X, DXB_FILTER_LINEAR)
+                DXB_MIP_FORMATS(DXB_X, DXB_FILTER_CUBIC)
+#undef DXB_X
+            }
+        }
         const uint32_t rowsPerCta = (P.mode == DXB_FILTER_CUBIC) ? 8u * DXB_CUBIC_KY : 8u;
         const dim3 g((hostJobs[0].dw + 31) / 32, (hostJobs[0].dh + rowsPerCta - 1) / rowsPerCta, P.njobs);
         if (g.y <= 65535u)
