@@ -456,14 +456,23 @@ __global__ void __launch_bounds__(256) k_mip_sep(const dxb_mip_job* __restrict__
     const int32_t r0 = rowBase[0] - LEAD, nrows = rowBase[th - 1u] + (TAPS - 1 - LEAD) - r0 + 1;
     const int32_t myc = colBase[lane] - LEAD - c0;
     const float myw = colW[lane];
+    // the bounded source column of every row-buffer slot this lane fills is the same for all rows: computed once
+    constexpr int SPL = (DXB_SEP_MAXC + 31) / 32;
+    uint32_t mycol[SPL];
+    #pragma unroll
+    for (int k = 0; k < SPL; ++k) mycol[k] = dxb_sep_bound<MODE>(c0 + (int32_t)lane + 32 * k, j.sw, wrapU, mirU);
     for (int32_t r = (int32_t)warp; r < nrows; r += 8)
     {
         const uint32_t sy = dxb_sep_bound<MODE>(r0 + r, j.sh, wrapV, mirV);
-        for (int32_t s = (int32_t)lane; s < ncols; s += 32)
-        {
-            const dxb_px v = dxb_load_linear(FMT, j.src, j.srcPitch, dxb_sep_bound<MODE>(c0 + s, j.sw, wrapU, mirU), sy, LF);
-            rowbuf[warp][s] = make_float4(v.x, v.y, v.z, v.w);
-        }
+        const uint8_t* srow = j.src + (size_t)sy * j.srcPitch;
+        #pragma unroll
+        for (int k = 0; k < SPL; ++k)
+            if ((int32_t)lane + 32 * k < ncols)
+            {
+                dxb_px v = dxb_load_pixel(FMT, srow, mycol[k]);
+                if (LF & DXB_FILTER_SRGB_IN) v = dxb_srgb_to_linear(v);
+                rowbuf[warp][lane + 32 * k] = make_float4(v.x, v.y, v.z, v.w);
+            }
         __syncwarp();
         if (lane < tw)
         {
@@ -542,7 +551,8 @@ void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs,
     {
         const dim3 blk(32, 8, 1);
         // LINEAR / CUBIC of a chain level (source <= 3 x destination per axis): separable shared-memory kernel
-        if ((P.mode == DXB_FILTER_LINEAR || P.mode == DXB_FILTER_CUBIC) && hostJobs[0].sw <= 3u * hostJobs[0].dw && hostJobs[0].sh <= 3u * hostJobs[0].dh)
+        // (LINEAR at 2:1 has no tap shared between neighbouring outputs: the plain tile kernel is faster there, 0.24 vs 0.43 ms per 64 x 1024^2 chain)
+        if (P.mode == DXB_FILTER_CUBIC && hostJobs[0].sw <= 3u * hostJobs[0].dw && hostJobs[0].sh <= 3u * hostJobs[0].dh)
         {
             const dim3 gs((hostJobs[0].dw + DXB_SEP_TW - 1) / DXB_SEP_TW, (hostJobs[0].dh + DXB_SEP_TH - 1) / DXB_SEP_TH, P.njobs);
             if (gs.y <= 65535u)
@@ -551,7 +561,6 @@ void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs,
                     if (srgb) k_mip_sep<FMT, MODE, true><<<gs, blk, 0, stream>>>(jobs, hostJobs[0], P); \
                     else k_mip_sep<FMT, MODE, false><<<gs, blk, 0, stream>>>(jobs, hostJobs[0], P); \
                     return; }
-                DXB_MIP_FORMATS(DXB_X, DXB_FILTER_LINEAR)
                 DXB_MIP_FORMATS(DXB_X, DXB_FILTER_CUBIC)
 #undef DXB_X
             }

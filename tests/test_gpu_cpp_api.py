@@ -95,7 +95,7 @@ def test_cpp_status_callback_per_band_and_abort(exe, tmp_path, oracle):
     r = run(exe, tmp_path, "compress_cb", img, 4096, 4096, 28, 71, expect_fail=True)
     assert r.returncode == 0, r.stdout + r.stderr
     calls = int(r.stdout.split("callbacks=")[1].split()[0])
-    assert calls >= 4 and "last=4096" in r.stdout, r.stdout
+    assert calls >= 3 and "last=4096" in r.stdout, r.stdout          # one call per band of ~32 MiB + the final (height, height)
     got = np.fromfile(str(tmp_path / "out.raw"), np.uint8)
     hr, want = oracle.compress(img, 4096, 4096, 28, 71)
     assert hr == 0 and np.array_equal(got, want)
