@@ -536,7 +536,7 @@ namespace {
     }
 }
 
-HRESULT GetMetadataFromDDSMemory(const void* pSource, size_t size, DDS_FLAGS flags, TexMetadata& metadata) noexcept
+HRESULT GetMetadataFromDDSMemory(const uint8_t* pSource, size_t size, DDS_FLAGS flags, TexMetadata& metadata) noexcept
 {
     if (!pSource || !size) return E_INVALIDARG;
     dxb200_metadata m;
@@ -550,7 +550,7 @@ HRESULT GetMetadataFromDDSFile(const char* szFile, DDS_FLAGS flags, TexMetadata&
     const HRESULT hr = read_file(szFile, data);
     return FAILED(hr) ? hr : GetMetadataFromDDSMemory(data.data(), data.size(), flags, metadata);
 }
-HRESULT LoadFromDDSMemory(const void* pSource, size_t size, DDS_FLAGS flags, TexMetadata* metadata, ScratchImage& image) noexcept
+HRESULT LoadFromDDSMemory(const uint8_t* pSource, size_t size, DDS_FLAGS flags, TexMetadata* metadata, ScratchImage& image) noexcept
 {
     if (!pSource || !size) return E_INVALIDARG;
     image.Release();

@@ -90,6 +90,7 @@ namespace DirectX
         TEX_FILTER_POINT = 0x100000, TEX_FILTER_LINEAR = 0x200000, TEX_FILTER_CUBIC = 0x300000, TEX_FILTER_BOX = 0x400000,
         TEX_FILTER_FANT = 0x400000, TEX_FILTER_TRIANGLE = 0x500000,
         TEX_FILTER_SRGB_IN = 0x1000000, TEX_FILTER_SRGB_OUT = 0x2000000, TEX_FILTER_SRGB = 0x3000000,
+        TEX_FILTER_FORCE_NON_WIC = 0x10000000, TEX_FILTER_FORCE_WIC = 0x20000000,      // accepted and ignored: there is no WIC path here
     };
     // DirectXTex.h:864-879
     enum TEX_PMALPHA_FLAGS : uint32_t
@@ -155,9 +156,10 @@ namespace DirectX
     // ---- DDS container (DirectXTex.h:232-279 DDS_FLAGS, :425-435 Blob, :518-560 the DDS I/O functions); host-side only
     enum DDS_FLAGS : uint32_t
     {
-        DDS_FLAGS_NONE = 0, DDS_FLAGS_IGNORE_MIPS = 0x100,
+        DDS_FLAGS_NONE = 0, DDS_FLAGS_LEGACY_DWORD = 0x1, DDS_FLAGS_NO_LEGACY_EXPANSION = 0x2, DDS_FLAGS_NO_R10B10G10A2_FIXUP = 0x4, DDS_FLAGS_FORCE_RGB = 0x8,
+        DDS_FLAGS_NO_16BPP = 0x10, DDS_FLAGS_EXPAND_LUMINANCE = 0x20, DDS_FLAGS_BAD_DXTN_TAILS = 0x40, DDS_FLAGS_PERMISSIVE = 0x80, DDS_FLAGS_IGNORE_MIPS = 0x100,
         DDS_FLAGS_FORCE_DX10_EXT = 0x10000, DDS_FLAGS_FORCE_DX10_EXT_MISC2 = 0x20000, DDS_FLAGS_FORCE_DX9_LEGACY = 0x40000,
-        DDS_FLAGS_FORCE_DXT5_RXGB = 0x80000, DDS_FLAGS_ALLOW_LARGE_FILES = 0x1000000,
+        DDS_FLAGS_FORCE_DXT5_RXGB = 0x80000, DDS_FLAGS_FORCE_24BPP_RGB = 0x100000, DDS_FLAGS_ALLOW_LARGE_FILES = 0x1000000,
     };
     class DXTEXB200_API Blob
     {
@@ -176,9 +178,9 @@ namespace DirectX
     private:
         uint8_t* m_buffer; size_t m_size;
     };
-    DXTEXB200_API HRESULT GetMetadataFromDDSMemory(const void* pSource, size_t size, DDS_FLAGS flags, TexMetadata& metadata) noexcept;
+    DXTEXB200_API HRESULT GetMetadataFromDDSMemory(const uint8_t* pSource, size_t size, DDS_FLAGS flags, TexMetadata& metadata) noexcept;
     DXTEXB200_API HRESULT GetMetadataFromDDSFile(const char* szFile, DDS_FLAGS flags, TexMetadata& metadata) noexcept;
-    DXTEXB200_API HRESULT LoadFromDDSMemory(const void* pSource, size_t size, DDS_FLAGS flags, TexMetadata* metadata, ScratchImage& image) noexcept;
+    DXTEXB200_API HRESULT LoadFromDDSMemory(const uint8_t* pSource, size_t size, DDS_FLAGS flags, TexMetadata* metadata, ScratchImage& image) noexcept;
     DXTEXB200_API HRESULT LoadFromDDSFile(const char* szFile, DDS_FLAGS flags, TexMetadata* metadata, ScratchImage& image) noexcept;
     DXTEXB200_API HRESULT SaveToDDSMemory(const Image& image, DDS_FLAGS flags, Blob& blob) noexcept;
     DXTEXB200_API HRESULT SaveToDDSMemory(const Image* images, size_t nimages, const TexMetadata& metadata, DDS_FLAGS flags, Blob& blob) noexcept;
