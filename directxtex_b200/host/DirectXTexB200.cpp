@@ -107,6 +107,7 @@ HRESULT ScratchImage::Initialize(const TexMetadata& mdata, CP_FLAGS) noexcept
 {
     if (mdata.dimension != TEX_DIMENSION_TEXTURE2D && mdata.dimension != TEX_DIMENSION_TEXTURE1D) return HRESULT_E_NOT_SUPPORTED;   // no volume maps on this path
     if (!mdata.width || !mdata.height || mdata.depth != 1 || !mdata.arraySize) return E_INVALIDARG;
+    if ((mdata.miscFlags & 0x4u) && (mdata.arraySize % 6) != 0) return E_INVALIDARG;      // TEX_MISC_TEXTURECUBE (DirectXTexImage.cpp:324-328)
     size_t mipLevels = mdata.mipLevels;
     if (!CalculateMipLevels(mdata.width, mdata.height, mipLevels)) return E_INVALIDARG;
     Release();
@@ -350,24 +351,34 @@ HRESULT GenerateMipMaps(const Image* srcImages, size_t nimages, const TexMetadat
     if (metadata.IsVolumemap() || IsCompressed(metadata.format)) return HRESULT_E_NOT_SUPPORTED;
     if (!CalculateMipLevels(metadata.width, metadata.height, levels)) return E_INVALIDARG;
     if (levels <= 1) return E_INVALIDARG;
-    if (nimages != metadata.arraySize) return E_FAIL;          // this path takes the base image of every array item
     if (!implemented_pixel_format(metadata.format)) return HRESULT_E_NOT_SUPPORTED;
+    // the base image of every item through ComputeIndex(0, item, 0) (DirectXTexMipmaps.cpp:3040-3059): the caller may pass a
+    // ScratchImage that still carries its old mip levels (nimages = arraySize * mipLevels) or just the base images
+    std::vector<const Image*> base(metadata.arraySize);
+    for (size_t item = 0; item < metadata.arraySize; ++item)
+    {
+        const size_t index = metadata.ComputeIndex(0, item, 0);
+        if (index >= nimages) return E_FAIL;
+        const Image& src = srcImages[index];
+        if (!src.pixels) return E_POINTER;
+        if (src.format != metadata.format || src.width != metadata.width || src.height != metadata.height) return E_FAIL;
+        base[item] = &src;
+    }
     TexMetadata m2 = metadata; m2.mipLevels = levels;
     HRESULT hr = mipChain.Initialize(m2);
     if (FAILED(hr)) return hr;
     // copy the base image of each item to the top of its chain (Setup2DMips)
-    for (size_t item = 0; item < nimages; ++item)
+    for (size_t item = 0; item < metadata.arraySize; ++item)
     {
-        const Image& src = srcImages[item];
+        const Image& src = *base[item];
         const Image* dest = mipChain.GetImage(0, item, 0);
-        if (!dest || !src.pixels) { mipChain.Release(); return E_POINTER; }
-        if (src.format != dest->format || src.width != dest->width || src.height != dest->height) { mipChain.Release(); return E_FAIL; }
+        if (!dest) { mipChain.Release(); return E_POINTER; }
         const size_t n = dest->rowPitch < src.rowPitch ? dest->rowPitch : src.rowPitch;
         for (size_t y = 0; y < src.height; ++y) std::memcpy(dest->pixels + y * dest->rowPitch, src.pixels + y * src.rowPitch, n);
     }
     std::vector<dxb200_image> chain(mipChain.GetImageCount());
     for (size_t i = 0; i < chain.size(); ++i) chain[i] = to_c(mipChain.GetImages()[i]);
-    hr = dxb200_generate_mipmaps(chain.data(), nimages, levels, static_cast<uint32_t>(filter));
+    hr = dxb200_generate_mipmaps(chain.data(), metadata.arraySize, levels, static_cast<uint32_t>(filter));
     if (FAILED(hr)) mipChain.Release();
     return hr;
 }

@@ -188,16 +188,26 @@ int32_t dxb200_dds_save_memory(const dxb200_image* images, size_t nimages, const
     size_t hdr = 0;
     int32_t hr = dxb200_dds_encode_header(md, flags, nullptr, 0, &hdr);
     if (hr != DXB_S_OK) return hr;
-    if (nimages < md->arraySize * md->mipLevels) return DXB_E_FAIL;
+    // exactly the images of the texture, item-major / mip-minor (TexMetadata::ComputeIndex order, :2477-2560); images beyond
+    // arraySize * mipLevels are not part of the file
+    const size_t count = md->arraySize * md->mipLevels;
+    if (!count || nimages < count) return DXB_E_FAIL;
     size_t total = hdr;
-    for (size_t i = 0; i < nimages; ++i)
+    for (size_t item = 0, i = 0; item < md->arraySize; ++item)
     {
-        if (!images[i].pixels) return DXB_E_POINTER;
-        if (images[i].format != md->format) return DXB_E_FAIL;
-        size_t row, slice;
-        hr = pitch(md->format, images[i].width, images[i].height, &row, &slice);
-        if (hr != DXB_S_OK) return hr;
-        total += slice;
+        size_t w = md->width, hgt = md->height;
+        for (size_t level = 0; level < md->mipLevels; ++level, ++i)
+        {
+            if (!images[i].pixels) return DXB_E_POINTER;
+            if (images[i].format != md->format) return DXB_E_FAIL;
+            if (images[i].width != w || images[i].height != hgt) return DXB_E_FAIL;
+            size_t row, slice;
+            hr = pitch(md->format, w, hgt, &row, &slice);
+            if (hr != DXB_S_OK) return hr;
+            total += slice;
+            if (w > 1) w >>= 1;
+            if (hgt > 1) hgt >>= 1;
+        }
     }
     *required = total;
     if (!dst) return DXB_S_OK;
@@ -205,11 +215,11 @@ int32_t dxb200_dds_save_memory(const dxb200_image* images, size_t nimages, const
     hr = dxb200_dds_encode_header(md, flags, dst, maxsize, &hdr);
     if (hr != DXB_S_OK) return hr;
     uint8_t* p = static_cast<uint8_t*>(dst) + hdr;
-    // item-major, mip-minor: exactly the order of a ScratchImage (:2477-2560)
-    for (size_t i = 0; i < md->arraySize * md->mipLevels; ++i)
+    for (size_t i = 0; i < count; ++i)
     {
         size_t row, slice;
-        pitch(md->format, images[i].width, images[i].height, &row, &slice);
+        hr = pitch(md->format, images[i].width, images[i].height, &row, &slice);
+        if (hr != DXB_S_OK) return hr;
         if (images[i].rowPitch == row) memcpy(p, images[i].pixels, slice);
         else
         {
@@ -231,7 +241,8 @@ int32_t dxb200_dds_get_metadata(const void* src, size_t size, uint32_t flags, dx
     uint32_t magic; memcpy(&magic, p, 4);
     if (magic != kMagic) return DXB_E_FAIL;
     Header h; memcpy(&h, p + 4, sizeof(h));
-    if (h.size != sizeof(Header) || h.ddspf.size != sizeof(PixelFormat)) return DXB_E_NOT_SUPPORTED;
+    // DecodeDDSHeader (:352-377): a zero ddspf.size is written by some tools and accepted by the reference
+    if (h.size != sizeof(Header) || (h.ddspf.size != 0 && h.ddspf.size != sizeof(PixelFormat))) return DXB_E_NOT_SUPPORTED;
     md->mipLevels = h.mipMapCount ? h.mipMapCount : 1;
     size_t offset = kMinHeader;
     if ((h.ddspf.flags & PF_FOURCC) && h.ddspf.fourCC == fourcc('D', 'X', '1', '0'))
@@ -258,12 +269,22 @@ int32_t dxb200_dds_get_metadata(const void* src, size_t size, uint32_t flags, dx
             md->arraySize = 6; md->miscFlags |= MISC_TEXTURECUBE;
         }
         md->width = h.width; md->height = h.height; md->depth = 1; md->dimension = 3;
+        // GetDXGIFormat (:149-230): FourCC entries compare the code; the others compare the flag class and only the masks that
+        // class defines (RGB(A): all four; luminance: R, plus A with DDPF_ALPHAPIXELS; alpha-only: A; bump: R, G).  The two
+        // flag bits nvidia texture tools add (DDPF_SRGB 0x40000000, DDPF_NORMAL 0x80000000) do not take part.
+        const uint32_t pfFlags = h.ddspf.flags & ~0xC0000000u;
         const Legacy* hit = nullptr;
         for (const Legacy& e : kLegacy)
         {
-            if ((h.ddspf.flags & PF_FOURCC) && (e.pf.flags & PF_FOURCC)) { if (h.ddspf.fourCC == e.pf.fourCC) { hit = &e; break; } }
-            else if (h.ddspf.flags == e.pf.flags && h.ddspf.bitCount == e.pf.bitCount &&
-                     h.ddspf.rMask == e.pf.rMask && h.ddspf.gMask == e.pf.gMask && h.ddspf.bMask == e.pf.bMask && h.ddspf.aMask == e.pf.aMask) { hit = &e; break; }
+            if ((pfFlags & PF_FOURCC) && (e.pf.flags & PF_FOURCC)) { if (h.ddspf.fourCC == e.pf.fourCC) { hit = &e; break; } continue; }
+            if ((pfFlags & PF_FOURCC) || (e.pf.flags & PF_FOURCC)) continue;
+            if (pfFlags != e.pf.flags || h.ddspf.bitCount != e.pf.bitCount) continue;
+            bool same;
+            if (pfFlags & 0x40u) same = h.ddspf.rMask == e.pf.rMask && h.ddspf.gMask == e.pf.gMask && h.ddspf.bMask == e.pf.bMask && ((pfFlags & 0x1u) == 0 || h.ddspf.aMask == e.pf.aMask);   // DDPF_RGB
+            else if (pfFlags & 0x20000u) same = h.ddspf.rMask == e.pf.rMask && ((pfFlags & 0x1u) == 0 || h.ddspf.aMask == e.pf.aMask);          // DDPF_LUMINANCE
+            else if (pfFlags & 0x2u) same = h.ddspf.aMask == e.pf.aMask;                                                                          // DDPF_ALPHA
+            else same = h.ddspf.rMask == e.pf.rMask && h.ddspf.gMask == e.pf.gMask && h.ddspf.bMask == e.pf.bMask && h.ddspf.aMask == e.pf.aMask;
+            if (same) { hit = &e; break; }
         }
         if (!hit) return DXB_E_NOT_SUPPORTED;
         md->format = hit->format;
@@ -293,6 +314,9 @@ int32_t dxb200_dds_load_memory(const void* src, size_t size, uint32_t flags, con
         size_t w = md.width, hgt = md.height;
         for (size_t level = 0; level < fileMips; ++level)
         {
+            // DDS_FLAGS_IGNORE_MIPS exists for files with broken or truncated mip tails: with a single item nothing after the
+            // requested levels is read or bounds-checked (:2046-2064); arrays still have to skip every item's tail
+            if (md.arraySize == 1 && level >= md.mipLevels) break;
             size_t row, slice;
             hr = pitch(md.format, w, hgt, &row, &slice);
             if (hr != DXB_S_OK) return hr;
