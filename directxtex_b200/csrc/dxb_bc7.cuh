@@ -685,10 +685,15 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
             // candidate error against the decoder's palette entry (e0 (64 - w) + e1 w + 32) >> 6 = round-half-up of D0 + sk d
             // (a multiple of 1/64, so adding 1/128 before the RNE never ties).  An unrounded model mis-ranks near-lossless
             // candidates: the rounding noise (1/12 per value) is half of the error of a smooth 8-bit gradient.
+#if defined(DXB_BC7_LASTERR)
+            if (last)
+#endif
+            {
             const float qx = dxb_rne(dxb_fma(dx, sk, D0[0] + (1.0f / 128.0f))), qy = dxb_rne(dxb_fma(dy, sk, D0[1] + (1.0f / 128.0f)));
             const float qz = dxb_rne(dxb_fma(dz, sk, D0[2] + (1.0f / 128.0f))), qw = dxb_rne(dxb_fma(dw, sk, D0[3] + (1.0f / 128.0f)));
             const float ex = X - qx, ey = Y - qy, ez = Z - qz, ew = Wv - qw;
             err = dxb_fma(f, dxb_fma(ex, ex, dxb_fma(ey, ey, dxb_fma(ez, ez, ew * ew))), err);
+            }
             if (!last)
             {
                 // refit sums: only sum f s, sum f s^2 and sum f s P are accumulated; the (1 - s) sums follow from the
@@ -705,13 +710,21 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
             la = (n - fs) - lb;                                    // sum f (1 - s)^2 = n - 2 sum f s + sum f s^2
             u0 = s[0] - v0; u1 = s[1] - v1; u2 = s[2] - v2; u3 = s[3] - v3;
         }
+#if defined(DXB_BC7_LASTERR)
+        const bool better = last;          // only the refitted endpoints are measured
+#else
         const bool better = live && (err < bestErr);
+#endif
         bestErr = better ? err : bestErr; bpb = better ? (p0 | (p1 << 1)) : bpb;
         bqa0 = better ? qa0 : bqa0; bqa1 = better ? qa1 : bqa1; bqb0 = better ? qb0 : bqb0; bqb1 = better ? qb1 : bqb1;
         if (last) break;
         // least-squares refit for the next round (skipped lanes keep their endpoints)
         const float det = dxb_fma(la, lc, -(lb * lb));
+#if defined(DXB_BC7_LASTERR)
+        live = live && (det > 1e-4f);
+#else
         live = live && (det > 1e-4f) && (bestErr > 0.0f);
+#endif
         const float id = live ? 1.0f / det : 0.0f;
         const float uu[4] = { u0, u1, u2, u3 }, vv[4] = { v0, v1, v2, v3 };
         for (int c = 0; c < 4; ++c)

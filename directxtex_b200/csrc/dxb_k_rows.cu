@@ -383,6 +383,18 @@ __global__ void __launch_bounds__(256) k_mip_tile(const dxb_mip_job* __restrict_
 }
 
 
+template <int N> __device__ __forceinline__ void dxb_copy_vec(uint8_t* dst, const uint8_t* src, bool streamLoad)
+{
+    constexpr int V = (N >= 16) ? 16 : N;
+    #pragma unroll
+    for (int k = 0; k < N; k += V)
+    {
+        typedef typename dxb_vec<V>::T T;
+        if (streamLoad) *reinterpret_cast<T*>(dst + k) = __ldcs(reinterpret_cast<const T*>(src + k));
+        else *reinterpret_cast<T*>(dst + k) = *reinterpret_cast<const T*>(src + k);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ separable LINEAR / CUBIC
 // One CTA (8 warps) = a 32 x 16 tile of destination pixels.  The reference filters every source row horizontally and then
 // combines 2 (LINEAR) or 4 (CUBIC) of those rows vertically (DirectXTexMipmaps.cpp:1087-1197, 1204-1388); k_mip_tile redoes the
@@ -461,18 +473,28 @@ __global__ void __launch_bounds__(256) k_mip_sep(const dxb_mip_job* __restrict__
     uint32_t mycol[SPL];
     #pragma unroll
     for (int k = 0; k < SPL; ++k) mycol[k] = dxb_sep_bound<MODE>(c0 + (int32_t)lane + 32 * k, j.sw, wrapU, mirU);
+    // software pipeline: the raw pixels of this warp's NEXT source row are in flight while the current row is decoded and filtered
+    constexpr int B = (int)dxb_bytes_per_pixel(FMT);
+    __align__(16) uint8_t raw[SPL][B];
+    auto fetch = [&](int32_t r)
+    {
+        const uint8_t* srow = j.src + (size_t)dxb_sep_bound<MODE>(r0 + r, j.sh, wrapV, mirV) * j.srcPitch;
+        #pragma unroll
+        for (int k = 0; k < SPL; ++k)
+            if ((int32_t)lane + 32 * k < ncols) dxb_copy_vec<B>(raw[k], srow + (size_t)mycol[k] * B, false);
+    };
+    if ((int32_t)warp < nrows) fetch((int32_t)warp);
     for (int32_t r = (int32_t)warp; r < nrows; r += 8)
     {
-        const uint32_t sy = dxb_sep_bound<MODE>(r0 + r, j.sh, wrapV, mirV);
-        const uint8_t* srow = j.src + (size_t)sy * j.srcPitch;
         #pragma unroll
         for (int k = 0; k < SPL; ++k)
             if ((int32_t)lane + 32 * k < ncols)
             {
-                dxb_px v = dxb_load_pixel(FMT, srow, mycol[k]);
+                dxb_px v = dxb_load_pixel(FMT, raw[k], 0);
                 if (LF & DXB_FILTER_SRGB_IN) v = dxb_srgb_to_linear(v);
                 rowbuf[warp][lane + 32 * k] = make_float4(v.x, v.y, v.z, v.w);
             }
+        if (r + 8 < nrows) fetch(r + 8);
         __syncwarp();
         if (lane < tw)
         {
@@ -552,7 +574,12 @@ void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs,
         const dim3 blk(32, 8, 1);
         // LINEAR / CUBIC of a chain level (source <= 3 x destination per axis): separable shared-memory kernel
         // (LINEAR at 2:1 has no tap shared between neighbouring outputs: the plain tile kernel is faster there, 0.24 vs 0.43 ms per 64 x 1024^2 chain)
-        if (P.mode == DXB_FILTER_CUBIC && hostJobs[0].sw <= 3u * hostJobs[0].dw && hostJobs[0].sh <= 3u * hostJobs[0].dh)
+        bool pixAligned = true;                     // k_mip_sep fetches whole pixels with one vector load each
+        {
+            const uint32_t bpp = dxb_bytes_per_pixel(P.format), va = bpp >= 16 ? 16 : bpp;
+            for (uint32_t i = 0; i < P.njobs; ++i) if (((uintptr_t)hostJobs[i].src % va) || (hostJobs[i].srcPitch % va)) pixAligned = false;
+        }
+        if (P.mode == DXB_FILTER_CUBIC && pixAligned && hostJobs[0].sw <= 3u * hostJobs[0].dw && hostJobs[0].sh <= 3u * hostJobs[0].dh)
         {
             const dim3 gs((hostJobs[0].dw + DXB_SEP_TW - 1) / DXB_SEP_TW, (hostJobs[0].dh + DXB_SEP_TH - 1) / DXB_SEP_TH, P.njobs);
             if (gs.y <= 65535u)
@@ -591,17 +618,6 @@ void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs,
 // so the result is bit-identical; the source is read once and the two intermediate levels are never re-read from HBM
 // (5.6 instead of 7.0 bytes moved per source texel-chain, one launch instead of three).
 // jobs: [level][item] records of the three levels; requires source width/height multiples of 8 and vector alignment.
-template <int N> __device__ __forceinline__ void dxb_copy_vec(uint8_t* dst, const uint8_t* src, bool streamLoad)
-{
-    constexpr int V = (N >= 16) ? 16 : N;
-    #pragma unroll
-    for (int k = 0; k < N; k += V)
-    {
-        typedef typename dxb_vec<V>::T T;
-        if (streamLoad) *reinterpret_cast<T*>(dst + k) = __ldcs(reinterpret_cast<const T*>(src + k));
-        else *reinterpret_cast<T*>(dst + k) = *reinterpret_cast<const T*>(src + k);
-    }
-}
 template <uint32_t FMT>
 __device__ __forceinline__ dxb_px dxb_box4(const uint8_t* r0, const uint8_t* r1, int k, uint32_t lflags)
 {
