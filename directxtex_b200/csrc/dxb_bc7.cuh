@@ -668,6 +668,13 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
         float err = 0.0f;
         float la = 0.0f, lb = 0.0f, lc = 0.0f;                     // sum (1-s)^2, s(1-s), s^2
         float u0 = 0, u1 = 0, u2 = 0, u3 = 0, v0 = 0, v1 = 0, v2 = 0, v3 = 0;     // sum (1-s) p, sum s p
+        // channel pairs (x, y) and (z, w) as packed fp32 (dxb_portable.h): same IEEE operations, half the issue slots
+        const dxb_f2 vm01 = dxb_mk2(vm[0], vm[1]), vm23 = dxb_mk2(vm[2], vm[3]);
+        const dxb_f2 nD01 = dxb_mk2(-D0[0], -D0[1]), nD23 = dxb_mk2(-D0[2], -D0[3]);
+        const dxb_f2 d01 = dxb_mk2(dx, dy), d23 = dxb_mk2(dz, dw);
+        const dxb_f2 Dc01 = dxb_mk2(D0[0] + (1.0f / 128.0f), D0[1] + (1.0f / 128.0f)), Dc23 = dxb_mk2(D0[2] + (1.0f / 128.0f), D0[3] + (1.0f / 128.0f));
+        const dxb_f2 MG = dxb_bc2(DXB_MAGIC), nMG = dxb_bc2(-DXB_MAGIC);
+        dxb_f2 V01 = dxb_bc2(0.0f), V23 = dxb_bc2(0.0f);
 #if DXB_ON_DEVICE
         #pragma unroll dxb_bc7_pixunroll
 #endif
@@ -675,9 +682,10 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
         {
             const float f = dxb_bit_as_float(mask, i);          // 1 if the pixel belongs to this lane's subset
             const dxb_px p = px[i];
-            const float X = p.x * vm[0], Y = p.y * vm[1], Z = p.z * vm[2], Wv = p.w * vm[3];
-            const float ax_ = X - D0[0], ay_ = Y - D0[1], az_ = Z - D0[2], aw_ = Wv - D0[3];
-            const float pr = dxb_fma(ax_, dx, dxb_fma(ay_, dy, dxb_fma(az_, dz, aw_ * dw)));
+            const dxb_f2 P01 = dxb_mul2(dxb_mk2(p.x, p.y), vm01), P23 = dxb_mul2(dxb_mk2(p.z, p.w), vm23);
+            const dxb_f2 A01 = dxb_add2(P01, nD01), A23 = dxb_add2(P23, nD23);
+            const dxb_f2 T = dxb_fma2(A23, d23, dxb_mul2(A01, d01));
+            const float pr = T.x + T.y;                           // (P - D0) . d
             const float tk = pr * idd;
             // index = nearest of the uniformly spaced positions (stage 4 assigns the winner's final indices exhaustively)
             const float kk = dxb_rne(fminf(fmaxf(tk, 0.0f), nmaxc));
@@ -685,24 +693,22 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
             // candidate error against the decoder's palette entry (e0 (64 - w) + e1 w + 32) >> 6 = round-half-up of D0 + sk d
             // (a multiple of 1/64, so adding 1/128 before the RNE never ties).  An unrounded model mis-ranks near-lossless
             // candidates: the rounding noise (1/12 per value) is half of the error of a smooth 8-bit gradient.
-#if defined(DXB_BC7_LASTERR)
-            if (last)
-#endif
-            {
-            const float qx = dxb_rne(dxb_fma(dx, sk, D0[0] + (1.0f / 128.0f))), qy = dxb_rne(dxb_fma(dy, sk, D0[1] + (1.0f / 128.0f)));
-            const float qz = dxb_rne(dxb_fma(dz, sk, D0[2] + (1.0f / 128.0f))), qw = dxb_rne(dxb_fma(dw, sk, D0[3] + (1.0f / 128.0f)));
-            const float ex = X - qx, ey = Y - qy, ez = Z - qz, ew = Wv - qw;
-            err = dxb_fma(f, dxb_fma(ex, ex, dxb_fma(ey, ey, dxb_fma(ez, ez, ew * ew))), err);
-            }
+            const dxb_f2 sk2 = dxb_bc2(sk);
+            const dxb_f2 q01 = dxb_add2(dxb_add2(dxb_fma2(d01, sk2, Dc01), MG), nMG), q23 = dxb_add2(dxb_add2(dxb_fma2(d23, sk2, Dc23), MG), nMG);
+            const dxb_f2 e01 = dxb_sub2(P01, q01), e23 = dxb_sub2(P23, q23);
+            const dxb_f2 sq = dxb_fma2(e23, e23, dxb_mul2(e01, e01));
+            err = dxb_fma(f, sq.x + sq.y, err);
             if (!last)
             {
                 // refit sums: only sum f s, sum f s^2 and sum f s P are accumulated; the (1 - s) sums follow from the
                 // subset's pixel count and channel sums (stage-1 moments) after the loop
                 const float skf = sk * f;
                 lb += skf; lc = dxb_fma(skf, sk, lc);
-                v0 = dxb_fma(skf, X, v0); v1 = dxb_fma(skf, Y, v1); v2 = dxb_fma(skf, Z, v2); v3 = dxb_fma(skf, Wv, v3);
+                const dxb_f2 skf2 = dxb_bc2(skf);
+                V01 = dxb_fma2(skf2, P01, V01); V23 = dxb_fma2(skf2, P23, V23);
             }
         }
+        v0 = V01.x; v1 = V01.y; v2 = V23.x; v3 = V23.y;
         if (!last)
         {
             const float fs = lb;                                   // sum f s
@@ -710,21 +716,13 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
             la = (n - fs) - lb;                                    // sum f (1 - s)^2 = n - 2 sum f s + sum f s^2
             u0 = s[0] - v0; u1 = s[1] - v1; u2 = s[2] - v2; u3 = s[3] - v3;
         }
-#if defined(DXB_BC7_LASTERR)
-        const bool better = last;          // only the refitted endpoints are measured
-#else
         const bool better = live && (err < bestErr);
-#endif
         bestErr = better ? err : bestErr; bpb = better ? (p0 | (p1 << 1)) : bpb;
         bqa0 = better ? qa0 : bqa0; bqa1 = better ? qa1 : bqa1; bqb0 = better ? qb0 : bqb0; bqb1 = better ? qb1 : bqb1;
         if (last) break;
         // least-squares refit for the next round (skipped lanes keep their endpoints)
         const float det = dxb_fma(la, lc, -(lb * lb));
-#if defined(DXB_BC7_LASTERR)
-        live = live && (det > 1e-4f);
-#else
         live = live && (det > 1e-4f) && (bestErr > 0.0f);
-#endif
         const float id = live ? 1.0f / det : 0.0f;
         const float uu[4] = { u0, u1, u2, u3 }, vv[4] = { v0, v1, v2, v3 };
         for (int c = 0; c < 4; ++c)

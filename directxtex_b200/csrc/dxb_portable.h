@@ -133,6 +133,25 @@ DXB_DEV float dxb_ssemin(float a, float b) { return (a < b) ? a : b; }
 // explicit fused multiply-add (identical on host and device by IEEE-754 definition)
 DXB_DEV float dxb_fma(float a, float b, float c) { return fmaf(a, b, c); }
 
+// ---- packed pairs of fp32 (sm_100a FFMA2 / FADD2 / FMUL2: two independent IEEE operations in one issue slot).
+// The BC7 encoder is issue-bound, and most of its arithmetic runs on 4-channel vectors = two pairs; each half is an
+// ordinary round-to-nearest fp32 operation, so the host emulator (two scalar operations) stays bit-identical.
+#if DXB_ON_DEVICE
+typedef float2 dxb_f2;
+DXB_DEV dxb_f2 dxb_mk2(float x, float y) { return make_float2(x, y); }
+DXB_DEV dxb_f2 dxb_fma2(dxb_f2 a, dxb_f2 b, dxb_f2 c) { return __ffma2_rn(a, b, c); }
+DXB_DEV dxb_f2 dxb_add2(dxb_f2 a, dxb_f2 b) { return __fadd2_rn(a, b); }
+DXB_DEV dxb_f2 dxb_mul2(dxb_f2 a, dxb_f2 b) { return __fmul2_rn(a, b); }
+#else
+struct dxb_f2 { float x, y; };
+DXB_DEV dxb_f2 dxb_mk2(float x, float y) { dxb_f2 r; r.x = x; r.y = y; return r; }
+DXB_DEV dxb_f2 dxb_fma2(dxb_f2 a, dxb_f2 b, dxb_f2 c) { return dxb_mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+DXB_DEV dxb_f2 dxb_add2(dxb_f2 a, dxb_f2 b) { return dxb_mk2(a.x + b.x, a.y + b.y); }
+DXB_DEV dxb_f2 dxb_mul2(dxb_f2 a, dxb_f2 b) { return dxb_mk2(a.x * b.x, a.y * b.y); }
+#endif
+DXB_DEV dxb_f2 dxb_sub2(dxb_f2 a, dxb_f2 b) { return dxb_add2(a, dxb_mk2(-b.x, -b.y)); }
+DXB_DEV dxb_f2 dxb_bc2(float v) { return dxb_mk2(v, v); }
+
 // ---- IEEE binary16 <-> binary32 (RNE, denormals kept, overflow -> Inf) ----
 DXB_DEV float dxb_half_to_float(uint16_t h)
 {
