@@ -347,45 +347,59 @@ DXB_DEV int32_t dxb_max3_s32(int32_t a, int32_t b, int32_t c)
 
 struct dxb_bc7_axis { uint32_t packed; float resid, inv_aa; };   // s8x4 axis, off-axis residual tr - a'Ca/|a|^2, 1/|a|^2
 
-// axis of one subset from its moments v[14] (n pixels): the covariance row with the largest diagonal (= one power-iteration
-// step from that unit vector; more steps do not change the ranking measurably), scaled by a power of two to integers of
-// magnitude <= 64.
-DXB_DEV dxb_bc7_axis dxb_bc7_subset_axis(uint32_t n, const float* v, bool opaque)
+// axes of BOTH subsets of a shape from their moments (V[k] = (subset 0, subset 1) as packed pairs; n0 / n1 pixels): per subset
+// the covariance row with the largest diagonal (= one power-iteration step from that unit vector; more steps do not change the
+// ranking measurably), scaled by a power of two to integers of magnitude <= 64.  The arithmetic of the two subsets runs as
+// packed fp32 pairs; the selects are per subset.
+DXB_DEV void dxb_bc7_subset_axes(uint32_t n0, uint32_t n1, const dxb_f2* V, bool opaque, dxb_bc7_axis* A0, dxb_bc7_axis* A1)
 {
-    const float inv = dxb_rcp16[n];
-    const float c00 = dxb_fma(-v[0] * inv, v[0], v[4]), c01 = dxb_fma(-v[0] * inv, v[1], v[5]), c02 = dxb_fma(-v[0] * inv, v[2], v[6]);
-    const float c11 = dxb_fma(-v[1] * inv, v[1], v[8]), c12 = dxb_fma(-v[1] * inv, v[2], v[9]), c22 = dxb_fma(-v[2] * inv, v[2], v[11]);
+    const dxb_f2 inv = dxb_mk2(dxb_rcp16[n0], dxb_rcp16[n1]);
+    const dxb_f2 m0 = dxb_mul2(dxb_mk2(-V[0].x, -V[0].y), inv), m1 = dxb_mul2(dxb_mk2(-V[1].x, -V[1].y), inv);
+    const dxb_f2 m2 = dxb_mul2(dxb_mk2(-V[2].x, -V[2].y), inv), m3 = dxb_mul2(dxb_mk2(-V[3].x, -V[3].y), inv);
+    const dxb_f2 c00 = dxb_fma2(m0, V[0], V[4]), c01 = dxb_fma2(m0, V[1], V[5]), c02 = dxb_fma2(m0, V[2], V[6]);
+    const dxb_f2 c11 = dxb_fma2(m1, V[1], V[8]), c12 = dxb_fma2(m1, V[2], V[9]), c22 = dxb_fma2(m2, V[2], V[11]);
     // opaque blocks: alpha is the constant 255, its covariance row is zero up to rounding: forced to zero (branch-free)
-    const float z = opaque ? 0.0f : 1.0f;
-    const float c03 = z * dxb_fma(-v[0] * inv, v[3], v[7]), c13 = z * dxb_fma(-v[1] * inv, v[3], v[10]);
-    const float c23 = z * dxb_fma(-v[2] * inv, v[3], v[12]), c33 = z * dxb_fma(-v[3] * inv, v[3], v[13]);
-    const float tr = (c00 + c11) + (c22 + c33);
-    const bool flat = !(tr > 1e-3f) || (n < 2u);
-    const bool b0 = (c00 >= c11 && c00 >= c22 && c00 >= c33);
-    const bool b1 = !b0 && (c11 >= c22 && c11 >= c33);
-    const bool b2 = !b0 && !b1 && (c22 >= c33);
-    const float v0 = b0 ? c00 : (b1 ? c01 : (b2 ? c02 : c03));
-    const float v1 = b0 ? c01 : (b1 ? c11 : (b2 ? c12 : c13));
-    const float v2 = b0 ? c02 : (b1 ? c12 : (b2 ? c22 : c23));
-    const float v3 = b0 ? c03 : (b1 ? c13 : (b2 ? c23 : c33));
-    // the largest component is the diagonal entry (|c_ij| <= max(c_ii, c_jj)): scale it into [32, 64)
-    const float mx = b0 ? c00 : (b1 ? c11 : (b2 ? c22 : c33));
-    const uint32_t E = dxb_float_as_uint(mx) >> 23;                      // biased exponent (mx > 0 unless flat)
-    const float sc = flat ? 0.0f : dxb_uint_as_float((259u - E) << 23);  // 2^(5 - (E - 127))
+    const dxb_f2 z = dxb_bc2(opaque ? 0.0f : 1.0f);
+    const dxb_f2 c03 = dxb_mul2(z, dxb_fma2(m0, V[3], V[7])), c13 = dxb_mul2(z, dxb_fma2(m1, V[3], V[10]));
+    const dxb_f2 c23 = dxb_mul2(z, dxb_fma2(m2, V[3], V[12])), c33 = dxb_mul2(z, dxb_fma2(m3, V[3], V[13]));
+    const dxb_f2 tr = dxb_add2(dxb_add2(c00, c11), dxb_add2(c22, c33));
+    dxb_f2 v0, v1, v2, v3, sc;
+    {
+        // per subset: the row with the largest diagonal; its diagonal entry is the largest component (|c_ij| <= max(c_ii, c_jj)):
+        // scale it into [32, 64)
+#define DXB_AX_ROW(H, N) { \
+        const bool flat = !(tr.H > 1e-3f) || ((N) < 2u); \
+        const bool b0 = (c00.H >= c11.H && c00.H >= c22.H && c00.H >= c33.H); \
+        const bool b1 = !b0 && (c11.H >= c22.H && c11.H >= c33.H); \
+        const bool b2 = !b0 && !b1 && (c22.H >= c33.H); \
+        v0.H = b0 ? c00.H : (b1 ? c01.H : (b2 ? c02.H : c03.H)); \
+        v1.H = b0 ? c01.H : (b1 ? c11.H : (b2 ? c12.H : c13.H)); \
+        v2.H = b0 ? c02.H : (b1 ? c12.H : (b2 ? c22.H : c23.H)); \
+        v3.H = b0 ? c03.H : (b1 ? c13.H : (b2 ? c23.H : c33.H)); \
+        const float mx = b0 ? c00.H : (b1 ? c11.H : (b2 ? c22.H : c33.H)); \
+        const uint32_t E = dxb_float_as_uint(mx) >> 23;                      /* biased exponent (mx > 0 unless flat) */ \
+        sc.H = flat ? 0.0f : dxb_uint_as_float((259u - E) << 23); }         /* 2^(5 - (E - 127)) */
+        DXB_AX_ROW(x, n0)
+        DXB_AX_ROW(y, n1)
+#undef DXB_AX_ROW
+    }
     // round to integers with the magic constant: the sum's low mantissa byte is the two's complement byte of the integer
-    const float t0 = dxb_fma(v0, sc, DXB_MAGIC), t1 = dxb_fma(v1, sc, DXB_MAGIC), t2 = dxb_fma(v2, sc, DXB_MAGIC), t3 = dxb_fma(v3, sc, DXB_MAGIC);
-    const float a0 = t0 - DXB_MAGIC, a1 = t1 - DXB_MAGIC, a2 = t2 - DXB_MAGIC, a3 = t3 - DXB_MAGIC;
-    dxb_bc7_axis A;
-    A.packed = (dxb_float_as_uint(t0) & 0xFFu) | ((dxb_float_as_uint(t1) & 0xFFu) << 8) | ((dxb_float_as_uint(t2) & 0xFFu) << 16) | (dxb_float_as_uint(t3) << 24);
-    const float aa = dxb_fma(a0, a0, dxb_fma(a1, a1, dxb_fma(a2, a2, a3 * a3)));
-    const float q0 = dxb_fma(c00, a0, dxb_fma(c01, a1, dxb_fma(c02, a2, c03 * a3)));
-    const float q1 = dxb_fma(c01, a0, dxb_fma(c11, a1, dxb_fma(c12, a2, c13 * a3)));
-    const float q2 = dxb_fma(c02, a0, dxb_fma(c12, a1, dxb_fma(c22, a2, c23 * a3)));
-    const float q3 = dxb_fma(c03, a0, dxb_fma(c13, a1, dxb_fma(c23, a2, c33 * a3)));
-    const float aCa = dxb_fma(a0, q0, dxb_fma(a1, q1, dxb_fma(a2, q2, a3 * q3)));
-    A.inv_aa = (aa > 0.0f) ? 1.0f / aa : 0.0f;
-    A.resid = flat ? 0.0f : fmaxf(dxb_fma(-aCa, A.inv_aa, tr), 0.0f);
-    return A;
+    const dxb_f2 MG = dxb_bc2(DXB_MAGIC), nMG = dxb_bc2(-DXB_MAGIC);
+    const dxb_f2 t0 = dxb_fma2(v0, sc, MG), t1 = dxb_fma2(v1, sc, MG), t2 = dxb_fma2(v2, sc, MG), t3 = dxb_fma2(v3, sc, MG);
+    const dxb_f2 a0 = dxb_add2(t0, nMG), a1 = dxb_add2(t1, nMG), a2 = dxb_add2(t2, nMG), a3 = dxb_add2(t3, nMG);
+    A0->packed = (dxb_float_as_uint(t0.x) & 0xFFu) | ((dxb_float_as_uint(t1.x) & 0xFFu) << 8) | ((dxb_float_as_uint(t2.x) & 0xFFu) << 16) | (dxb_float_as_uint(t3.x) << 24);
+    A1->packed = (dxb_float_as_uint(t0.y) & 0xFFu) | ((dxb_float_as_uint(t1.y) & 0xFFu) << 8) | ((dxb_float_as_uint(t2.y) & 0xFFu) << 16) | (dxb_float_as_uint(t3.y) << 24);
+    const dxb_f2 aa = dxb_fma2(a0, a0, dxb_fma2(a1, a1, dxb_fma2(a2, a2, dxb_mul2(a3, a3))));
+    const dxb_f2 q0 = dxb_fma2(c00, a0, dxb_fma2(c01, a1, dxb_fma2(c02, a2, dxb_mul2(c03, a3))));
+    const dxb_f2 q1 = dxb_fma2(c01, a0, dxb_fma2(c11, a1, dxb_fma2(c12, a2, dxb_mul2(c13, a3))));
+    const dxb_f2 q2 = dxb_fma2(c02, a0, dxb_fma2(c12, a1, dxb_fma2(c22, a2, dxb_mul2(c23, a3))));
+    const dxb_f2 q3 = dxb_fma2(c03, a0, dxb_fma2(c13, a1, dxb_fma2(c23, a2, dxb_mul2(c33, a3))));
+    const dxb_f2 aCa = dxb_fma2(a0, q0, dxb_fma2(a1, q1, dxb_fma2(a2, q2, dxb_mul2(a3, q3))));
+    A0->inv_aa = (aa.x > 0.0f) ? 1.0f / aa.x : 0.0f;
+    A1->inv_aa = (aa.y > 0.0f) ? 1.0f / aa.y : 0.0f;
+    const dxb_f2 rs = dxb_fma2(dxb_mk2(-aCa.x, -aCa.y), dxb_mk2(A0->inv_aa, A1->inv_aa), tr);
+    A0->resid = (sc.x == 0.0f) ? 0.0f : fmaxf(rs.x, 0.0f);
+    A1->resid = (sc.y == 0.0f) ? 0.0f : fmaxf(rs.y, 0.0f);
 }
 
 #define DXB_BC7_H1_OFF (1 << 20)          // separates the two subsets' projections (|t| <= 4 * 255 * 64 < 2^17)
@@ -394,12 +408,14 @@ DXB_DEV dxb_bc7_axis dxb_bc7_subset_axis(uint32_t n, const float* v, bool opaque
 // opaque blocks: the better of 3-bit indices (mode 1) and 2-bit indices (mode 3); alpha blocks: 2-bit (mode 7).
 DXB_DEV float dxb_bc7_shape_h1(const uint32_t* pq, const float* mt, uint32_t shape, const float* tot, bool opaque)
 {
-    float v1[14], v0[14];
+    float v1[14];
+    dxb_f2 V[14];
     dxb_bc7_mt_load(mt, (int)shape, v1);
-    for (int k = 0; k < 14; ++k) v0[k] = tot[k] - v1[k];
+    for (int k = 0; k < 14; ++k) V[k] = dxb_mk2(tot[k] - v1[k], v1[k]);
     const uint32_t mask = dxb_part2[shape];
     const uint32_t n1 = dxb_popc16(mask);
-    const dxb_bc7_axis A0 = dxb_bc7_subset_axis(16u - n1, v0, opaque), A1 = dxb_bc7_subset_axis(n1, v1, opaque);
+    dxb_bc7_axis A0, A1;
+    dxb_bc7_subset_axes(16u - n1, n1, V, opaque, &A0, &A1);
     int32_t T[16];                         // projection + (subset 1 ? OFF : 0)
     int32_t mnv = 0x7fffffff, mxv = -0x7fffffff, mny = 0x7fffffff, mxy = -0x7fffffff;
 #if DXB_ON_DEVICE
@@ -420,8 +436,9 @@ DXB_DEV float dxb_bc7_shape_h1(const uint32_t* pq, const float* mt, uint32_t sha
     const float r0 = (float)(tmax0 - tmin0), r1 = (float)(tmax1 - tmin1);
     const float i0 = (r0 > 0.0f) ? 1.0f / r0 : 0.0f, i1 = (r1 > 0.0f) ? 1.0f / r1 : 0.0f;
     const int32_t base1 = tmin1 + DXB_BC7_H1_OFF;
-    // e?a = squared index rounding error in units of (range / 7)^2, e?b in units of (range / 3)^2
-    float e0a = 0.0f, e1a = 0.0f, e0b = 0.0f, e1b = 0.0f;
+    // squared index rounding errors as packed pairs (units of (range / 7)^2, units of (range / 3)^2), one accumulator per subset
+    dxb_f2 E0 = dxb_bc2(0.0f), E1 = dxb_bc2(0.0f);
+    const dxb_f2 NL = dxb_mk2(7.0f, 3.0f), MG = dxb_bc2(DXB_MAGIC), nMG = dxb_bc2(-DXB_MAGIC);
 #if DXB_ON_DEVICE
     #pragma unroll
 #endif
@@ -429,10 +446,11 @@ DXB_DEV float dxb_bc7_shape_h1(const uint32_t* pq, const float* mt, uint32_t sha
     {
         const bool m = (T[p] >= (DXB_BC7_H1_OFF >> 1));
         const float x = (float)(T[p] - (m ? base1 : tmin0)) * (m ? i1 : i0);        // position in [0, 1]
-        const float ub = x * 3.0f, ua = x * 7.0f;
-        const float db = ub - dxb_rne(ub), da = ua - dxb_rne(ua);
-        if (m) { e1b = dxb_fma(db, db, e1b); e1a = dxb_fma(da, da, e1a); } else { e0b = dxb_fma(db, db, e0b); e0a = dxb_fma(da, da, e0a); }
+        const dxb_f2 U = dxb_mul2(dxb_bc2(x), NL);
+        const dxb_f2 D = dxb_sub2(U, dxb_add2(dxb_add2(U, MG), nMG));               // u - rne(u)
+        if (m) E1 = dxb_fma2(D, D, E1); else E0 = dxb_fma2(D, D, E0);
     }
+    const float e0a = E0.x, e0b = E0.y, e1a = E1.x, e1b = E1.y;
     // index-quantisation error in pixel units: e * (range / nl)^2 / |a|^2
     const float w0 = (r0 * r0) * A0.inv_aa, w1 = (r1 * r1) * A1.inv_aa;
     const float qb = dxb_fma(e0b, w0, e1b * w1) * (1.0f / 9.0f);
@@ -500,13 +518,15 @@ DXB_DEV dxb_bc7_qconst dxb_bc7_make_qconst(uint32_t bits, uint32_t hasP)
     return k;
 }
 // pE = p * hasP as float.  Returns the field q (float integer); *deq = reconstructed 8-bit value (float integer)
-DXB_DEV float dxb_bc7_quant1f(float e, const dxb_bc7_qconst& k, float pE, float* deq)
+DXB_DEV dxb_f2 dxb_bc7_quant2f(dxb_f2 e, const dxb_bc7_qconst& k, float pE, dxb_f2* deq)
 {
-    const float h = dxb_fma(e, k.scaleH, -(pE * k.half));
-    const float q = fminf(fmaxf(dxb_rne(h), 0.0f), k.qmax);
-    const float full = dxb_fma(q, k.mul, pE);
-    const float r = dxb_rne(dxb_fma(full, k.c2, -(0.5f - 1.0f / 512.0f)));
-    *deq = dxb_fma(full, k.c8, r);
+    const dxb_f2 MG = dxb_bc2(DXB_MAGIC), nMG = dxb_bc2(-DXB_MAGIC);
+    const dxb_f2 h = dxb_fma2(e, dxb_bc2(k.scaleH), dxb_bc2(-(pE * k.half)));
+    const dxb_f2 hr = dxb_add2(dxb_add2(h, MG), nMG);
+    const dxb_f2 q = dxb_mk2(fminf(fmaxf(hr.x, 0.0f), k.qmax), fminf(fmaxf(hr.y, 0.0f), k.qmax));
+    const dxb_f2 full = dxb_fma2(q, dxb_bc2(k.mul), dxb_bc2(pE));
+    const dxb_f2 r = dxb_add2(dxb_add2(dxb_fma2(full, dxb_bc2(k.c2), dxb_bc2(-(0.5f - 1.0f / 512.0f))), MG), nMG);
+    *deq = dxb_fma2(full, dxb_bc2(k.c8), r);
     return q;
 }
 
@@ -603,7 +623,9 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
     for (int i = 0; i < 16; ++i)
     {
         const dxb_px p = px[i];
-        const float t = dxb_fma(p.x - mean[0], ax[0], dxb_fma(p.y - mean[1], ax[1], dxb_fma(p.z - mean[2], ax[2], (p.w - mean[3]) * ax[3])));
+        const dxb_f2 T2 = dxb_fma2(dxb_add2(dxb_mk2(p.z, p.w), dxb_mk2(-mean[2], -mean[3])), dxb_mk2(ax[2], ax[3]),
+                                   dxb_mul2(dxb_add2(dxb_mk2(p.x, p.y), dxb_mk2(-mean[0], -mean[1])), dxb_mk2(ax[0], ax[1])));
+        const float t = T2.x + T2.y;
         const bool in = ((mask >> i) & 1u) != 0u;
         tmin = in ? fminf(tmin, t) : tmin; tmax = in ? fmaxf(tmax, t) : tmax;
     }
@@ -632,24 +654,26 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
         const bool last = (round + 1 == DXB_BC7_ROUNDS);       // compile-time after unrolling: the refit sums vanish from the last round
         dxb_warp_sync();
         dxb_phase_sync();
-        // quantise both endpoints for p = 0 and p = 1; fields packed as float integers q0 + 256 q1 + 65536 q2, q3 apart
-        float qa[2][2], qb[2][2], d0[2][4], d1[2][4], err0[2] = { 0.0f, 0.0f }, err1[2] = { 0.0f, 0.0f };
+        // quantise both endpoints for p = 0 and p = 1; fields packed as float integers q0 + 256 q1 + 65536 q2, q3 apart.
+        // The two endpoints of a channel travel as one packed pair (x = endpoint 0, y = endpoint 1).
+        float qa[2][2], qb[2][2], d0[2][4], d1[2][4], err0[2], err1[2];
         for (int p = 0; p < 2; ++p)
         {
             const float pE = (p && hasP) ? 1.0f : 0.0f;
-            float f0[4], f1[4];
+            dxb_f2 F[4], E2 = dxb_bc2(0.0f);
             for (int c = 0; c < 4; ++c)
             {
-                float a, b;
-                f0[c] = dxb_bc7_quant1f(E0[c], qk, pE, &a) * vm[c];
-                f1[c] = dxb_bc7_quant1f(E1[c], qk, pE, &b) * vm[c];
-                a *= vm[c]; b *= vm[c];
-                d0[p][c] = a; d1[p][c] = b;
-                const float ea = a - E0[c], eb = b - E1[c];      // masked channels: E = 0 and a = b = 0
-                err0[p] = dxb_fma(ea, ea, err0[p]); err1[p] = dxb_fma(eb, eb, err1[p]);
+                dxb_f2 A;
+                const dxb_f2 Ec = dxb_mk2(E0[c], E1[c]), vmc = dxb_bc2(vm[c]);
+                F[c] = dxb_mul2(dxb_bc7_quant2f(Ec, qk, pE, &A), vmc);
+                A = dxb_mul2(A, vmc);
+                d0[p][c] = A.x; d1[p][c] = A.y;
+                const dxb_f2 ea = dxb_sub2(A, Ec);                  // masked channels: E = 0 and a = b = 0
+                E2 = dxb_fma2(ea, ea, E2);
             }
-            qa[p][0] = dxb_fma(f0[2], 65536.0f, dxb_fma(f0[1], 256.0f, f0[0])); qb[p][0] = f0[3];
-            qa[p][1] = dxb_fma(f1[2], 65536.0f, dxb_fma(f1[1], 256.0f, f1[0])); qb[p][1] = f1[3];
+            err0[p] = E2.x; err1[p] = E2.y;
+            const dxb_f2 QA = dxb_fma2(F[2], dxb_bc2(65536.0f), dxb_fma2(F[1], dxb_bc2(256.0f), F[0]));
+            qa[p][0] = QA.x; qa[p][1] = QA.y; qb[p][0] = F[3].x; qb[p][1] = F[3].y;
         }
         // p-bit choice: by endpoint reconstruction error, then the overrides; all selects
         uint32_t p0 = (err0[1] < err0[0]) ? 1u : 0u;
