@@ -446,8 +446,12 @@ DXB_DEV float dxb_bc7_shape_h1(const uint32_t* pq, const float* mt, uint32_t sha
     {
         const bool m = (T[p] >= (DXB_BC7_H1_OFF >> 1));
         const float x = (float)(T[p] - (m ? base1 : tmin0)) * (m ? i1 : i0);        // position in [0, 1]
-        const dxb_f2 U = dxb_mul2(dxb_bc2(x), NL);
-        const dxb_f2 D = dxb_sub2(U, dxb_add2(dxb_add2(U, MG), nMG));               // u - rne(u)
+        // u = x * (7, 3):  k = rne(u) = fma(x, nl, MAGIC) - MAGIC,  d = fma(x, nl, -k).  Written as explicit fused operations:
+        // ptxas contracts a packed multiply that feeds a packed add into FFMA2 even for the .rn forms and with -fmad=false
+        // (dxb_portable.h), so an unfused formulation would not be what runs.
+        const dxb_f2 x2 = dxb_bc2(x);
+        const dxb_f2 K = dxb_add2(dxb_fma2(x2, NL, MG), nMG);
+        const dxb_f2 D = dxb_fma2(x2, NL, dxb_mk2(-K.x, -K.y));
         if (m) E1 = dxb_fma2(D, D, E1); else E0 = dxb_fma2(D, D, E0);
     }
     const float e0a = E0.x, e0b = E0.y, e1a = E1.x, e1b = E1.y;

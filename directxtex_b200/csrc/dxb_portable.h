@@ -135,8 +135,12 @@ DXB_DEV float dxb_fma(float a, float b, float c) { return fmaf(a, b, c); }
 
 // ---- packed pairs of fp32 (sm_100a FFMA2 / FADD2 / FMUL2: two independent IEEE operations in one issue slot).
 // The BC7 encoder is issue-bound, and most of its arithmetic runs on 4-channel vectors = two pairs; each half is an
-// ordinary round-to-nearest fp32 operation, so the host emulator (two scalar operations) stays bit-identical.
-#if DXB_ON_DEVICE
+// ordinary round-to-nearest fp32 operation (checked on B200 against the scalar instructions over 2^26 operand pairs incl.
+// denormals), so the host emulator (two scalar operations) stays bit-identical -- with ONE rule: ptxas (12.9) contracts
+// mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 even with -fmad=false, which it never does for the scalar .rn forms.  A packed
+// product may therefore only flow into a packed add / sub when the product is exact (0/1 masks, small integers); everywhere
+// else the code states the fused operation itself (dxb_fma2) so that host and device agree.
+#if DXB_ON_DEVICE && !defined(DXB_SCALAR_F2)
 typedef float2 dxb_f2;
 DXB_DEV dxb_f2 dxb_mk2(float x, float y) { return make_float2(x, y); }
 DXB_DEV dxb_f2 dxb_fma2(dxb_f2 a, dxb_f2 b, dxb_f2 c) { return __ffma2_rn(a, b, c); }
