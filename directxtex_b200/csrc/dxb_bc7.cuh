@@ -44,6 +44,18 @@ static constexpr int dxb_bc7_pixunroll = DXB_BC7_PIXUNROLL;
 #define DXB_BC7_ROUNDS 2          // endpoint evaluation rounds per task (1 = PCA only, each extra = one LS refit)
 #endif
 
+
+// packed-fp32 regions (R<n>_*): -DDXB_SCALAR_REGION=<n> issues region n as scalar instructions (bisecting tool)
+#ifndef DXB_SCALAR_REGION
+#define DXB_SCALAR_REGION 0
+#endif
+#define DXB_RDEF(N) \
+    DXB_DEV dxb_f2 R##N##_fma2(dxb_f2 a, dxb_f2 b, dxb_f2 c) { return (DXB_SCALAR_REGION == N) ? dxb_fma2s(a, b, c) : dxb_fma2(a, b, c); } \
+    DXB_DEV dxb_f2 R##N##_add2(dxb_f2 a, dxb_f2 b) { return (DXB_SCALAR_REGION == N) ? dxb_add2s(a, b) : dxb_add2(a, b); } \
+    DXB_DEV dxb_f2 R##N##_mul2(dxb_f2 a, dxb_f2 b) { return (DXB_SCALAR_REGION == N) ? dxb_mul2s(a, b) : dxb_mul2(a, b); } \
+    DXB_DEV dxb_f2 R##N##_sub2(dxb_f2 a, dxb_f2 b) { return (DXB_SCALAR_REGION == N) ? dxb_sub2s(a, b) : dxb_sub2(a, b); }
+DXB_RDEF(1) DXB_RDEF(2) DXB_RDEF(3) DXB_RDEF(4) DXB_RDEF(5) DXB_RDEF(6)
+
 struct dxb_bc7_res { float err; uint32_t q0, q1, pbits; };
 
 #define DXB_MAGIC 12582912.0f                      // 1.5 * 2^23: (x + MAGIC) - MAGIC == round-to-nearest-even(x), |x| < 2^22
@@ -354,15 +366,15 @@ struct dxb_bc7_axis { uint32_t packed; float resid, inv_aa; };   // s8x4 axis, o
 DXB_DEV void dxb_bc7_subset_axes(uint32_t n0, uint32_t n1, const dxb_f2* V, bool opaque, dxb_bc7_axis* A0, dxb_bc7_axis* A1)
 {
     const dxb_f2 inv = dxb_mk2(dxb_rcp16[n0], dxb_rcp16[n1]);
-    const dxb_f2 m0 = dxb_mul2(dxb_mk2(-V[0].x, -V[0].y), inv), m1 = dxb_mul2(dxb_mk2(-V[1].x, -V[1].y), inv);
-    const dxb_f2 m2 = dxb_mul2(dxb_mk2(-V[2].x, -V[2].y), inv), m3 = dxb_mul2(dxb_mk2(-V[3].x, -V[3].y), inv);
-    const dxb_f2 c00 = dxb_fma2(m0, V[0], V[4]), c01 = dxb_fma2(m0, V[1], V[5]), c02 = dxb_fma2(m0, V[2], V[6]);
-    const dxb_f2 c11 = dxb_fma2(m1, V[1], V[8]), c12 = dxb_fma2(m1, V[2], V[9]), c22 = dxb_fma2(m2, V[2], V[11]);
+    const dxb_f2 m0 = R1_mul2(dxb_mk2(-V[0].x, -V[0].y), inv), m1 = R1_mul2(dxb_mk2(-V[1].x, -V[1].y), inv);
+    const dxb_f2 m2 = R1_mul2(dxb_mk2(-V[2].x, -V[2].y), inv), m3 = R1_mul2(dxb_mk2(-V[3].x, -V[3].y), inv);
+    const dxb_f2 c00 = R1_fma2(m0, V[0], V[4]), c01 = R1_fma2(m0, V[1], V[5]), c02 = R1_fma2(m0, V[2], V[6]);
+    const dxb_f2 c11 = R1_fma2(m1, V[1], V[8]), c12 = R1_fma2(m1, V[2], V[9]), c22 = R1_fma2(m2, V[2], V[11]);
     // opaque blocks: alpha is the constant 255, its covariance row is zero up to rounding: forced to zero (branch-free)
     const dxb_f2 z = dxb_bc2(opaque ? 0.0f : 1.0f);
-    const dxb_f2 c03 = dxb_mul2(z, dxb_fma2(m0, V[3], V[7])), c13 = dxb_mul2(z, dxb_fma2(m1, V[3], V[10]));
-    const dxb_f2 c23 = dxb_mul2(z, dxb_fma2(m2, V[3], V[12])), c33 = dxb_mul2(z, dxb_fma2(m3, V[3], V[13]));
-    const dxb_f2 tr = dxb_add2(dxb_add2(c00, c11), dxb_add2(c22, c33));
+    const dxb_f2 c03 = R1_mul2(z, R1_fma2(m0, V[3], V[7])), c13 = R1_mul2(z, R1_fma2(m1, V[3], V[10]));
+    const dxb_f2 c23 = R1_mul2(z, R1_fma2(m2, V[3], V[12])), c33 = R1_mul2(z, R1_fma2(m3, V[3], V[13]));
+    const dxb_f2 tr = R1_add2(R1_add2(c00, c11), R1_add2(c22, c33));
     dxb_f2 v0, v1, v2, v3, sc;
     {
         // per subset: the row with the largest diagonal; its diagonal entry is the largest component (|c_ij| <= max(c_ii, c_jj)):
@@ -385,19 +397,19 @@ DXB_DEV void dxb_bc7_subset_axes(uint32_t n0, uint32_t n1, const dxb_f2* V, bool
     }
     // round to integers with the magic constant: the sum's low mantissa byte is the two's complement byte of the integer
     const dxb_f2 MG = dxb_bc2(DXB_MAGIC), nMG = dxb_bc2(-DXB_MAGIC);
-    const dxb_f2 t0 = dxb_fma2(v0, sc, MG), t1 = dxb_fma2(v1, sc, MG), t2 = dxb_fma2(v2, sc, MG), t3 = dxb_fma2(v3, sc, MG);
-    const dxb_f2 a0 = dxb_add2(t0, nMG), a1 = dxb_add2(t1, nMG), a2 = dxb_add2(t2, nMG), a3 = dxb_add2(t3, nMG);
+    const dxb_f2 t0 = R1_fma2(v0, sc, MG), t1 = R1_fma2(v1, sc, MG), t2 = R1_fma2(v2, sc, MG), t3 = R1_fma2(v3, sc, MG);
+    const dxb_f2 a0 = R1_add2(t0, nMG), a1 = R1_add2(t1, nMG), a2 = R1_add2(t2, nMG), a3 = R1_add2(t3, nMG);
     A0->packed = (dxb_float_as_uint(t0.x) & 0xFFu) | ((dxb_float_as_uint(t1.x) & 0xFFu) << 8) | ((dxb_float_as_uint(t2.x) & 0xFFu) << 16) | (dxb_float_as_uint(t3.x) << 24);
     A1->packed = (dxb_float_as_uint(t0.y) & 0xFFu) | ((dxb_float_as_uint(t1.y) & 0xFFu) << 8) | ((dxb_float_as_uint(t2.y) & 0xFFu) << 16) | (dxb_float_as_uint(t3.y) << 24);
-    const dxb_f2 aa = dxb_fma2(a0, a0, dxb_fma2(a1, a1, dxb_fma2(a2, a2, dxb_mul2(a3, a3))));
-    const dxb_f2 q0 = dxb_fma2(c00, a0, dxb_fma2(c01, a1, dxb_fma2(c02, a2, dxb_mul2(c03, a3))));
-    const dxb_f2 q1 = dxb_fma2(c01, a0, dxb_fma2(c11, a1, dxb_fma2(c12, a2, dxb_mul2(c13, a3))));
-    const dxb_f2 q2 = dxb_fma2(c02, a0, dxb_fma2(c12, a1, dxb_fma2(c22, a2, dxb_mul2(c23, a3))));
-    const dxb_f2 q3 = dxb_fma2(c03, a0, dxb_fma2(c13, a1, dxb_fma2(c23, a2, dxb_mul2(c33, a3))));
-    const dxb_f2 aCa = dxb_fma2(a0, q0, dxb_fma2(a1, q1, dxb_fma2(a2, q2, dxb_mul2(a3, q3))));
+    const dxb_f2 aa = R1_fma2(a0, a0, R1_fma2(a1, a1, R1_fma2(a2, a2, R1_mul2(a3, a3))));
+    const dxb_f2 q0 = R1_fma2(c00, a0, R1_fma2(c01, a1, R1_fma2(c02, a2, R1_mul2(c03, a3))));
+    const dxb_f2 q1 = R1_fma2(c01, a0, R1_fma2(c11, a1, R1_fma2(c12, a2, R1_mul2(c13, a3))));
+    const dxb_f2 q2 = R1_fma2(c02, a0, R1_fma2(c12, a1, R1_fma2(c22, a2, R1_mul2(c23, a3))));
+    const dxb_f2 q3 = R1_fma2(c03, a0, R1_fma2(c13, a1, R1_fma2(c23, a2, R1_mul2(c33, a3))));
+    const dxb_f2 aCa = R1_fma2(a0, q0, R1_fma2(a1, q1, R1_fma2(a2, q2, R1_mul2(a3, q3))));
     A0->inv_aa = (aa.x > 0.0f) ? 1.0f / aa.x : 0.0f;
     A1->inv_aa = (aa.y > 0.0f) ? 1.0f / aa.y : 0.0f;
-    const dxb_f2 rs = dxb_fma2(dxb_mk2(-aCa.x, -aCa.y), dxb_mk2(A0->inv_aa, A1->inv_aa), tr);
+    const dxb_f2 rs = R1_fma2(dxb_mk2(-aCa.x, -aCa.y), dxb_mk2(A0->inv_aa, A1->inv_aa), tr);
     A0->resid = (sc.x == 0.0f) ? 0.0f : fmaxf(rs.x, 0.0f);
     A1->resid = (sc.y == 0.0f) ? 0.0f : fmaxf(rs.y, 0.0f);
 }
@@ -450,9 +462,9 @@ DXB_DEV float dxb_bc7_shape_h1(const uint32_t* pq, const float* mt, uint32_t sha
         // ptxas contracts a packed multiply that feeds a packed add into FFMA2 even for the .rn forms and with -fmad=false
         // (dxb_portable.h), so an unfused formulation would not be what runs.
         const dxb_f2 x2 = dxb_bc2(x);
-        const dxb_f2 K = dxb_add2(dxb_fma2(x2, NL, MG), nMG);
-        const dxb_f2 D = dxb_fma2(x2, NL, dxb_mk2(-K.x, -K.y));
-        if (m) E1 = dxb_fma2(D, D, E1); else E0 = dxb_fma2(D, D, E0);
+        const dxb_f2 K = R2_add2(R2_fma2(x2, NL, MG), nMG);
+        const dxb_f2 D = R2_fma2(x2, NL, dxb_mk2(-K.x, -K.y));
+        if (m) E1 = R2_fma2(D, D, E1); else E0 = R2_fma2(D, D, E0);
     }
     const float e0a = E0.x, e0b = E0.y, e1a = E1.x, e1b = E1.y;
     // index-quantisation error in pixel units: e * (range / nl)^2 / |a|^2
@@ -525,12 +537,17 @@ DXB_DEV dxb_bc7_qconst dxb_bc7_make_qconst(uint32_t bits, uint32_t hasP)
 DXB_DEV dxb_f2 dxb_bc7_quant2f(dxb_f2 e, const dxb_bc7_qconst& k, float pE, dxb_f2* deq)
 {
     const dxb_f2 MG = dxb_bc2(DXB_MAGIC), nMG = dxb_bc2(-DXB_MAGIC);
-    const dxb_f2 h = dxb_fma2(e, dxb_bc2(k.scaleH), dxb_bc2(-(pE * k.half)));
-    const dxb_f2 hr = dxb_add2(dxb_add2(h, MG), nMG);
+    // rne(e * scaleH - pE * half).  Without a p-bit the addend is zero, the FFMA2 degenerates to a packed multiply and ptxas
+    // contracts it with the packed add of the rounding constant (dxb_portable.h): that case is therefore WRITTEN as the fused
+    // operation, so that the source says what runs (the host emulator executes the same branch).
+    dxb_f2 hm;
+    if (pE == 0.0f) hm = R3_fma2(e, dxb_bc2(k.scaleH), MG);
+    else hm = R3_add2(R3_fma2(e, dxb_bc2(k.scaleH), dxb_bc2(-(pE * k.half))), MG);
+    const dxb_f2 hr = R3_add2(hm, nMG);
     const dxb_f2 q = dxb_mk2(fminf(fmaxf(hr.x, 0.0f), k.qmax), fminf(fmaxf(hr.y, 0.0f), k.qmax));
-    const dxb_f2 full = dxb_fma2(q, dxb_bc2(k.mul), dxb_bc2(pE));
-    const dxb_f2 r = dxb_add2(dxb_add2(dxb_fma2(full, dxb_bc2(k.c2), dxb_bc2(-(0.5f - 1.0f / 512.0f))), MG), nMG);
-    *deq = dxb_fma2(full, dxb_bc2(k.c8), r);
+    const dxb_f2 full = R3_fma2(q, dxb_bc2(k.mul), dxb_bc2(pE));
+    const dxb_f2 r = R3_add2(R3_add2(R3_fma2(full, dxb_bc2(k.c2), dxb_bc2(-(0.5f - 1.0f / 512.0f))), MG), nMG);
+    *deq = R3_fma2(full, dxb_bc2(k.c8), r);
     return q;
 }
 
@@ -627,8 +644,8 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
     for (int i = 0; i < 16; ++i)
     {
         const dxb_px p = px[i];
-        const dxb_f2 T2 = dxb_fma2(dxb_add2(dxb_mk2(p.z, p.w), dxb_mk2(-mean[2], -mean[3])), dxb_mk2(ax[2], ax[3]),
-                                   dxb_mul2(dxb_add2(dxb_mk2(p.x, p.y), dxb_mk2(-mean[0], -mean[1])), dxb_mk2(ax[0], ax[1])));
+        const dxb_f2 T2 = R4_fma2(R4_add2(dxb_mk2(p.z, p.w), dxb_mk2(-mean[2], -mean[3])), dxb_mk2(ax[2], ax[3]),
+                                   R4_mul2(R4_add2(dxb_mk2(p.x, p.y), dxb_mk2(-mean[0], -mean[1])), dxb_mk2(ax[0], ax[1])));
         const float t = T2.x + T2.y;
         const bool in = ((mask >> i) & 1u) != 0u;
         tmin = in ? fminf(tmin, t) : tmin; tmax = in ? fmaxf(tmax, t) : tmax;
@@ -669,14 +686,14 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
             {
                 dxb_f2 A;
                 const dxb_f2 Ec = dxb_mk2(E0[c], E1[c]), vmc = dxb_bc2(vm[c]);
-                F[c] = dxb_mul2(dxb_bc7_quant2f(Ec, qk, pE, &A), vmc);
-                A = dxb_mul2(A, vmc);
+                F[c] = R5_mul2(dxb_bc7_quant2f(Ec, qk, pE, &A), vmc);
+                A = R5_mul2(A, vmc);
                 d0[p][c] = A.x; d1[p][c] = A.y;
-                const dxb_f2 ea = dxb_sub2(A, Ec);                  // masked channels: E = 0 and a = b = 0
-                E2 = dxb_fma2(ea, ea, E2);
+                const dxb_f2 ea = R5_sub2(A, Ec);                  // masked channels: E = 0 and a = b = 0
+                E2 = R5_fma2(ea, ea, E2);
             }
             err0[p] = E2.x; err1[p] = E2.y;
-            const dxb_f2 QA = dxb_fma2(F[2], dxb_bc2(65536.0f), dxb_fma2(F[1], dxb_bc2(256.0f), F[0]));
+            const dxb_f2 QA = R5_fma2(F[2], dxb_bc2(65536.0f), R5_fma2(F[1], dxb_bc2(256.0f), F[0]));
             qa[p][0] = QA.x; qa[p][1] = QA.y; qb[p][0] = F[3].x; qb[p][1] = F[3].y;
         }
         // p-bit choice: by endpoint reconstruction error, then the overrides; all selects
@@ -710,9 +727,9 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
         {
             const float f = dxb_bit_as_float(mask, i);          // 1 if the pixel belongs to this lane's subset
             const dxb_px p = px[i];
-            const dxb_f2 P01 = dxb_mul2(dxb_mk2(p.x, p.y), vm01), P23 = dxb_mul2(dxb_mk2(p.z, p.w), vm23);
-            const dxb_f2 A01 = dxb_add2(P01, nD01), A23 = dxb_add2(P23, nD23);
-            const dxb_f2 T = dxb_fma2(A23, d23, dxb_mul2(A01, d01));
+            const dxb_f2 P01 = R6_mul2(dxb_mk2(p.x, p.y), vm01), P23 = R6_mul2(dxb_mk2(p.z, p.w), vm23);
+            const dxb_f2 A01 = R6_add2(P01, nD01), A23 = R6_add2(P23, nD23);
+            const dxb_f2 T = R6_fma2(A23, d23, R6_mul2(A01, d01));
             const float pr = T.x + T.y;                           // (P - D0) . d
             const float tk = pr * idd;
             // index = nearest of the uniformly spaced positions (stage 4 assigns the winner's final indices exhaustively)
@@ -722,9 +739,9 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
             // (a multiple of 1/64, so adding 1/128 before the RNE never ties).  An unrounded model mis-ranks near-lossless
             // candidates: the rounding noise (1/12 per value) is half of the error of a smooth 8-bit gradient.
             const dxb_f2 sk2 = dxb_bc2(sk);
-            const dxb_f2 q01 = dxb_add2(dxb_add2(dxb_fma2(d01, sk2, Dc01), MG), nMG), q23 = dxb_add2(dxb_add2(dxb_fma2(d23, sk2, Dc23), MG), nMG);
-            const dxb_f2 e01 = dxb_sub2(P01, q01), e23 = dxb_sub2(P23, q23);
-            const dxb_f2 sq = dxb_fma2(e23, e23, dxb_mul2(e01, e01));
+            const dxb_f2 q01 = R6_add2(R6_add2(R6_fma2(d01, sk2, Dc01), MG), nMG), q23 = R6_add2(R6_add2(R6_fma2(d23, sk2, Dc23), MG), nMG);
+            const dxb_f2 e01 = R6_sub2(P01, q01), e23 = R6_sub2(P23, q23);
+            const dxb_f2 sq = R6_fma2(e23, e23, R6_mul2(e01, e01));
             err = dxb_fma(f, sq.x + sq.y, err);
             if (!last)
             {
@@ -733,7 +750,7 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
                 const float skf = sk * f;
                 lb += skf; lc = dxb_fma(skf, sk, lc);
                 const dxb_f2 skf2 = dxb_bc2(skf);
-                V01 = dxb_fma2(skf2, P01, V01); V23 = dxb_fma2(skf2, P23, V23);
+                V01 = R6_fma2(skf2, P01, V01); V23 = R6_fma2(skf2, P23, V23);
             }
         }
         v0 = V01.x; v1 = V01.y; v2 = V23.x; v3 = V23.y;

@@ -154,6 +154,11 @@ DXB_DEV dxb_f2 dxb_add2(dxb_f2 a, dxb_f2 b) { return dxb_mk2(a.x + b.x, a.y + b.
 DXB_DEV dxb_f2 dxb_mul2(dxb_f2 a, dxb_f2 b) { return dxb_mk2(a.x * b.x, a.y * b.y); }
 #endif
 DXB_DEV dxb_f2 dxb_sub2(dxb_f2 a, dxb_f2 b) { return dxb_add2(a, dxb_mk2(-b.x, -b.y)); }
+// the same operations issued as two scalar instructions each (experiments: -DDXB_SCALAR_REGION=<n> in dxb_bc7.cuh)
+DXB_DEV dxb_f2 dxb_fma2s(dxb_f2 a, dxb_f2 b, dxb_f2 c) { return dxb_mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+DXB_DEV dxb_f2 dxb_add2s(dxb_f2 a, dxb_f2 b) { return dxb_mk2(a.x + b.x, a.y + b.y); }
+DXB_DEV dxb_f2 dxb_mul2s(dxb_f2 a, dxb_f2 b) { return dxb_mk2(a.x * b.x, a.y * b.y); }
+DXB_DEV dxb_f2 dxb_sub2s(dxb_f2 a, dxb_f2 b) { return dxb_mk2(a.x - b.x, a.y - b.y); }
 DXB_DEV dxb_f2 dxb_bc2(float v) { return dxb_mk2(v, v); }
 
 // ---- IEEE binary16 <-> binary32 (RNE, denormals kept, overflow -> Inf) ----
