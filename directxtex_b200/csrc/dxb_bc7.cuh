@@ -23,7 +23,7 @@
 //            fix-up, every lane shifts its index fields and one endpoint field into a 128-bit word, half-warp
 //            OR-reduction, one 128-bit store per block
 // Modes tried with default flags equal the reference's (1,3,4,5,6 and 7 when alpha != 255, :2803-2821);
-// BC7_QUICK keeps only mode 6 (:2811); USE_3SUBSETS is accepted and ignored (modes 0/2 are never emitted).
+// BC7_QUICK keeps only mode 6 (:2811); with USE_3SUBSETS a second pass of lane tasks tries the three-subset modes 0 and 2 (:2807).
 // Error metric = the reference's: sum of squared 8-bit differences over R,G,B,A (ComputeError :1559-1596).
 #pragma once
 #include "dxb_warp.cuh"
@@ -556,13 +556,15 @@ struct dxb_bc7_modecfg { uint32_t cbits, abits, ptype /*0 none,1 unique,2 shared
 DXB_DEV dxb_bc7_modecfg dxb_bc7_cfg(int mode)
 {
     // packed per mode: cbits | abits<<4 | ptype<<8 | ib<<12 | ib2<<16   (mode table BC6HBC7.cpp:1106-1124)
+    const uint32_t t0 = 4u | (0u << 4) | (1u << 8) | (3u << 12) | (0u << 16);
+    const uint32_t t2 = 5u | (0u << 4) | (0u << 8) | (2u << 12) | (0u << 16);
     const uint32_t t1 = 6u | (0u << 4) | (2u << 8) | (3u << 12) | (0u << 16);
     const uint32_t t3 = 7u | (0u << 4) | (1u << 8) | (2u << 12) | (0u << 16);
     const uint32_t t4 = 5u | (6u << 4) | (0u << 8) | (2u << 12) | (3u << 16);
     const uint32_t t5 = 7u | (8u << 4) | (0u << 8) | (2u << 12) | (2u << 16);
     const uint32_t t6 = 7u | (7u << 4) | (1u << 8) | (4u << 12) | (0u << 16);
     const uint32_t t7 = 5u | (5u << 4) | (1u << 8) | (2u << 12) | (0u << 16);
-    const uint32_t t = (mode == 1) ? t1 : (mode == 3) ? t3 : (mode == 4) ? t4 : (mode == 5) ? t5 : (mode == 6) ? t6 : t7;
+    const uint32_t t = (mode == 0) ? t0 : (mode == 2) ? t2 : (mode == 1) ? t1 : (mode == 3) ? t3 : (mode == 4) ? t4 : (mode == 5) ? t5 : (mode == 6) ? t6 : t7;
     dxb_bc7_modecfg c;
     c.cbits = t & 15u; c.abits = (t >> 4) & 15u; c.ptype = (t >> 8) & 15u; c.ib = (t >> 12) & 15u; c.ib2 = (t >> 16) & 15u;
     return c;
@@ -577,7 +579,7 @@ DXB_DEV dxb_bc7_modecfg dxb_bc7_cfg(int mode)
 // table.  Channels outside chmask have zero moments, axis and endpoints, so one instruction stream serves every task.
 // Idle lanes (idle = true) run the same code on dummy parameters.  The result's q0/q1 byte c = the field of natural
 // channel c (0 for channels outside chmask).
-struct dxb_bc7_task { uint32_t shape, mask, chmask, bits, ptype, ib; bool idle; };
+struct dxb_bc7_task { uint32_t shape, mask, chmask, bits, ptype, ib; bool idle, direct; };   // direct: moments summed from the pixels (masks without a row in the stage-1 table: three-subset shapes)
 
 DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc7_task& T)
 {
@@ -593,10 +595,28 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
     {
         const bool whole = (mask == 0xFFFFu);
         const bool sub0 = !whole && ((mask & 1u) != 0u);        // pixel 0 always belongs to subset 0
-        float R[14], T[14];
-        dxb_bc7_mt_load(mt, whole ? 64 : (int)shape, R);
-        dxb_bc7_mt_load(mt, 64, T);
-        for (int k = 0; k < 14; ++k) R[k] = sub0 ? T[k] - R[k] : R[k];
+        float R[14], TT[14];
+        if (T.direct)
+        {
+            // exact integers < 2^24 in any order, like the table's entries
+            for (int k = 0; k < 14; ++k) R[k] = 0.0f;
+            for (int i = 0; i < 16; ++i)
+            {
+                const float f = dxb_bit_as_float(mask, i);
+                const dxb_px p = px[i];
+                const float x = p.x * f, y = p.y * f, z = p.z * f, w = p.w * f;
+                R[0] += x; R[1] += y; R[2] += z; R[3] += w;
+                R[4] = dxb_fma(x, p.x, R[4]); R[5] = dxb_fma(x, p.y, R[5]); R[6] = dxb_fma(x, p.z, R[6]); R[7] = dxb_fma(x, p.w, R[7]);
+                R[8] = dxb_fma(y, p.y, R[8]); R[9] = dxb_fma(y, p.z, R[9]); R[10] = dxb_fma(y, p.w, R[10]);
+                R[11] = dxb_fma(z, p.z, R[11]); R[12] = dxb_fma(z, p.w, R[12]); R[13] = dxb_fma(w, p.w, R[13]);
+            }
+        }
+        else
+        {
+            dxb_bc7_mt_load(mt, whole ? 64 : (int)shape, R);
+            dxb_bc7_mt_load(mt, 64, TT);
+            for (int k = 0; k < 14; ++k) R[k] = sub0 ? TT[k] - R[k] : R[k];
+        }
         for (int c = 0; c < 4; ++c) s[c] = R[c] * vm[c];
         m00 = R[4] * vm[0]; m01 = R[5] * (vm[0] * vm[1]); m02 = R[6] * (vm[0] * vm[2]); m03 = R[7] * (vm[0] * vm[3]);
         m11 = R[8] * vm[1]; m12 = R[9] * (vm[1] * vm[2]); m13 = R[10] * (vm[1] * vm[3]);
@@ -843,7 +863,7 @@ DXB_DEV void dxb_put_bits(dxb_u128* b, uint32_t pos, uint32_t nbits, uint32_t va
 //   S->px : LDR pixels of both blocks (floats 0..255): S->px[16 h + i] = pixel i of the half-h block
 //   out0/out1 : 16 output bytes of the half-0 / half-1 block (nullptr = that half carries no block)
 // Everything "per block" below is a lane-private value that is uniform inside a half.
-struct dxb_bc7_win { uint32_t mode, shape, rot, idx, q0[2], q1[2], pb[2]; };
+struct dxb_bc7_win { uint32_t mode, shape, rot, idx, q0[3], q1[3], pb[3]; };
 #if !DXB_ON_DEVICE
 // test-infrastructure hook of the host emulator only (tools/bc_quality.py experiments): force the first candidate
 // shape of the half-0 / half-1 block (-1 = none)
@@ -943,7 +963,7 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
         int mode = -1, idxMode = 0, part = hl;
         uint32_t rot = 0;
         dxb_bc7_task T;
-        T.shape = 0; T.mask = 0xFFFFu; T.chmask = 0xFu; T.bits = 7u; T.ptype = 1u; T.ib = 4u; T.idle = false;
+        T.shape = 0; T.mask = 0xFFFFu; T.chmask = 0xFu; T.bits = 7u; T.ptype = 1u; T.ib = 4u; T.idle = false; T.direct = false;
         // rotation ranking from the block totals
         uint32_t r1 = 0, r2 = 0, r4 = 0;     // mode 5 rotations (best, second), mode 4 rotation
         {
@@ -1028,6 +1048,7 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
     // ---- stage 3: candidate error = the task's error + its partner's; winner of each half by integer key (ties: lowest lane,
     // which is the subset-0 / vector lane of its pair)
     dxb_bc7_win W[DXB_NL];
+    uint32_t wkeyA[DXB_NL];
     {
         uint32_t pe[DXB_NL], key[DXB_NL], wkey[DXB_NL], src[DXB_NL], src1[DXB_NL], wm[DXB_NL];
         uint32_t g0[DXB_NL], g1[DXB_NL], g2[DXB_NL], h0[DXB_NL], h1[DXB_NL], h2[DXB_NL];
@@ -1040,7 +1061,7 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
         DXB_LANES_END
         dxb_half_min_u32(key, wkey);
         DXB_LANES_BEGIN
-            src[L] = wkey[L] & 15u;
+            src[L] = wkey[L] & 15u; wkeyA[L] = wkey[L];
         DXB_LANES_END
         dxb_half_gather_u32(partner, src, src1);
         dxb_half_gather_u32(tMeta, src, wm);
@@ -1054,22 +1075,148 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
             const uint32_t a1 = sepA ? dxb_bc7_rotate_fields(g1[L] | h1[L], W[L].rot) : g1[L];
             W[L].q0[0] = a0; W[L].q1[0] = a1; W[L].pb[0] = (g2[L] >> 12) & 3u;
             W[L].q0[1] = sepA ? a0 : h0[L]; W[L].q1[1] = sepA ? a1 : h1[L]; W[L].pb[1] = (h2[L] >> 12) & 3u;
+            W[L].q0[2] = 0u; W[L].q1[2] = 0u; W[L].pb[2] = 0u;
+        DXB_LANES_END
+    }
+
+    // ---- three-subset modes 0 and 2 (TEX_COMPRESS_BC7_USE_3SUBSETS; the reference tries them only with the flag,
+    // BC6HBC7.cpp:2807): a second pass of lane tasks, taken only with the flag.  Both modes are RGB-only (alpha decodes as 255), so
+    // blocks with alpha skip the pass.
+    //   ranking   every three-subset shape (4 per lane) by the closed-form line-fit estimate of its three subsets; moments of
+    //             subsets 1 and 2 are summed from the pixels, subset 0 = block totals - the others.  Mode 0 has 4 partition
+    //             bits: shapes 0..15 = the first shape of every lane.
+    //   tasks     lanes 0-8 = mode 2, 3 best shapes x 3 subsets;  lanes 9-14 = mode 0, 2 best of shapes 0..15 x 3 subsets
+    //   winner    candidate = three consecutive lanes; replaces the winner of the first pass when its error is smaller
+    if ((bcflags & DXB_BC_FLAGS_USE_3SUBSETS) != 0u && !quick)
+    {
+        uint32_t k0[DXB_NL], k1[DXB_NL], k2[DXB_NL], z0[DXB_NL], selB[3][DXB_NL], selZ[2][DXB_NL];
+        DXB_LANES_BEGIN
+            const dxb_px* px = S->px + (lane & 16);
+            float tot[14];
+            dxb_bc7_mt_load(S->mt[lane >> 4], 64, tot);
+            uint32_t a = 0xFFFFFFFFu, b = 0xFFFFFFFFu, c = 0xFFFFFFFFu;
+            z0[L] = 0xFFFFFFFFu;
+#if DXB_ON_DEVICE
+            #pragma unroll 1
+#endif
+            for (int j = 0; j < 4; ++j)
+            {
+                const uint32_t shape = (uint32_t)(lane & 15) + 16u * (uint32_t)j;
+                const uint32_t part = dxb_part3[shape];
+                float s1[14], s2[14], s0[14];
+                for (int k = 0; k < 14; ++k) { s1[k] = 0.0f; s2[k] = 0.0f; }
+                uint32_t n1 = 0, n2 = 0;
+                for (int i = 0; i < 16; ++i)
+                {
+                    const uint32_t sub = (part >> (2 * i)) & 3u;
+                    const float f1 = (sub == 1u) ? 1.0f : 0.0f, f2 = (sub == 2u) ? 1.0f : 0.0f;
+                    n1 += (sub == 1u) ? 1u : 0u; n2 += (sub == 2u) ? 1u : 0u;
+                    const dxb_px p = px[i];
+                    const float xx = p.x * p.x, xy = p.x * p.y, xz = p.x * p.z, yy = p.y * p.y, yz = p.y * p.z, zz = p.z * p.z;
+                    s1[0] = dxb_fma(f1, p.x, s1[0]); s1[1] = dxb_fma(f1, p.y, s1[1]); s1[2] = dxb_fma(f1, p.z, s1[2]);
+                    s1[4] = dxb_fma(f1, xx, s1[4]); s1[5] = dxb_fma(f1, xy, s1[5]); s1[6] = dxb_fma(f1, xz, s1[6]);
+                    s1[8] = dxb_fma(f1, yy, s1[8]); s1[9] = dxb_fma(f1, yz, s1[9]); s1[11] = dxb_fma(f1, zz, s1[11]);
+                    s2[0] = dxb_fma(f2, p.x, s2[0]); s2[1] = dxb_fma(f2, p.y, s2[1]); s2[2] = dxb_fma(f2, p.z, s2[2]);
+                    s2[4] = dxb_fma(f2, xx, s2[4]); s2[5] = dxb_fma(f2, xy, s2[5]); s2[6] = dxb_fma(f2, xz, s2[6]);
+                    s2[8] = dxb_fma(f2, yy, s2[8]); s2[9] = dxb_fma(f2, yz, s2[9]); s2[11] = dxb_fma(f2, zz, s2[11]);
+                }
+                for (int k = 0; k < 14; ++k) s0[k] = (tot[k] - s1[k]) - s2[k];
+                const uint32_t n0 = 16u - n1 - n2;
+                // mode 2: 2-bit indices; mode 0: 3-bit indices
+                const float e2 = (dxb_bc7_subset_estimate3(n0, s0, 1.0f / 9.0f) + dxb_bc7_subset_estimate3(n1, s1, 1.0f / 9.0f)) + dxb_bc7_subset_estimate3(n2, s2, 1.0f / 9.0f);
+                const uint32_t x = (dxb_float_as_uint(e2) & 0xFFFFFFC0u) | shape;
+                const uint32_t lo = (x < a) ? x : a, hi = (x < a) ? a : x;               // sorted insert
+                const uint32_t lo2 = (hi < b) ? hi : b, hi2 = (hi < b) ? b : hi;
+                a = lo; b = lo2; c = (hi2 < c) ? hi2 : c;
+                if (j == 0)
+                {
+                    const float e0 = (dxb_bc7_subset_estimate3(n0, s0, 1.0f / 49.0f) + dxb_bc7_subset_estimate3(n1, s1, 1.0f / 49.0f)) + dxb_bc7_subset_estimate3(n2, s2, 1.0f / 49.0f);
+                    z0[L] = (dxb_float_as_uint(e0) & 0xFFFFFFC0u) | shape;
+                }
+            }
+            k0[L] = a; k1[L] = b; k2[L] = c;
+        DXB_LANES_END
+        for (int r = 0; r < 3; ++r)
+        {
+            uint32_t win[DXB_NL];
+            dxb_half_min_u32(k0, win);
+            DXB_LANES_BEGIN
+                selB[r][L] = win[L] & 63u;
+                if (k0[L] == win[L]) { k0[L] = k1[L]; k1[L] = k2[L]; k2[L] = 0xFFFFFFFFu; }
+            DXB_LANES_END
+        }
+        for (int r = 0; r < 2; ++r)
+        {
+            uint32_t win[DXB_NL];
+            dxb_half_min_u32(z0, win);
+            DXB_LANES_BEGIN
+                selZ[r][L] = win[L] & 63u;
+                if (z0[L] == win[L]) z0[L] = 0xFFFFFFFFu;
+            DXB_LANES_END
+        }
+        dxb_phase_sync();
+        uint32_t bMeta[DXB_NL], bErr[DXB_NL], bQ0[DXB_NL], bQ1[DXB_NL], n1i[DXB_NL], n2i[DXB_NL];
+        DXB_LANES_BEGIN
+            const int hl = lane & 15;
+            const bool m2 = (hl < 9);
+            const int t = m2 ? hl : hl - 9;
+            const int k = t / 3, sub = t - 3 * k;
+            dxb_bc7_task T;
+            T.shape = m2 ? ((k == 0) ? selB[0][L] : (k == 1) ? selB[1][L] : selB[2][L]) : ((k == 0) ? selZ[0][L] : selZ[1][L]);
+            const uint32_t part = dxb_part3[T.shape];
+            uint32_t mask = 0;
+            for (int i = 0; i < 16; ++i) mask |= (((part >> (2 * i)) & 3u) == (uint32_t)sub) ? (1u << i) : 0u;
+            T.mask = mask; T.chmask = 0x7u; T.bits = m2 ? 5u : 4u; T.ptype = m2 ? 0u : 1u; T.ib = m2 ? 2u : 3u;
+            T.direct = true; T.idle = (hl == 15) || (hasA[L] != 0u);
+            const dxb_bc7_res res = dxb_bc7_eval(S->px + (lane & 16), S->mt[lane >> 4], T);
+            bMeta[L] = (m2 ? 2u : 0u) | (T.shape << 3) | (res.pbits << 12) | ((uint32_t)sub << 16);
+            bErr[L] = T.idle ? 0x03FFFFFFu : (uint32_t)dxb_f2i(fminf(res.err, 6.0e7f));
+            bQ0[L] = res.q0; bQ1[L] = res.q1;
+            n1i[L] = (uint32_t)((hl + 1) & 15); n2i[L] = (uint32_t)((hl + 2) & 15);
+        DXB_LANES_END
+        dxb_phase_sync();
+        uint32_t e1[DXB_NL], e2[DXB_NL], key[DXB_NL], wkey[DXB_NL], src[DXB_NL], src1[DXB_NL], src2[DXB_NL];
+        dxb_half_gather_u32(bErr, n1i, e1); dxb_half_gather_u32(bErr, n2i, e2);
+        DXB_LANES_BEGIN
+            uint32_t e = bErr[L] + e1[L] + e2[L];
+            e = (e > 0x03FFFFFFu || ((bMeta[L] >> 16) & 3u) != 0u || (lane & 15) == 15) ? 0x03FFFFFFu : e;
+            key[L] = (e << 5) | (uint32_t)(lane & 15);
+        DXB_LANES_END
+        dxb_half_min_u32(key, wkey);
+        DXB_LANES_BEGIN
+            src[L] = wkey[L] & 15u; src1[L] = (src[L] + 1u) & 15u; src2[L] = (src[L] + 2u) & 15u;
+        DXB_LANES_END
+        uint32_t gm[DXB_NL], g0[DXB_NL], g1[DXB_NL], h0[DXB_NL], h1[DXB_NL], hm[DXB_NL], i0[DXB_NL], i1[DXB_NL], im[DXB_NL];
+        dxb_half_gather_u32(bMeta, src, gm); dxb_half_gather_u32(bQ0, src, g0); dxb_half_gather_u32(bQ1, src, g1);
+        dxb_half_gather_u32(bMeta, src1, hm); dxb_half_gather_u32(bQ0, src1, h0); dxb_half_gather_u32(bQ1, src1, h1);
+        dxb_half_gather_u32(bMeta, src2, im); dxb_half_gather_u32(bQ0, src2, i0); dxb_half_gather_u32(bQ1, src2, i1);
+        DXB_LANES_BEGIN
+            if ((wkey[L] >> 5) < (wkeyA[L] >> 5))
+            {
+                W[L].mode = gm[L] & 7u; W[L].shape = (gm[L] >> 3) & 63u; W[L].rot = 0u; W[L].idx = 0u;
+                W[L].q0[0] = g0[L]; W[L].q1[0] = g1[L]; W[L].pb[0] = (gm[L] >> 12) & 3u;
+                W[L].q0[1] = h0[L]; W[L].q1[1] = h1[L]; W[L].pb[1] = (hm[L] >> 12) & 3u;
+                W[L].q0[2] = i0[L]; W[L].q1[2] = i1[L]; W[L].pb[2] = (im[L] >> 12) & 3u;
+            }
         DXB_LANES_END
     }
 
     // ---- stage 4: every lane = one pixel of its block: exhaustive nearest palette entry
-    uint32_t idxC[DXB_NL], idxA[DXB_NL], anchorSrc[DXB_NL], zeroSrc[DXB_NL];
+    uint32_t idxC[DXB_NL], idxA[DXB_NL], anchor1Src[DXB_NL], anchor2Src[DXB_NL], zeroSrc[DXB_NL];
     DXB_LANES_BEGIN
         const int hl = lane & 15;
         const uint32_t wMode = W[L].mode;
         const dxb_bc7_modecfg cfg = dxb_bc7_cfg((int)wMode);
         const bool two = (wMode == 1u || wMode == 3u || wMode == 7u);
+        const bool three = (wMode == 0u || wMode == 2u);
         const bool sepA = (wMode == 4u || wMode == 5u);
         const uint32_t ibc = (wMode == 4u && W[L].idx) ? 3u : cfg.ib;
         const uint32_t iba = (wMode == 4u) ? (W[L].idx ? 2u : 3u) : cfg.ib2;
-        const uint32_t part = two ? dxb_part2[W[L].shape] : 0u;
-        const int sb = (int)((part >> hl) & 1u);
-        const uint32_t q0 = sb ? W[L].q0[1] : W[L].q0[0], q1 = sb ? W[L].q1[1] : W[L].q1[0], pb = sb ? W[L].pb[1] : W[L].pb[0];
+        // subset of this lane's pixel
+        const uint32_t sb = three ? ((dxb_part3[W[L].shape] >> (2 * hl)) & 3u) : (two ? ((dxb_part2[W[L].shape] >> hl) & 1u) : 0u);
+        const uint32_t q0 = (sb == 2u) ? W[L].q0[2] : (sb == 1u) ? W[L].q0[1] : W[L].q0[0];
+        const uint32_t q1 = (sb == 2u) ? W[L].q1[2] : (sb == 1u) ? W[L].q1[1] : W[L].q1[0];
+        const uint32_t pb = (sb == 2u) ? W[L].pb[2] : (sb == 1u) ? W[L].pb[1] : W[L].pb[0];
         const uint32_t hasP = (cfg.ptype != 0 && !sepA) ? 1u : 0u;
         int32_t e0[4], e1[4];
         for (uint32_t c = 0; c < 4; ++c)
@@ -1089,43 +1236,47 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
         }
         else
             idxC[L] = dxb_bc7_nearest(p, e0, e1, 0, (wMode == 6u || wMode == 7u) ? 4 : 3, ibc);
-        anchorSrc[L] = two ? dxb_anchor2[W[L].shape] : 0u;
+        anchor1Src[L] = three ? dxb_anchor3a[W[L].shape] : (two ? dxb_anchor2[W[L].shape] : 0u);
+        anchor2Src[L] = three ? dxb_anchor3b[W[L].shape] : 0u;
         zeroSrc[L] = 0u;
     DXB_LANES_END
 
     // anchor fix-up: the anchor index of each subset must have its MSB clear; otherwise swap that
     // subset's endpoints and mirror its indices (weights are symmetric: w[n-k] = 64 - w[k])
-    uint32_t aC0[DXB_NL], aC1[DXB_NL], aA0[DXB_NL];
+    uint32_t aC0[DXB_NL], aC1[DXB_NL], aC2[DXB_NL], aA0[DXB_NL];
     dxb_half_gather_u32(idxC, zeroSrc, aC0);
-    dxb_half_gather_u32(idxC, anchorSrc, aC1);
+    dxb_half_gather_u32(idxC, anchor1Src, aC1);
+    dxb_half_gather_u32(idxC, anchor2Src, aC2);
     dxb_half_gather_u32(idxA, zeroSrc, aA0);
 
     // bit layout (D3DX_BC7::Decode, BC6HBC7.cpp:2566-2780): mode (unary), partition, rotation, index
     // selector, then R of every endpoint, G, B, A, p-bits, colour indices, alpha indices.
-    // Every lane contributes its pixel's index fields AND one endpoint field (lane = 4 * channel + endpoint);
-    // lanes 0..3 add the p-bits, lane 0 the header.
+    // Every lane contributes its pixel's index fields AND the endpoint fields hl and hl + 16 (field = channel x endpoint, up to
+    // 18 for the three-subset modes); lanes 0..5 add the p-bits, lane 0 the header.
     uint32_t w0[DXB_NL], w1[DXB_NL], w2[DXB_NL], w3[DXB_NL];
     DXB_LANES_BEGIN
         const uint32_t hl = (uint32_t)(lane & 15);
         const uint32_t wMode = W[L].mode, wIdx = W[L].idx;
         const dxb_bc7_modecfg cfg = dxb_bc7_cfg((int)wMode);
         const bool two = (wMode == 1u || wMode == 3u || wMode == 7u);
+        const bool three = (wMode == 0u || wMode == 2u);
         const bool sepA = (wMode == 4u || wMode == 5u);
         const uint32_t ibc = (wMode == 4u && wIdx) ? 3u : cfg.ib;
         const uint32_t iba = (wMode == 4u) ? (wIdx ? 2u : 3u) : cfg.ib2;
-        const uint32_t part = two ? dxb_part2[W[L].shape] : 0u;
-        const uint32_t anchor1 = anchorSrc[L];
+        const uint32_t nsub = three ? 3u : (two ? 2u : 1u);
+        const uint32_t sb = three ? ((dxb_part3[W[L].shape] >> (2 * hl)) & 3u) : (two ? ((dxb_part2[W[L].shape] >> hl) & 1u) : 0u);
+        const uint32_t anchor1 = anchor1Src[L], anchor2 = anchor2Src[L];
         const bool flipC0 = ((aC0[L] >> (ibc - 1u)) & 1u) != 0;
-        const bool flipC1 = two && (((aC1[L] >> (ibc - 1u)) & 1u) != 0);
+        const bool flipC1 = (nsub >= 2u) && (((aC1[L] >> (ibc - 1u)) & 1u) != 0);
+        const bool flipC2 = (nsub == 3u) && (((aC2[L] >> (ibc - 1u)) & 1u) != 0);
         const bool flipA = (iba != 0) && (((aA0[L] >> (iba - 1u)) & 1u) != 0);
         uint32_t iC = idxC[L], iA = idxA[L];
         {
-            const bool fl = ((part >> hl) & 1u) ? flipC1 : flipC0;
+            const bool fl = (sb == 2u) ? flipC2 : (sb == 1u) ? flipC1 : flipC0;
             if (fl) iC = ((1u << ibc) - 1u) - iC;
             if (flipA) iA = ((1u << iba) - 1u) - iA;
         }
-        const uint32_t nsub = two ? 2u : 1u;
-        const uint32_t partBits = two ? 6u : 0u;
+        const uint32_t partBits = three ? ((wMode == 0u) ? 4u : 6u) : (two ? 6u : 0u);
         const uint32_t rotBits = sepA ? 2u : 0u;
         const uint32_t imBits = (wMode == 4u) ? 1u : 0u;
         const uint32_t hdr = (wMode + 1u) + partBits + rotBits + imBits;
@@ -1142,28 +1293,32 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
         {
             // index fields of pixel hl
             const uint32_t first = swapSets ? iA : iC, second = swapSets ? iC : iA;
-            const uint32_t before = (hl > 0 ? 1u : 0u) + ((two && hl > anchor1) ? 1u : 0u);   // anchors before this pixel
-            const bool isAnchor = (hl == 0) || (two && hl == anchor1);
+            const uint32_t before = (hl > 0 ? 1u : 0u) + ((nsub >= 2u && hl > anchor1) ? 1u : 0u) + ((nsub == 3u && hl > anchor2) ? 1u : 0u);   // anchors before this pixel
+            const bool isAnchor = (hl == 0) || (nsub >= 2u && hl == anchor1) || (nsub == 3u && hl == anchor2);
             dxb_put_bits(&bits, idxStart + hl * ib1 - before, isAnchor ? ib1 - 1u : ib1, first);
             dxb_put_bits(&bits, secondStart + (hl ? hl * ib2v - 1u : 0u), ib2v ? (hl ? ib2v : ib2v - 1u) : 0u, second);
         }
+        for (uint32_t fi = hl; fi < 2u * nsub * 4u; fi += 16u)
         {
-            // endpoint field: channel c, endpoint e = 2 * subset + which.  Colour channels follow the colour
+            // endpoint field fi: channel c = fi / (2 nsub), endpoint e = 2 * subset + which.  Colour channels follow the colour
             // flip of their subset; in modes 4/5 the alpha channel has its own index set and follows flipA.
-            const uint32_t c = hl >> 2, e = hl & 3u, sub = e >> 1, which = e & 1u;
-            const bool fl = (sepA && c == 3u) ? flipA : (sub ? flipC1 : flipC0);
-            const uint32_t qa = sub ? W[L].q0[1] : W[L].q0[0], qb = sub ? W[L].q1[1] : W[L].q1[0];
+            const uint32_t per = 2u * nsub;
+            const uint32_t c = (per == 2u) ? (fi >> 1) : (per == 4u) ? (fi >> 2) : (fi / 6u);
+            const uint32_t e = fi - c * per, sub = e >> 1, which = e & 1u;
+            const bool fl = (sepA && c == 3u) ? flipA : ((sub == 2u) ? flipC2 : (sub == 1u) ? flipC1 : flipC0);
+            const uint32_t qa = (sub == 2u) ? W[L].q0[2] : (sub == 1u) ? W[L].q0[1] : W[L].q0[0];
+            const uint32_t qb = (sub == 2u) ? W[L].q1[2] : (sub == 1u) ? W[L].q1[1] : W[L].q1[0];
             const uint32_t field = (((which != 0u) != fl) ? qb : qa) >> (8u * c);
             const uint32_t nb = (c == 3u) ? cfg.abits : cfg.cbits;
-            const uint32_t pos = hdr + ((c == 3u) ? 3u * 2u * nsub * cfg.cbits + e * cfg.abits : (c * 2u * nsub + e) * cfg.cbits);
-            dxb_put_bits(&bits, pos, (e < 2u * nsub) ? nb : 0u, field & 0xFFu);
+            const uint32_t pos = hdr + ((c == 3u) ? 3u * per * cfg.cbits + e * cfg.abits : (c * per + e) * cfg.cbits);
+            dxb_put_bits(&bits, pos, nb, field & 0xFFu);
         }
         if (hl < npb)
         {
             // p-bits: unique (ptype 1): endpoint order; shared (ptype 2): one per subset
             const uint32_t sub = (cfg.ptype == 2) ? hl : (hl >> 1), which = (cfg.ptype == 2) ? 0u : (hl & 1u);
-            const bool fl = sub ? flipC1 : flipC0;
-            const uint32_t pbv = sub ? W[L].pb[1] : W[L].pb[0];
+            const bool fl = (sub == 2u) ? flipC2 : (sub == 1u) ? flipC1 : flipC0;
+            const uint32_t pbv = (sub == 2u) ? W[L].pb[2] : (sub == 1u) ? W[L].pb[1] : W[L].pb[0];
             const uint32_t bit = (cfg.ptype == 2) ? (pbv & 1u) : ((pbv >> (((which != 0u) != fl) ? 1u : 0u)) & 1u);
             dxb_put_bits(&bits, hdr + epBits + hl, 1, bit);
         }

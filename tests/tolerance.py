@@ -32,7 +32,8 @@ def golden():
 
 def bc7_cases():
     """(class, TEX_COMPRESS flags)"""
-    return [(k, 0) for k in synth.LDR_CLASSES]
+    # default flags on every class; TEX_COMPRESS_BC7_USE_3SUBSETS (modes 0 / 2) on the classes where the reference gains from it
+    return [(k, 0) for k in synth.LDR_CLASSES] + [(k, F.TEX_COMPRESS_BC7_USE_3SUBSETS) for k in ("noise", "cluster3", "cluster4", "chan_uncorr", "photo", "c2", "text")]
 
 
 def bc6h_cases():
