@@ -870,6 +870,9 @@ struct dxb_bc7_win { uint32_t mode, shape, rot, idx, q0[3], q1[3], pb[3]; };
 static thread_local int dxb_bc7_dbg_force_shape[2] = { -1, -1 };
 #endif
 
+// THREE: compile the three-subset pass (TEX_COMPRESS_BC7_USE_3SUBSETS); the default kernel is instantiated without it so that
+// its instruction footprint (the kernel is sensitive to instruction-cache misses) does not grow for a non-default flag.
+template <bool THREE>
 DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* out0, uint8_t* out1)
 {
     const bool quick = (bcflags & DXB_BC_FLAGS_FORCE_BC7_MODE6) != 0;
@@ -1087,7 +1090,7 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
     //             bits: shapes 0..15 = the first shape of every lane.
     //   tasks     lanes 0-8 = mode 2, 3 best shapes x 3 subsets;  lanes 9-14 = mode 0, 2 best of shapes 0..15 x 3 subsets
     //   winner    candidate = three consecutive lanes; replaces the winner of the first pass when its error is smaller
-    if ((bcflags & DXB_BC_FLAGS_USE_3SUBSETS) != 0u && !quick)
+    if (THREE && (bcflags & DXB_BC_FLAGS_USE_3SUBSETS) != 0u && !quick)
     {
         uint32_t k0[DXB_NL], k1[DXB_NL], k2[DXB_NL], z0[DXB_NL], selB[3][DXB_NL], selZ[2][DXB_NL];
         DXB_LANES_BEGIN
@@ -1355,6 +1358,6 @@ static inline void dxb_bc7_encode_pair_emul(const dxb_px* pxA, const dxb_px* pxB
         S.px[16 + i] = pxB ? dxb_make_px(dxb_bc7_ldr(pxB[i].x), dxb_bc7_ldr(pxB[i].y), dxb_bc7_ldr(pxB[i].z), dxb_bc7_ldr(pxB[i].w))
                            : dxb_make_px(0.0f, 0.0f, 0.0f, 255.0f);
     }
-    dxb_bc7_encode_pair(&S, bcflags, outA, pxB ? outB : nullptr);
+    dxb_bc7_encode_pair<true>(&S, bcflags, outA, pxB ? outB : nullptr);
 }
 #endif

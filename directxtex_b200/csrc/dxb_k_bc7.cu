@@ -2,6 +2,7 @@
 #include "dxb_launch.h"
 #include "dxb_bc7.cuh"
 
+template <bool THREE>
 __global__ void __launch_bounds__(DXB_BC7_WARPS * 32, DXB_BC7_MINB) k_compress_bc7(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(DXB_BC7_WARPS * 32, DXB_BC7_MINB) k_compress_b
         S->px[lane] = ldr;
         __syncwarp();
         // the encoder takes one output pointer per half; every lane passes its own half's pointer in both slots
-        dxb_bc7_encode_pair(S, P.bcflags, out, out);
+        dxb_bc7_encode_pair<THREE>(S, P.bcflags, out, out);
         __syncwarp();
     }
 }
@@ -46,18 +47,21 @@ __global__ void __launch_bounds__(DXB_BC7_WARPS * 32, DXB_BC7_MINB) k_compress_b
 static const size_t kBC7Smem = sizeof(dxb_bc7_scratch) * DXB_BC7_WARPS;
 static bool bc7_attr_set()
 {
-    static const bool ok = (cudaFuncSetAttribute(k_compress_bc7, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7Smem) == cudaSuccess);
+    static const bool ok = (cudaFuncSetAttribute(k_compress_bc7<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7Smem) == cudaSuccess) &&
+                           (cudaFuncSetAttribute(k_compress_bc7<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBC7Smem) == cudaSuccess);
     return ok;
 }
 
 void dxb_launch_bc7(unsigned grid, cudaStream_t stream, const dxb_job* jobs, const dxb_job& single, const dxb_compress_params& P)
 {
     bc7_attr_set();
-    k_compress_bc7<<<grid, DXB_BC7_WARPS * 32, kBC7Smem, stream>>>(jobs, single, P);
+    // the three-subset pass (a non-default flag) lives in its own instantiation
+    if (P.bcflags & DXB_BC_FLAGS_USE_3SUBSETS) k_compress_bc7<true><<<grid, DXB_BC7_WARPS * 32, kBC7Smem, stream>>>(jobs, single, P);
+    else k_compress_bc7<false><<<grid, DXB_BC7_WARPS * 32, kBC7Smem, stream>>>(jobs, single, P);
 }
 int dxb_occupancy_bc7()
 {
     int b = 0;
-    if (!bc7_attr_set() || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc7, DXB_BC7_WARPS * 32, kBC7Smem) != cudaSuccess) { (void)cudaGetLastError(); b = 1; }
+    if (!bc7_attr_set() || cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc7<false>, DXB_BC7_WARPS * 32, kBC7Smem) != cudaSuccess) { (void)cudaGetLastError(); b = 1; }
     return b > 0 ? b : 1;
 }
