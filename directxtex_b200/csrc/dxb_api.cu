@@ -495,6 +495,9 @@ int32_t plan_convert(const dxb200_image* src, size_t n, uint32_t dstFormat, uint
     if (!is_supported_pixel_format(srcFormat) || !is_supported_pixel_format(dstFormat)) return DXB_E_NOT_SUPPORTED;
     // TEX_FILTER_DITHER = ordered 4x4 dithering; TEX_FILTER_DITHER_DIFFUSION = Floyd-Steinberg (serial per image, :4815-4858)
     if (filter & (DXB_FILTER_DITHER_MASK & ~(DXB_FILTER_DITHER | DXB_FILTER_DITHER_DIFFUSION))) return DXB_E_NOT_SUPPORTED;
+    // the 16-bit packed destinations have dithered stores in the reference (:4302-4500) that this backend does not restate yet
+    if ((filter & DXB_FILTER_DITHER_MASK) && (dstFormat == DXB_FMT_B5G6R5_UNORM || dstFormat == DXB_FMT_B5G5R5A1_UNORM || dstFormat == DXB_FMT_B4G4R4A4_UNORM))
+        return DXB_E_NOT_SUPPORTED;
     for (size_t i = 0; i < n; ++i)
     {
         if (!src[i].pixels || !dst[i].pixels) return DXB_E_POINTER;
@@ -505,6 +508,7 @@ int32_t plan_convert(const dxb200_image* src, size_t n, uint32_t dstFormat, uint
     P->srcFormat = srcFormat; P->dstFormat = dstFormat;
     P->inF = dxb_convert_flags(srcFormat); P->outF = dxb_convert_flags(dstFormat);
     P->flags = dxb_resolve_srgb_convert(filter, srcFormat, dstFormat);
+    P->threshold = 0.5f;
     return DXB_S_OK;
 }
 
@@ -991,10 +995,10 @@ int32_t dxb200_decompress(const dxb200_image* src, size_t nimages, uint32_t dstF
 int32_t dxb200_convert_device(const dxb200_image* src, size_t nimages, uint32_t dstFormat, uint32_t filter, float threshold,
                               const dxb200_image* dst, void* stream)
 {
-    (void)threshold;        // only used by 1-bit alpha destinations (B5G5R5A1), not in the implemented set
     dxb_convert_params P;
     int32_t hr = plan_convert(src, nimages, dstFormat, filter, dst, &P);
     if (hr != DXB_S_OK) return hr;
+    P.threshold = threshold;       // alpha threshold of the 1-bit alpha destination (B5G5R5A1)
     DevScope scope;
     hr = scope.enter(src[0].pixels);
     if (hr != DXB_S_OK) return hr;
@@ -1004,10 +1008,10 @@ int32_t dxb200_convert_device(const dxb200_image* src, size_t nimages, uint32_t 
 int32_t dxb200_convert_ex(const dxb200_image* src, size_t nimages, uint32_t dstFormat, uint32_t filter, float threshold, const dxb200_image* dst,
                           dxb200_status_fn status, void* user)
 {
-    (void)threshold;
     dxb_convert_params P;
     int32_t hr = plan_convert(src, nimages, dstFormat, filter, dst, &P);
     if (hr != DXB_S_OK) return hr;
+    P.threshold = threshold;
     BandSplit bands;
     // bands start on multiples of 4 rows so that the 4x4 ordered-dither matrix keeps its phase
     // (error diffusion carries state from row to row: whole images only)

@@ -15,6 +15,7 @@ enum
     DXB_FMT_R16G16B16A16_SNORM = 13,
     DXB_FMT_R32G32_FLOAT = 16,
     DXB_FMT_R10G10B10A2_UNORM = 24,
+    DXB_FMT_R11G11B10_FLOAT = 26,
     DXB_FMT_R8G8B8A8_UNORM = 28,
     DXB_FMT_R8G8B8A8_UNORM_SRGB = 29,
     DXB_FMT_R8G8B8A8_SNORM = 31,
@@ -30,6 +31,7 @@ enum
     DXB_FMT_R8_UNORM = 61,
     DXB_FMT_R8_SNORM = 63,
     DXB_FMT_A8_UNORM = 65,
+    DXB_FMT_R9G9B9E5_SHAREDEXP = 67,
     DXB_FMT_BC1_UNORM = 71,
     DXB_FMT_BC1_UNORM_SRGB = 72,
     DXB_FMT_BC2_UNORM = 74,
@@ -40,6 +42,8 @@ enum
     DXB_FMT_BC4_SNORM = 81,
     DXB_FMT_BC5_UNORM = 83,
     DXB_FMT_BC5_SNORM = 84,
+    DXB_FMT_B5G6R5_UNORM = 85,
+    DXB_FMT_B5G5R5A1_UNORM = 86,
     DXB_FMT_B8G8R8A8_UNORM = 87,
     DXB_FMT_B8G8R8X8_UNORM = 88,
     DXB_FMT_B8G8R8A8_UNORM_SRGB = 91,
@@ -48,6 +52,7 @@ enum
     DXB_FMT_BC6H_SF16 = 96,
     DXB_FMT_BC7_UNORM = 98,
     DXB_FMT_BC7_UNORM_SRGB = 99,
+    DXB_FMT_B4G4R4A4_UNORM = 115,
 };
 
 // CONVERT_FLAGS (DirectXTexP.h:355-377)
@@ -112,6 +117,11 @@ DXB_FMT_FN uint32_t dxb_convert_flags(uint32_t fmt)
     case DXB_FMT_R16G16B16A16_SNORM:  return DXB_CONVF_SNORM | R | G | B | A;
     case DXB_FMT_R32G32_FLOAT:        return DXB_CONVF_FLOAT | R | G;
     case DXB_FMT_R10G10B10A2_UNORM:   return DXB_CONVF_UNORM | R | G | B | A;
+    case DXB_FMT_R11G11B10_FLOAT:     return DXB_CONVF_FLOAT | DXB_CONVF_POS_ONLY | R | G | B;
+    case DXB_FMT_R9G9B9E5_SHAREDEXP:  return DXB_CONVF_FLOAT | DXB_CONVF_SHAREDEXP | DXB_CONVF_POS_ONLY | R | G | B;
+    case DXB_FMT_B5G6R5_UNORM:        return DXB_CONVF_UNORM | R | G | B;                     // no CONVF_BGR: the swizzle is in Load / Store (:3024-3025)
+    case DXB_FMT_B5G5R5A1_UNORM:      return DXB_CONVF_UNORM | R | G | B | A;
+    case DXB_FMT_B4G4R4A4_UNORM:      return DXB_CONVF_UNORM | DXB_CONVF_BGR | R | G | B | A;
     case DXB_FMT_R8G8B8A8_UNORM:
     case DXB_FMT_R8G8B8A8_UNORM_SRGB: return DXB_CONVF_UNORM | R | G | B | A;
     case DXB_FMT_R8G8B8A8_SNORM:      return DXB_CONVF_SNORM | R | G | B | A;
@@ -156,8 +166,10 @@ DXB_FMT_FN uint32_t dxb_bytes_per_pixel(uint32_t fmt)
     case DXB_FMT_R16G16B16A16_FLOAT: case DXB_FMT_R16G16B16A16_UNORM: case DXB_FMT_R16G16B16A16_SNORM: case DXB_FMT_R32G32_FLOAT: return 8;
     case DXB_FMT_R10G10B10A2_UNORM: case DXB_FMT_R8G8B8A8_UNORM: case DXB_FMT_R8G8B8A8_UNORM_SRGB: case DXB_FMT_R8G8B8A8_SNORM:
     case DXB_FMT_R16G16_FLOAT: case DXB_FMT_R16G16_UNORM: case DXB_FMT_R16G16_SNORM: case DXB_FMT_R32_FLOAT:
-    case DXB_FMT_B8G8R8A8_UNORM: case DXB_FMT_B8G8R8X8_UNORM: case DXB_FMT_B8G8R8A8_UNORM_SRGB: case DXB_FMT_B8G8R8X8_UNORM_SRGB: return 4;
-    case DXB_FMT_R8G8_UNORM: case DXB_FMT_R8G8_SNORM: case DXB_FMT_R16_FLOAT: case DXB_FMT_R16_UNORM: case DXB_FMT_R16_SNORM: return 2;
+    case DXB_FMT_B8G8R8A8_UNORM: case DXB_FMT_B8G8R8X8_UNORM: case DXB_FMT_B8G8R8A8_UNORM_SRGB: case DXB_FMT_B8G8R8X8_UNORM_SRGB:
+    case DXB_FMT_R11G11B10_FLOAT: case DXB_FMT_R9G9B9E5_SHAREDEXP: return 4;
+    case DXB_FMT_R8G8_UNORM: case DXB_FMT_R8G8_SNORM: case DXB_FMT_R16_FLOAT: case DXB_FMT_R16_UNORM: case DXB_FMT_R16_SNORM:
+    case DXB_FMT_B5G6R5_UNORM: case DXB_FMT_B5G5R5A1_UNORM: case DXB_FMT_B4G4R4A4_UNORM: return 2;
     case DXB_FMT_R8_UNORM: case DXB_FMT_R8_SNORM: case DXB_FMT_A8_UNORM: return 1;
     default: return 0;
     }

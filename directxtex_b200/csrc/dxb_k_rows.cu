@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(256) k_convert(const dxb_job* __restrict__ job
         dxb_px v = dxb_load_pixel(P.srcFormat, j.src + (size_t)y * j.srcPitch, x);
         v = dxb_convert_pixel(v, P.inF, P.outF, P.flags);
         if (P.flags & DXB_FILTER_DITHER) dxb_store_pixel_dither(P.dstFormat, j.dst + (size_t)y * j.dstPitch, x, y, v);     // ordered dither (:4861-4879)
-        else dxb_store_pixel(P.dstFormat, j.dst + (size_t)y * j.dstPitch, x, v);
+        else dxb_store_pixel(P.dstFormat, j.dst + (size_t)y * j.dstPitch, x, v, P.threshold);
     }
 }
 

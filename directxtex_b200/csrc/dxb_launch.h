@@ -28,6 +28,7 @@ struct dxb_convert_params
 {
     uint32_t srcFormat, dstFormat, inF, outF, flags;
     uint32_t totalUnits, njobs;
+    float threshold;               // alpha threshold of 1-bit alpha destinations (B5G5R5A1)
 };
 
 struct dxb_mip_params

@@ -30,10 +30,88 @@ DXB_DEV float dxb_clamp(float v, float lo, float hi) { return dxb_ssemin(dxb_sse
 
 // ---------------------------------------------------------------------------------------------
 // Load pixel `i` of a row starting at `row` (byte pointer).  Missing channels default to (0,0,0,1).
+
+// ---- packed small-float formats, restated from the oracle's DirectXMath stand-in (oracle/compat/DirectXPackedVector.h,
+// XMLoadFloat3PK / XMStoreFloat3PK / XMLoadFloat3SE / XMStoreFloat3SE; marked (M) there: DirectXMath itself is not in the tree)
+DXB_DEV float dxb_smallfloat_decode(uint32_t m, uint32_t e, uint32_t mbits)
+{
+    uint32_t bits;
+    if (e == 0x1fu) bits = 0x7f800000u | (m << (23u - mbits));
+    else
+    {
+        int32_t ex;
+        if (e != 0u) ex = (int32_t)e;
+        else if (m != 0u)
+        {
+            ex = 1;
+            do { ex--; m <<= 1; } while ((m & (1u << mbits)) == 0u);
+            m &= (1u << mbits) - 1u;
+        }
+        else ex = -112;
+        bits = ((uint32_t)(ex + 112) << 23) | (m << (23u - mbits));
+    }
+    return dxb_uint_as_float(bits);
+}
+DXB_DEV uint32_t dxb_smallfloat_encode(float f, uint32_t mbits)
+{
+    uint32_t I = dxb_float_as_uint(f);
+    const uint32_t sign = I & 0x80000000u;
+    I &= 0x7FFFFFFFu;
+    const uint32_t maxv = (mbits == 6u) ? 0x7C0u : 0x3E0u;
+    const uint32_t shift = 23u - mbits;
+    if ((I & 0x7F800000u) == 0x7F800000u)
+    {
+        uint32_t r = maxv;
+        if (I & 0x7FFFFFu) r = maxv | (((I >> shift) | (I >> (shift - 6u)) | (I >> (shift - 12u)) | I) & ((1u << mbits) - 1u));
+        else if (sign) r = 0u;
+        return r;
+    }
+    if (sign) return 0u;
+    if (I > 0x477E0000u && mbits == 6u) return 0x7BFu;
+    if (I > 0x477C0000u && mbits == 5u) return 0x3DFu;
+    if (I < 0x38800000u)
+    {
+        const uint32_t sh = 113u - (I >> 23);
+        I = (sh < 32u) ? ((0x800000u | (I & 0x7FFFFFu)) >> sh) : 0u;
+    }
+    else I += 0xC8000000u;
+    const uint32_t half = (1u << (shift - 1u)) - 1u;
+    return ((I + half + ((I >> shift) & 1u)) >> shift) & ((mbits == 6u) ? 0x7FFu : 0x3FFu);
+}
+// pk::st_int of the stand-in: clamp, round to nearest even
+DXB_DEV uint32_t dxb_store_int_rne(float v, float hi) { return (uint32_t)dxb_f2i_rn(dxb_clamp(v, 0.0f, hi)); }
+
 DXB_DEV dxb_px dxb_load_pixel(uint32_t fmt, const uint8_t* row, size_t i)
 {
     switch (fmt)
     {
+    case DXB_FMT_R11G11B10_FLOAT:        // XMLoadFloat3PK, alpha 1 (DirectXTexConvert.cpp:906-920)
+    {
+        const uint32_t v = ((const uint32_t*)row)[i];
+        return dxb_make_px(dxb_smallfloat_decode(v & 0x3Fu, (v >> 6) & 0x1Fu, 6u), dxb_smallfloat_decode((v >> 11) & 0x3Fu, (v >> 17) & 0x1Fu, 6u),
+                           dxb_smallfloat_decode((v >> 22) & 0x1Fu, (v >> 27) & 0x1Fu, 5u), 1.0f);
+    }
+    case DXB_FMT_R9G9B9E5_SHAREDEXP:     // XMLoadFloat3SE, alpha 1 (:1189-1203)
+    {
+        const uint32_t v = ((const uint32_t*)row)[i];
+        const float scale = dxb_uint_as_float(0x33800000u + ((v >> 27) << 23));
+        return dxb_make_px(scale * (float)(v & 0x1FFu), scale * (float)((v >> 9) & 0x1FFu), scale * (float)((v >> 18) & 0x1FFu), 1.0f);
+    }
+    case DXB_FMT_B5G6R5_UNORM:           // XMLoadU565 * {1/31, 1/63, 1/31}, swizzled to RGB, alpha 1 (:1227-1242)
+    {
+        const uint32_t v = ((const uint16_t*)row)[i];
+        return dxb_make_px((float)((v >> 11) & 0x1Fu) * (1.0f / 31.0f), (float)((v >> 5) & 0x3Fu) * (1.0f / 63.0f), (float)(v & 0x1Fu) * (1.0f / 31.0f), 1.0f);
+    }
+    case DXB_FMT_B5G5R5A1_UNORM:         // XMLoadU555 * {1/31 x3, 1}, swizzled (:1244-1258)
+    {
+        const uint32_t v = ((const uint16_t*)row)[i];
+        return dxb_make_px((float)((v >> 10) & 0x1Fu) * (1.0f / 31.0f), (float)((v >> 5) & 0x1Fu) * (1.0f / 31.0f), (float)(v & 0x1Fu) * (1.0f / 31.0f), (float)(v >> 15) * 1.0f);
+    }
+    case DXB_FMT_B4G4R4A4_UNORM:         // XMLoadUNibble4 * 1/15, swizzled (:1511-1526)
+    {
+        const uint32_t v = ((const uint16_t*)row)[i];
+        return dxb_make_px((float)((v >> 8) & 0xFu) * (1.0f / 15.0f), (float)((v >> 4) & 0xFu) * (1.0f / 15.0f), (float)(v & 0xFu) * (1.0f / 15.0f), (float)(v >> 12) * (1.0f / 15.0f));
+    }
     case DXB_FMT_R32G32B32A32_FLOAT:
     {
         const float* p = (const float*)row + i * 4;
@@ -199,7 +277,7 @@ DXB_DEV dxb_px dxb_convert_pixel(dxb_px v, uint32_t inF, uint32_t outF, uint32_t
             }
             else if (inF & DXB_CONVF_FLOAT)
             {
-                if (flags & DXB_FILTER_FLOAT_X2BIAS)
+                if (!(inF & DXB_CONVF_POS_ONLY) && (flags & DXB_FILTER_FLOAT_X2BIAS))
                 {
                     v.x = dxb_madd(dxb_clamp(v.x, -1.0f, 1.0f), 0.5f, 0.5f); v.y = dxb_madd(dxb_clamp(v.y, -1.0f, 1.0f), 0.5f, 0.5f);
                     v.z = dxb_madd(dxb_clamp(v.z, -1.0f, 1.0f), 0.5f, 0.5f); v.w = dxb_madd(dxb_clamp(v.w, -1.0f, 1.0f), 0.5f, 0.5f);
@@ -218,14 +296,47 @@ DXB_DEV dxb_px dxb_convert_pixel(dxb_px v, uint32_t inF, uint32_t outF, uint32_t
             }
             else if (inF & DXB_CONVF_FLOAT)
             {
-                v.x = dxb_clamp(v.x, -1.0f, 1.0f); v.y = dxb_clamp(v.y, -1.0f, 1.0f); v.z = dxb_clamp(v.z, -1.0f, 1.0f); v.w = dxb_clamp(v.w, -1.0f, 1.0f);
+                if ((inF & DXB_CONVF_POS_ONLY) && (flags & DXB_FILTER_FLOAT_X2BIAS))
+                {
+                    // FLOAT (positive only, x2 bias) -> SNORM (:3506-3516)
+                    v.x = dxb_madd(dxb_clamp(v.x, 0.0f, 1.0f), 2.0f, -1.0f); v.y = dxb_madd(dxb_clamp(v.y, 0.0f, 1.0f), 2.0f, -1.0f);
+                    v.z = dxb_madd(dxb_clamp(v.z, 0.0f, 1.0f), 2.0f, -1.0f); v.w = dxb_madd(dxb_clamp(v.w, 0.0f, 1.0f), 2.0f, -1.0f);
+                }
+                else
+                {
+                    v.x = dxb_clamp(v.x, -1.0f, 1.0f); v.y = dxb_clamp(v.y, -1.0f, 1.0f); v.z = dxb_clamp(v.z, -1.0f, 1.0f); v.w = dxb_clamp(v.w, -1.0f, 1.0f);
+                }
             }
         }
         else if (diff & DXB_CONVF_UNORM)
         {
-            if ((outF & DXB_CONVF_FLOAT) && (flags & DXB_FILTER_FLOAT_X2BIAS))
+            if ((outF & DXB_CONVF_FLOAT) && !(outF & DXB_CONVF_POS_ONLY) && (flags & DXB_FILTER_FLOAT_X2BIAS))
             {
                 v.x = dxb_madd(v.x, 2.0f, -1.0f); v.y = dxb_madd(v.y, 2.0f, -1.0f); v.z = dxb_madd(v.z, 2.0f, -1.0f); v.w = dxb_madd(v.w, 2.0f, -1.0f);
+            }
+        }
+        else if ((diff & DXB_CONVF_POS_ONLY) && (flags & DXB_FILTER_FLOAT_X2BIAS))
+        {
+            // positive-only float formats with the x2 bias (:3545-3583)
+            if (inF & DXB_CONVF_POS_ONLY)
+            {
+                if (outF & DXB_CONVF_FLOAT)
+                {
+                    v.x = dxb_madd(dxb_clamp(v.x, 0.0f, 1.0f), 2.0f, -1.0f); v.y = dxb_madd(dxb_clamp(v.y, 0.0f, 1.0f), 2.0f, -1.0f);
+                    v.z = dxb_madd(dxb_clamp(v.z, 0.0f, 1.0f), 2.0f, -1.0f); v.w = dxb_madd(dxb_clamp(v.w, 0.0f, 1.0f), 2.0f, -1.0f);
+                }
+            }
+            else if (outF & DXB_CONVF_POS_ONLY)
+            {
+                if (inF & DXB_CONVF_FLOAT)
+                {
+                    v.x = dxb_madd(dxb_clamp(v.x, -1.0f, 1.0f), 0.5f, 0.5f); v.y = dxb_madd(dxb_clamp(v.y, -1.0f, 1.0f), 0.5f, 0.5f);
+                    v.z = dxb_madd(dxb_clamp(v.z, -1.0f, 1.0f), 0.5f, 0.5f); v.w = dxb_madd(dxb_clamp(v.w, -1.0f, 1.0f), 0.5f, 0.5f);
+                }
+                else if (inF & DXB_CONVF_SNORM)
+                {
+                    v.x = dxb_madd(v.x, 0.5f, 0.5f); v.y = dxb_madd(v.y, 0.5f, 0.5f); v.z = dxb_madd(v.z, 0.5f, 0.5f); v.w = dxb_madd(v.w, 0.5f, 0.5f);
+                }
             }
         }
 
@@ -332,11 +443,41 @@ DXB_DEV float dxb_stdclamp(float v, float lo, float hi)   // std::max(std::min(v
     return v;
 }
 
-// Store pixel `i` of a row starting at `row`.
-DXB_DEV void dxb_store_pixel(uint32_t fmt, uint8_t* row, size_t i, dxb_px v)
+// Store pixel `i` of a row starting at `row`.  `threshold`: alpha threshold of the 1-bit alpha format (StoreScanline's
+// last parameter, default 0; Convert passes the caller's, DirectXTexConvert.cpp:2116-2140).
+DXB_DEV void dxb_store_pixel(uint32_t fmt, uint8_t* row, size_t i, dxb_px v, float threshold = 0.0f)
 {
     switch (fmt)
     {
+    case DXB_FMT_R11G11B10_FLOAT:        // XMStoreFloat3PK (:1756-1767)
+        ((uint32_t*)row)[i] = (dxb_smallfloat_encode(v.x, 6u) & 0x7FFu) | ((dxb_smallfloat_encode(v.y, 6u) & 0x7FFu) << 11) | ((dxb_smallfloat_encode(v.z, 5u) & 0x3FFu) << 22);
+        return;
+    case DXB_FMT_R9G9B9E5_SHAREDEXP:     // XMStoreFloat3SE (:2057-2068)
+    {
+        const float maxf9 = (float)(0x1FF << 7), minf9 = 1.0f / (float)(1 << 16);
+        const float x = (v.x >= 0.0f) ? ((v.x > maxf9) ? maxf9 : v.x) : 0.0f;
+        const float y = (v.y >= 0.0f) ? ((v.y > maxf9) ? maxf9 : v.y) : 0.0f;
+        const float z = (v.z >= 0.0f) ? ((v.z > maxf9) ? maxf9 : v.z) : 0.0f;
+        const float mxy = (x > y) ? x : y, mxyz = (mxy > z) ? mxy : z;
+        const float maxColor = (mxyz > minf9) ? mxyz : minf9;
+        const uint32_t mi = dxb_float_as_uint(maxColor) + 0x00004000u;
+        const uint32_t ex = mi >> 23;
+        const float scaleR = dxb_uint_as_float(0x83000000u - (ex << 23));
+        ((uint32_t*)row)[i] = ((uint32_t)dxb_lround(x * scaleR) & 0x1FFu) | (((uint32_t)dxb_lround(y * scaleR) & 0x1FFu) << 9)
+                            | (((uint32_t)dxb_lround(z * scaleR) & 0x1FFu) << 18) | (((ex - 0x6fu) & 0x1Fu) << 27);
+        return;
+    }
+    case DXB_FMT_B5G6R5_UNORM:           // swizzle to BGR, * {31, 63, 31}, XMStoreU565 (:2096-2114)
+        ((uint16_t*)row)[i] = (uint16_t)(((dxb_store_int_rne(v.x * 31.0f, 31.0f) & 0x1Fu) << 11) | ((dxb_store_int_rne(v.y * 63.0f, 63.0f) & 0x3Fu) << 5) | (dxb_store_int_rne(v.z * 31.0f, 31.0f) & 0x1Fu));
+        return;
+    case DXB_FMT_B5G5R5A1_UNORM:         // * 31, XMStoreU555, alpha bit = (alpha > threshold) (:2116-2140)
+        ((uint16_t*)row)[i] = (uint16_t)(((v.w > threshold) ? 0x8000u : 0u) | ((dxb_store_int_rne(v.x * 31.0f, 31.0f) & 0x1Fu) << 10)
+                                         | ((dxb_store_int_rne(v.y * 31.0f, 31.0f) & 0x1Fu) << 5) | (dxb_store_int_rne(v.z * 31.0f, 31.0f) & 0x1Fu));
+        return;
+    case DXB_FMT_B4G4R4A4_UNORM:         // swizzle, * 15, XMStoreUNibble4 (:2399-2417)
+        ((uint16_t*)row)[i] = (uint16_t)(((dxb_store_int_rne(v.w * 15.0f, 15.0f) & 0xFu) << 12) | ((dxb_store_int_rne(v.x * 15.0f, 15.0f) & 0xFu) << 8)
+                                         | ((dxb_store_int_rne(v.y * 15.0f, 15.0f) & 0xFu) << 4) | (dxb_store_int_rne(v.z * 15.0f, 15.0f) & 0xFu));
+        return;
     case DXB_FMT_R32G32B32A32_FLOAT:
     {
         float* p = (float*)row + i * 4; p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w; return;

@@ -2,16 +2,16 @@
 
 DXGI_FORMAT = {
     "UNKNOWN": 0, "R32G32B32A32_FLOAT": 2, "R32G32B32_FLOAT": 6, "R16G16B16A16_FLOAT": 10, "R16G16B16A16_UNORM": 11,
-    "R16G16B16A16_SNORM": 13, "R32G32_FLOAT": 16, "R10G10B10A2_UNORM": 24, "R8G8B8A8_UNORM": 28, "R8G8B8A8_UNORM_SRGB": 29,
+    "R16G16B16A16_SNORM": 13, "R32G32_FLOAT": 16, "R10G10B10A2_UNORM": 24, "R11G11B10_FLOAT": 26, "R8G8B8A8_UNORM": 28, "R8G8B8A8_UNORM_SRGB": 29,
     "R8G8B8A8_SNORM": 31, "R16G16_FLOAT": 34, "R16G16_UNORM": 35, "R16G16_SNORM": 37, "R32_FLOAT": 41, "R8G8_UNORM": 49,
-    "R8G8_SNORM": 51, "R16_FLOAT": 54, "R16_UNORM": 56, "R16_SNORM": 58, "R8_UNORM": 61, "R8_SNORM": 63, "A8_UNORM": 65,
+    "R8G8_SNORM": 51, "R16_FLOAT": 54, "R16_UNORM": 56, "R16_SNORM": 58, "R8_UNORM": 61, "R8_SNORM": 63, "A8_UNORM": 65, "R9G9B9E5_SHAREDEXP": 67,
     "BC1_UNORM": 71, "BC1_UNORM_SRGB": 72, "BC2_UNORM": 74, "BC2_UNORM_SRGB": 75, "BC3_UNORM": 77, "BC3_UNORM_SRGB": 78,
-    "BC4_UNORM": 80, "BC4_SNORM": 81, "BC5_UNORM": 83, "BC5_SNORM": 84, "B8G8R8A8_UNORM": 87, "B8G8R8X8_UNORM": 88,
-    "B8G8R8A8_UNORM_SRGB": 91, "B8G8R8X8_UNORM_SRGB": 93, "BC6H_UF16": 95, "BC6H_SF16": 96, "BC7_UNORM": 98, "BC7_UNORM_SRGB": 99,
+    "BC4_UNORM": 80, "BC4_SNORM": 81, "BC5_UNORM": 83, "BC5_SNORM": 84, "B5G6R5_UNORM": 85, "B5G5R5A1_UNORM": 86, "B8G8R8A8_UNORM": 87, "B8G8R8X8_UNORM": 88,
+    "B8G8R8A8_UNORM_SRGB": 91, "B8G8R8X8_UNORM_SRGB": 93, "BC6H_UF16": 95, "BC6H_SF16": 96, "BC7_UNORM": 98, "BC7_UNORM_SRGB": 99, "B4G4R4A4_UNORM": 115,
 }
 globals().update({"DXGI_FORMAT_" + k: v for k, v in DXGI_FORMAT.items()})
 
-BYTES_PER_PIXEL = {2: 16, 6: 12, 10: 8, 11: 8, 13: 8, 16: 8, 24: 4, 28: 4, 29: 4, 31: 4, 34: 4, 35: 4, 37: 4, 41: 4,
+BYTES_PER_PIXEL = {26: 4, 67: 4, 85: 2, 86: 2, 115: 2, 2: 16, 6: 12, 10: 8, 11: 8, 13: 8, 16: 8, 24: 4, 28: 4, 29: 4, 31: 4, 34: 4, 35: 4, 37: 4, 41: 4,
                    49: 2, 51: 2, 54: 2, 56: 2, 58: 2, 61: 1, 63: 1, 65: 1, 87: 4, 88: 4, 91: 4, 93: 4}
 BLOCK_BYTES = {71: 8, 72: 8, 74: 16, 75: 16, 77: 16, 78: 16, 80: 8, 81: 8, 83: 16, 84: 16, 95: 16, 96: 16, 98: 16, 99: 16}
 

@@ -58,6 +58,9 @@ const Legacy kLegacy[] = {
     { DXB_FMT_B8G8R8A8_UNORM,     { 32, PF_RGBA, 0, 32, 0x00ff0000, 0x0000ff00, 0x000000ff, 0xff000000 }, false, false },
     { DXB_FMT_B8G8R8X8_UNORM,     { 32, PF_RGB,  0, 32, 0x00ff0000, 0x0000ff00, 0x000000ff, 0 }, false, false },
     { DXB_FMT_R16G16_UNORM,       { 32, PF_RGB,  0, 32, 0x0000ffff, 0xffff0000, 0, 0 }, false, false },
+    { DXB_FMT_B5G6R5_UNORM,       { 32, PF_RGB,  0, 16, 0xf800, 0x07e0, 0x001f, 0 }, false, false },                  // DDSPF_R5G6B5 (DDS.h:125)
+    { DXB_FMT_B5G5R5A1_UNORM,     { 32, PF_RGBA, 0, 16, 0x7c00, 0x03e0, 0x001f, 0x8000 }, false, false },             // DDSPF_A1R5G5B5
+    { DXB_FMT_B4G4R4A4_UNORM,     { 32, PF_RGBA, 0, 16, 0x0f00, 0x00f0, 0x000f, 0xf000 }, false, false },             // DDSPF_A4R4G4B4
     { DXB_FMT_R8G8_UNORM,         { 32, PF_LUMA, 0, 16, 0x00ff, 0, 0, 0xff00 }, false, false },
     { DXB_FMT_R16_UNORM,          { 32, PF_LUM,  0, 16, 0xffff, 0, 0, 0 }, false, false },
     { DXB_FMT_R8_UNORM,           { 32, PF_LUM,  0, 8, 0xff, 0, 0, 0 }, false, false },

@@ -123,7 +123,7 @@ int32_t emul_convert(const uint8_t* src, size_t w, size_t h, uint32_t srcFmt, si
             dxb_px v = dxb_load_pixel(srcFmt, src + y * srcPitch, x);
             v = dxb_convert_pixel(v, inF, outF, flags);
             if (flags & DXB_FILTER_DITHER) dxb_store_pixel_dither(dstFmt, dst + y * dstPitch, x, (uint32_t)y, v);
-            else dxb_store_pixel(dstFmt, dst + y * dstPitch, x, v);
+            else dxb_store_pixel(dstFmt, dst + y * dstPitch, x, v, 0.5f);       // TEX_THRESHOLD_DEFAULT (B5G5R5A1 alpha bit)
         }
     return DXB_S_OK;
 }

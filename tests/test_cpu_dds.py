@@ -18,6 +18,7 @@ CASES = [
     (71, 16, 16, 1, 5, 0, 0, 0), (72, 16, 16, 1, 1, 0, 0, 0), (74, 8, 8, 1, 1, 0, 0, 0), (74, 8, 8, 1, 1, 0, 2, 0),
     (77, 8, 8, 1, 1, 0, 0, 0), (77, 8, 8, 1, 1, 0, 2, 0), (80, 12, 12, 1, 1, 0, 0, 0), (81, 12, 12, 1, 1, 0, 0, 0),
     (83, 12, 12, 1, 1, 0, 0, 0), (84, 12, 12, 1, 1, 0, 0, 0), (95, 8, 8, 1, 4, 0, 0, 0), (98, 20, 12, 2, 3, 0, 0, 0),
+    (85, 8, 8, 1, 1, 0, 0, 0), (86, 8, 8, 1, 3, 0, 0, 0), (115, 6, 6, 1, 1, 0, 0, 0), (26, 8, 4, 1, 1, 0, 0, 0), (67, 8, 4, 2, 2, 0, 0, 0), (85, 8, 8, 1, 1, 0, 0, DX10),
     (28, 8, 8, 6, 1, CUBE, 0, 0), (28, 8, 8, 12, 2, CUBE, 0, 0), (98, 8, 8, 1, 1, 0, 1, DX10_MISC2), (71, 5, 5, 4, 1, 0, 0, 0),
 ]
 

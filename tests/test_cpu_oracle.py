@@ -275,3 +275,30 @@ def test_emulator_bc6h_flat_and_two_colour_blocks(oracle, emul):
         ours, ref = err
         assert ours[:48].mean() <= ref[:48].mean() + 1.0, (fmt, ours[:48].mean(), ref[:48].mean())
         assert ours[48:].mean() <= ref[48:].mean() * 1.02 + 1.0, (fmt, ours[48:].mean(), ref[48:].mean())
+
+
+NEXT_TIER = (26, 67, 85, 86, 115)          # R11G11B10_FLOAT, R9G9B9E5_SHAREDEXP, B5G6R5, B5G5R5A1, B4G4R4A4
+NEXT_TIER_PAIRS = [(85, 28), (86, 28), (115, 28), (28, 85), (28, 86), (28, 115), (2, 85), (2, 86), (2, 115), (26, 2), (67, 2), (2, 26), (2, 67),
+                   (10, 26), (28, 26), (26, 28), (67, 28), (31, 26), (26, 31), (85, 86), (26, 67), (67, 26), (87, 85), (115, 10)]
+
+
+def test_emulator_next_tier_formats_bit_exact(oracle, emul):
+    """R11G11B10_FLOAT, R9G9B9E5_SHAREDEXP, B5G6R5, B5G5R5A1 (alpha threshold 0.5), B4G4R4A4 (DirectXTexConvert.cpp:906, 1189, 1227, 1244, 1511 /
+    1756, 2057, 2096, 2116, 2399; CONVF_POS_ONLY x2-bias cases :3469-3583): Convert in both directions, mip chains and BC compression from them."""
+    rng = np.random.default_rng(77)
+    for sf, df in NEXT_TIER_PAIRS:
+        src = oracle_lib.random_image(sf, 37, 9, rng)
+        for fl in (0, F.TEX_FILTER_FLOAT_X2BIAS, F.TEX_FILTER_RGB_COPY_GREEN):
+            hr, want = oracle.convert(src, 37, 9, sf, df, fl)
+            he, got = emul.convert(src, 37, 9, sf, df, fl)
+            assert hr == 0 and he == 0 and np.array_equal(got, want), (sf, df, hex(fl))
+    for fmt in NEXT_TIER:
+        src = oracle_lib.random_image(fmt, 20, 12, rng)
+        for fl in (F.TEX_FILTER_POINT, F.TEX_FILTER_LINEAR, F.TEX_FILTER_CUBIC, F.TEX_FILTER_TRIANGLE, 0):
+            hr, want = oracle.generate_mipmaps(src, 20, 12, fmt, fl)
+            he, got = emul.generate_mipmaps(src, 20, 12, fmt, fl)
+            assert hr == 0 and he == 0 and np.array_equal(got, want), (fmt, hex(fl))
+        for bc in (71, 77, 80, 83):
+            hr, want = oracle.compress(src, 20, 12, fmt, bc)
+            he, got = emul.compress(src, 20, 12, fmt, bc)
+            assert hr == 0 and he == 0 and np.array_equal(got, want), (fmt, bc)

@@ -475,3 +475,33 @@ def test_multi_device_sharding_inside_the_library(oracle):
         layout, _ = F.mip_chain_layout(28, 128, 64, 0)
         want = np.concatenate([oracle.compress(rchain[off:off + sl], lw, lh, 28, 71)[1] for (off, lw, lh, row, sl) in layout])
         assert hr == 0 and np.array_equal(o, want)
+
+
+def test_next_tier_formats_vs_oracle(oracle):
+    """R11G11B10_FLOAT, R9G9B9E5_SHAREDEXP, B5G6R5, B5G5R5A1, B4G4R4A4 through the C ABI: Convert both ways (incl. x2 bias and the alpha
+    threshold), mip chains, BC compression; dithered stores to the 16-bit packed formats are refused (HRESULT_E_NOT_SUPPORTED)."""
+    from tests.test_cpu_oracle import NEXT_TIER, NEXT_TIER_PAIRS
+    rng = np.random.default_rng(79)
+    for sf, df in NEXT_TIER_PAIRS:
+        src = oracle_lib.random_image(sf, 133, 21, rng)
+        for fl in (0, F.TEX_FILTER_FLOAT_X2BIAS):
+            hr, want = oracle.convert(src, 133, 21, sf, df, fl)
+            got = capi.convert(src, 133, 21, sf, df, fl)
+            assert hr == 0 and np.array_equal(got, want), (sf, df, hex(fl))
+    src = oracle_lib.random_image(2, 64, 8, rng)
+    for thr in (0.0, 0.25, 0.9):
+        hr, want = oracle.convert(src, 64, 8, 2, 86, 0, threshold=thr)
+        got = capi.convert(src, 64, 8, 2, 86, 0, threshold=thr)
+        assert hr == 0 and np.array_equal(got, want), thr
+    for fmt in NEXT_TIER:
+        src = oracle_lib.random_image(fmt, 40, 24, rng)
+        for fl in (F.TEX_FILTER_POINT, F.TEX_FILTER_LINEAR, F.TEX_FILTER_CUBIC, F.TEX_FILTER_TRIANGLE, 0):
+            hr, want = oracle.generate_mipmaps(src, 40, 24, fmt, fl)
+            got, _ = capi.generate_mipmaps(src, 40, 24, fmt, fl)
+            assert hr == 0 and np.array_equal(got, want), (fmt, hex(fl))
+        for bc in (71, 77, 80, 83):
+            hr, want = oracle.compress(src, 40, 24, fmt, bc)
+            assert hr == 0 and np.array_equal(capi.compress(src, 40, 24, fmt, bc), want), (fmt, bc)
+    with pytest.raises(capi.DxTexError) as e:
+        capi.convert(oracle_lib.random_image(28, 16, 16, rng), 16, 16, 28, 85, F.TEX_FILTER_DITHER)
+    assert e.value.hr == F.HRESULT_E_NOT_SUPPORTED
