@@ -506,7 +506,7 @@ class C5:
     small_sample = {"side": 1024}
 
     def __init__(self, args, world):
-        self.B = args.batch or 48
+        self.B = args.batch or 24
         self.world = world
 
     def workload(self):

@@ -17,7 +17,7 @@ __device__ __forceinline__ void bc15_body(const dxb_job* __restrict__ jobs, cons
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x; unit < P.totalUnits; unit += stride)
     {
-        const dxb_job& j = dxb_find_job(jobs, P.njobs, single, unit);
+        const dxb_job& j = dxb_find_job(jobs, P.njobs, single, unit, P.periodUnits, P.periodJobs);
         const uint32_t local = unit - j.firstUnit;
         const uint32_t by = local / j.nbx, bx = local - by * j.nbx;
         dxb_image_desc img; img.pixels = j.src; img.rowPitch = j.srcPitch; img.width = j.width; img.height = j.height; img.format = srcFormat;
