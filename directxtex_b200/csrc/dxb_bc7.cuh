@@ -490,17 +490,20 @@ DXB_DEV float dxb_bc7_rotation_estimate1(float c00, float c01, float c02, float 
     const float lam = (vv > 0.0f) ? fminf(vw / vv, tr) : 0.0f;
     return dxb_fma(lam, qfv, fmaxf(tr - lam, 0.0f)) + css * qfs;
 }
-DXB_DEV void dxb_bc7_rotation_estimates(const float* tot, bool opaque, float qfv, float qfs, float* est)
+// estimate for ONE candidate scalar channel c (0..3; 3 = alpha = rotation 0): the four candidates of a block are evaluated by four
+// lanes and exchanged (each lane used to evaluate all four)
+DXB_DEV float dxb_bc7_rotation_estimate_c(const float* tot, bool opaque, float qfv, float qfs, uint32_t c)
 {
     const float inv = 1.0f / 16.0f, z = opaque ? 0.0f : 1.0f;
     const float c00 = dxb_fma(-tot[0] * inv, tot[0], tot[4]), c01 = dxb_fma(-tot[0] * inv, tot[1], tot[5]), c02 = dxb_fma(-tot[0] * inv, tot[2], tot[6]);
     const float c11 = dxb_fma(-tot[1] * inv, tot[1], tot[8]), c12 = dxb_fma(-tot[1] * inv, tot[2], tot[9]), c22 = dxb_fma(-tot[2] * inv, tot[2], tot[11]);
     const float c03 = z * dxb_fma(-tot[0] * inv, tot[3], tot[7]), c13 = z * dxb_fma(-tot[1] * inv, tot[3], tot[10]);
     const float c23 = z * dxb_fma(-tot[2] * inv, tot[3], tot[12]), c33 = z * dxb_fma(-tot[3] * inv, tot[3], tot[13]);
-    est[0] = dxb_bc7_rotation_estimate1(c11, c12, c13, c22, c23, c33, c00, qfv, qfs);     // scalar = R, vector = G B A
-    est[1] = dxb_bc7_rotation_estimate1(c00, c02, c03, c22, c23, c33, c11, qfv, qfs);     // scalar = G
-    est[2] = dxb_bc7_rotation_estimate1(c00, c01, c03, c11, c13, c33, c22, qfv, qfs);     // scalar = B
-    est[3] = dxb_bc7_rotation_estimate1(c00, c01, c02, c11, c12, c22, c33, qfv, qfs);     // scalar = A (rotation 0)
+    // covariance of the three remaining channels (a, b, d) and the variance of the scalar channel
+    const float aa = (c == 0u) ? c11 : c00, ab = (c == 0u) ? c12 : ((c == 1u) ? c02 : c01), ad = (c == 0u) ? c13 : ((c == 3u) ? c02 : c03);
+    const float bb = (c <= 1u) ? c22 : c11, bd = (c <= 1u) ? c23 : ((c == 2u) ? c13 : c12), dd = (c == 3u) ? c22 : c33;
+    const float css = (c == 0u) ? c00 : ((c == 1u) ? c11 : ((c == 2u) ? c22 : c33));
+    return dxb_bc7_rotation_estimate1(aa, ab, ad, bb, bd, dd, css, qfv, qfs);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -643,13 +646,15 @@ DXB_DEV dxb_bc7_res dxb_bc7_eval(const dxb_px* px, const float* mt, const dxb_bc
         float v1 = b0 ? k01 : (b1 ? k11 : (b2 ? k12 : k13));
         float v2 = b0 ? k02 : (b1 ? k12 : (b2 ? k22 : k23));
         float v3 = b0 ? k03 : (b1 ? k13 : (b2 ? k23 : k33));
+        // matrix columns as packed row pairs: (w0, w1) and (w2, w3) of K v, each component with the scalar association
+        const dxb_f2 K0a = dxb_mk2(k00, k01), K1a = dxb_mk2(k01, k11), K2a = dxb_mk2(k02, k12), K3a = dxb_mk2(k03, k13);
+        const dxb_f2 K0b = dxb_mk2(k02, k03), K1b = dxb_mk2(k12, k13), K2b = dxb_mk2(k22, k23), K3b = dxb_mk2(k23, k33);
         for (int it = 0; it < DXB_BC7_PCA_ITERS; ++it)
         {
-            const float w0 = dxb_fma(k00, v0, dxb_fma(k01, v1, dxb_fma(k02, v2, k03 * v3)));
-            const float w1 = dxb_fma(k01, v0, dxb_fma(k11, v1, dxb_fma(k12, v2, k13 * v3)));
-            const float w2 = dxb_fma(k02, v0, dxb_fma(k12, v1, dxb_fma(k22, v2, k23 * v3)));
-            const float w3 = dxb_fma(k03, v0, dxb_fma(k13, v1, dxb_fma(k23, v2, k33 * v3)));
-            v0 = w0; v1 = w1; v2 = w2; v3 = w3;
+            const dxb_f2 V0 = dxb_bc2(v0), V1 = dxb_bc2(v1), V2 = dxb_bc2(v2), V3 = dxb_bc2(v3);
+            const dxb_f2 Wa = R4_fma2(K0a, V0, R4_fma2(K1a, V1, R4_fma2(K2a, V2, R4_mul2(K3a, V3))));
+            const dxb_f2 Wb = R4_fma2(K0b, V0, R4_fma2(K1b, V1, R4_fma2(K2b, V2, R4_mul2(K3b, V3))));
+            v0 = Wa.x; v1 = Wa.y; v2 = Wb.x; v3 = Wb.y;
         }
         const float vv = dxb_fma(v0, v0, dxb_fma(v1, v1, dxb_fma(v2, v2, v3 * v3)));
         const float r = (vv > 1e-30f) ? 1.0f / sqrtf(vv) : 0.0f;
@@ -961,26 +966,31 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
     //   r* = the rotation (scalar channel) with the smallest modelled cost (dxb_bc7_rotation_estimates); the reference
     //   tries every rotation (:2823-2829).  Lane 15 idles.
     uint32_t tMeta[DXB_NL], rErr[DXB_NL], rQ0[DXB_NL], rQ1[DXB_NL], partner[DXB_NL];
+    // rotation ranking from the block totals: lane c (mod 4) evaluates scalar channel c, the four keys are exchanged.
+    // keys: estimate bits | rotation (channel c = 3 is rotation 0, channel c < 3 rotation c + 1); opaque blocks never rotate alpha
+    uint32_t rk[DXB_NL], rk0[DXB_NL], rk1[DXB_NL], rk2[DXB_NL], rk3[DXB_NL], li0[DXB_NL], li1[DXB_NL], li2[DXB_NL], li3[DXB_NL];
+    DXB_LANES_BEGIN
+        float tot[14];
+        dxb_bc7_mt_load(S->mt[lane >> 4], 64, tot);
+        const uint32_t c = (uint32_t)lane & 3u;
+        const float est = dxb_bc7_rotation_estimate_c(tot, hasA[L] == 0u, 1.0f / 9.0f, 1.0f / 49.0f, c);
+        rk[L] = (c == 3u && !hasA[L]) ? 0xFFFFFFFFu : ((dxb_float_as_uint(est) & 0xFFFFFFFCu) | ((c + 1u) & 3u));
+        li0[L] = 0u; li1[L] = 1u; li2[L] = 2u; li3[L] = 3u;
+    DXB_LANES_END
+    dxb_half_gather_u32(rk, li0, rk0); dxb_half_gather_u32(rk, li1, rk1); dxb_half_gather_u32(rk, li2, rk2); dxb_half_gather_u32(rk, li3, rk3);
     DXB_LANES_BEGIN
         const int hl = lane & 15;
         int mode = -1, idxMode = 0, part = hl;
         uint32_t rot = 0;
         dxb_bc7_task T;
         T.shape = 0; T.mask = 0xFFFFu; T.chmask = 0xFu; T.bits = 7u; T.ptype = 1u; T.ib = 4u; T.idle = false; T.direct = false;
-        // rotation ranking from the block totals
         uint32_t r1 = 0, r2 = 0, r4 = 0;     // mode 5 rotations (best, second), mode 4 rotation
         {
-            float tot[14], est[4];
-            dxb_bc7_mt_load(S->mt[lane >> 4], 64, tot);
-            dxb_bc7_rotation_estimates(tot, hasA[L] == 0u, 1.0f / 9.0f, 1.0f / 49.0f, est);
-            // keys: estimate bits | rotation (channel c = 3 is rotation 0, channel c < 3 rotation c + 1); opaque blocks never rotate alpha
+            const uint32_t keys[4] = { rk0[L], rk1[L], rk2[L], rk3[L] };
             uint32_t ka = 0xFFFFFFFFu, kb = 0xFFFFFFFFu;
-#if DXB_ON_DEVICE
-            #pragma unroll
-#endif
             for (uint32_t c = 0; c < 4; ++c)
             {
-                const uint32_t x = (c == 3u && !hasA[L]) ? 0xFFFFFFFFu : ((dxb_float_as_uint(est[c]) & 0xFFFFFFFCu) | ((c + 1u) & 3u));
+                const uint32_t x = keys[c];
                 const uint32_t lo = (x < ka) ? x : ka, hi = (x < ka) ? ka : x;
                 ka = lo; kb = (hi < kb) ? hi : kb;
             }
