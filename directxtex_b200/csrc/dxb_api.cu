@@ -388,7 +388,8 @@ int32_t launch_compress(const CompressPlan& plan, const dxb200_image* src, const
         // one CTA per 2 * DXB_BC7_WARPS blocks (no grid-stride cap): block costs differ (alpha blocks run the separate-alpha
         // tasks), so the hardware CTA scheduler balances better than a static stride
         const uint32_t grid = std::max(1u, need);
-        dxb_launch_bc7(grid, stream, dj.d, jobs[0], P);
+        // RGBA32F sources of full blocks: persistent kernel fed by TMA tile loads; everything else: the direct kernel
+        if (!dxb_launch_bc7_tma((unsigned)t_v.dev->gridBC7, stream, jobs.data(), P)) dxb_launch_bc7(grid, stream, dj.d, jobs[0], P);
         hr = check_launch("k_compress_bc7");
     }
     else

@@ -305,6 +305,40 @@ def test_bc7_rgba8_source_partial_blocks_and_quick(oracle, emul):
             assert np.isfinite(dec).all()
 
 
+def test_bc7_tma_fed_kernel_equals_emulator(emul):
+    """RGBA32F sources made of full 4x4 blocks go through k_compress_bc7_tma (persistent CTAs, one TMA box of 64 x 4 pixels per
+    tile): widths that end in a partial, zero-filled tile, a single tile, more tiles than resident CTAs, the three-subset
+    instantiation, and an array at a constant pointer stride (rank-3 tensor map) on the device API -- all must equal the emulator,
+    as must a source whose rows are not 16-byte aligned for the tensor map (pitch padded by 4 bytes: the direct kernel)."""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(23)
+    for (w, h, flags) in [(100, 52, 0), (64, 4, 0), (4, 4, 0), (260, 8, 0), (1024, 512, 0), (72, 20, F.TEX_COMPRESS_BC7_USE_3SUBSETS)]:
+        img = rng.random((h, w, 4), dtype=np.float32)
+        if w == 100:
+            img[:, :48, 3] = 1.0
+        got = capi.compress(img, w, h, 2, 98, flags)
+        he, em = emul.compress(img, w, h, 2, 98, flags)
+        assert he == 0 and np.array_equal(got, em), (w, h, flags)
+    w, h, n = 72, 20, 3
+    imgs = rng.random((n, h, w, 4), dtype=np.float32)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    row, sl = F.compute_pitch(98, w, h)
+    for pad in (0, 4):
+        pitch = w * 16 + pad
+        buf = np.zeros((n, h, pitch), np.uint8)
+        buf[:, :, :w * 16] = imgs.view(np.uint8).reshape(n, h, w * 16)
+        d_in = torch.from_numpy(buf.reshape(-1)).cuda()
+        d_out = torch.zeros(n * sl, dtype=torch.uint8, device="cuda")
+        s = capi.images([capi.Image(w, h, 2, pitch, pitch * h, d_in.data_ptr() + i * pitch * h) for i in range(n)])
+        d = capi.images([capi.Image(w, h, 98, row, sl, d_out.data_ptr() + i * sl) for i in range(n)])
+        assert capi.lib.dxb200_compress_device(s, n, 98, 0, 0.5, 1.0, d, st) == 0
+        torch.cuda.synchronize()
+        out = d_out.cpu().numpy().reshape(n, sl)
+        for i in range(n):
+            he, em = emul.compress(imgs[i], w, h, 2, 98, 0)
+            assert he == 0 and np.array_equal(out[i], em), (pad, i)
+
+
 def test_device_api_with_torch_pointers(oracle):
     torch = pytest.importorskip("torch")
     img = synth.c1_rgba8(128, 64, seed=2)

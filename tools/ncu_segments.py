@@ -47,15 +47,21 @@ tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "directxtex_b200", "_lib", "libdxtex_b200.so")], cwd=tmp, capture_output=True)
 cub = [f for f in os.listdir(tmp) if f.startswith(tu + ".")][0]
 dis = run(["nvdisasm", "--print-line-info", os.path.join(tmp, cub)]).split("\n")
-ins, cur = [], None
+funcs, ins, cur = [], None, None          # one instruction list per function of the cubin; the profiled one = the list of equal length
 for l in dis:
+    m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
+    if m:
+        ins = []
+        funcs.append(ins)
+        continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2)))
         continue
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
-    if m:
+    if m and ins is not None:
         ins.append(cur)
+ins = ([f for f in funcs if len(f) == len(prof)] or [max(funcs, key=len) if funcs else []])[0]
 if len(ins) != len(prof):
     print("warning: disassembly (%d) and profile (%d) lengths differ (library rebuilt since the capture?)" % (len(ins), len(prof)))
     ins = (ins + [None] * len(prof))[:len(prof)]

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Runs each hot-path kernel a few times on device-resident data so that `ncu` can capture it
-(profiles/README.md lists the exact ncu command lines).  Usage: python tools/prof_driver.py [bc7|bc6h|bc15|dec|rows|all] [reps]"""
+(profiles/README.md lists the exact ncu command lines).  Usage: python tools/prof_driver.py [bc7|bc6h|bc15|bc3|dec|rows|rowscubic|rowslinear|all] [reps]"""
 import ctypes as C
 import os
 import sys
@@ -68,6 +68,14 @@ if what in ("bc15", "all"):
         d = capi.images([capi.Image(w, h, fmt, *F.compute_pitch(fmt, w, h), d_out.data_ptr())])
         timed("%s 4096^2 rgba8" % nm, lambda: capi.lib.dxb200_compress_device(s, 1, fmt, 0, 0.5, 1.0, d, st), w * h)
 
+if what == "bc3":
+    w = h = 4096
+    d_in = dev(np.tile(synth.c1_rgba8(1024, 1024), (4, 4, 1)))
+    d_out = torch.zeros(F.compute_pitch(77, w, h)[1], dtype=torch.uint8, device="cuda")
+    s = capi.images([capi.Image(w, h, 28, *F.compute_pitch(28, w, h), d_in.data_ptr())])
+    d = capi.images([capi.Image(w, h, 77, *F.compute_pitch(77, w, h), d_out.data_ptr())])
+    timed("bc3 4096^2 rgba8", lambda: capi.lib.dxb200_compress_device(s, 1, 77, 0, 0.5, 1.0, d, st), w * h)
+
 if what in ("dec", "all"):
     w = h = 4096
     for bc, dfmt, nm in ((98, 28, "bc7"), (71, 28, "bc1"), (80, 61, "bc4")):
@@ -80,7 +88,7 @@ if what in ("dec", "all"):
         d = capi.images([capi.Image(w, h, dfmt, *F.compute_pitch(dfmt, w, h), d_out.data_ptr())])
         timed("decompress %s 4096^2" % nm, lambda: capi.lib.dxb200_decompress_device(s, 1, dfmt, d, st), w * h)
 
-if what in ("rows", "all"):
+if what in ("rows", "all", "rowscubic", "rowslinear"):
     w = h = 8192
     d_in = dev(synth.c5_r8(w, h))
     d_f = torch.zeros(w * h * 4, dtype=torch.uint8, device="cuda")
@@ -103,4 +111,6 @@ if what in ("rows", "all"):
             imgs.append(capi.Image(lw, lh, 28, row, sl, chain.data_ptr() + it * total + off))
     arr = capi.images(imgs)
     for fl, nm in ((F.TEX_FILTER_BOX, "box"), (F.TEX_FILTER_CUBIC, "cubic"), (F.TEX_FILTER_LINEAR, "linear")):
+        if what.startswith("rows") and what != "rows" and what != "rows" + nm:
+            continue
         timed("mips %s 64x1024^2 rgba8" % nm, lambda: capi.lib.dxb200_generate_mipmaps_device(arr, items, len(layout), fl, st), items * w * h * 4 // 3)
