@@ -31,7 +31,7 @@ constexpr int NSLOT = 3;        // (stream, device buffer pair) slots of one lan
 constexpr int NLANE = 2;        // host-staged calls that can be in flight on one device at the same time (each owns a lane)
 
 std::mutex g_mu;                // guards the device table only; calls on different lanes / devices run concurrently
-std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_launches{0}, g_tma_launches{0};
 thread_local std::string t_lastError;
 
 struct Lane
@@ -389,7 +389,8 @@ int32_t launch_compress(const CompressPlan& plan, const dxb200_image* src, const
         // tasks), so the hardware CTA scheduler balances better than a static stride
         const uint32_t grid = std::max(1u, need);
         // RGBA32F sources of full blocks: persistent kernel fed by TMA tile loads; everything else: the direct kernel
-        if (!dxb_launch_bc7_tma((unsigned)t_v.dev->gridBC7, stream, jobs.data(), P)) dxb_launch_bc7(grid, stream, dj.d, jobs[0], P);
+        if (dxb_launch_bc7_tma((unsigned)t_v.dev->gridBC7, stream, jobs.data(), P)) g_tma_launches.fetch_add(1, std::memory_order_relaxed);
+        else dxb_launch_bc7(grid, stream, dj.d, jobs[0], P);
         hr = check_launch("k_compress_bc7");
     }
     else
@@ -709,7 +710,7 @@ int32_t launch_mips(const dxb200_image* chain, size_t items, size_t levels, uint
     for (size_t l = 1; l < levels; ++l)
         if (chain[l - 1].width <= 64 && chain[l - 1].height <= 64) { tailStart = l; break; }
     const bool wantTail = (mode == DXB_FILTER_BOX || mode == DXB_FILTER_LINEAR || mode == DXB_FILTER_CUBIC) && (levels - tailStart) >= 2 && items <= 0x7FFFFFFFull;
-    const bool wantFused = (mode == DXB_FILTER_BOX) && levels >= 4;
+    const bool wantFused = (mode == DXB_FILTER_BOX || mode == DXB_FILTER_LINEAR) && levels >= 4;      // LINEAR at 2:1 reads the same 2x2 patches
     if (items > 1 || wantTail || wantFused)
     {
         DXB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&dAll), all.size() * sizeof(dxb_mip_job), stream));
@@ -717,7 +718,7 @@ int32_t launch_mips(const dxb200_image* chain, size_t items, size_t levels, uint
     }
     for (size_t l = 1; l < levels && hr == DXB_S_OK; ++l)
     {
-        // three BOX levels per launch while the source is larger than the tail kernel's 64x64 and divides by 8
+        // three BOX / LINEAR levels per launch while the source is larger than the tail kernel's 64x64 and divides by 8
         if (wantFused && l + 2 < levels && (chain[l - 1].width > 64 || chain[l - 1].height > 64))
         {
             P.njobs = (uint32_t)items;
@@ -784,6 +785,7 @@ extern "C" {
 const char* dxb200_version(void) { return "dxtex_b200 0.1 (sm_100a)"; }
 const char* dxb200_last_error(void) { return t_lastError.c_str(); }
 uint64_t dxb200_launch_count(void) { return g_launches.load(); }
+uint64_t dxb200_tma_launch_count(void) { return g_tma_launches.load(); }
 
 int32_t dxb200_device_count(void)
 {

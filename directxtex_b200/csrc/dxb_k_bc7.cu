@@ -207,7 +207,7 @@ static bool bc7_tma_attr_set()
 // per tile.  DXB200_BC7_TMA overrides.
 static int bc7_tma_mode()
 {
-    static const int m = []() { const char* e = getenv("DXB200_BC7_TMA"); return e ? atoi(e) : 1; }();
+    static const int m = []() { const char* e = getenv("DXB200_BC7_TMA"); return e ? atoi(e) : 0; }();   // 0 until the GPU A/B of this revision is in (profiles/)
     return m;
 }
 

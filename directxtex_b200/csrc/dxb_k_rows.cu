@@ -618,20 +618,33 @@ void dxb_launch_mip(unsigned grid, cudaStream_t stream, const dxb_mip_job* jobs,
 // so the result is bit-identical; the source is read once and the two intermediate levels are never re-read from HBM
 // (5.6 instead of 7.0 bytes moved per source texel-chain, one launch instead of three).
 // jobs: [level][item] records of the three levels; requires source width/height multiples of 8 and vector alignment.
-template <uint32_t FMT>
+// LIN: the LINEAR filter at an exact 2:1 ratio.  CreateLinearFilter (filters.h:64-104) gives destination u the taps 2u and 2u + 1 with
+// weights 0.5 / 0.5 (srcB = 2u + 1.5, no edge clamp, WRAP irrelevant), so a destination pixel reads the same 2x2 patch as BOX and only the
+// arithmetic differs: ((a0 w + a1 w) w) + ((b0 w + b1 w) w) in the reference's operation order (dxb_mip_linear, DirectXTexMipmaps.cpp:1087-1197).
+template <uint32_t FMT, bool LIN>
 __device__ __forceinline__ dxb_px dxb_box4(const uint8_t* r0, const uint8_t* r1, int k, uint32_t lflags)
 {
     dxb_px p00 = dxb_load_pixel(FMT, r0, 2 * k), p01 = dxb_load_pixel(FMT, r0, 2 * k + 1);
     dxb_px p10 = dxb_load_pixel(FMT, r1, 2 * k), p11 = dxb_load_pixel(FMT, r1, 2 * k + 1);
     if (lflags & DXB_FILTER_SRGB_IN) { p00 = dxb_srgb_to_linear(p00); p01 = dxb_srgb_to_linear(p01); p10 = dxb_srgb_to_linear(p10); p11 = dxb_srgb_to_linear(p11); }
-    dxb_px v = dxb_px_add(p00, p10);
-    v = dxb_px_add(v, p01);
-    v = dxb_px_add(v, p11);
-    v = dxb_px_scale(v, 0.25f);
+    dxb_px v;
+    if (LIN)
+    {
+        const dxb_px r0v = dxb_px_scale(dxb_px_add(dxb_px_scale(p00, 0.5f), dxb_px_scale(p01, 0.5f)), 0.5f);
+        const dxb_px r1v = dxb_px_scale(dxb_px_add(dxb_px_scale(p10, 0.5f), dxb_px_scale(p11, 0.5f)), 0.5f);
+        v = dxb_px_add(r0v, r1v);
+    }
+    else
+    {
+        v = dxb_px_add(p00, p10);
+        v = dxb_px_add(v, p01);
+        v = dxb_px_add(v, p11);
+        v = dxb_px_scale(v, 0.25f);
+    }
     if (lflags & DXB_FILTER_SRGB_OUT) v = dxb_linear_to_srgb(v);
     return v;
 }
-template <uint32_t FMT, bool SRGB>
+template <uint32_t FMT, bool SRGB, bool LIN>
 __global__ void __launch_bounds__(256) k_mip_box3(const dxb_mip_job* __restrict__ jobs, uint32_t items, dxb_mip_params P)
 {
     constexpr int B = (int)dxb_bytes_per_pixel(FMT);
@@ -658,26 +671,27 @@ __global__ void __launch_bounds__(256) k_mip_box3(const dxb_mip_job* __restrict_
         {
             const int arow = grp * (PRE / 2) + pr;                   // level-A row 0..3 of this thread
             #pragma unroll
-            for (int k = 0; k < 4; ++k) dxb_store_pixel(FMT, rowA[arow & 1], k, dxb_box4<FMT>(s[2 * pr], s[2 * pr + 1], k, DXB_LF(SRGB)));
+            for (int k = 0; k < 4; ++k) dxb_store_pixel(FMT, rowA[arow & 1], k, dxb_box4<FMT, LIN>(s[2 * pr], s[2 * pr + 1], k, DXB_LF(SRGB)));
             dxb_copy_vec<4 * B>(jA.dst + (size_t)(4u * ty + arow) * jA.dstPitch + (size_t)(4u * tx) * B, rowA[arow & 1], false);
             if (arow & 1)
             {
                 const int half = arow >> 1;
                 #pragma unroll
-                for (int k = 0; k < 2; ++k) dxb_store_pixel(FMT, rowB[half], k, dxb_box4<FMT>(rowA[0], rowA[1], k, DXB_LF(SRGB)));
+                for (int k = 0; k < 2; ++k) dxb_store_pixel(FMT, rowB[half], k, dxb_box4<FMT, LIN>(rowA[0], rowA[1], k, DXB_LF(SRGB)));
                 dxb_copy_vec<2 * B>(jB.dst + (size_t)(2u * ty + half) * jB.dstPitch + (size_t)(2u * tx) * B, rowB[half], false);
             }
         }
     }
     __align__(16) uint8_t pc[B];
-    dxb_store_pixel(FMT, pc, 0, dxb_box4<FMT>(rowB[0], rowB[1], 0, DXB_LF(SRGB)));
+    dxb_store_pixel(FMT, pc, 0, dxb_box4<FMT, LIN>(rowB[0], rowB[1], 0, DXB_LF(SRGB)));
     dxb_copy_vec<B>(jC.dst + (size_t)ty * jC.dstPitch + (size_t)tx * B, pc, false);
 }
 
 // hostJobs: [3][items] records of levels l, l+1, l+2.  Returns false when the fused kernel does not apply.
 bool dxb_launch_mip_box3(cudaStream_t stream, const dxb_mip_job* jobsDev, const dxb_mip_job* hostJobs, uint32_t items, const dxb_mip_params& P)
 {
-    if (P.mode != DXB_FILTER_BOX || items == 0 || items > 65535u || jobsDev == nullptr) return false;
+    if ((P.mode != DXB_FILTER_BOX && P.mode != DXB_FILTER_LINEAR) || items == 0 || items > 65535u || jobsDev == nullptr) return false;
+    const bool lin = (P.mode == DXB_FILTER_LINEAR);
     const bool srgb = (P.lflags == (DXB_FILTER_SRGB_IN | DXB_FILTER_SRGB_OUT));
     if (!srgb && P.lflags != 0) return false;
     const uint32_t B = dxb_bytes_per_pixel(P.format);
@@ -695,7 +709,8 @@ bool dxb_launch_mip_box3(cudaStream_t stream, const dxb_mip_job* jobsDev, const 
     const dim3 g((a0.sw / 8 + 31) / 32, (a0.sh / 8 + 7) / 8, items);
     if (g.y > 65535u) return false;
 #define DXB_X(FMT, MODE) if (P.format == FMT) { \
-        if (srgb) k_mip_box3<FMT, true><<<g, blk, 0, stream>>>(jobsDev, items, P); else k_mip_box3<FMT, false><<<g, blk, 0, stream>>>(jobsDev, items, P); \
+        if (lin) { if (srgb) k_mip_box3<FMT, true, true><<<g, blk, 0, stream>>>(jobsDev, items, P); else k_mip_box3<FMT, false, true><<<g, blk, 0, stream>>>(jobsDev, items, P); } \
+        else { if (srgb) k_mip_box3<FMT, true, false><<<g, blk, 0, stream>>>(jobsDev, items, P); else k_mip_box3<FMT, false, false><<<g, blk, 0, stream>>>(jobsDev, items, P); } \
         return true; }
     DXB_MIP_FORMATS(DXB_X, 0)
 #undef DXB_X

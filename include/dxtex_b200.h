@@ -61,6 +61,7 @@ DXB200_API int32_t  dxb200_initialized_devices(int* devices, int maxDevices);   
 DXB200_API void     dxb200_shutdown(void);                   /* release cached device / pinned buffers */
 DXB200_API int32_t  dxb200_device_count(void);
 DXB200_API uint64_t dxb200_launch_count(void);               /* number of kernels this library has launched so far */
+DXB200_API uint64_t dxb200_tma_launch_count(void);           /* ... of which fed by TMA tensor-map tile loads (k_compress_bc7_tma) */
 DXB200_API const char* dxb200_last_error(void);              /* text of the last CUDA error seen by the calling thread's call */
 
 /* pinned host allocations for callers that want full-rate H2D/D2H (optional; any host pointer works) */

@@ -148,10 +148,11 @@ def test_mips_golden():
         assert np.array_equal(got, exp), name
 
 
-@pytest.mark.parametrize("fl", [F.TEX_FILTER_BOX, F.TEX_FILTER_LINEAR, F.TEX_FILTER_CUBIC, F.TEX_FILTER_TRIANGLE, F.TEX_FILTER_POINT, 0])
+@pytest.mark.parametrize("fl", [F.TEX_FILTER_BOX, F.TEX_FILTER_LINEAR, F.TEX_FILTER_CUBIC, F.TEX_FILTER_TRIANGLE, F.TEX_FILTER_POINT, 0,
+                                F.TEX_FILTER_LINEAR | F.TEX_FILTER_WRAP])
 def test_mips_vs_oracle(oracle, fl):
     rng = np.random.default_rng(6)
-    # sizes above 64 that divide by 8 take the fused three-level BOX kernel, the others the per-level / tail kernels
+    # sizes above 64 that divide by 8 take the fused three-level BOX / LINEAR kernel, the others the per-level / tail kernels
     for (fmt, w, h) in [(28, 256, 256), (10, 128, 64), (2, 64, 64), (61, 256, 64), (28, 100, 60), (2, 128, 128), (87, 256, 128), (41, 512, 8)]:
         if (fl == F.TEX_FILTER_BOX) and (w & (w - 1) or h & (h - 1)):
             continue
