@@ -130,15 +130,17 @@ class C2:
     scaling = "weak"
     W = H = 4096
     SRC, DST = 2, 98
-    kernel = "k_compress_bc7"
+    kernel = "k_compress_bc7_tma"     # batches: the TMA-fed persistent kernel (DXB200_OPT_BC7_FEED = 4, automatic); a single image: k_compress_bc7
     bound_note = ("BC7 mode/partition search is issue-bound, not HBM-bound (SURVEY 8(d)); DRAM traffic = algorithmic bytes; "
                   "issue-slot utilisation and warp-instructions per block: profiles/r02_ncu_k_compress_bc7.txt")
-    ncu_file = "r02_ncu_k_compress_bc7.txt"
+    ncu_file = "r02_ncu_k_compress_bc7_tma.txt"
     small_sample = {"side": 64}          # the 1-thread rate of the reference is measured on this smaller sample
 
     def __init__(self, args, world):
         self.B = args.batch or 32
         self.world = world
+        if self.B == 1:                    # a single image takes the direct kernel under the automatic feed
+            self.kernel, self.ncu_file = "k_compress_bc7", "r02_ncu_k_compress_bc7.txt"
 
     def workload(self):
         return ("4096x4096 RGBA32F -> BC7_UNORM, TEX_COMPRESS_DEFAULT (BASELINE.json configs[1]); a step = a batch of %d such images per GPU "
@@ -174,6 +176,31 @@ class C2:
         if hr != 0:
             raise ctx.capi.DxTexError(hr, "dxb200_compress_device")
         return e0, e1, self.d_out[i & 1]
+
+    def alternates(self, ctx):
+        """the same batch through the other feed of the BC7 kernel (dxb200_set_option(DXB200_OPT_BC7_FEED, ..)): ms per step, output equal.
+        The default (4 = automatic) feeds batches by TMA tensor-map tile loads (k_compress_bc7_tma) and single images by direct loads."""
+        capi, torch = ctx.capi, ctx.torch
+        feed = capi.lib.dxb200_get_option(capi.OPT_BC7_FEED)
+        used_tma = feed in (1, 2, 3) or (feed == 4 and self.B > 1)
+        other, name = (0, "k_compress_bc7 (direct loads)") if used_tma else (1, "k_compress_bc7_tma")
+        want = self.d_out[ctx.last_step & 1].clone()
+        t0 = capi.tma_launch_count()
+        capi.lib.dxb200_set_option(capi.OPT_BC7_FEED, other)
+        try:
+            for _ in range(2):
+                self.step(ctx, ctx.last_step)
+            a, b = ctx.event(), ctx.event()
+            a.record()
+            for _ in range(3):
+                self.step(ctx, ctx.last_step)
+            b.record()
+            torch.cuda.synchronize()
+        finally:
+            capi.lib.dxb200_set_option(capi.OPT_BC7_FEED, feed)
+        same = bool(torch.equal(want, self.d_out[ctx.last_step & 1]))
+        return {name: {"ms_per_step": a.elapsed_time(b) / 3.0, "tma_launches": capi.tma_launch_count() - t0, "output_equal": same,
+                       "what": "the same batch with DXB200_OPT_BC7_FEED = %d instead of the default %d" % (other, feed)}}
 
     def e2e_setup(self, ctx):
         capi = ctx.capi
@@ -726,6 +753,7 @@ def main():
     if rank == 0:
         sampler.start()
     launches0 = capi.launch_count()
+    tma0 = capi.tma_launch_count()
     kern_ev = []
     e0, e1 = ctx.event(), ctx.event()
     barrier()
@@ -738,6 +766,7 @@ def main():
     barrier()
     ctx.last_step = args.steps - 1
     launches = capi.launch_count() - launches0
+    tma_timed = capi.tma_launch_count() - tma0
     clocks = sampler.stop() if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
@@ -750,6 +779,8 @@ def main():
     ms_per_step = float(t[0]) / args.steps
     kern_ms = float(t[1])
     value = float(units[0]) / (ms_per_step * 1e-3) / 1e6
+
+    alternates = wl.alternates(ctx) if (hasattr(wl, "alternates") and world == 1) else {}
 
     # ---- end to end through the host-pointer C ABI (pinned host memory, H2D + D2H inside the timed region)
     info = wl.e2e_setup(ctx)
@@ -797,7 +828,7 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Mtexels/s", "h2d_bytes_per_step": info["h2d"], "d2h_bytes_per_step": info["d2h"],
                     "ms_per_step": float(te[0]), "api": info["api"], "steps": e2e_steps},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "tma_launches": int(tma_timed),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                          "traffic": traffic, "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/" + wl.ncu_file) if traffic else None,
                          "peak_source": pk_kind, "kernel": wl.kernel, "kernel_ms": kern_ms, "algorithmic_bytes": wl.algo_bytes(),
@@ -805,6 +836,7 @@ def main():
                          "warp_inst_per_block": (inst / (4096 * 4096 / 16)) if (inst and args.config == "c2") else None,
                          "note": wl.bound_note},
             "kernels": dict({wl.kernel: kern_ms}, **extra_ms),
+            "alternates": alternates,
             "cpu_baseline": {"value": u / sec / 1e6, "unit": "Mtexels/s", "cores": threads, "kind": "reference",
                              "sample": desc + ", %.2f s" % sec, "threads": threads, "proc_bind": os.environ.get("OMP_PROC_BIND"),
                              "one_thread_value": u1 / sec1 / 1e6, "per_core_scaling": (u / sec) / (u1 / sec1) / max(threads, 1),

@@ -786,6 +786,12 @@ const char* dxb200_version(void) { return "dxtex_b200 0.1 (sm_100a)"; }
 const char* dxb200_last_error(void) { return t_lastError.c_str(); }
 uint64_t dxb200_launch_count(void) { return g_launches.load(); }
 uint64_t dxb200_tma_launch_count(void) { return g_tma_launches.load(); }
+int32_t dxb200_set_option(uint32_t option, int32_t value)
+{
+    if (option == DXB200_OPT_BC7_FEED) { dxb_bc7_set_feed(value); return DXB_S_OK; }
+    return DXB_E_INVALIDARG;
+}
+int32_t dxb200_get_option(uint32_t option) { return (option == DXB200_OPT_BC7_FEED) ? dxb_bc7_get_feed() : -1; }
 
 int32_t dxb200_device_count(void)
 {

@@ -877,17 +877,8 @@ static thread_local int dxb_bc7_dbg_force_shape[2] = { -1, -1 };
 
 // THREE: compile the three-subset pass (TEX_COMPRESS_BC7_USE_3SUBSETS); the default kernel is instantiated without it so that
 // its instruction footprint (the kernel is sensitive to instruction-cache misses) does not grow for a non-default flag.
-// afterRank(): called by every lane right behind the CTA barrier that follows stage 1 -- the first point at which every warp of the
-// CTA is known to have finished staging its pixels.  The TMA-fed kernel requests its next tile there (dxb_k_bc7.cu).
-struct dxb_bc7_nohook
-{
-#if DXB_ON_DEVICE
-    __device__ __forceinline__
-#endif
-    void operator()() const {}
-};
-template <bool THREE, typename HOOK = dxb_bc7_nohook>
-DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* out0, uint8_t* out1, HOOK afterRank = HOOK())
+template <bool THREE>
+DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* out0, uint8_t* out1)
 {
     const bool quick = (bcflags & DXB_BC_FLAGS_FORCE_BC7_MODE6) != 0;
 
@@ -961,7 +952,6 @@ DXB_DEV void dxb_bc7_encode_pair(dxb_bc7_scratch* S, uint32_t bcflags, uint8_t* 
     DXB_LANES_END
 #endif
     dxb_phase_sync();
-    afterRank();
     // ---- stage 2: one fit task per lane (dxb_bc7_eval); a candidate encoding = one task or the sum of two.
     //   opaque block (the modes the reference tries, BC6HBC7.cpp:2803-2821: 1, 3, 4, 5, 6):
     //     0-7   2 best shapes x 2 subsets x {mode 1, mode 3}          (lane = 4 shape + 2 subset + modebit, partner lane ^ 2)

@@ -37,8 +37,13 @@ __global__ void __launch_bounds__(128) k_compress_bc15(const dxb_job* __restrict
 {
     bc15_body<true, 0, 0>(jobs, single, P);
 }
+// Register cap per destination format (CTAs of 128 threads per SM the kernel is compiled for).  The encoders are latency- and
+// instruction-fetch-bound at 12 resident warps per SM (ncu: 44 % issue utilisation, no_instruction the top stall), so BC3 / BC4 / BC5
+// gain from 64 registers and 32 warps although they spill (B200, 4096^2 / 8192^2: BC3 0.578 -> 0.509 ms, BC4 0.591 -> 0.509 ms); BC1 / BC2
+// keep all 16 pixels of the Newton fit in registers and lose (0.364 -> 0.471 ms), so they stay at the compiler's own choice (168).
+__host__ __device__ constexpr int dxb_bc15_minb(uint32_t df) { return (df == 71u || df == 74u) ? 3 : 8; }
 template <uint32_t DF, uint32_t SF>
-__global__ void __launch_bounds__(128) k_compress_bc15_t(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
+__global__ void __launch_bounds__(128, dxb_bc15_minb(DF)) k_compress_bc15_t(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
 {
     bc15_body<false, DF, SF>(jobs, single, P);
 }
@@ -69,7 +74,8 @@ void dxb_launch_bc15(unsigned grid, cudaStream_t stream, const dxb_job* jobs, co
 }
 int dxb_occupancy_bc15()
 {
+    // the densest of the specialised kernels (BC3 / BC4 / BC5 at 64 registers); launches cap their grid at 4 x SMs x this
     int b = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc15_t<71, 28>, 128, 0) != cudaSuccess) { (void)cudaGetLastError(); b = 1; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc15_t<77, 28>, 128, 0) != cudaSuccess) { (void)cudaGetLastError(); b = 1; }
     return b > 0 ? b : 1;
 }

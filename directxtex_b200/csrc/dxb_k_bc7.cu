@@ -2,11 +2,9 @@
 #include <cuda.h>            // CUtensorMap and the cuTensorMapEncodeTiled prototype only: the entry point is resolved at run time
 #include <stdlib.h>
 #include <algorithm>
+#include <atomic>
 #include "dxb_launch.h"
 #include "dxb_bc7.cuh"
-#ifdef DXB_BC7_NO_CTA_SYNC
-#error "k_compress_bc7_tma relies on the CTA barrier behind stage 1 of the encoder"
-#endif
 
 template <bool THREE>
 __global__ void __launch_bounds__(DXB_BC7_WARPS * 32, DXB_BC7_MINB) k_compress_bc7(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
@@ -81,17 +79,38 @@ int dxb_occupancy_bc7()
 //     64 ends in a zero-filled partial tile whose extra blocks are simply not stored;
 //   * one `cp.async.bulk.tensor.3d` per tile, issued by thread 0, completion on an mbarrier (complete_tx::bytes); every lane then
 //     takes its pixel from the tile with one 128-bit shared load and converts it exactly like the direct kernel does;
-//   * the 4 KB landing buffer is free again as soon as every warp has taken its pixels; the encoder's own first CTA barrier (behind
-//     its shape ranking) establishes that, so the next tile is requested right behind it and no barrier is added to the iteration;
-//     with the buffer the CTA needs 75.9 KB of shared memory, which still leaves 3 CTAs per SM resident;
+//   * the 4 KB landing buffer is free again as soon as every warp has taken its pixels (the barrier at the top of the iteration), so
+//     the next tile is requested right there and has the whole encode of the current tile to arrive; with it the CTA needs 75.9 KB of
+//     shared memory, which still leaves 3 CTAs per SM resident (requesting behind the encoder's own first barrier instead, to save
+//     this one, measured slower: 4.57 vs 4.43 ms);
 //   * tiles are handed out by an atomic counter (blocks with alpha cost more than opaque ones); the counter is read one tile ahead
 //     of the request, so its round trip is off the critical path too.  T.counter == nullptr: statically strided tiles.
 // Eligibility (dxb_launch_bc7_tma): RGBA32F source, full 4x4 blocks only (partial blocks need CompressBC's {0,0,0,1} replication,
 // which a tensor map's zero fill cannot express), 16-byte aligned rows, images of one size at a constant pointer stride.
+// unsigned division by a run-time constant (Granlund / Montgomery round-up form): q = n / d for every 32-bit n
+struct dxb_udiv { uint32_t d, M, sh; };
+static dxb_udiv dxb_udiv_make(uint32_t d)
+{
+    dxb_udiv r; r.d = d; r.M = 0; r.sh = 0;
+    if (d > 1u)
+    {
+        uint32_t l = 0; while ((1ull << l) < d) ++l;                      // ceil(log2 d)
+        r.M = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d + 1ull); r.sh = l - 1u;
+    }
+    return r;
+}
+__device__ __forceinline__ uint32_t dxb_udiv_do(uint32_t n, const dxb_udiv& k)
+{
+    if (k.d <= 1u) return n;
+    const uint32_t t = __umulhi(k.M, n);
+    return (t + ((n - t) >> 1)) >> k.sh;
+}
+
 struct dxb_bc7_tma_params
 {
     uint8_t* dst0; size_t dstPitch, dstImageStride;
     uint32_t nbx, tilesX, tilesPerImage, totalTiles;
+    dxb_udiv divImage, divRow;        // tile / tilesPerImage, (tile in image) / tilesX
     uint32_t* counter;
 };
 
@@ -106,7 +125,7 @@ __global__ void __launch_bounds__(DXB_BC7_WARPS * 32, DXB_BC7_MINB) k_compress_b
     extern __shared__ __align__(128) unsigned char smem_tma[];
     const float4* tileBuf = (const float4*)smem_tma;                      // [row 0..3][pixel 0..63]
     uint64_t* mbar = (uint64_t*)(smem_tma + DXB_BC7_TILE_BYTES);
-    volatile uint32_t* tileOf = (volatile uint32_t*)(mbar + 1);           // tile index of the data the barrier's current phase delivers
+    volatile uint32_t* tileOf = (volatile uint32_t*)(mbar + 1);           // {tile, image, block row, tile column} of the data the barrier's current phase delivers
     dxb_bc7_scratch* scratch = (dxb_bc7_scratch*)(smem_tma + DXB_BC7_TILE_BYTES + 128u);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u, hl = lane & 15u;
     dxb_bc7_scratch* S = &scratch[warp];
@@ -115,11 +134,14 @@ __global__ void __launch_bounds__(DXB_BC7_WARPS * 32, DXB_BC7_MINB) k_compress_b
     // thread 0: request `tile` (or publish the end marker)
     auto request = [&](uint32_t tile)
     {
-        *tileOf = tile;
+        tileOf[0] = tile;
         if (tile < T.totalTiles)
         {
-            const uint32_t img = tile / T.tilesPerImage, r = tile - img * T.tilesPerImage;
-            const uint32_t by = r / T.tilesX, tx = r - by * T.tilesX;
+            // everything the other 255 threads need travels with the tile, and the two divisions are multiplications: this runs on one
+            // thread between two CTA barriers, so every instruction here delays all eight warps
+            const uint32_t img = dxb_udiv_do(tile, T.divImage), r = tile - img * T.tilesPerImage;
+            const uint32_t by = dxb_udiv_do(r, T.divRow), tx = r - by * T.tilesX;
+            tileOf[1] = img; tileOf[2] = by; tileOf[3] = tx;
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(barAddr), "r"(DXB_BC7_TILE_BYTES) : "memory");
             asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                          :: "r"(tileAddr), "l"(&tmap), "r"(barAddr), "r"((int)(tx * 256u)), "r"((int)(by * 4u)), "r"((int)img) : "memory");
@@ -145,10 +167,9 @@ __global__ void __launch_bounds__(DXB_BC7_WARPS * 32, DXB_BC7_MINB) k_compress_b
         asm volatile("{\n\t.reg .pred P1;\n\tDXB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DXB_DONE;\n\tbra DXB_WAIT;\n\tDXB_DONE:\n\t}"
                      :: "r"(barAddr), "r"(parity) : "memory");
         parity ^= 1u;
-        const uint32_t tile = *tileOf;
+        const uint32_t tile = tileOf[0];
         if (tile >= T.totalTiles) break;
-        const uint32_t img = tile / T.tilesPerImage, r = tile - img * T.tilesPerImage;
-        const uint32_t by = r / T.tilesX, tx = r - by * T.tilesX;
+        const uint32_t img = tileOf[1], by = tileOf[2], tx = tileOf[3];
         const uint32_t blk = warp * 2u + (lane >> 4), bx = tx * 16u + blk;
         uint8_t* out = nullptr;
         dxb_px ldr = dxb_make_px(0.0f, 0.0f, 0.0f, 255.0f);
@@ -160,21 +181,15 @@ __global__ void __launch_bounds__(DXB_BC7_WARPS * 32, DXB_BC7_MINB) k_compress_b
             out = T.dst0 + (size_t)img * T.dstImageStride + (size_t)by * T.dstPitch + (size_t)bx * 16u;
         }
         S->px[lane] = ldr;
-        __syncwarp();
-        // the landing buffer is free once EVERY warp has taken its pixels: the first CTA barrier inside the encoder (behind its stage 1)
-        // establishes that without an extra barrier here; thread 0 requests the next tile right behind it, which then has the candidate
-        // search, index assignment and bit packing of this tile (~60 % of the iteration) to arrive
-        auto hook = [&]()
+        __syncthreads();                // every warp has taken its pixels (and the tile index): the landing buffer is free
+        if (threadIdx.x == 0)
         {
-            if (threadIdx.x == 0)
-            {
-                const uint32_t nxt = ahead;
-                request(nxt);
-                // hand-out for the iteration after the next; its value is not needed before the next request, so the round trip hides
-                ahead = (nxt >= T.totalTiles) ? nxt : (T.counter ? gridDim.x + atomicAdd(T.counter, 1u) : nxt + gridDim.x);
-            }
-        };
-        dxb_bc7_encode_pair<THREE>(S, P.bcflags, out, out, hook);
+            const uint32_t nxt = ahead;
+            request(nxt);
+            // hand-out for the iteration after the next; its value is not needed before the next request, so the round trip hides
+            ahead = (nxt >= T.totalTiles) ? nxt : (T.counter ? gridDim.x + atomicAdd(T.counter, 1u) : nxt + gridDim.x);
+        }
+        dxb_bc7_encode_pair<THREE>(S, P.bcflags, out, out);
         __syncwarp();
     }
 }
@@ -203,17 +218,29 @@ static bool bc7_tma_attr_set()
     return ok;
 }
 
-// mode: 0 = never (direct kernel), 1 = TMA with the atomic tile counter, 2 = TMA with statically strided tiles, 3 = TMA with one CTA
-// per tile.  DXB200_BC7_TMA overrides.
-static int bc7_tma_mode()
+// mode: 0 = direct kernel only, 1 = TMA with the atomic tile counter, 2 = TMA with statically strided tiles, 3 = TMA with one CTA per
+// tile, 4 = automatic (default): mode 1 for batches of images, the direct kernel for a single image.  DXB200_BC7_TMA / dxb200_set_option
+// select.  Measured on B200 (profiles/r02_prof_driver_timings.txt, r02_bench_lines.jsonl):
+//   one 4096^2 RGBA32F image:      direct 4.30 ms, mode 1 4.41 ms, mode 2 4.75 ms (tile costs differ: static striding loses to any dynamic
+//                                  hand-out), mode 3 4.33 ms
+//   batch of 32 such images (C2):  direct 141.7 ms, mode 1 140.9 ms (one tensor map serves the whole batch: no per-block job search)
+// The feed is not what bounds the encoder (issue-bound, 1 % of HBM); the persistent loop pays two CTA-wide synchronisations per tile
+// (ncu: barrier stall 0.98 vs 0.53 cycles per issue) and saves the job lookup.  Variants tried and dropped: request behind the
+// encoder's own first barrier 4.57 ms, staggered CTA starts 4.42 ms, landing zone aliased onto dead scratch 4.46 ms.
+static std::atomic<int> g_bc7_feed{-1};
+int dxb_bc7_get_feed()
 {
-    static const int m = []() { const char* e = getenv("DXB200_BC7_TMA"); return e ? atoi(e) : 0; }();   // 0 until the GPU A/B of this revision is in (profiles/)
+    int m = g_bc7_feed.load(std::memory_order_relaxed);
+    if (m < 0) { const char* e = getenv("DXB200_BC7_TMA"); m = e ? atoi(e) : 4; if (m < 0 || m > 4) m = 4; g_bc7_feed.store(m, std::memory_order_relaxed); }
     return m;
 }
+void dxb_bc7_set_feed(int mode) { g_bc7_feed.store((mode < 0 || mode > 4) ? 4 : mode, std::memory_order_relaxed); }
+static int bc7_tma_mode() { return dxb_bc7_get_feed(); }
 
 bool dxb_launch_bc7_tma(unsigned residentCtas, cudaStream_t stream, const dxb_job* hostJobs, const dxb_compress_params& P)
 {
-    const int mode = bc7_tma_mode();
+    int mode = bc7_tma_mode();
+    if (mode == 4) mode = (P.njobs > 1u) ? 1 : 0;
     if (mode == 0 || P.srcFormat != DXB_FMT_R32G32B32A32_FLOAT || P.njobs == 0) return false;
     const dxb_job& j0 = hostJobs[0];
     if ((j0.width & 3u) || (j0.height & 3u) || (j0.srcPitch & 15u) || ((uintptr_t)j0.src & 15u) || j0.srcPitch >= (1ull << 40)) return false;
@@ -242,6 +269,7 @@ bool dxb_launch_bc7_tma(unsigned residentCtas, cudaStream_t stream, const dxb_jo
     dxb_bc7_tma_params T;
     T.dst0 = j0.dst; T.dstPitch = j0.dstPitch; T.dstImageStride = (size_t)dstStride;
     T.nbx = j0.nbx; T.tilesX = (j0.nbx + 15u) / 16u; T.tilesPerImage = T.tilesX * j0.nby;
+    T.divImage = dxb_udiv_make(T.tilesPerImage); T.divRow = dxb_udiv_make(T.tilesX);
     const uint64_t total = (uint64_t)T.tilesPerImage * P.njobs;
     if (total >= 0x7FFFFFFFull) return false;
     T.totalTiles = (uint32_t)total;

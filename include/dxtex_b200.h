@@ -62,6 +62,14 @@ DXB200_API void     dxb200_shutdown(void);                   /* release cached d
 DXB200_API int32_t  dxb200_device_count(void);
 DXB200_API uint64_t dxb200_launch_count(void);               /* number of kernels this library has launched so far */
 DXB200_API uint64_t dxb200_tma_launch_count(void);           /* ... of which fed by TMA tensor-map tile loads (k_compress_bc7_tma) */
+/* process-wide tuning options (no reference counterpart; results never depend on them).
+ *   DXB200_OPT_BC7_FEED  how k_compress_bc7 gets RGBA32F sources made of full blocks: 0 = direct vector loads, one CTA per 16 blocks,
+ *                        1 = persistent CTAs fed by TMA tensor-map tile loads with an atomic tile counter, 2 = the same with statically
+ *                        strided tiles, 3 = TMA with one CTA per tile, 4 = automatic (default): 1 for batches of images, 0 for a single
+ *                        image -- whichever measured faster.  Initial value: environment variable DXB200_BC7_TMA. */
+#define DXB200_OPT_BC7_FEED 1u
+DXB200_API int32_t  dxb200_set_option(uint32_t option, int32_t value);      /* E_INVALIDARG for an unknown option */
+DXB200_API int32_t  dxb200_get_option(uint32_t option);                     /* -1 for an unknown option */
 DXB200_API const char* dxb200_last_error(void);              /* text of the last CUDA error seen by the calling thread's call */
 
 /* pinned host allocations for callers that want full-rate H2D/D2H (optional; any host pointer works) */

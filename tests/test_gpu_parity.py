@@ -313,6 +313,16 @@ def test_bc7_tma_fed_kernel_equals_emulator(emul):
     as must a source whose rows are not 16-byte aligned for the tensor map (pitch padded by 4 bytes: the direct kernel)."""
     torch = pytest.importorskip("torch")
     rng = np.random.default_rng(23)
+    before, feed = capi.tma_launch_count(), capi.lib.dxb200_get_option(capi.OPT_BC7_FEED)
+    assert capi.lib.dxb200_set_option(capi.OPT_BC7_FEED, 1) == 0          # the default (4) takes the direct kernel for single images
+    try:
+        _tma_cases(emul, torch, rng)
+    finally:
+        capi.lib.dxb200_set_option(capi.OPT_BC7_FEED, feed)
+    assert capi.tma_launch_count() >= before + 7                           # six single images + the stride-aligned array went through TMA
+
+
+def _tma_cases(emul, torch, rng):
     for (w, h, flags) in [(100, 52, 0), (64, 4, 0), (4, 4, 0), (260, 8, 0), (1024, 512, 0), (72, 20, F.TEX_COMPRESS_BC7_USE_3SUBSETS)]:
         img = rng.random((h, w, 4), dtype=np.float32)
         if w == 100:
