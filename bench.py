@@ -47,7 +47,10 @@ def ncu_metric(path, key):
         for line in open(os.path.join(ROOT, "profiles", path)):
             parts = line.split()
             if parts and parts[0] == key:
-                return float(parts[-1])
+                v = float(parts[-1])
+                if len(parts) >= 3 and parts[1].lower().endswith("byte"):          # ncu scales byte counts: normalise to Mbyte
+                    v *= {"byte": 1e-6, "kbyte": 1e-3, "mbyte": 1.0, "gbyte": 1e3}.get(parts[1].lower(), 1.0)
+                return v
     except Exception:
         pass
     return None
