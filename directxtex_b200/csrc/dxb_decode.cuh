@@ -14,26 +14,33 @@
 
 DXB_DEV float dxb_lerp1(float a, float b, float t) { const float l = b - a; const float m = l * t; return m + a; }   // XMVectorLerp
 
-// DecodeBC1 (BC.cpp:318-366); blk = 8 bytes
-DXB_DEV void dxb_decode_bc1(const uint8_t* blk, bool isbc1, dxb_px* out)
+// DecodeBC1 (BC.cpp:318-366); blk = 8 bytes.  The four colours of the block ...
+DXB_DEV void dxb_bc1_palette(const uint8_t* blk, bool isbc1, dxb_px* clr)
 {
     const uint32_t c01 = ((const uint32_t*)blk)[0];
     const uint32_t rgb0 = c01 & 0xFFFFu, rgb1 = c01 >> 16;
-    dxb_px clr0, clr1, clr2, clr3;
     // XMLoadU565: x = bits 0-4, y = 5-10, z = 11-15; * {1/31, 1/63, 1/31, 1}; swizzle <2,1,0,3>; w = 1
-    clr0 = dxb_make_px((float)((rgb0 >> 11) & 31u) * (1.0f / 31.0f), (float)((rgb0 >> 5) & 63u) * (1.0f / 63.0f), (float)(rgb0 & 31u) * (1.0f / 31.0f), 1.0f);
-    clr1 = dxb_make_px((float)((rgb1 >> 11) & 31u) * (1.0f / 31.0f), (float)((rgb1 >> 5) & 63u) * (1.0f / 63.0f), (float)(rgb1 & 31u) * (1.0f / 31.0f), 1.0f);
+    clr[0] = dxb_make_px((float)((rgb0 >> 11) & 31u) * (1.0f / 31.0f), (float)((rgb0 >> 5) & 63u) * (1.0f / 63.0f), (float)(rgb0 & 31u) * (1.0f / 31.0f), 1.0f);
+    clr[1] = dxb_make_px((float)((rgb1 >> 11) & 31u) * (1.0f / 31.0f), (float)((rgb1 >> 5) & 63u) * (1.0f / 63.0f), (float)(rgb1 & 31u) * (1.0f / 31.0f), 1.0f);
+    const dxb_px clr0 = clr[0], clr1 = clr[1];
     if (isbc1 && (rgb0 <= rgb1))
     {
-        clr2 = dxb_make_px(dxb_lerp1(clr0.x, clr1.x, 0.5f), dxb_lerp1(clr0.y, clr1.y, 0.5f), dxb_lerp1(clr0.z, clr1.z, 0.5f), dxb_lerp1(clr0.w, clr1.w, 0.5f));
-        clr3 = dxb_make_px(0.0f, 0.0f, 0.0f, 0.0f);
+        clr[2] = dxb_make_px(dxb_lerp1(clr0.x, clr1.x, 0.5f), dxb_lerp1(clr0.y, clr1.y, 0.5f), dxb_lerp1(clr0.z, clr1.z, 0.5f), dxb_lerp1(clr0.w, clr1.w, 0.5f));
+        clr[3] = dxb_make_px(0.0f, 0.0f, 0.0f, 0.0f);
     }
     else
     {
         const float t1 = 1.0f / 3.0f, t2 = 2.0f / 3.0f;
-        clr2 = dxb_make_px(dxb_lerp1(clr0.x, clr1.x, t1), dxb_lerp1(clr0.y, clr1.y, t1), dxb_lerp1(clr0.z, clr1.z, t1), dxb_lerp1(clr0.w, clr1.w, t1));
-        clr3 = dxb_make_px(dxb_lerp1(clr0.x, clr1.x, t2), dxb_lerp1(clr0.y, clr1.y, t2), dxb_lerp1(clr0.z, clr1.z, t2), dxb_lerp1(clr0.w, clr1.w, t2));
+        clr[2] = dxb_make_px(dxb_lerp1(clr0.x, clr1.x, t1), dxb_lerp1(clr0.y, clr1.y, t1), dxb_lerp1(clr0.z, clr1.z, t1), dxb_lerp1(clr0.w, clr1.w, t1));
+        clr[3] = dxb_make_px(dxb_lerp1(clr0.x, clr1.x, t2), dxb_lerp1(clr0.y, clr1.y, t2), dxb_lerp1(clr0.z, clr1.z, t2), dxb_lerp1(clr0.w, clr1.w, t2));
     }
+}
+// ... and the 16 pixels they are assigned to
+DXB_DEV void dxb_decode_bc1(const uint8_t* blk, bool isbc1, dxb_px* out)
+{
+    dxb_px clr[4];
+    dxb_bc1_palette(blk, isbc1, clr);
+    const dxb_px clr0 = clr[0], clr1 = clr[1], clr2 = clr[2], clr3 = clr[3];
     uint32_t dw = ((const uint32_t*)blk)[1];
     for (int i = 0; i < 16; ++i, dw >>= 2)
     {
@@ -51,6 +58,30 @@ DXB_DEV void dxb_decode_bc2(const uint8_t* blk, dxb_px* out)
     for (int i = 8; i < 16; ++i, dw >>= 4) out[i].w = (float)(dw & 0xFu) * (1.0f / 15.0f);
 }
 
+// the eight alpha values of a BC3 block (BC.cpp:902-941)
+DXB_DEV void dxb_bc3_alpha_table(const uint8_t* blk, float* fAlpha)
+{
+    const uint32_t a0 = blk[0], a1 = blk[1];
+    fAlpha[0] = (float)a0 * (1.0f / 255.0f);
+    fAlpha[1] = (float)a1 * (1.0f / 255.0f);
+    if (a0 > a1)
+    {
+        for (int i = 1; i < 7; ++i)
+        {
+            const float x = fAlpha[0] * (float)(7 - i), y = fAlpha[1] * (float)i;
+            fAlpha[i + 1] = (x + y) * (1.0f / 7.0f);
+        }
+    }
+    else
+    {
+        for (int i = 1; i < 5; ++i)
+        {
+            const float x = fAlpha[0] * (float)(5 - i), y = fAlpha[1] * (float)i;
+            fAlpha[i + 1] = (x + y) * (1.0f / 5.0f);
+        }
+        fAlpha[6] = 0.0f; fAlpha[7] = 1.0f;
+    }
+}
 DXB_DEV void dxb_decode_bc3(const uint8_t* blk, dxb_px* out)
 {
     dxb_decode_bc1(blk + 8, false, out);
@@ -81,6 +112,20 @@ DXB_DEV void dxb_decode_bc3(const uint8_t* blk, dxb_px* out)
     for (int i = 8; i < 16; ++i, dw >>= 3) out[i].w = fAlpha[dw & 7u];
 }
 
+// the eight values of one BC4 channel
+DXB_DEV void dxb_bc4_table(const uint8_t* blk, bool bSigned, float* grad)
+{
+    if (bSigned)
+    {
+        const int32_t r0 = (int32_t)(int8_t)blk[0], r1 = (int32_t)(int8_t)blk[1];
+        for (uint32_t k = 0; k < 8; ++k) grad[k] = dxb_bc4s_decode(r0, r1, k);
+    }
+    else
+    {
+        const uint32_t r0 = blk[0], r1 = blk[1];
+        for (uint32_t k = 0; k < 8; ++k) grad[k] = dxb_bc4u_decode(r0, r1, k);
+    }
+}
 // one BC4 channel: 16 values
 DXB_DEV void dxb_decode_bc4_channel(const uint8_t* blk, bool bSigned, float* v)
 {

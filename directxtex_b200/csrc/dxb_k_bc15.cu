@@ -41,7 +41,10 @@ __global__ void __launch_bounds__(128) k_compress_bc15(const dxb_job* __restrict
 // instruction-fetch-bound at 12 resident warps per SM (ncu: 44 % issue utilisation, no_instruction the top stall), so BC3 / BC4 / BC5
 // gain from 64 registers and 32 warps although they spill (B200, 4096^2 / 8192^2: BC3 0.578 -> 0.509 ms, BC4 0.591 -> 0.509 ms); BC1 / BC2
 // keep all 16 pixels of the Newton fit in registers and lose (0.364 -> 0.471 ms), so they stay at the compiler's own choice (168).
-__host__ __device__ constexpr int dxb_bc15_minb(uint32_t df) { return (df == 71u || df == 74u) ? 3 : 8; }
+#ifndef DXB_BC15_MINB_HI
+#define DXB_BC15_MINB_HI 8
+#endif
+__host__ __device__ constexpr int dxb_bc15_minb(uint32_t df) { return (df == 71u || df == 74u) ? 3 : DXB_BC15_MINB_HI; }
 template <uint32_t DF, uint32_t SF>
 __global__ void __launch_bounds__(128, dxb_bc15_minb(DF)) k_compress_bc15_t(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
 {
