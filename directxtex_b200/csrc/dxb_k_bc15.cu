@@ -4,9 +4,19 @@
 //                              "no dithering" are compile-time constants.  The generic kernel carries every format
 //                              loader, the sRGB powf paths and all five encoders with their dither variants: 106 k SASS
 //                              instructions, and it ran at 13 % issue utilisation stalled on instruction fetch.
+#include <algorithm>
 #include "dxb_launch.h"
 #include "dxb_bc15.cuh"
 
+// Launch shape per destination format, from measurements on B200 (4096^2 RGBA8 / 8192^2 R8; profiles/r02_prof_driver_timings.txt).
+// The encoders are thousands of instructions of mostly straight-line code per block and instruction fetch is their top stall
+// (ncu `no_instruction` 2.3 - 4 cycles per issue, profiles/r02_ncu_c4.txt), so what helps is more resident warps and warps that run the same
+// code at the same time:
+//   registers  BC3 / BC4 / BC5: 64 (32 warps/SM, spills and all): BC3 0.578 -> 0.509 ms, BC4 0.591 -> 0.510 ms.  BC1 / BC2 keep the 16 pixels of
+//              their Newton fit in registers and lose at 64 (0.364 -> 0.471 ms): compiler's choice (168).
+//   CTA shape  BC3: 512 threads that start every block together (one barrier per block): 0.509 -> 0.469 ms.  BC1 and BC4 lose with it.
+__host__ __device__ constexpr uint32_t dxb_bc15_threads(uint32_t df) { return (df == 77u) ? 512u : 128u; }
+__host__ __device__ constexpr bool dxb_bc15_sync(uint32_t df) { return df == 77u; }
 template <bool GENERIC, uint32_t DF, uint32_t SF>
 __device__ __forceinline__ void bc15_body(const dxb_job* __restrict__ jobs, const dxb_job& single, const dxb_compress_params& P)
 {
@@ -15,8 +25,14 @@ __device__ __forceinline__ void bc15_body(const dxb_job* __restrict__ jobs, cons
     const uint32_t cflags = GENERIC ? P.cflags : dxb_bc15_default_cflags(DF);
     const uint32_t bcflags = GENERIC ? P.bcflags : 0u;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t unit = blockIdx.x * blockDim.x + threadIdx.x; unit < P.totalUnits; unit += stride)
+    // SYNC: every warp of the CTA starts a block together, so that the warps share their instruction fetches.  The loop bound is
+    // CTA-uniform; threads past the end skip the body.
+    constexpr bool SYNC = !GENERIC && dxb_bc15_sync(GENERIC ? 0u : DF);
+    for (uint32_t base = blockIdx.x * blockDim.x; base < P.totalUnits; base += stride)
     {
+        if (SYNC) __syncthreads();
+        const uint32_t unit = base + threadIdx.x;
+        if (unit >= P.totalUnits) continue;
         const dxb_job& j = dxb_find_job(jobs, P.njobs, single, unit, P.periodUnits, P.periodJobs);
         const uint32_t local = unit - j.firstUnit;
         const uint32_t by = local / j.nbx, bx = local - by * j.nbx;
@@ -37,16 +53,9 @@ __global__ void __launch_bounds__(128) k_compress_bc15(const dxb_job* __restrict
 {
     bc15_body<true, 0, 0>(jobs, single, P);
 }
-// Register cap per destination format (CTAs of 128 threads per SM the kernel is compiled for).  The encoders are latency- and
-// instruction-fetch-bound at 12 resident warps per SM (ncu: 44 % issue utilisation, no_instruction the top stall), so BC3 / BC4 / BC5
-// gain from 64 registers and 32 warps although they spill (B200, 4096^2 / 8192^2: BC3 0.578 -> 0.509 ms, BC4 0.591 -> 0.509 ms); BC1 / BC2
-// keep all 16 pixels of the Newton fit in registers and lose (0.364 -> 0.471 ms), so they stay at the compiler's own choice (168).
-#ifndef DXB_BC15_MINB_HI
-#define DXB_BC15_MINB_HI 8
-#endif
-__host__ __device__ constexpr int dxb_bc15_minb(uint32_t df) { return (df == 71u || df == 74u) ? 3 : DXB_BC15_MINB_HI; }
+__host__ __device__ constexpr int dxb_bc15_minb(uint32_t df) { return (df == 71u || df == 74u) ? 3 : (int)(8u * 128u / dxb_bc15_threads(df)); }
 template <uint32_t DF, uint32_t SF>
-__global__ void __launch_bounds__(128, dxb_bc15_minb(DF)) k_compress_bc15_t(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
+__global__ void __launch_bounds__(dxb_bc15_threads(DF), dxb_bc15_minb(DF)) k_compress_bc15_t(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
 {
     bc15_body<false, DF, SF>(jobs, single, P);
 }
@@ -69,7 +78,7 @@ void dxb_launch_bc15(unsigned grid, cudaStream_t stream, const dxb_job* jobs, co
     if (sf == DXB_FMT_B8G8R8A8_UNORM_SRGB) sf = DXB_FMT_B8G8R8A8_UNORM;
     if (P.bcflags == 0 && P.cflags == dxb_bc15_default_cflags(df))
     {
-#define DXB_X(DF, SF) if (df == DF && sf == SF) { k_compress_bc15_t<DF, SF><<<grid, 128, 0, stream>>>(jobs, single, P); return; }
+#define DXB_X(DF, SF) if (df == DF && sf == SF) { k_compress_bc15_t<DF, SF><<<std::max(1u, grid * 128u / dxb_bc15_threads(DF)), dxb_bc15_threads(DF), 0, stream>>>(jobs, single, P); return; }
         DXB_BC15_PAIRS(DXB_X)
 #undef DXB_X
     }
@@ -77,8 +86,9 @@ void dxb_launch_bc15(unsigned grid, cudaStream_t stream, const dxb_job* jobs, co
 }
 int dxb_occupancy_bc15()
 {
-    // the densest of the specialised kernels (BC3 / BC4 / BC5 at 64 registers); launches cap their grid at 4 x SMs x this
+    // the densest of the specialised kernels (BC4 at 64 registers, 128-thread CTAs); callers size their grids in 128-thread CTAs and
+    // cap them at 4 x SMs x this
     int b = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc15_t<77, 28>, 128, 0) != cudaSuccess) { (void)cudaGetLastError(); b = 1; }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_compress_bc15_t<80, 61>, 128, 0) != cudaSuccess) { (void)cudaGetLastError(); b = 1; }
     return b > 0 ? b : 1;
 }
