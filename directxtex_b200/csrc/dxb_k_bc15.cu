@@ -14,8 +14,13 @@
 // code at the same time:
 //   registers  BC3 / BC4 / BC5: 64 (32 warps/SM, spills and all): BC3 0.578 -> 0.509 ms, BC4 0.591 -> 0.510 ms.  BC1 / BC2 keep the 16 pixels of
 //              their Newton fit in registers and lose at 64 (0.364 -> 0.471 ms): compiler's choice (168).
-//   CTA shape  BC3: 512 threads that start every block together (one barrier per block): 0.509 -> 0.469 ms.  BC1 and BC4 lose with it.
-__host__ __device__ constexpr uint32_t dxb_bc15_threads(uint32_t df) { return (df == 77u) ? 512u : 128u; }
+//   CTA shape  BC3: 512 threads that start every block together (one barrier per block): 0.509 -> 0.471 ms, C4 step 54.5 -> 43.9 ms; ncu:
+//              no_instruction 4.05 -> 0.58 cycles per issue.  256 / 384 / 1024 threads and 85 / 128 registers measured within 2 % of it on C4.
+//              BC1 and BC4 lose with big CTAs.
+#ifndef DXB_BC3_THREADS
+#define DXB_BC3_THREADS 512u
+#endif
+__host__ __device__ constexpr uint32_t dxb_bc15_threads(uint32_t df) { return (df == 77u) ? DXB_BC3_THREADS : 128u; }
 __host__ __device__ constexpr bool dxb_bc15_sync(uint32_t df) { return df == 77u; }
 template <bool GENERIC, uint32_t DF, uint32_t SF>
 __device__ __forceinline__ void bc15_body(const dxb_job* __restrict__ jobs, const dxb_job& single, const dxb_compress_params& P)
@@ -53,7 +58,10 @@ __global__ void __launch_bounds__(128) k_compress_bc15(const dxb_job* __restrict
 {
     bc15_body<true, 0, 0>(jobs, single, P);
 }
-__host__ __device__ constexpr int dxb_bc15_minb(uint32_t df) { return (df == 71u || df == 74u) ? 3 : (int)(8u * 128u / dxb_bc15_threads(df)); }
+#ifndef DXB_BC3_MINB
+#define DXB_BC3_MINB 2
+#endif
+__host__ __device__ constexpr int dxb_bc15_minb(uint32_t df) { return (df == 71u || df == 74u) ? 3 : (df == 77u) ? DXB_BC3_MINB : 8; }
 template <uint32_t DF, uint32_t SF>
 __global__ void __launch_bounds__(dxb_bc15_threads(DF), dxb_bc15_minb(DF)) k_compress_bc15_t(const dxb_job* __restrict__ jobs, dxb_job single, dxb_compress_params P)
 {
