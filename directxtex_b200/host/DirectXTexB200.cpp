@@ -6,6 +6,7 @@
 #include "DirectXTexB200.h"
 #include "../../include/dxtex_b200.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -28,42 +29,229 @@ namespace
     }
 }
 
+namespace
+{
+
+// ---- format utilities (DirectXTex.h:72-99, 144-154; DirectXTexUtil.cpp:760-960, 1186-1690) -----------------------------------------
+// The reference answers these from one switch statement per question.  Here every answer is derived from the format's NAME: a DXGI
+// name is a list of channel groups (a letter and a bit count each: R8G8B8A8, D24 + S8, R9G9B9E5, X8X24 ...) followed by a type
+// (UNORM, FLOAT, TYPELESS, ... SRGB), so bits per pixel is the sum of the bit counts, bits per colour their maximum, "has alpha" an A
+// channel, BGR a leading B channel, and the Make* conversions are look-ups of the sibling name.  The video / planar / palettized /
+// block-compressed formats, whose names are not channel lists, have one small table.  tests/test_cpu_abi.py compares all of it, for
+// every value 0..200, with the reference's own functions.
+struct FormatName { uint32_t value; const char* name; };
+const FormatName kFormatNames[] = {
+#define DXB_X(name, value) { value, #name },
+    DXB_DXGI_FORMATS(DXB_X)
+#undef DXB_X
+    // extension values the reference classifies although they are not DXGI_FORMAT enumerators (XBOX_DXGI_FORMAT_*, DirectXTexP.h:188-204;
+    // 189 / 190 take the Xbox meaning there, which shadows the sampler-feedback names of the public enum: listed first = found first)
+};
+const FormatName kExtensionNames[] = {
+    { 116, "R10G10B10_7E3_A2_FLOAT" }, { 117, "R10G10B10_6E4_A2_FLOAT" }, { 118, "D16_UNORM_S8_UINT" }, { 119, "R16_UNORM_X8_TYPELESS" },
+    { 120, "X16_TYPELESS_G8_UINT" }, { 189, "R10G10B10_SNORM_A2_UNORM" }, { 190, "R4G4_UNORM" },
+};
+const char* format_name(DXGI_FORMAT f)
+{
+    for (const FormatName& e : kExtensionNames) if (e.value == static_cast<uint32_t>(f)) return e.name;
+    for (const FormatName& e : kFormatNames) if (e.value == static_cast<uint32_t>(f)) return e.name;
+    return nullptr;
+}
+DXGI_FORMAT format_by_name(const std::string& n, DXGI_FORMAT fallback)
+{
+    for (const FormatName& e : kFormatNames) if (n == e.name) return static_cast<DXGI_FORMAT>(e.value);
+    return fallback;
+}
+struct FormatClass
+{
+    bool known = false, regular = false;            // regular: the name is a channel list
+    bool typeless = false, partialTypeless = false, srgb = false, depth = false, stencilPlane = false, xboxPlanar = false, alpha = false, bgr = false;
+    size_t bits = 0, maxBits = 0;
+    int bc = 0;                                     // 1..7 for BCn
+    std::string family;                             // name without its trailing type tokens ("R8G8B8A8", "BC6H")
+};
+bool is_type_token(const std::string& t)
+{
+    return t == "TYPELESS" || t == "UNORM" || t == "SNORM" || t == "UINT" || t == "SINT" || t == "FLOAT" || t == "SRGB" || t == "UF16" || t == "SF16" ||
+           t == "SHAREDEXP";
+}
+// "R32G8X24" -> channels; false when the token is not (letter, digits)+
+bool parse_group(const std::string& t, FormatClass& c, bool first)
+{
+    size_t i = 0, sum = 0, mx = 0, posB = 99, posR = 99, idx = 0; bool a = false, d = false, any = false;
+    while (i < t.size())
+    {
+        const char ch = t[i];
+        if (!(ch == 'R' || ch == 'G' || ch == 'B' || ch == 'A' || ch == 'X' || ch == 'D' || ch == 'S' || ch == 'E')) return false;
+        size_t k = i + 1, v = 0;
+        while (k < t.size() && t[k] >= '0' && t[k] <= '9') { v = v * 10 + size_t(t[k] - '0'); ++k; }
+        if (k == i + 1) return false;
+        if (ch == 'A') a = true;
+        if (ch == 'D') d = true;
+        if (ch == 'B' && posB == 99) posB = idx;
+        if (ch == 'R' && posR == 99) posR = idx;
+        mx = std::max(mx, v);                       // padding (X) planes count: X32_TYPELESS_G8X24_UINT answers 32
+        sum += v; i = k; any = true; ++idx;
+    }
+    if (!any) return false;
+    c.bits += sum; c.maxBits = std::max(c.maxBits, mx); c.alpha |= a; c.depth |= d;
+    if (first) c.bgr = (posB < posR && posR != 99);   // blue stored before red: B8G8R8A8, B5G6R5, A4B4G4R4
+    return true;
+}
+FormatClass classify(DXGI_FORMAT f)
+{
+    FormatClass c;
+    const char* nm = format_name(f);
+    if (!nm || f == DXGI_FORMAT_UNKNOWN) return c;
+    c.known = true;
+    std::vector<std::string> tok;
+    { std::string cur; for (const char* p = nm;; ++p) { if (*p == '_' || *p == 0) { tok.push_back(cur); cur.clear(); if (!*p) break; } else cur += *p; } }
+    if (tok[0].size() >= 3 && tok[0][0] == 'B' && tok[0][1] == 'C' && tok[0][2] >= '1' && tok[0][2] <= '7')
+    {
+        c.bc = tok[0][2] - '0';
+        c.bits = (c.bc == 1 || c.bc == 4) ? 4 : 8;
+        c.maxBits = (c.bc == 6) ? 16 : (c.bc == 7) ? 7 : (c.bc <= 3) ? 6 : 8;          // 5:6:5 end points; mode-dependent 4..8 for BC7
+        c.alpha = (c.bc == 1 || c.bc == 2 || c.bc == 3 || c.bc == 7);
+    }
+    else
+    {
+        bool all = true, first = true; size_t groups = 0, types = 0;
+        FormatClass t = c;
+        for (const std::string& s : tok)
+        {
+            if (is_type_token(s)) { ++types; continue; }
+            if (s == "XR" || s == "BIAS" || s == "7E3" || s == "6E4") continue;      // R10G10B10_XR_BIAS_A2_UNORM, the Xbox 7e3 / 6e4 floats
+            if (!parse_group(s, t, first)) { all = false; break; }
+            first = false; ++groups;
+        }
+        if (all && groups > 0) { c = t; c.regular = true; }
+        (void)types;
+    }
+    size_t ntypes = 0;
+    for (const std::string& s : tok) if (is_type_token(s)) { ++ntypes; if (s == "TYPELESS") c.typeless = true; if (s == "SRGB") c.srgb = true; }
+    c.partialTypeless = c.typeless && ntypes > 1;
+    // a stencil plane next to a 24 / 32-bit depth plane: the D3D12 planar depth formats (R32G8X24, R24G8 and their views)
+    { const std::string n(nm); c.stencilPlane = n.find("G8X24") != std::string::npos || n.find("S8X24") != std::string::npos || n.find("X8X24") != std::string::npos ||
+                                               n.find("R24G8") != std::string::npos || n.find("D24_UNORM_S8") != std::string::npos || n.find("R24_UNORM_X8") != std::string::npos ||
+                                               n.find("X24_TYPELESS_G8") != std::string::npos;
+      c.xboxPlanar = n.find("D16_UNORM_S8") != std::string::npos || n.find("R16_UNORM_X8") != std::string::npos || n.find("X16_TYPELESS_G8") != std::string::npos;
+      c.stencilPlane |= c.xboxPlanar;
+      if (n == "R9G9B9E5_SHAREDEXP") c.maxBits = 14; }        // 9 mantissa + 5 shared exponent bits
+    // family = the name up to (not including) its trailing run of type tokens
+    size_t last = tok.size();
+    while (last > 0 && is_type_token(tok[last - 1])) --last;
+    for (size_t k = 0; k < last; ++k) c.family += (k ? "_" : "") + tok[k];
+    return c;
+}
+// formats whose names are not channel lists: { bits per pixel, bits per colour (0: palettized), alpha, video, planar, palettized, packed }
+struct OddFormat { DXGI_FORMAT f; uint8_t bpp, bpc; bool alpha, video, planar, pal, packed; };
+const OddFormat kOdd[] = {
+    { DXGI_FORMAT_AYUV, 32, 8, true, true, false, false, false },   { DXGI_FORMAT_Y410, 32, 10, true, true, false, false, false },
+    { DXGI_FORMAT_Y416, 64, 16, true, true, false, false, false },  { DXGI_FORMAT_NV12, 12, 8, false, true, true, false, false },
+    { DXGI_FORMAT_P010, 24, 10, false, true, true, false, false },  { DXGI_FORMAT_P016, 24, 16, false, true, true, false, false },
+    { DXGI_FORMAT_420_OPAQUE, 12, 8, false, true, true, false, false }, { DXGI_FORMAT_YUY2, 32, 8, false, true, false, false, true },
+    { DXGI_FORMAT_Y210, 64, 10, false, true, false, false, true },  { DXGI_FORMAT_Y216, 64, 16, false, true, false, false, true },
+    { DXGI_FORMAT_NV11, 12, 8, false, true, true, false, false },   { DXGI_FORMAT_AI44, 8, 0, true, true, false, true, false },
+    { DXGI_FORMAT_IA44, 8, 0, true, true, false, true, false },     { DXGI_FORMAT_P8, 8, 0, false, true, false, true, false },
+    { DXGI_FORMAT_A8P8, 16, 0, true, true, false, true, false },    { DXGI_FORMAT_P208, 16, 8, false, true, true, false, false },
+    { DXGI_FORMAT_V208, 16, 8, false, true, true, false, false },   { DXGI_FORMAT_V408, 24, 8, false, true, true, false, false },
+};
+const OddFormat* odd(DXGI_FORMAT f) { for (const OddFormat& o : kOdd) if (o.f == f) return &o; return nullptr; }
+}   // namespace
+
 namespace DirectX
 {
 
-bool IsCompressed(DXGI_FORMAT fmt) noexcept
+bool IsValid(DXGI_FORMAT fmt) noexcept { const uint32_t v = static_cast<uint32_t>(fmt); return v >= 1u && v <= 191u; }
+bool IsCompressed(DXGI_FORMAT fmt) noexcept { return classify(fmt).bc != 0; }
+bool IsPacked(DXGI_FORMAT fmt) noexcept
 {
-    switch (fmt)
-    {
-    case DXGI_FORMAT_BC1_UNORM: case DXGI_FORMAT_BC1_UNORM_SRGB: case DXGI_FORMAT_BC2_UNORM: case DXGI_FORMAT_BC2_UNORM_SRGB:
-    case DXGI_FORMAT_BC3_UNORM: case DXGI_FORMAT_BC3_UNORM_SRGB: case DXGI_FORMAT_BC4_UNORM: case DXGI_FORMAT_BC4_SNORM:
-    case DXGI_FORMAT_BC5_UNORM: case DXGI_FORMAT_BC5_SNORM: case DXGI_FORMAT_BC6H_UF16: case DXGI_FORMAT_BC6H_SF16:
-    case DXGI_FORMAT_BC7_UNORM: case DXGI_FORMAT_BC7_UNORM_SRGB: return true;
-    default: return false;
-    }
+    if (fmt == DXGI_FORMAT_R8G8_B8G8_UNORM || fmt == DXGI_FORMAT_G8R8_G8B8_UNORM) return true;
+    const OddFormat* o = odd(fmt); return o && o->packed;
 }
-
-bool IsSRGB(DXGI_FORMAT fmt) noexcept
+bool IsVideo(DXGI_FORMAT fmt) noexcept { const OddFormat* o = odd(fmt); return o && o->video; }
+bool IsPlanar(DXGI_FORMAT fmt, bool isd3d12) noexcept
 {
-    switch (fmt)
-    {
-    case DXGI_FORMAT_R8G8B8A8_UNORM_SRGB: case DXGI_FORMAT_BC1_UNORM_SRGB: case DXGI_FORMAT_BC2_UNORM_SRGB: case DXGI_FORMAT_BC3_UNORM_SRGB:
-    case DXGI_FORMAT_B8G8R8A8_UNORM_SRGB: case DXGI_FORMAT_B8G8R8X8_UNORM_SRGB: case DXGI_FORMAT_BC7_UNORM_SRGB: return true;
-    default: return false;
-    }
+    const OddFormat* o = odd(fmt);
+    if (o) return o->planar;
+    const FormatClass c = classify(fmt);
+    return c.xboxPlanar || (isd3d12 && c.stencilPlane);
 }
-
+bool IsPalettized(DXGI_FORMAT fmt) noexcept { const OddFormat* o = odd(fmt); return o && o->pal; }
+bool IsDepthStencil(DXGI_FORMAT fmt) noexcept { const FormatClass c = classify(fmt); return c.regular && (c.depth || c.stencilPlane); }
+bool IsSRGB(DXGI_FORMAT fmt) noexcept { return classify(fmt).srgb; }
+bool IsBGR(DXGI_FORMAT fmt) noexcept { const FormatClass c = classify(fmt); return c.regular && c.bgr; }
+bool IsTypeless(DXGI_FORMAT fmt, bool partialTypeless) noexcept
+{
+    const FormatClass c = classify(fmt);
+    if (!c.typeless) return false;
+    return c.partialTypeless ? partialTypeless : true;
+}
+bool HasAlpha(DXGI_FORMAT fmt) noexcept
+{
+    const OddFormat* o = odd(fmt);
+    if (o) return o->alpha;
+    return classify(fmt).alpha;
+}
 size_t BitsPerPixel(DXGI_FORMAT fmt) noexcept
 {
-    if (IsCompressed(fmt))
+    const OddFormat* o = odd(fmt);
+    if (o) return o->bpp;
+    return classify(fmt).bits;
+}
+size_t BitsPerColor(DXGI_FORMAT fmt) noexcept
+{
+    const OddFormat* o = odd(fmt);
+    if (o) return o->bpc;
+    return classify(fmt).maxBits;
+}
+size_t ComputeScanlines(DXGI_FORMAT fmt, size_t height) noexcept
+{
+    if (fmt == DXGI_FORMAT_UNKNOWN) return 0;
+    if (IsCompressed(fmt)) return std::max<size_t>(1, (height + 3) / 4);
+    if (classify(fmt).xboxPlanar) return height + ((height + 1) >> 1);                        // 16-bit depth plane + half-height stencil rows
+    switch (fmt)
     {
-        size_t r = 0, s = 0;
-        dxb200_compute_pitch(static_cast<uint32_t>(fmt), 4, 4, &r, &s);
-        return r / 2;                     // 8-byte blocks: 4 bpp, 16-byte blocks: 8 bpp
+    case DXGI_FORMAT_NV11: case DXGI_FORMAT_P208: return height * 2;                          // 4:1:1 / 4:2:2 planar: a full-height chroma plane
+    case DXGI_FORMAT_V208: return height + (((height + 1) >> 1) * 2);                         // two half-height chroma planes
+    case DXGI_FORMAT_V408: return height + ((height >> 1) * 4);
+    case DXGI_FORMAT_NV12: case DXGI_FORMAT_P010: case DXGI_FORMAT_P016: case DXGI_FORMAT_420_OPAQUE: return height + ((height + 1) >> 1);   // 4:2:0
+    default: return height;
     }
-    size_t r = 0, s = 0;
-    if (dxb200_compute_pitch(static_cast<uint32_t>(fmt), 1, 1, &r, &s) != 0) return 0;
-    return r * 8;
+}
+DXGI_FORMAT MakeSRGB(DXGI_FORMAT fmt) noexcept
+{
+    const char* n = format_name(fmt);
+    return n ? format_by_name(std::string(n) + "_SRGB", fmt) : fmt;
+}
+DXGI_FORMAT MakeLinear(DXGI_FORMAT fmt) noexcept
+{
+    const char* n = format_name(fmt);
+    if (!n) return fmt;
+    const std::string s(n);
+    return (s.size() > 5 && s.compare(s.size() - 5, 5, "_SRGB") == 0) ? format_by_name(s.substr(0, s.size() - 5), fmt) : fmt;
+}
+DXGI_FORMAT MakeTypeless(DXGI_FORMAT fmt) noexcept
+{
+    const FormatClass c = classify(fmt);
+    if (!c.known || c.typeless || c.family.empty()) return fmt;
+    const uint32_t v = static_cast<uint32_t>(fmt);
+    if (v == 116u || v == 117u || v == 189u) return DXGI_FORMAT_R10G10B10A2_TYPELESS;        // the Xbox 10:10:10:2 variants
+    if (v == 190u) return DXGI_FORMAT_R8_TYPELESS;                                            // R4G4
+    if (c.depth) return (c.family == "D32") ? DXGI_FORMAT_R32_TYPELESS : (c.family == "D16") ? DXGI_FORMAT_R16_TYPELESS : fmt;
+    return format_by_name(c.family + "_TYPELESS", fmt);
+}
+DXGI_FORMAT MakeTypelessUNORM(DXGI_FORMAT fmt) noexcept
+{
+    const FormatClass c = classify(fmt);
+    if (!c.known || !c.typeless || c.partialTypeless) return fmt;
+    return format_by_name(c.family + "_UNORM", fmt);
+}
+DXGI_FORMAT MakeTypelessFLOAT(DXGI_FORMAT fmt) noexcept
+{
+    const FormatClass c = classify(fmt);
+    if (!c.known || !c.typeless || c.partialTypeless) return fmt;
+    return format_by_name(c.family + "_FLOAT", fmt);
 }
 
 HRESULT ComputePitch(DXGI_FORMAT fmt, size_t width, size_t height, size_t& rowPitch, size_t& slicePitch, CP_FLAGS) noexcept

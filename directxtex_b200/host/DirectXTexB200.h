@@ -31,32 +31,39 @@ typedef int32_t HRESULT;
 #endif
 #define HRESULT_E_NOT_SUPPORTED static_cast<HRESULT>(0x80070032)
 
-// DXGI_FORMAT values of the formats this backend implements (public D3D ABI)
+// DXGI_FORMAT: the full public list (dxb_dxgi_formats.h); the backend implements the subset listed in DESIGN.md section 1
+#include "dxb_dxgi_formats.h"
 enum DXGI_FORMAT : uint32_t
 {
-    DXGI_FORMAT_UNKNOWN = 0,
-    DXGI_FORMAT_R32G32B32A32_FLOAT = 2, DXGI_FORMAT_R32G32B32_FLOAT = 6,
-    DXGI_FORMAT_R16G16B16A16_FLOAT = 10, DXGI_FORMAT_R16G16B16A16_UNORM = 11, DXGI_FORMAT_R16G16B16A16_SNORM = 13,
-    DXGI_FORMAT_R32G32_FLOAT = 16, DXGI_FORMAT_R10G10B10A2_UNORM = 24, DXGI_FORMAT_R11G11B10_FLOAT = 26,
-    DXGI_FORMAT_R8G8B8A8_UNORM = 28, DXGI_FORMAT_R8G8B8A8_UNORM_SRGB = 29, DXGI_FORMAT_R8G8B8A8_SNORM = 31,
-    DXGI_FORMAT_R16G16_FLOAT = 34, DXGI_FORMAT_R16G16_UNORM = 35, DXGI_FORMAT_R16G16_SNORM = 37,
-    DXGI_FORMAT_R32_FLOAT = 41, DXGI_FORMAT_R8G8_UNORM = 49, DXGI_FORMAT_R8G8_SNORM = 51,
-    DXGI_FORMAT_R16_FLOAT = 54, DXGI_FORMAT_R16_UNORM = 56, DXGI_FORMAT_R16_SNORM = 58,
-    DXGI_FORMAT_R8_UNORM = 61, DXGI_FORMAT_R8_SNORM = 63, DXGI_FORMAT_A8_UNORM = 65, DXGI_FORMAT_R9G9B9E5_SHAREDEXP = 67,
-    DXGI_FORMAT_BC1_UNORM = 71, DXGI_FORMAT_BC1_UNORM_SRGB = 72, DXGI_FORMAT_BC2_UNORM = 74, DXGI_FORMAT_BC2_UNORM_SRGB = 75,
-    DXGI_FORMAT_BC3_UNORM = 77, DXGI_FORMAT_BC3_UNORM_SRGB = 78, DXGI_FORMAT_BC4_UNORM = 80, DXGI_FORMAT_BC4_SNORM = 81,
-    DXGI_FORMAT_BC5_UNORM = 83, DXGI_FORMAT_BC5_SNORM = 84, DXGI_FORMAT_B5G6R5_UNORM = 85, DXGI_FORMAT_B5G5R5A1_UNORM = 86,
-    DXGI_FORMAT_B8G8R8A8_UNORM = 87, DXGI_FORMAT_B8G8R8X8_UNORM = 88, DXGI_FORMAT_B8G8R8A8_UNORM_SRGB = 91, DXGI_FORMAT_B8G8R8X8_UNORM_SRGB = 93,
-    DXGI_FORMAT_BC6H_UF16 = 95, DXGI_FORMAT_BC6H_SF16 = 96, DXGI_FORMAT_BC7_UNORM = 98, DXGI_FORMAT_BC7_UNORM_SRGB = 99,
-    DXGI_FORMAT_B4G4R4A4_UNORM = 115,
+#define DXB_X(name, value) DXGI_FORMAT_##name = value,
+    DXB_DXGI_FORMATS(DXB_X)
+#undef DXB_X
+    DXGI_FORMAT_FORCE_UINT = 0xffffffff
 };
 
 namespace DirectX
 {
-    // ---- format utilities (DirectXTex.h:72-99) for the implemented formats
+    // ---- format utilities (DirectXTex.h:72-99, 144-154) for EVERY DXGI format: callers like texconv classify formats the backend
+    // does not convert as well.  Classified from the format's name (channel list, type suffix), see DirectXTexB200.cpp.
+    DXTEXB200_API bool IsValid(DXGI_FORMAT fmt) noexcept;
     DXTEXB200_API bool IsCompressed(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API bool IsPacked(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API bool IsVideo(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API bool IsPlanar(DXGI_FORMAT fmt, bool isd3d12 = false) noexcept;
+    DXTEXB200_API bool IsPalettized(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API bool IsDepthStencil(DXGI_FORMAT fmt) noexcept;
     DXTEXB200_API bool IsSRGB(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API bool IsBGR(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API bool IsTypeless(DXGI_FORMAT fmt, bool partialTypeless = true) noexcept;
+    DXTEXB200_API bool HasAlpha(DXGI_FORMAT fmt) noexcept;
     DXTEXB200_API size_t BitsPerPixel(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API size_t BitsPerColor(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API size_t ComputeScanlines(DXGI_FORMAT fmt, size_t height) noexcept;
+    DXTEXB200_API DXGI_FORMAT MakeSRGB(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API DXGI_FORMAT MakeLinear(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API DXGI_FORMAT MakeTypeless(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API DXGI_FORMAT MakeTypelessUNORM(DXGI_FORMAT fmt) noexcept;
+    DXTEXB200_API DXGI_FORMAT MakeTypelessFLOAT(DXGI_FORMAT fmt) noexcept;
 
     enum CP_FLAGS : uint32_t { CP_FLAGS_NONE = 0 };
     DXTEXB200_API HRESULT ComputePitch(DXGI_FORMAT fmt, size_t width, size_t height, size_t& rowPitch, size_t& slicePitch, CP_FLAGS flags = CP_FLAGS_NONE) noexcept;   // DirectXTex.h:141-143

@@ -35,6 +35,32 @@ def test_struct_layout_and_enumerators_match_the_reference_header(tmp_path):
     assert ours.splitlines() == theirs.splitlines()
 
 
+SNAP_FMT = os.path.join(ROOT, "tests", "golden", "format_reference.txt")
+
+
+def test_format_utilities_answer_like_the_reference_for_every_dxgi_value(tmp_path):
+    """tests/cpp/format_probe.cpp prints IsValid / IsCompressed / IsPacked / IsVideo / IsPlanar / IsPalettized / IsDepthStencil / IsSRGB / IsBGR /
+    IsTypeless / HasAlpha / BitsPerPixel / BitsPerColor / Make{SRGB,Linear,Typeless,TypelessUNORM,TypelessFLOAT} / ComputeScanlines for the values
+    0..200: linked against the mirror (name-driven classification, DirectXTexB200.cpp) and against the reference build the output is identical."""
+    lib_dir = os.path.join(ROOT, "directxtex_b200", "_lib")
+    exe = str(tmp_path / "fmt_ours")
+    subprocess.run([CXX, "-std=c++17", "-w", "-I", os.path.join(ROOT, "directxtex_b200", "host"), os.path.join(ROOT, "tests", "cpp", "format_probe.cpp"), "-o", exe,
+                    os.path.join(lib_dir, "libdxtex_b200.so"), "-Wl,-rpath," + lib_dir], check=True)
+    ours = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.isdir(REF) and os.path.exists(os.path.join(ref_dir, "libdxtex_ref.so")):
+        exe = str(tmp_path / "fmt_ref")
+        subprocess.run([CXX, "-std=c++17", "-w", "-msse2", "-DPROBE_REFERENCE", "-I", os.path.join(ROOT, "oracle", "compat"), "-I", REF,
+                        os.path.join(ROOT, "tests", "cpp", "format_probe.cpp"), "-o", exe, os.path.join(ref_dir, "libdxtex_ref.so"), "-Wl,-rpath," + ref_dir], check=True)
+        theirs = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+        if not os.path.exists(SNAP_FMT) or open(SNAP_FMT).read() != theirs:
+            open(SNAP_FMT, "w").write(theirs)            # snapshot for machines without the reference tree (committed)
+    else:
+        theirs = open(SNAP_FMT).read()
+    assert len(ours.splitlines()) == 201
+    assert ours.splitlines() == theirs.splitlines()
+
+
 def _exports(path):
     out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
     return {l.split()[-1] for l in out.splitlines() if l.strip()}
@@ -43,6 +69,8 @@ def _exports(path):
 MIRRORED = ["Compress", "CompressEx", "Decompress", "Convert", "ConvertEx", "GenerateMipMaps", "Resize", "PremultiplyAlpha",
             "ScaleMipMapsAlphaForCoverage", "ComputePitch", "CalculateMipLevels", "IsCompressed", "IsSRGB", "BitsPerPixel",
             "SaveToDDSMemory", "SaveToDDSFile", "LoadFromDDSMemory", "LoadFromDDSFile", "GetMetadataFromDDSMemory", "GetMetadataFromDDSFile",
+            "IsValid", "IsPacked", "IsVideo", "IsPlanar", "IsPalettized", "IsDepthStencil", "IsBGR", "IsTypeless", "HasAlpha", "BitsPerColor",
+            "ComputeScanlines", "MakeSRGB", "MakeLinear", "MakeTypeless", "MakeTypelessUNORM", "MakeTypelessFLOAT",
             "ScratchImage", "Blob", "TexMetadata"]
 
 
@@ -60,7 +88,7 @@ def test_exported_cpp_symbols_exist_in_the_reference_build():
     missing = [d for s, d in zip(sorted(mine), dem) if s not in theirs]
     # the only symbols the reference build does not export: narrow-character DDS file paths (our addition; the reference is wchar_t
     # only, DirectXTex.h:588-616) and the functions the reference defines inline (DirectXTex.inl:63, 112, 135, 150)
-    inline_in_reference = ("DirectX::IsCompressed(DXGI_FORMAT)", "DirectX::IsSRGB(DXGI_FORMAT)",
+    inline_in_reference = ("DirectX::IsCompressed(DXGI_FORMAT)", "DirectX::IsSRGB(DXGI_FORMAT)", "DirectX::IsValid(DXGI_FORMAT)", "DirectX::IsPalettized(DXGI_FORMAT)",
                            "DirectX::SaveToDDSMemory(DirectX::Image const&, DirectX::DDS_FLAGS, DirectX::Blob&)",
                            "DirectX::SaveToDDSFile(DirectX::Image const&, DirectX::DDS_FLAGS, wchar_t const*)")
     allowed = [m for m in missing if ("char const*" in m and "DDSFile" in m and "wchar_t" not in m) or m in inline_in_reference]
