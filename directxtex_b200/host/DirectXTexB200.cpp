@@ -349,15 +349,72 @@ HRESULT ScratchImage::Initialize2D(DXGI_FORMAT fmt, size_t width, size_t height,
     return Initialize(m, flags);
 }
 
-HRESULT ScratchImage::InitializeFromImage(const Image& src, bool, CP_FLAGS flags) noexcept
+// DirectXTexImage.cpp:400-455, 510-640: the 1D / cube / from-images variants are the 2D array case plus a dimension or cube flag and a
+// row-by-row copy of the callers' pixels (min of the two pitches per row, ComputeScanlines rows).
+HRESULT ScratchImage::Initialize1D(DXGI_FORMAT fmt, size_t length, size_t arraySize, size_t mipLevels, CP_FLAGS flags) noexcept
 {
-    if (!src.pixels) return E_POINTER;
-    HRESULT hr = Initialize2D(src.format, src.width, src.height, 1, 1, flags);
+    if (!length || !arraySize) return E_INVALIDARG;
+    const HRESULT hr = Initialize2D(fmt, length, 1, arraySize, mipLevels, flags);
+    if (SUCCEEDED(hr)) m_metadata.dimension = TEX_DIMENSION_TEXTURE1D;
+    return hr;
+}
+
+HRESULT ScratchImage::InitializeCube(DXGI_FORMAT fmt, size_t width, size_t height, size_t nCubes, size_t mipLevels, CP_FLAGS flags) noexcept
+{
+    if (!width || !height || !nCubes) return E_INVALIDARG;
+    const HRESULT hr = Initialize2D(fmt, width, height, nCubes * 6, mipLevels, flags);
+    if (SUCCEEDED(hr)) m_metadata.miscFlags |= 0x4u;                     // TEX_MISC_TEXTURECUBE
+    return hr;
+}
+
+namespace
+{
+    HRESULT copy_rows(const Image& src, const Image& dst)
+    {
+        const size_t rows = ComputeScanlines(src.format, src.height);
+        if (!rows) return static_cast<HRESULT>(0x8000FFFF);               // E_UNEXPECTED
+        if (!src.pixels || !dst.pixels) return E_POINTER;
+        const size_t n = dst.rowPitch < src.rowPitch ? dst.rowPitch : src.rowPitch;
+        for (size_t y = 0; y < rows; ++y) std::memcpy(dst.pixels + y * dst.rowPitch, src.pixels + y * src.rowPitch, n);
+        return S_OK;
+    }
+}
+
+HRESULT ScratchImage::InitializeFromImage(const Image& src, bool allow1D, CP_FLAGS flags) noexcept
+{
+    const HRESULT hr = (src.height > 1 || !allow1D) ? Initialize2D(src.format, src.width, src.height, 1, 1, flags) : Initialize1D(src.format, src.width, 1, 1, flags);
     if (FAILED(hr)) return hr;
-    const size_t rows = IsCompressed(src.format) ? (src.height + 3) / 4 : src.height;
-    const size_t n = m_image[0].rowPitch < src.rowPitch ? m_image[0].rowPitch : src.rowPitch;
-    for (size_t y = 0; y < rows; ++y) std::memcpy(m_image[0].pixels + y * m_image[0].rowPitch, src.pixels + y * src.rowPitch, n);
-    return S_OK;
+    return copy_rows(src, m_image[0]);
+}
+
+HRESULT ScratchImage::InitializeArrayFromImages(const Image* images, size_t nImages, bool allow1D, CP_FLAGS flags) noexcept
+{
+    if (!images || !nImages) return E_INVALIDARG;
+    for (size_t i = 0; i < nImages; ++i)
+    {
+        if (!images[i].pixels) return E_POINTER;
+        if (images[i].format != images[0].format || images[i].width != images[0].width || images[i].height != images[0].height) return E_FAIL;   // one format and size
+    }
+    const Image& f = images[0];
+    HRESULT hr = (f.height > 1 || !allow1D) ? Initialize2D(f.format, f.width, f.height, nImages, 1, flags) : Initialize1D(f.format, f.width, nImages, 1, flags);
+    for (size_t i = 0; i < nImages && SUCCEEDED(hr); ++i) hr = copy_rows(images[i], m_image[i]);
+    return hr;
+}
+
+HRESULT ScratchImage::InitializeCubeFromImages(const Image* images, size_t nImages, CP_FLAGS flags) noexcept
+{
+    if (!images || !nImages || (nImages % 6) != 0) return E_INVALIDARG;  // whole cubes only
+    const HRESULT hr = InitializeArrayFromImages(images, nImages, false, flags);
+    if (SUCCEEDED(hr)) m_metadata.miscFlags |= 0x4u;
+    return hr;
+}
+
+bool ScratchImage::OverrideFormat(DXGI_FORMAT f) noexcept
+{
+    if (!m_image || !IsValid(f) || IsPlanar(f) || IsPalettized(f)) return false;
+    for (size_t i = 0; i < m_nimages; ++i) m_image[i].format = f;
+    m_metadata.format = f;
+    return true;
 }
 
 const Image* ScratchImage::GetImage(size_t mip, size_t item, size_t slice) const noexcept

@@ -61,6 +61,31 @@ def test_format_utilities_answer_like_the_reference_for_every_dxgi_value(tmp_pat
     assert ours.splitlines() == theirs.splitlines()
 
 
+SNAP_CONT = os.path.join(ROOT, "tests", "golden", "container_reference.txt")
+
+
+def _linked_probe(tmp_path, source, reference):
+    lib_dir = os.path.join(ROOT, "oracle", "_ref") if reference else os.path.join(ROOT, "directxtex_b200", "_lib")
+    lib = os.path.join(lib_dir, "libdxtex_ref.so" if reference else "libdxtex_b200.so")
+    inc = ["-msse2", "-DPROBE_REFERENCE", "-I", os.path.join(ROOT, "oracle", "compat"), "-I", REF] if reference else ["-I", os.path.join(ROOT, "directxtex_b200", "host")]
+    exe = str(tmp_path / (os.path.splitext(source)[0] + ("_ref" if reference else "_ours")))
+    subprocess.run([CXX, "-std=c++17", "-w"] + inc + [os.path.join(ROOT, "tests", "cpp", source), "-o", exe, lib, "-Wl,-rpath," + lib_dir], check=True)
+    return subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+
+
+def test_scratchimage_constructors_match_the_reference(tmp_path):
+    """Initialize1D / 2D / Cube, InitializeFromImage (1D and 2D), InitializeArrayFromImages, InitializeCubeFromImages and OverrideFormat: HRESULTs,
+    metadata, per-image layout and a checksum of the copied pixels equal the reference build's (tests/cpp/container_probe.cpp)."""
+    ours = _linked_probe(tmp_path, "container_probe.cpp", False)
+    if os.path.isdir(REF) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdxtex_ref.so")):
+        theirs = _linked_probe(tmp_path, "container_probe.cpp", True)
+        if not os.path.exists(SNAP_CONT) or open(SNAP_CONT).read() != theirs:
+            open(SNAP_CONT, "w").write(theirs)
+    else:
+        theirs = open(SNAP_CONT).read()
+    assert len(ours.splitlines()) > 80 and ours.splitlines() == theirs.splitlines()
+
+
 def _exports(path):
     out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
     return {l.split()[-1] for l in out.splitlines() if l.strip()}
