@@ -262,7 +262,7 @@ bool dxb_launch_bc7_tma(unsigned residentCtas, cudaStream_t stream, const dxb_jo
     const cuuint64_t dims[3] = { (cuuint64_t)j0.width * 4u, j0.height, P.njobs };
     const cuuint64_t strides[2] = { (cuuint64_t)j0.srcPitch, (cuuint64_t)srcStride };
     const cuuint32_t box[3] = { 256u, 4u, 1u }, estr[3] = { 1u, 1u, 1u };
-    if (dims[0] > 0xFFFFFFFFull ||
+    if (dims[0] > 0x7FFFFFFFull || dims[1] > 0x7FFFFFFFull ||          // tile coordinates travel as int32
         enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)j0.src, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return false;
