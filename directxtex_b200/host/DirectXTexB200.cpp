@@ -98,7 +98,16 @@ bool parse_group(const std::string& t, FormatClass& c, bool first)
     if (first) c.bgr = (posB < posR && posR != 99);   // blue stored before red: B8G8R8A8, B5G6R5, A4B4G4R4
     return true;
 }
-FormatClass classify(DXGI_FORMAT f)
+FormatClass classify_name(DXGI_FORMAT f);
+// every value 0..255 is classified once (the names are parsed on first use); anything else is unknown
+const FormatClass& classify(DXGI_FORMAT f)
+{
+    static const std::vector<FormatClass> table = []() { std::vector<FormatClass> t(256); for (uint32_t v = 0; v < 256; ++v) t[v] = classify_name(static_cast<DXGI_FORMAT>(v)); return t; }();
+    static const FormatClass unknown;
+    const uint32_t v = static_cast<uint32_t>(f);
+    return (v < 256u) ? table[v] : unknown;
+}
+FormatClass classify_name(DXGI_FORMAT f)
 {
     FormatClass c;
     const char* nm = format_name(f);
@@ -174,16 +183,16 @@ bool IsPlanar(DXGI_FORMAT fmt, bool isd3d12) noexcept
 {
     const OddFormat* o = odd(fmt);
     if (o) return o->planar;
-    const FormatClass c = classify(fmt);
+    const FormatClass& c = classify(fmt);
     return c.xboxPlanar || (isd3d12 && c.stencilPlane);
 }
 bool IsPalettized(DXGI_FORMAT fmt) noexcept { const OddFormat* o = odd(fmt); return o && o->pal; }
-bool IsDepthStencil(DXGI_FORMAT fmt) noexcept { const FormatClass c = classify(fmt); return c.regular && (c.depth || c.stencilPlane); }
+bool IsDepthStencil(DXGI_FORMAT fmt) noexcept { const FormatClass& c = classify(fmt); return c.regular && (c.depth || c.stencilPlane); }
 bool IsSRGB(DXGI_FORMAT fmt) noexcept { return classify(fmt).srgb; }
-bool IsBGR(DXGI_FORMAT fmt) noexcept { const FormatClass c = classify(fmt); return c.regular && c.bgr; }
+bool IsBGR(DXGI_FORMAT fmt) noexcept { const FormatClass& c = classify(fmt); return c.regular && c.bgr; }
 bool IsTypeless(DXGI_FORMAT fmt, bool partialTypeless) noexcept
 {
-    const FormatClass c = classify(fmt);
+    const FormatClass& c = classify(fmt);
     if (!c.typeless) return false;
     return c.partialTypeless ? partialTypeless : true;
 }
@@ -233,7 +242,7 @@ DXGI_FORMAT MakeLinear(DXGI_FORMAT fmt) noexcept
 }
 DXGI_FORMAT MakeTypeless(DXGI_FORMAT fmt) noexcept
 {
-    const FormatClass c = classify(fmt);
+    const FormatClass& c = classify(fmt);
     if (!c.known || c.typeless || c.family.empty()) return fmt;
     const uint32_t v = static_cast<uint32_t>(fmt);
     if (v == 116u || v == 117u || v == 189u) return DXGI_FORMAT_R10G10B10A2_TYPELESS;        // the Xbox 10:10:10:2 variants
@@ -243,13 +252,13 @@ DXGI_FORMAT MakeTypeless(DXGI_FORMAT fmt) noexcept
 }
 DXGI_FORMAT MakeTypelessUNORM(DXGI_FORMAT fmt) noexcept
 {
-    const FormatClass c = classify(fmt);
+    const FormatClass& c = classify(fmt);
     if (!c.known || !c.typeless || c.partialTypeless) return fmt;
     return format_by_name(c.family + "_UNORM", fmt);
 }
 DXGI_FORMAT MakeTypelessFLOAT(DXGI_FORMAT fmt) noexcept
 {
-    const FormatClass c = classify(fmt);
+    const FormatClass& c = classify(fmt);
     if (!c.known || !c.typeless || c.partialTypeless) return fmt;
     return format_by_name(c.family + "_FLOAT", fmt);
 }
