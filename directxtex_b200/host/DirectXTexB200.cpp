@@ -263,9 +263,59 @@ DXGI_FORMAT MakeTypelessFLOAT(DXGI_FORMAT fmt) noexcept
     return format_by_name(c.family + "_FLOAT", fmt);
 }
 
-HRESULT ComputePitch(DXGI_FORMAT fmt, size_t width, size_t height, size_t& rowPitch, size_t& slicePitch, CP_FLAGS) noexcept
+// DirectXTexUtil.cpp:961-1183 for EVERY format and every CP_FLAGS rule.  Three layouts cover all of them:
+//   blocks        4x4 texels in 8 or 16 bytes (BAD_DXTN_TAILS: whole blocks only, at least one byte)
+//   pixel groups  the packed and planar video formats: a row is ceil(width / g) groups of b bytes, a slice is ComputeScanlines rows
+//                 (the planar formats' chroma planes are the extra rows); 4:2:0 needs an even height
+//   pixels        everything else: ceil(width * bpp / A) units of A bits, A from the alignment flag (8 without one); the 24 / 16 / 8 BPP
+//                 flags override the format's bits per pixel
+// With no flags the result equals dxb200_compute_pitch for the formats the backend implements (tests/test_cpu_capi.py).
+HRESULT ComputePitch(DXGI_FORMAT fmt, size_t width, size_t height, size_t& rowPitch, size_t& slicePitch, CP_FLAGS flags) noexcept
 {
-    return dxb200_compute_pitch(static_cast<uint32_t>(fmt), width, height, &rowPitch, &slicePitch);
+    if (fmt == DXGI_FORMAT_UNKNOWN) return E_INVALIDARG;
+    const FormatClass& c = classify(fmt);
+    uint64_t pitch = 0, slice = 0;
+    struct Group { DXGI_FORMAT f; uint32_t px, bytes; bool evenHeight; };
+    static const Group groups[] = {
+        { DXGI_FORMAT_R8G8_B8G8_UNORM, 2, 4, false }, { DXGI_FORMAT_G8R8_G8B8_UNORM, 2, 4, false }, { DXGI_FORMAT_YUY2, 2, 4, false },
+        { DXGI_FORMAT_Y210, 2, 8, false }, { DXGI_FORMAT_Y216, 2, 8, false },
+        { DXGI_FORMAT_NV12, 2, 2, true }, { DXGI_FORMAT_420_OPAQUE, 2, 2, true }, { DXGI_FORMAT_P010, 2, 4, true }, { DXGI_FORMAT_P016, 2, 4, true },
+        { static_cast<DXGI_FORMAT>(118), 2, 4, false }, { static_cast<DXGI_FORMAT>(119), 2, 4, false }, { static_cast<DXGI_FORMAT>(120), 2, 4, false },   // Xbox D16 + S8 planes
+        { DXGI_FORMAT_NV11, 4, 4, false }, { DXGI_FORMAT_P208, 2, 2, false }, { DXGI_FORMAT_V208, 1, 1, true }, { DXGI_FORMAT_V408, 1, 1, false },
+    };
+    const Group* g = nullptr;
+    for (const Group& e : groups) if (e.f == fmt) g = &e;
+    if (c.bc)
+    {
+        const uint64_t bytes = (c.bits == 4) ? 8u : 16u;
+        if (flags & CP_FLAGS_BAD_DXTN_TAILS)
+        {
+            pitch = std::max<uint64_t>(1u, uint64_t(width >> 2) * bytes);
+            slice = std::max<uint64_t>(1u, pitch * uint64_t(height >> 2));
+        }
+        else
+        {
+            pitch = std::max<uint64_t>(1u, (uint64_t(width) + 3u) / 4u) * bytes;
+            slice = pitch * std::max<uint64_t>(1u, (uint64_t(height) + 3u) / 4u);
+        }
+    }
+    else if (g)
+    {
+        if (g->evenHeight && (height & 1u)) return E_INVALIDARG;
+        pitch = ((uint64_t(width) + g->px - 1u) / g->px) * g->bytes;
+        slice = pitch * uint64_t(ComputeScanlines(fmt, height));
+    }
+    else
+    {
+        const uint64_t bpp = (flags & CP_FLAGS_24BPP) ? 24u : (flags & CP_FLAGS_16BPP) ? 16u : (flags & CP_FLAGS_8BPP) ? 8u : uint64_t(BitsPerPixel(fmt));
+        if (!bpp) return E_INVALIDARG;
+        const uint64_t align = (flags & CP_FLAGS_PAGE4K) ? 32768u : (flags & CP_FLAGS_ZMM) ? 512u : (flags & CP_FLAGS_YMM) ? 256u : (flags & CP_FLAGS_PARAGRAPH) ? 128u :
+                               (flags & CP_FLAGS_LEGACY_DWORD) ? 32u : 8u;          // bits; the largest requested alignment wins
+        pitch = ((uint64_t(width) * bpp + align - 1u) / align) * (align / 8u);
+        slice = pitch * uint64_t(height);
+    }
+    rowPitch = static_cast<size_t>(pitch); slicePitch = static_cast<size_t>(slice);
+    return S_OK;
 }
 
 bool CalculateMipLevels(size_t width, size_t height, size_t& mipLevels) noexcept
@@ -300,7 +350,7 @@ void ScratchImage::Release() noexcept
     std::memset(&m_metadata, 0, sizeof(m_metadata));
 }
 
-HRESULT ScratchImage::Initialize(const TexMetadata& mdata, CP_FLAGS) noexcept
+HRESULT ScratchImage::Initialize(const TexMetadata& mdata, CP_FLAGS flags) noexcept
 {
     if (mdata.dimension != TEX_DIMENSION_TEXTURE2D && mdata.dimension != TEX_DIMENSION_TEXTURE1D) return HRESULT_E_NOT_SUPPORTED;   // no volume maps on this path
     if (!mdata.width || !mdata.height || mdata.depth != 1 || !mdata.arraySize) return E_INVALIDARG;
@@ -315,7 +365,7 @@ HRESULT ScratchImage::Initialize(const TexMetadata& mdata, CP_FLAGS) noexcept
         for (size_t l = 0; l < mipLevels; ++l)
         {
             size_t row = 0, slice = 0;
-            const HRESULT hr = ComputePitch(mdata.format, w, h, row, slice);
+            const HRESULT hr = ComputePitch(mdata.format, w, h, row, slice, flags);
             if (FAILED(hr)) return hr;
             total += slice;
             if (h > 1) h >>= 1;
@@ -339,7 +389,7 @@ HRESULT ScratchImage::Initialize(const TexMetadata& mdata, CP_FLAGS) noexcept
         for (size_t l = 0; l < mipLevels; ++l, ++idx)
         {
             size_t row = 0, slice = 0;
-            ComputePitch(mdata.format, w, h, row, slice);
+            ComputePitch(mdata.format, w, h, row, slice, flags);
             Image& im = m_image[idx];
             im.width = w; im.height = h; im.format = mdata.format; im.rowPitch = row; im.slicePitch = slice; im.pixels = p;
             p += slice;

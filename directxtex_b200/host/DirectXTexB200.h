@@ -65,25 +65,43 @@ namespace DirectX
     DXTEXB200_API DXGI_FORMAT MakeTypelessUNORM(DXGI_FORMAT fmt) noexcept;
     DXTEXB200_API DXGI_FORMAT MakeTypelessFLOAT(DXGI_FORMAT fmt) noexcept;
 
-    enum CP_FLAGS : uint32_t { CP_FLAGS_NONE = 0 };
+    // row-pitch rules of ComputePitch / ScratchImage::Initialize* (DirectXTex.h:104-138)
+    enum CP_FLAGS : uint32_t
+    {
+        CP_FLAGS_NONE = 0, CP_FLAGS_LEGACY_DWORD = 0x1, CP_FLAGS_PARAGRAPH = 0x2, CP_FLAGS_YMM = 0x4, CP_FLAGS_ZMM = 0x8, CP_FLAGS_PAGE4K = 0x200,
+        CP_FLAGS_BAD_DXTN_TAILS = 0x1000, CP_FLAGS_24BPP = 0x10000, CP_FLAGS_16BPP = 0x20000, CP_FLAGS_8BPP = 0x40000, CP_FLAGS_LIMIT_4GB = 0x10000000,
+    };
     DXTEXB200_API HRESULT ComputePitch(DXGI_FORMAT fmt, size_t width, size_t height, size_t& rowPitch, size_t& slicePitch, CP_FLAGS flags = CP_FLAGS_NONE) noexcept;   // DirectXTex.h:141-143
     DXTEXB200_API bool CalculateMipLevels(size_t width, size_t height, size_t& mipLevels) noexcept;                                                                   // DirectXTex.h:147
 
     // ---- metadata (DirectXTex.h:160-216)
     enum TEX_DIMENSION : uint32_t { TEX_DIMENSION_TEXTURE1D = 2, TEX_DIMENSION_TEXTURE2D = 3, TEX_DIMENSION_TEXTURE3D = 4 };
 
-    struct TexMetadata
+    struct DXTEXB200_API TexMetadata
     {
         size_t width, height, depth, arraySize, mipLevels;
         uint32_t miscFlags, miscFlags2;
         DXGI_FORMAT format;
         TEX_DIMENSION dimension;
         size_t ComputeIndex(size_t mip, size_t item, size_t slice) const noexcept;     // DirectXTexUtil.cpp:1695-1741 (2D only)
+        bool IsCubemap() const noexcept { return (miscFlags & 0x4u) != 0; }            // TEX_MISC_TEXTURECUBE
         bool IsVolumemap() const noexcept { return dimension == TEX_DIMENSION_TEXTURE3D; }
         // alpha mode lives in the low 3 bits of miscFlags2 (TEX_MISC2_ALPHA_MODE_MASK, DirectXTex.h:169-185, 214-216)
         bool IsPMAlpha() const noexcept { return (miscFlags2 & 0x7u) == 2u; }
         void SetAlphaMode(uint32_t mode) noexcept { miscFlags2 = (miscFlags2 & ~0x7u) | (mode & 0x7u); }
+        uint32_t GetAlphaMode() const noexcept { return miscFlags2 & 0x7u; }
+        // D3D subresource index: mip + item * mipLevels (+ plane * mipLevels * arraySize); uint32_t(-1) when out of range (DirectXTexUtil.cpp:1744-1807)
+        uint32_t CalculateSubresource(size_t mip, size_t item) const noexcept { return CalculateSubresource(mip, item, 0); }
+        uint32_t CalculateSubresource(size_t mip, size_t item, size_t plane) const noexcept
+        {
+            if (mip >= mipLevels) return uint32_t(-1);
+            if (dimension == TEX_DIMENSION_TEXTURE3D) return (item == 0) ? static_cast<uint32_t>(mip + plane * mipLevels) : uint32_t(-1);
+            if (dimension != TEX_DIMENSION_TEXTURE1D && dimension != TEX_DIMENSION_TEXTURE2D) return uint32_t(-1);
+            return (item < arraySize) ? static_cast<uint32_t>(mip + item * mipLevels + plane * mipLevels * arraySize) : uint32_t(-1);
+        }
     };
+    enum TEX_MISC_FLAG : uint32_t { TEX_MISC_TEXTURECUBE = 0x4 };
+    enum TEX_MISC_FLAG2 : uint32_t { TEX_MISC2_ALPHA_MODE_MASK = 0x7 };
     enum TEX_ALPHA_MODE : uint32_t { TEX_ALPHA_MODE_UNKNOWN = 0, TEX_ALPHA_MODE_STRAIGHT = 1, TEX_ALPHA_MODE_PREMULTIPLIED = 2, TEX_ALPHA_MODE_OPAQUE = 3, TEX_ALPHA_MODE_CUSTOM = 4 };
 
     // ---- flags (DirectXTex.h:741-797, 887-917)

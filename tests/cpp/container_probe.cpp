@@ -52,5 +52,9 @@ int main()
     { ScratchImage s; dump("cubeimg-5", s.InitializeCubeFromImages(im.data(), 5), s); }
     { ScratchImage s; s.Initialize2D(DXGI_FORMAT_R8G8B8A8_UNORM, 8, 4, 1, 2); const bool a = s.OverrideFormat(DXGI_FORMAT_R8G8B8A8_UNORM_SRGB), b = s.OverrideFormat(DXGI_FORMAT_NV12), c = s.OverrideFormat(DXGI_FORMAT_UNKNOWN), d = s.OverrideFormat(DXGI_FORMAT_P8);
       printf("override %d %d %d %d\n", (int)a, (int)b, (int)c, (int)d); dump("override", 0, s); ScratchImage e; printf("override-empty %d\n", (int)e.OverrideFormat(DXGI_FORMAT_R8G8B8A8_UNORM)); }
+    { TexMetadata m{}; m.width = 64; m.height = 32; m.depth = 1; m.arraySize = 6; m.mipLevels = 4; m.miscFlags = TEX_MISC_TEXTURECUBE; m.miscFlags2 = 2; m.format = DXGI_FORMAT_BC1_UNORM; m.dimension = TEX_DIMENSION_TEXTURE2D;
+      printf("meta cube %d pm %d vol %d alpha %u sub %u %u %u %u idx %zu %zu\n", (int)m.IsCubemap(), (int)m.IsPMAlpha(), (int)m.IsVolumemap(), (unsigned)m.GetAlphaMode(),
+             (unsigned)m.CalculateSubresource(3, 5), (unsigned)m.CalculateSubresource(4, 0), (unsigned)m.CalculateSubresource(1, 6), (unsigned)m.CalculateSubresource(2, 1, 1),
+             m.ComputeIndex(3, 5, 0), m.ComputeIndex(0, 6, 0)); }
     return 0;
 }

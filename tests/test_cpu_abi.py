@@ -86,6 +86,24 @@ def test_scratchimage_constructors_match_the_reference(tmp_path):
     assert len(ours.splitlines()) > 80 and ours.splitlines() == theirs.splitlines()
 
 
+SNAP_PITCH = os.path.join(ROOT, "tests", "golden", "pitch_reference.txt.gz")
+
+
+def test_compute_pitch_with_every_cp_flag_matches_the_reference(tmp_path):
+    """ComputePitch over the values 0..200 x 5 sizes x 11 CP_FLAGS settings (alignment, BAD_DXTN_TAILS, forced bits per pixel) and a ScratchImage
+    laid out with alignment flags: 11 107 lines identical to the reference build's (tests/cpp/pitch_probe.cpp)."""
+    import gzip
+    ours = _linked_probe(tmp_path, "pitch_probe.cpp", False)
+    if os.path.isdir(REF) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libdxtex_ref.so")):
+        theirs = _linked_probe(tmp_path, "pitch_probe.cpp", True)
+        if not os.path.exists(SNAP_PITCH) or gzip.open(SNAP_PITCH, "rt").read() != theirs:
+            with gzip.open(SNAP_PITCH, "wt") as f:
+                f.write(theirs)
+    else:
+        theirs = gzip.open(SNAP_PITCH, "rt").read()
+    assert len(ours.splitlines()) > 11000 and ours.splitlines() == theirs.splitlines()
+
+
 def _exports(path):
     out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
     return {l.split()[-1] for l in out.splitlines() if l.strip()}
