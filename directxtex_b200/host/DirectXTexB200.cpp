@@ -214,6 +214,26 @@ size_t BitsPerColor(DXGI_FORMAT fmt) noexcept
     if (o) return o->bpc;
     return classify(fmt).maxBits;
 }
+FORMAT_TYPE FormatDataType(DXGI_FORMAT fmt) noexcept
+{
+    // any TYPELESS part makes the format typeless; otherwise the first type token of the name decides (D24_UNORM_S8_UINT is UNORM,
+    // BC6H_UF16 / SHAREDEXP are FLOAT); the non-planar YUV formats count as UNORM, the other video formats and the Xbox depth planes as typeless
+    const char* nm = format_name(fmt);
+    if (!nm) return FORMAT_TYPE_TYPELESS;
+    const std::string n(nm);
+    if (n.find("TYPELESS") != std::string::npos || classify(fmt).xboxPlanar) return FORMAT_TYPE_TYPELESS;
+    if (const OddFormat* o = odd(fmt)) return (!o->planar && !o->pal) ? FORMAT_TYPE_UNORM : FORMAT_TYPE_TYPELESS;
+    size_t best = std::string::npos; FORMAT_TYPE t = FORMAT_TYPE_TYPELESS;
+    const struct { const char* tok; FORMAT_TYPE ty; } types[] = {
+        { "_FLOAT", FORMAT_TYPE_FLOAT }, { "_UF16", FORMAT_TYPE_FLOAT }, { "_SF16", FORMAT_TYPE_FLOAT }, { "_SHAREDEXP", FORMAT_TYPE_FLOAT },
+        { "_UNORM", FORMAT_TYPE_UNORM }, { "_SNORM", FORMAT_TYPE_SNORM }, { "_UINT", FORMAT_TYPE_UINT }, { "_SINT", FORMAT_TYPE_SINT }, { "_TYPELESS", FORMAT_TYPE_TYPELESS } };
+    for (const auto& e : types)
+    {
+        const size_t p = n.find(e.tok);
+        if (p != std::string::npos && p < best) { best = p; t = e.ty; }
+    }
+    return t;
+}
 size_t ComputeScanlines(DXGI_FORMAT fmt, size_t height) noexcept
 {
     if (fmt == DXGI_FORMAT_UNKNOWN) return 0;

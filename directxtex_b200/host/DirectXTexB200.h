@@ -58,6 +58,8 @@ namespace DirectX
     DXTEXB200_API bool HasAlpha(DXGI_FORMAT fmt) noexcept;
     DXTEXB200_API size_t BitsPerPixel(DXGI_FORMAT fmt) noexcept;
     DXTEXB200_API size_t BitsPerColor(DXGI_FORMAT fmt) noexcept;
+    enum FORMAT_TYPE : uint32_t { FORMAT_TYPE_TYPELESS, FORMAT_TYPE_FLOAT, FORMAT_TYPE_UNORM, FORMAT_TYPE_SNORM, FORMAT_TYPE_UINT, FORMAT_TYPE_SINT };
+    DXTEXB200_API FORMAT_TYPE FormatDataType(DXGI_FORMAT fmt) noexcept;      // DirectXTex.h:92-102
     DXTEXB200_API size_t ComputeScanlines(DXGI_FORMAT fmt, size_t height) noexcept;
     DXTEXB200_API DXGI_FORMAT MakeSRGB(DXGI_FORMAT fmt) noexcept;
     DXTEXB200_API DXGI_FORMAT MakeLinear(DXGI_FORMAT fmt) noexcept;

@@ -16,6 +16,7 @@ int main()
         printf("%u valid %d bc %d packed %d video %d planar %d planar12 %d pal %d ds %d srgb %d bgr %d typeless %d typelessfull %d alpha %d bpp %zu bpc %zu",
                v, (int)IsValid(f), (int)IsCompressed(f), (int)IsPacked(f), (int)IsVideo(f), (int)IsPlanar(f), (int)IsPlanar(f, true), (int)IsPalettized(f),
                (int)IsDepthStencil(f), (int)IsSRGB(f), (int)IsBGR(f), (int)IsTypeless(f), (int)IsTypeless(f, false), (int)HasAlpha(f), BitsPerPixel(f), BitsPerColor(f));
+        printf(" type %u", (unsigned)FormatDataType(f));
         printf(" mk %u %u %u %u %u", (unsigned)MakeSRGB(f), (unsigned)MakeLinear(f), (unsigned)MakeTypeless(f), (unsigned)MakeTypelessUNORM(f), (unsigned)MakeTypelessFLOAT(f));
         printf(" scan %zu %zu %zu %zu\n", ComputeScanlines(f, 1), ComputeScanlines(f, 5), ComputeScanlines(f, 64), ComputeScanlines(f, 1023));
     }

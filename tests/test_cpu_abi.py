@@ -40,7 +40,7 @@ SNAP_FMT = os.path.join(ROOT, "tests", "golden", "format_reference.txt")
 
 def test_format_utilities_answer_like_the_reference_for_every_dxgi_value(tmp_path):
     """tests/cpp/format_probe.cpp prints IsValid / IsCompressed / IsPacked / IsVideo / IsPlanar / IsPalettized / IsDepthStencil / IsSRGB / IsBGR /
-    IsTypeless / HasAlpha / BitsPerPixel / BitsPerColor / Make{SRGB,Linear,Typeless,TypelessUNORM,TypelessFLOAT} / ComputeScanlines for the values
+    IsTypeless / HasAlpha / BitsPerPixel / BitsPerColor / FormatDataType / Make{SRGB,Linear,Typeless,TypelessUNORM,TypelessFLOAT} / ComputeScanlines for the values
     0..200: linked against the mirror (name-driven classification, DirectXTexB200.cpp) and against the reference build the output is identical."""
     lib_dir = os.path.join(ROOT, "directxtex_b200", "_lib")
     exe = str(tmp_path / "fmt_ours")
@@ -112,7 +112,7 @@ def _exports(path):
 MIRRORED = ["Compress", "CompressEx", "Decompress", "Convert", "ConvertEx", "GenerateMipMaps", "Resize", "PremultiplyAlpha",
             "ScaleMipMapsAlphaForCoverage", "ComputePitch", "CalculateMipLevels", "IsCompressed", "IsSRGB", "BitsPerPixel",
             "SaveToDDSMemory", "SaveToDDSFile", "LoadFromDDSMemory", "LoadFromDDSFile", "GetMetadataFromDDSMemory", "GetMetadataFromDDSFile",
-            "IsValid", "IsPacked", "IsVideo", "IsPlanar", "IsPalettized", "IsDepthStencil", "IsBGR", "IsTypeless", "HasAlpha", "BitsPerColor",
+            "IsValid", "IsPacked", "IsVideo", "IsPlanar", "IsPalettized", "IsDepthStencil", "IsBGR", "IsTypeless", "HasAlpha", "BitsPerColor", "FormatDataType",
             "ComputeScanlines", "MakeSRGB", "MakeLinear", "MakeTypeless", "MakeTypelessUNORM", "MakeTypelessFLOAT",
             "ScratchImage", "Blob", "TexMetadata"]
 
