@@ -5,7 +5,9 @@
 // meaning, memory layout, ownership and HRESULTs follow the reference (citations: DirectXTex/DirectXTex.h of
 // microsoft/DirectXTex @ 0bb96f0); the implementation (DirectXTexB200.cpp) is new code that validates,
 // allocates the destination exactly like the reference and forwards to the C ABI in include/dxtex_b200.h.
-// Not provided (out of the hot path): file I/O, WIC, D3D interop, Resize, normal maps, ...
+// Provided besides the accelerated operations: the containers (ScratchImage / Image / TexMetadata / Blob with every constructor of the 2D
+// path), every DXGI format utility, ComputePitch with all CP_FLAGS, the DDS container.  Not provided (out of the hot path):
+// WIC / TGA / HDR / EXR codecs, D3D interop, 3D textures, normal maps, TransformImage / EvaluateImage / CopyRectangle / FlipRotate.
 #pragma once
 #include <cstddef>
 #include <cstdint>
