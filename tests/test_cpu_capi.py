@@ -123,3 +123,21 @@ def test_compute_entry_points_fail_loudly_without_gpu():
         capi.resize(a, 8, 8, 28, 5, 3)
     with pytest.raises(capi.DxTexError):
         capi.premultiply_alpha(a, 8, 8, 28)
+
+
+def test_options_round_trip_and_reject_unknown_ids():
+    """dxb200_set_option / dxb200_get_option (no device needed): the BC7 feed option keeps what is set, maps out-of-range values to the
+    automatic mode (4), and unknown option ids answer E_INVALIDARG / -1; the TMA launch counter starts at zero on a box without a GPU."""
+    L = capi.lib
+    before = L.dxb200_get_option(capi.OPT_BC7_FEED)
+    assert before in (0, 1, 2, 3, 4)
+    try:
+        for v in (0, 1, 2, 3, 4):
+            assert L.dxb200_set_option(capi.OPT_BC7_FEED, v) == 0 and L.dxb200_get_option(capi.OPT_BC7_FEED) == v
+        assert L.dxb200_set_option(capi.OPT_BC7_FEED, 99) == 0 and L.dxb200_get_option(capi.OPT_BC7_FEED) == 4
+        assert L.dxb200_set_option(capi.OPT_BC7_FEED, -5) == 0 and L.dxb200_get_option(capi.OPT_BC7_FEED) == 4
+    finally:
+        L.dxb200_set_option(capi.OPT_BC7_FEED, before)
+    assert F.hr_u32(L.dxb200_set_option(12345, 1)) == 0x80070057
+    assert L.dxb200_get_option(12345) == -1
+    assert capi.tma_launch_count() >= 0
